@@ -1,0 +1,280 @@
+/* pt_b200.h — C ABI of the B200-native wavefront integrator.
+ *
+ * Drop-in boundary for the reference's `Camera::render(&self, world: &World, filename: &str)`
+ * (reference src/camera.rs:79), which is the single call every scene function makes
+ * (src/main.rs:81,131,235,273,368,531,617).  The reference has no FFI of its own; a host
+ * (Rust via a -sys crate, or the C++ mirror in thu-acg-f2024-path-tracer_b200/host) walks
+ * its `World` once, fills the closed, flattened `pt_scene_desc` below and calls
+ * `pt_scene_create` + `pt_render`.  The host keeps scene construction, asset decoding and
+ * the SAH BVH build (src/hittable/bvh.rs:24-120); everything under `Camera::trace`
+ * (src/camera.rs:170-228) runs on the GPU.
+ *
+ * Conventions: plain pointers and sizes, no exceptions across the boundary, every call
+ * returns 0 on success or a negative pt_status; pt_last_error() gives the message of the last
+ * failure on the calling thread.  All arrays are copied by pt_scene_create (caller keeps
+ * ownership).  All geometry is f64, matching the reference (src/vec3.rs:3-6).
+ */
+#ifndef PT_B200_H
+#define PT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PT_NONE 0xFFFFFFFFu
+#define PT_ABI_VERSION 1
+
+typedef enum {
+    PT_OK = 0,
+    PT_ERR_INVALID = -1,      /* bad argument / malformed scene description */
+    PT_ERR_CUDA = -2,         /* CUDA runtime error (message in pt_last_error) */
+    PT_ERR_UNSUPPORTED = -3,  /* construct outside the closed device subset */
+    PT_ERR_NO_DEVICE = -4     /* no CUDA device: there is no CPU fallback */
+} pt_status;
+
+typedef struct { double x, y, z; } pt_vec3;
+
+/* ---- textures: src/texture.rs:11-92 ------------------------------------------------ */
+enum { PT_TEX_SOLID = 0, PT_TEX_CHECKER = 1, PT_TEX_IMAGE = 2 };
+typedef struct {
+    uint32_t kind;
+    uint32_t tex1, tex2;   /* CHECKER children (texture indices), texture.rs:27-31 */
+    uint32_t image;        /* IMAGE: index into pt_scene_desc.images */
+    double   inv_scale;    /* CHECKER: 1/scale, texture.rs:36 */
+    pt_vec3  value;        /* SOLID: colour; Texture<f64> keeps the scalar in .x */
+} pt_texture;
+
+/* RGB8, row-major, top row first — what image::to_rgb8() yields (texture.rs:62-69). */
+typedef struct { const uint8_t* rgb; uint32_t width, height; } pt_image;
+
+/* ---- materials: src/bsdf/*.rs, src/material.rs:150-191 ------------------------------ */
+enum {
+    PT_MAT_DIFFUSE = 0,    /* bsdf/diffuse.rs   */
+    PT_MAT_METAL = 1,      /* bsdf/metal.rs     */
+    PT_MAT_GLASS = 2,      /* bsdf/glass.rs     */
+    PT_MAT_PRINCIPLED = 3, /* bsdf/principled.rs*/
+    PT_MAT_LIGHT = 4,      /* material.rs DiffuseLight */
+    PT_MAT_SHEEN = 5,      /* bsdf/sheen.rs     */
+    PT_MAT_CLEARCOAT = 6,  /* bsdf/clearcoat.rs */
+    PT_MAT_MIX = 7         /* bsdf/mix.rs       */
+};
+/* indices into pt_material.p */
+enum {
+    PT_P_METALLIC = 0, PT_P_ROUGHNESS = 1, PT_P_SUBSURFACE = 2, PT_P_SPECULAR = 3,
+    PT_P_SPECULAR_TINT = 4, PT_P_IOR = 5, PT_P_SPEC_TRANS = 6, PT_P_SHEEN = 7,
+    PT_P_SHEEN_TINT = 8, PT_P_CLEARCOAT = 9, PT_P_CLEARCOAT_GLOSS = 10,
+    PT_P_ALPHA_G = 0,      /* CLEARCOAT: alpha_g (clearcoat.rs:16-18) */
+    PT_P_MIX_T = 0,        /* MIX: t, already clamped (mix.rs:17) */
+    PT_P_COLOR_R = 0, PT_P_COLOR_G = 1, PT_P_COLOR_B = 2 /* SHEEN base colour (sheen.rs:12) */
+};
+typedef struct {
+    uint32_t kind;
+    uint32_t base_color_tex; /* DIFFUSE/METAL/GLASS/PRINCIPLED base colour; LIGHT: emission */
+    uint32_t roughness_tex;  /* METAL, GLASS: Texture<f64> */
+    uint32_t normal_map;     /* DIFFUSE: image index or PT_NONE (diffuse.rs:16) */
+    uint32_t mix_a, mix_b;   /* MIX: bxdf1, bxdf2 (material indices) */
+    double   p[12];
+} pt_material;
+
+/* ---- hittables: src/hittable/*.rs ---------------------------------------------------- */
+enum {
+    PT_PRIM_SPHERE = 0, PT_PRIM_QUAD = 1, PT_PRIM_TRIANGLE = 2,
+    PT_OBJ_CUBOID = 3, PT_OBJ_MESH = 4, PT_OBJ_INSTANCE = 5
+};
+typedef struct { uint32_t kind, index; } pt_ref;
+
+typedef struct {            /* sphere.rs:13-19 */
+    pt_vec3 position1, position2;
+    double radius;          /* as passed to Sphere::new_*; intersection uses max(0,r) (sphere.rs:26) */
+    uint32_t material;
+    uint32_t is_moving;     /* built by new_moving (sphere.rs:34): affects only the host-side bbox */
+} pt_sphere;
+
+typedef struct {            /* quad.rs:5-36; derived fields computed by the host */
+    pt_vec3 q, u, v, w, normal;
+    double d;
+    uint32_t material, _pad;
+} pt_quad;
+
+typedef struct { pt_vec3 v0, v1, v2; } pt_triangle;   /* mesh.rs:13-19, vertices only */
+
+typedef struct {            /* cuboid.rs:5-9: six quads, linear (BVH-less) list */
+    uint32_t first_quad;    /* quads[first_quad .. first_quad+6) in cuboid.rs:18-53 order */
+    uint32_t material;
+    pt_vec3 a, b;           /* arguments of Cuboid::new (cuboid.rs:11), informational */
+} pt_cuboid;
+
+typedef struct {            /* mesh.rs:144-198 */
+    uint32_t first_triangle, n_triangles;
+    uint32_t material;
+    uint32_t bvh_root;      /* node index, or PT_NONE => linear scan (list.rs:57-66) */
+    uint32_t has_normals;   /* tri_normals[3*t .. 3*t+3) valid (mesh.rs:85-86) */
+    uint32_t has_uvs;       /* tri_uvs[6*t .. 6*t+6) valid (mesh.rs:91-98) */
+} pt_mesh;
+
+typedef struct {            /* instance.rs:12-31; column-major 4x4 like glam::DMat4 */
+    pt_ref child;           /* SPHERE, QUAD, CUBOID or MESH (no nesting) */
+    pt_vec3 axis;           /* arguments of Instance::new (instance.rs:20), informational: */
+    double angle;           /*   the device consumes only the three matrices below        */
+    pt_vec3 translation;
+    double transform[16];
+    double inverse[16];     /* transform.inverse(), instance.rs:36 */
+    double normal_matrix[16]; /* Mat4::from_quat(rot).inverse().transpose(), instance.rs:45 */
+} pt_instance;
+
+/* Host-built BVH (bvh.rs:6-16), consumed as-is: tie-breaks depend on its DFS order. */
+typedef struct {
+    double bmin[3], bmax[3];
+    uint32_t left, right;       /* internal: child node indices; leaf: PT_NONE */
+    uint32_t first_ref, n_refs; /* leaf: leaf_refs[first_ref .. first_ref+n_refs) */
+} pt_bvh_node;
+
+typedef struct {
+    uint32_t abi_version;       /* PT_ABI_VERSION */
+    uint32_t n_textures, n_images, n_materials;
+    uint32_t n_spheres, n_quads, n_triangles, n_cuboids, n_meshes, n_instances;
+    uint32_t n_nodes, n_leaf_refs, n_objects, n_lights;
+    const pt_texture*  textures;
+    const pt_image*    images;
+    const pt_material* materials;
+    const pt_sphere*   spheres;
+    const pt_quad*     quads;
+    const pt_triangle* triangles;
+    const pt_vec3*     tri_normals;  /* 3 per triangle, or NULL */
+    const double*      tri_uvs;      /* 6 per triangle (u0,v0,u1,v1,u2,v2), or NULL */
+    const pt_cuboid*   cuboids;
+    const pt_mesh*     meshes;
+    const pt_instance* instances;
+    const pt_bvh_node* nodes;
+    const pt_ref*      leaf_refs;
+    const pt_ref*      objects;      /* World.objects in insertion order (world.rs:6) */
+    const pt_ref*      lights;       /* World.lights in insertion order (world.rs:7) */
+    uint32_t objects_bvh_root;       /* PT_NONE => linear scan */
+    uint32_t lights_bvh_root;        /* PT_NONE => linear scan / empty */
+} pt_scene_desc;
+
+/* ---- camera: public fields of src/camera.rs:23-36; init() (camera.rs:51-77) is
+ *      re-derived inside the library ------------------------------------------------- */
+typedef struct {
+    double aspect_ratio;
+    uint32_t image_width;
+    uint32_t samples_per_pixel;
+    uint32_t max_depth;
+    uint32_t env_is_map;        /* 0: EnvironmentType::Color, 1: ::Map (camera.rs:16-19) */
+    double vfov;
+    pt_vec3 look_from, look_at, vup;
+    double blur_strength, focal_length, defocus_angle;
+    pt_vec3 env_color;
+    uint32_t env_image;         /* image index when env_is_map */
+    uint32_t _pad;
+} pt_camera;
+
+/* ---- render control --------------------------------------------------------------- */
+enum { PT_NAN_REFERENCE = 0, /* non-finite samples poison the pixel like camera.rs:129 */
+       PT_NAN_DROP = 1 };    /* drop + count non-finite samples (documented divergence) */
+typedef struct {
+    uint64_t seed;
+    uint32_t sample_begin;   /* first sample index of this call (per pixel) */
+    uint32_t sample_count;   /* samples this call renders per pixel */
+    uint32_t sample_stride;  /* sample index = sample_begin + i*stride (multi-GPU spp split) */
+    uint32_t nan_policy;
+    uint32_t pool_paths;     /* in-flight path pool size; 0 = default */
+    uint32_t _pad;
+} pt_render_params;
+
+typedef struct {
+    uint64_t paths;          /* Camera::trace calls */
+    uint64_t segments;       /* World::intersect_all calls (camera.rs:179) = "rays" */
+    uint64_t nonfinite;      /* samples dropped/poisoned */
+    uint64_t kernel_launches;
+    uint32_t iterations;     /* wavefront iterations */
+    uint32_t width, height;
+    float    device_ms;      /* CUDA-event time of the render loop */
+    float    trace_ms, shade_ms, raygen_ms; /* per-stage totals when profiling enabled, else 0 */
+} pt_stats;
+
+typedef struct pt_ctx pt_ctx;
+typedef struct pt_scene pt_scene;
+
+/* ---- lifecycle -------------------------------------------------------------------- */
+int  pt_ctx_create(int device, pt_ctx** out);
+void pt_ctx_destroy(pt_ctx* ctx);
+/* Use an external stream (e.g. torch's current stream handle); NULL = the ctx's own. */
+int  pt_ctx_set_stream(pt_ctx* ctx, void* cuda_stream);
+int  pt_ctx_set_profiling(pt_ctx* ctx, int per_stage_timing);
+const char* pt_last_error(void);
+int  pt_device_count(void);
+
+int  pt_scene_create(pt_ctx* ctx, const pt_scene_desc* desc, pt_scene** out);
+void pt_scene_destroy(pt_scene* scene);
+/* bytes uploaded host->device by pt_scene_create */
+uint64_t pt_scene_device_bytes(const pt_scene* scene);
+
+/* ---- Camera::render replacement (camera.rs:79-126 minus the PNG encode) ------------ */
+/* image height as Camera::init computes it (camera.rs:52) */
+uint32_t pt_camera_image_height(const pt_camera* cam);
+/* Adds the SUM of radiance samples into d_accum (device pointer, W*H*3 fp32, caller zeroes).
+ * This is the multi-GPU building block: each rank renders its sample subset, then one
+ * reduce(sum) of d_accum over NCCL. */
+int  pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* cam,
+                          const pt_render_params* params, float* d_accum, pt_stats* stats);
+/* Host-buffer convenience = the e2e call: renders params->sample_count samples and writes the
+ * mean radiance (W*H*3 fp32, row-major, top row first) to host memory. */
+int  pt_render(pt_ctx* ctx, const pt_scene* scene, const pt_camera* cam,
+               const pt_render_params* params, float* h_mean_rgb, pt_stats* stats);
+/* sqrt-gamma, clamp(0,0.999)*256 as u8 (camera.rs:109-114,128-130). Device in, host out. */
+int  pt_tonemap_rgb8(pt_ctx* ctx, const float* d_accum, double scale, uint32_t n_pixels,
+                     uint8_t* h_rgb8);
+
+/* ---- parity/test entry points ------------------------------------------------------ */
+typedef struct { pt_vec3 origin, direction; double time; } pt_ray; /* as built by Ray::new (ray.rs:23-29) */
+typedef struct {
+    double t, u, v;
+    pt_vec3 point, geometric_normal, shading_normal;
+    uint32_t hit;          /* 0 = miss */
+    uint32_t prim_kind;    /* PT_PRIM_* */
+    uint32_t prim_index;   /* index into spheres/quads/triangles */
+    uint32_t instance;     /* instance index or PT_NONE */
+    uint32_t material;
+    uint32_t front_face;
+    uint32_t is_light;     /* came from World.lights (world.rs:47-62) */
+    uint32_t _pad;
+} pt_hit;
+/* World::intersect_all(ray, [t_min, inf)) for a batch of host rays. */
+int  pt_trace_closest(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_ray* rays,
+                      double t_min, pt_hit* hits);
+/* World::shadow_ray-style any-hit against World.objects on [t_min, t_max] (world.rs:31-36). */
+int  pt_trace_any(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_ray* rays,
+                  double t_min, const double* t_max, uint8_t* occluded);
+
+typedef struct {
+    pt_vec3 view_dir, light_dir;         /* world space; view_dir = -ray.direction */
+    pt_vec3 point, geometric_normal, shading_normal;
+    double u, v;
+    uint32_t front_face, _pad;
+} pt_bsdf_query;
+typedef struct { pt_vec3 eval; double pdf; pt_vec3 emitted; double _pad; } pt_bsdf_result;
+/* BxDFMaterial::{eval,pdf,emitted} (bsdf/mod.rs:21-57) */
+int  pt_bsdf_eval_pdf(pt_ctx* ctx, const pt_scene* scene, uint32_t material, size_t n,
+                      const pt_bsdf_query* q, pt_bsdf_result* out);
+/* BxDFMaterial::sample with explicit uniforms (8 per query, consumed in reference order). */
+typedef struct { pt_vec3 dir; uint32_t valid; uint32_t n_uniforms; } pt_bsdf_sample_result;
+int  pt_bsdf_sample(pt_ctx* ctx, const pt_scene* scene, uint32_t material, size_t n,
+                    const pt_bsdf_query* q, const double* uniforms8, pt_bsdf_sample_result* out);
+/* Camera::generate_ray for explicit (pixel row, col, sample) triples with the library's
+ * counter-based RNG (Philox4x32-10). */
+int  pt_camera_rays(pt_ctx* ctx, const pt_camera* cam, uint64_t seed, size_t n,
+                    const uint32_t* row, const uint32_t* col, const uint32_t* sample,
+                    pt_ray* out);
+/* World.lights.{sample,pdf} (list.rs:78-96): sample uses 3 uniforms per query. */
+int  pt_lights_sample_pdf(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_vec3* origin,
+                          const double* time, const double* uniforms3, pt_vec3* dir,
+                          uint32_t* valid, double* pdf);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PT_B200_H */

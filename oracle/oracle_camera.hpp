@@ -1,0 +1,105 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.hpp header).  PARITY UNPINNED except via demo/*.png.
+//
+// CPU restatement of the reference integrator: src/camera.rs:51-228.
+#pragma once
+#include "oracle_bsdf.hpp"
+
+namespace orc {
+
+struct Camera {
+    // public fields, camera.rs:23-36
+    double aspect_ratio = 1.0; uint32_t image_width = 0, samples_per_pixel = 0, max_depth = 0;
+    double vfov = 0; Vec3 look_from, look_at, vup;
+    double blur_strength = 0, focal_length = 0, defocus_angle = 0;
+    bool env_is_map = false; Vec3 env_color; const ImageTexture* env_map = nullptr;
+    // derived, camera.rs:38-47
+    Vec3 forward, right, up; uint32_t image_height = 0; double pixel_sample_scale = 0;
+    Vec3 center, pixel00, pixel_du, pixel_dv;
+
+    void init() {  // camera.rs:51-77
+        image_height = (uint32_t)((double)image_width / aspect_ratio);
+        pixel_sample_scale = 1.0 / (double)samples_per_pixel;
+        center = look_from;
+        double theta = to_radians(vfov);
+        double h = std::tan(theta / 2.0);
+        double viewport_height = 2.0 * h * focal_length;
+        double viewport_width = viewport_height * ((double)image_width / (double)image_height);
+        forward = normalize(look_from - look_at);
+        right = normalize(cross(vup, forward));
+        up = cross(forward, right);
+        Vec3 viewport_u = right * viewport_width;
+        Vec3 viewport_v = up * -viewport_height;
+        pixel_du = viewport_u / (double)image_width;
+        pixel_dv = viewport_v / (double)image_height;
+        Vec3 upperleft = center - (forward * focal_length) - (viewport_u / 2.0) - (viewport_v / 2.0);
+        pixel00 = upperleft + (pixel_du + pixel_dv) * 0.5;
+    }
+    static void random_offsets(Rng& rng, double& x, double& y) {  // camera.rs:133-138
+        double radius = std::sqrt(rng.next());
+        double angle = rng.next() * 2.0 * PI;
+        x = radius * std::cos(angle); y = radius * std::sin(angle);
+    }
+    Vec3 sample_environment(const Ray& ray) const {  // camera.rs:140-151
+        if (!env_is_map) return env_color;
+        double theta = std::acos(ray.direction.y);
+        double phi = std::atan2(ray.direction.z, ray.direction.x);
+        double u = (phi + PI) / (2.0 * PI);
+        double v = 1.0 - theta / PI;
+        return env_map->value(u, v, Vec3(0, 0, 0));
+    }
+    Ray generate_ray(uint32_t r, uint32_t c, Rng& rng) const {  // camera.rs:153-168
+        double bx, by; random_offsets(rng, bx, by);
+        bx = bx * blur_strength; by = by * blur_strength;
+        Vec3 sample_location = pixel00 + (pixel_dv * ((double)r + bx)) + (pixel_du * ((double)c + by));
+        double radius = std::tan(to_radians(defocus_angle / 2.0)) * focal_length;
+        Vec3 dof_right = right * radius, dof_up = up * radius;
+        double px, py; random_offsets(rng, px, py);
+        Vec3 origin = center + (dof_right * px) + (dof_up * py);
+        Vec3 direction = sample_location - origin;
+        double time = rng.next();
+        return Ray::make(origin, direction, time);
+    }
+    // camera.rs:170-228.  `record`, when non-null, receives every ray handed to intersect_all.
+    Vec3 trace(uint32_t r, uint32_t c, const World& world, Rng& rng, std::vector<Ray>* record = nullptr) const {
+        const double eps = 1e-3;
+        const uint32_t min_bounces = 5;
+        Vec3 radiance(0, 0, 0), throughput(1, 1, 1);
+        Ray ray = generate_ray(r, c, rng);
+        g_cnt.paths++;
+        for (uint32_t bounces = 0; bounces < max_depth; bounces++) {
+            if (record) record->push_back(ray);
+            auto hit = world.intersect_all(ray, Interval{eps, INF});
+            if (!hit) {
+                radiance += throughput * sample_environment(ray);
+                break;
+            }
+            const HitInfo& info = hit->first;
+            Vec3 emission = info.mat->emitted(info.u, info.v, info.point);
+            radiance += throughput * emission;
+            if (bounces > min_bounces) {  // Russian roulette, camera.rs:190-196
+                double p = clamp_(luminance(throughput), 0.01, 1.0);
+                if (rng.next() > p) break;
+                throughput /= p;
+            }
+            double p_light = world.lights.is_empty() ? 0.0 : 0.5;  // camera.rs:199
+            double p_bsdf = 1.0 - p_light;
+            double rr = rng.next();
+            std::optional<Vec3> dir;
+            if (rr < p_light) dir = world.lights.sample(info.point, ray.time, rng);
+            else dir = info.mat->sample(ray, info, rng);
+            if (!dir) break;
+            double bsdf_pdf = info.mat->pdf(-ray.direction, *dir, info);
+            double light_pdf = world.lights.pdf(info.point, *dir, ray.time);
+            double pdf = p_bsdf * bsdf_pdf + p_light * light_pdf;
+            Vec3 brdf = info.mat->eval(-ray.direction, *dir, info);
+            Vec3 attenuation = brdf / pdf;
+            double e = 1e-3 * signum_(dot(*dir, info.geometric_normal));  // bsdf::EPS, camera.rs:217
+            Ray next = Ray::make(info.point + e * info.geometric_normal, *dir, ray.time);
+            throughput *= attenuation;
+            ray = next;
+        }
+        return radiance;
+    }
+};
+
+}  // namespace orc

@@ -1,0 +1,578 @@
+// C ABI implementation (include/pt_b200.h): context, scene upload, the wavefront render loop and the
+// parity entry points.  There is NO CPU fallback: without a CUDA device every call fails loudly.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace ptd;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(call)                                                                                                   \
+    do {                                                                                                           \
+        cudaError_t e_ = (call);                                                                                   \
+        if (e_ != cudaSuccess) return fail(PT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
+    } while (0)
+
+struct pt_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    bool profiling = false;
+    // path pool (ping-pong SoA) + hit records, grown on demand
+    uint32_t pool = 0;
+    double* pool_f[2] = {nullptr, nullptr};
+    uint4* pool_ids[2] = {nullptr, nullptr};
+    HitRec* hits = nullptr;
+    uint32_t* d_count = nullptr;            // [2]: survivors counter, spare
+    unsigned long long* d_nonfinite = nullptr;
+    uint32_t* h_count = nullptr;            // pinned
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs[6] = {nullptr};
+};
+struct pt_scene {
+    pt_ctx* ctx = nullptr;
+    std::vector<void*> allocs;
+    DScene d{};
+    uint64_t bytes = 0;
+    uint32_t n_materials = 0, n_images = 0, max_stack = 0;
+    std::vector<DImage> images;
+};
+
+extern "C" {
+
+const char* pt_last_error(void) { return g_err.c_str(); }
+int pt_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+
+int pt_ctx_create(int device, pt_ctx** out) {
+    if (!out) return fail(PT_ERR_INVALID, "pt_ctx_create: null out");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return fail(PT_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
+    if (device < 0 || device >= n) return fail(PT_ERR_INVALID, "pt_ctx_create: bad device index");
+    CU(cudaSetDevice(device));
+    auto* c = new pt_ctx(); c->device = device;
+    CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    CU(cudaMalloc(&c->d_count, 2 * sizeof(uint32_t)));
+    CU(cudaMalloc(&c->d_nonfinite, sizeof(unsigned long long)));
+    CU(cudaMallocHost(&c->h_count, 2 * sizeof(uint32_t)));
+    CU(cudaEventCreate(&c->ev0)); CU(cudaEventCreate(&c->ev1));
+    for (auto& e : c->evs) CU(cudaEventCreate(&e));
+    *out = c;
+    return PT_OK;
+}
+static void free_pool(pt_ctx* c) {
+    for (int i = 0; i < 2; i++) { cudaFree(c->pool_f[i]); cudaFree(c->pool_ids[i]); c->pool_f[i] = nullptr; c->pool_ids[i] = nullptr; }
+    cudaFree(c->hits); c->hits = nullptr; c->pool = 0;
+}
+void pt_ctx_destroy(pt_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    free_pool(c);
+    cudaFree(c->d_count); cudaFree(c->d_nonfinite); cudaFreeHost(c->h_count);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    for (auto& e : c->evs) cudaEventDestroy(e);
+    cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+int pt_ctx_set_stream(pt_ctx* c, void* s) { if (!c) return fail(PT_ERR_INVALID, "null ctx"); c->stream = s ? (cudaStream_t)s : c->own_stream; return PT_OK; }
+int pt_ctx_set_profiling(pt_ctx* c, int on) { if (!c) return fail(PT_ERR_INVALID, "null ctx"); c->profiling = on != 0; return PT_OK; }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ scene upload
+namespace {
+struct Uploader {
+    pt_scene* s;
+    template <class T> int up(const std::vector<T>& v, const T** out) {
+        *out = nullptr;
+        if (v.empty()) return PT_OK;
+        void* p = nullptr;
+        CU(cudaMalloc(&p, v.size() * sizeof(T)));
+        s->allocs.push_back(p);
+        CU(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s->ctx->stream));
+        s->bytes += v.size() * sizeof(T);
+        *out = (const T*)p;
+        return PT_OK;
+    }
+};
+float round_down(double v) { float f = (float)v; if ((double)f > v) f = std::nextafterf(f, -INFINITY); return f; }
+float round_up(double v) { float f = (float)v; if ((double)f < v) f = std::nextafterf(f, INFINITY); return f; }
+
+struct Converter {
+    const pt_scene_desc* d;
+    std::vector<DNode> nodes;
+    std::vector<DRef> refs;
+    uint32_t tie_counter = 0;
+    uint32_t max_depth = 0;
+    std::string err;
+
+    static bool tie_is_sphere(const pt_scene_desc* d, pt_ref r) {
+        if (r.kind == PT_PRIM_SPHERE) return true;
+        if (r.kind == PT_OBJ_INSTANCE) return d->instances[r.index].child.kind == PT_PRIM_SPHERE;
+        return false;
+    }
+    void set_box(DNode& n, const double* lo, const double* hi) {
+        double m = 0.0;
+        for (int k = 0; k < 3; k++) { m = std::max(m, std::fabs(lo[k])); m = std::max(m, std::fabs(hi[k])); }
+        if (!std::isfinite(m)) { for (int k = 0; k < 3; k++) { n.lo[k] = -INFINITY; n.hi[k] = INFINITY; } return; }
+        double pad = m * 9.5367431640625e-07;  // 8 ulp(fp32) of the largest coordinate: inv/product rounding in the slab test
+        for (int k = 0; k < 3; k++) { n.lo[k] = round_down(lo[k] - pad); n.hi[k] = round_up(hi[k] + pad); }
+    }
+    // leaf refs of host node `hn` -> device refs (appended), with exact-tie ranks in DFS order
+    void make_leaf(DNode& out, const pt_ref* items, uint32_t n, uint32_t top_bit, bool box_inf, const double* lo, const double* hi) {
+        out.a = (uint32_t)refs.size(); out.b = n;
+        if (box_inf) { for (int k = 0; k < 3; k++) { out.lo[k] = -INFINITY; out.hi[k] = INFINITY; } } else set_box(out, lo, hi);
+        uint32_t base = tie_counter; tie_counter += 2 * n + 2;
+        for (uint32_t p = 0; p < n; p++) {
+            // later non-sphere wins a tie; a later sphere loses it
+            uint32_t rank = tie_is_sphere(d, items[p]) ? base + n - 1 - p : base + n + p;
+            refs.push_back(DRef{ref_pack(items[p].kind, items[p].index), rank | top_bit});
+        }
+    }
+    // writes host node hn into nodes[slot]; children become a fresh adjacent pair
+    bool fill(uint32_t slot, uint32_t hn, uint32_t top_bit, uint32_t depth) {
+        if (hn >= d->n_nodes) { err = "bvh node index out of range"; return false; }
+        if (depth > 200) { err = "bvh too deep / cyclic"; return false; }
+        max_depth = std::max(max_depth, depth);
+        const pt_bvh_node& h = d->nodes[hn];
+        if (h.left == PT_NONE) {
+            if ((uint64_t)h.first_ref + h.n_refs > d->n_leaf_refs) { err = "leaf refs out of range"; return false; }
+            DNode n{}; make_leaf(n, d->leaf_refs + h.first_ref, h.n_refs, top_bit, false, h.bmin, h.bmax);
+            nodes[slot] = n;
+            return true;
+        }
+        uint32_t pair = (uint32_t)nodes.size();
+        nodes.resize(nodes.size() + 2);
+        DNode n{}; set_box(n, h.bmin, h.bmax); n.a = pair; n.b = kNone;
+        nodes[slot] = n;
+        return fill(pair, h.left, top_bit, depth + 1) && fill(pair + 1, h.right, top_bit, depth + 1);  // DFS: left before right
+    }
+    void dummy(uint32_t slot) { DNode n{}; for (int k = 0; k < 3; k++) { n.lo[k] = INFINITY; n.hi[k] = -INFINITY; } n.a = 0; n.b = 0; nodes[slot] = n; }
+};
+}  // namespace
+
+static int check_desc(const pt_scene_desc* d) {
+    if (!d) return fail(PT_ERR_INVALID, "null scene description");
+    if (d->abi_version != PT_ABI_VERSION) return fail(PT_ERR_INVALID, "pt_scene_desc.abi_version mismatch");
+    auto need = [](uint32_t n, const void* p) { return n == 0 || p != nullptr; };
+    if (!need(d->n_textures, d->textures) || !need(d->n_images, d->images) || !need(d->n_materials, d->materials) ||
+        !need(d->n_spheres, d->spheres) || !need(d->n_quads, d->quads) || !need(d->n_triangles, d->triangles) ||
+        !need(d->n_cuboids, d->cuboids) || !need(d->n_meshes, d->meshes) || !need(d->n_instances, d->instances) ||
+        !need(d->n_nodes, d->nodes) || !need(d->n_leaf_refs, d->leaf_refs) || !need(d->n_objects, d->objects) || !need(d->n_lights, d->lights))
+        return fail(PT_ERR_INVALID, "scene description has a null array with a non-zero count");
+    if (d->n_triangles >= (1u << 29) || d->n_quads >= (1u << 29) || d->n_spheres >= (1u << 29)) return fail(PT_ERR_UNSUPPORTED, "too many primitives");
+    auto ref_ok = [&](pt_ref r, bool top) {
+        switch (r.kind) {
+            case PT_PRIM_SPHERE: return r.index < d->n_spheres;
+            case PT_PRIM_QUAD: return r.index < d->n_quads;
+            case PT_PRIM_TRIANGLE: return !top && r.index < d->n_triangles;
+            case PT_OBJ_CUBOID: return r.index < d->n_cuboids;
+            case PT_OBJ_MESH: return r.index < d->n_meshes;
+            case PT_OBJ_INSTANCE: return top && r.index < d->n_instances;
+            default: return false;
+        }
+    };
+    for (uint32_t i = 0; i < d->n_objects; i++) if (!ref_ok(d->objects[i], true)) return fail(PT_ERR_INVALID, "bad ref in objects");
+    for (uint32_t i = 0; i < d->n_lights; i++) if (!ref_ok(d->lights[i], true)) return fail(PT_ERR_INVALID, "bad ref in lights");
+    for (uint32_t i = 0; i < d->n_leaf_refs; i++) if (!ref_ok(d->leaf_refs[i], false) && !ref_ok(d->leaf_refs[i], true)) return fail(PT_ERR_INVALID, "bad leaf ref");
+    for (uint32_t i = 0; i < d->n_instances; i++) {
+        pt_ref c = d->instances[i].child;
+        if (c.kind == PT_OBJ_INSTANCE || c.kind == PT_PRIM_TRIANGLE || !ref_ok(c, false)) return fail(PT_ERR_UNSUPPORTED, "instance child must be a sphere, quad, cuboid or mesh");
+    }
+    for (uint32_t i = 0; i < d->n_lights; i++)
+        if (d->lights[i].kind != PT_PRIM_QUAD && d->lights[i].kind != PT_PRIM_SPHERE)
+            return fail(PT_ERR_UNSUPPORTED, "World.lights may hold quads and spheres only on the device (sample/pdf subset)");
+    for (uint32_t i = 0; i < d->n_materials; i++) {
+        const pt_material& m = d->materials[i];
+        auto tex_ok = [&](uint32_t t) { return t < d->n_textures; };
+        bool ok = true;
+        switch (m.kind) {
+            case PT_MAT_DIFFUSE: ok = tex_ok(m.base_color_tex) && (m.normal_map == PT_NONE || m.normal_map < d->n_images); break;
+            case PT_MAT_METAL: case PT_MAT_GLASS: ok = tex_ok(m.base_color_tex) && tex_ok(m.roughness_tex); break;
+            case PT_MAT_PRINCIPLED: case PT_MAT_LIGHT: ok = tex_ok(m.base_color_tex); break;
+            case PT_MAT_SHEEN: case PT_MAT_CLEARCOAT: break;
+            case PT_MAT_MIX: ok = m.mix_a < i && m.mix_b < i; break;
+            default: ok = false;
+        }
+        if (!ok) return fail(PT_ERR_INVALID, "bad material " + std::to_string(i));
+    }
+    for (uint32_t i = 0; i < d->n_textures; i++) {
+        const pt_texture& t = d->textures[i];
+        if (t.kind == PT_TEX_CHECKER && (t.tex1 >= d->n_textures || t.tex2 >= d->n_textures)) return fail(PT_ERR_INVALID, "bad checker child");
+        if (t.kind == PT_TEX_IMAGE && t.image >= d->n_images) return fail(PT_ERR_INVALID, "bad image index");
+        if (t.kind > PT_TEX_IMAGE) return fail(PT_ERR_INVALID, "bad texture kind");
+    }
+    return PT_OK;
+}
+
+extern "C" {
+
+int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
+    if (!ctx || !out) return fail(PT_ERR_INVALID, "pt_scene_create: null argument");
+    int rc = check_desc(d);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    auto s = std::unique_ptr<pt_scene>(new pt_scene());
+    s->ctx = ctx;
+    Uploader U{s.get()};
+    Converter C; C.d = d;
+
+    // ---- BVH: pair 0 = (objects root, lights root); every mesh gets its own (root, dummy) pair
+    C.nodes.resize(2);
+    auto top_list = [&](uint32_t slot, uint32_t root, const pt_ref* items, uint32_t n, uint32_t top_bit) -> bool {
+        if (n == 0) { C.dummy(slot); return true; }
+        if (root == PT_NONE) { DNode leaf{}; C.make_leaf(leaf, items, n, top_bit, true, nullptr, nullptr); C.nodes[slot] = leaf; return true; }  // list.rs:57-66
+        return C.fill(slot, root, top_bit, 1);
+    };
+    // lights first so that their ranks are lower; objects additionally carry bit 31 (object beats light, world.rs:55-59)
+    if (!top_list(1, d->lights_bvh_root, d->lights, d->n_lights, 0u)) return fail(PT_ERR_INVALID, C.err);
+    if (!top_list(0, d->objects_bvh_root, d->objects, d->n_objects, 0x80000000u)) return fail(PT_ERR_INVALID, C.err);
+    const uint32_t tlas_depth = C.max_depth;
+    if (C.tie_counter >= 0x7FFFFFFFu) return fail(PT_ERR_UNSUPPORTED, "too many top-level objects");
+    std::vector<DMesh> meshes(d->n_meshes);
+    std::vector<uint32_t> tri_mesh(d->n_triangles, 0);
+    uint32_t blas_depth = 0;
+    for (uint32_t mi = 0; mi < d->n_meshes; mi++) {
+        const pt_mesh& m = d->meshes[mi];
+        if ((uint64_t)m.first_triangle + m.n_triangles > d->n_triangles || m.material >= d->n_materials) return fail(PT_ERR_INVALID, "bad mesh");
+        if ((m.has_normals && !d->tri_normals) || (m.has_uvs && !d->tri_uvs)) return fail(PT_ERR_INVALID, "mesh flags without arrays");
+        for (uint32_t k = 0; k < m.n_triangles; k++) tri_mesh[m.first_triangle + k] = mi;
+        uint32_t pair = (uint32_t)C.nodes.size();
+        C.nodes.resize(C.nodes.size() + 2);
+        C.dummy(pair + 1);
+        C.max_depth = 0; C.tie_counter = 0;
+        if (m.bvh_root == PT_NONE) {
+            std::vector<pt_ref> items(m.n_triangles);
+            for (uint32_t k = 0; k < m.n_triangles; k++) items[k] = pt_ref{PT_PRIM_TRIANGLE, m.first_triangle + k};
+            DNode leaf{}; C.make_leaf(leaf, items.data(), m.n_triangles, 0u, true, nullptr, nullptr); C.nodes[pair] = leaf;
+        } else if (!C.fill(pair, m.bvh_root, 0u, 1)) return fail(PT_ERR_INVALID, C.err);
+        blas_depth = std::max(blas_depth, C.max_depth);
+        meshes[mi] = DMesh{pair, m.first_triangle, m.n_triangles, m.material, m.has_normals, m.has_uvs, m.bvh_root == PT_NONE, 0};
+    }
+    // stack bound: one pending sibling per level + deferred refs of a leaf (<= refs in a TLAS leaf) + sentinel
+    uint32_t max_leaf = 0;
+    for (auto& n : C.nodes) if (n.b != kNone) max_leaf = std::max(max_leaf, n.b);
+    uint32_t top_leaf = std::max(d->objects_bvh_root == PT_NONE ? d->n_objects : 0u, d->lights_bvh_root == PT_NONE ? d->n_lights : 0u);
+    (void)max_leaf;
+    s->max_stack = tlas_depth + blas_depth + 2 + std::max(top_leaf, 8u);
+    if (s->max_stack > (uint32_t)kStack) return fail(PT_ERR_UNSUPPORTED, "BVH too deep for the device traversal stack (" + std::to_string(s->max_stack) + " > " + std::to_string(kStack) + ")");
+
+    // ---- primitives
+    std::vector<DSphere> spheres(d->n_spheres);
+    for (uint32_t i = 0; i < d->n_spheres; i++) {
+        const pt_sphere& p = d->spheres[i];
+        if (p.material >= d->n_materials) return fail(PT_ERR_INVALID, "bad sphere material");
+        DSphere o{}; o.p1[0] = p.position1.x; o.p1[1] = p.position1.y; o.p1[2] = p.position1.z; o.p2[0] = p.position2.x; o.p2[1] = p.position2.y; o.p2[2] = p.position2.z;
+        o.radius = p.radius; o.material = p.material; spheres[i] = o;
+    }
+    std::vector<DQuad> quads(d->n_quads); std::vector<uint32_t> quad_mat(d->n_quads);
+    for (uint32_t i = 0; i < d->n_quads; i++) {
+        const pt_quad& p = d->quads[i];
+        if (p.material >= d->n_materials) return fail(PT_ERR_INVALID, "bad quad material");
+        DQuad o{}; const pt_vec3* src[5] = {&p.q, &p.u, &p.v, &p.w, &p.normal}; double* dst[5] = {o.q, o.u, o.v, o.w, o.n};
+        for (int k = 0; k < 5; k++) { dst[k][0] = src[k]->x; dst[k][1] = src[k]->y; dst[k][2] = src[k]->z; }
+        o.d = p.d; quads[i] = o; quad_mat[i] = p.material;
+    }
+    std::vector<DTri> tris(d->n_triangles);
+    for (uint32_t i = 0; i < d->n_triangles; i++) {
+        const pt_triangle& p = d->triangles[i];
+        DTri o{}; o.v0[0] = p.v0.x; o.v0[1] = p.v0.y; o.v0[2] = p.v0.z;
+        o.e1[0] = p.v1.x - p.v0.x; o.e1[1] = p.v1.y - p.v0.y; o.e1[2] = p.v1.z - p.v0.z;  // mesh.rs:55-56, same IEEE subtraction
+        o.e2[0] = p.v2.x - p.v0.x; o.e2[1] = p.v2.y - p.v0.y; o.e2[2] = p.v2.z - p.v0.z;
+        tris[i] = o;
+    }
+    std::vector<double> tri_normals, tri_uvs;
+    bool any_n = false, any_uv = false;
+    for (auto& m : meshes) { any_n |= m.has_normals != 0; any_uv |= m.has_uvs != 0; }
+    if (any_n) { tri_normals.resize(9ull * d->n_triangles); memcpy(tri_normals.data(), d->tri_normals, tri_normals.size() * 8); }
+    if (any_uv) { tri_uvs.assign(d->tri_uvs, d->tri_uvs + 6ull * d->n_triangles); }
+    std::vector<DCuboid> cuboids(d->n_cuboids);
+    for (uint32_t i = 0; i < d->n_cuboids; i++) {
+        if ((uint64_t)d->cuboids[i].first_quad + 6 > d->n_quads) return fail(PT_ERR_INVALID, "bad cuboid");
+        cuboids[i] = DCuboid{d->cuboids[i].first_quad, d->cuboids[i].material};
+    }
+    std::vector<DInstance> instances(d->n_instances);
+    for (uint32_t i = 0; i < d->n_instances; i++) {
+        const pt_instance& p = d->instances[i];
+        DInstance o{};
+        for (int c = 0; c < 4; c++) for (int r = 0; r < 3; r++) { o.inv[c * 3 + r] = p.inverse[c * 4 + r]; o.fwd[c * 3 + r] = p.transform[c * 4 + r]; o.nrm[c * 3 + r] = p.normal_matrix[c * 4 + r]; }
+        o.child_kind = p.child.kind; o.child_index = p.child.index; o.tie_is_sphere = p.child.kind == PT_PRIM_SPHERE;
+        instances[i] = o;
+    }
+    // ---- textures, images, materials
+    std::vector<DTexture> textures(d->n_textures);
+    for (uint32_t i = 0; i < d->n_textures; i++) {
+        const pt_texture& t = d->textures[i];
+        textures[i] = DTexture{t.kind, t.tex1, t.tex2, t.image, t.inv_scale, {t.value.x, t.value.y, t.value.z}};
+    }
+    std::vector<DImage> images(d->n_images);
+    uint64_t img_bytes = 0;
+    for (uint32_t i = 0; i < d->n_images; i++) {
+        if (!d->images[i].rgb && d->images[i].width * d->images[i].height) return fail(PT_ERR_INVALID, "null image data");
+        images[i] = DImage{img_bytes, d->images[i].width, d->images[i].height};
+        img_bytes += ((3ull * d->images[i].width * d->images[i].height + 255) / 256) * 256;
+    }
+    uint8_t* d_img = nullptr;
+    if (img_bytes) {
+        CU(cudaMalloc(&d_img, img_bytes)); s->allocs.push_back(d_img);
+        for (uint32_t i = 0; i < d->n_images; i++) {
+            size_t nb = 3ull * d->images[i].width * d->images[i].height;
+            if (nb) CU(cudaMemcpyAsync(d_img + images[i].offset, d->images[i].rgb, nb, cudaMemcpyHostToDevice, ctx->stream));
+            s->bytes += nb;
+        }
+    }
+    std::vector<DMaterial> materials(d->n_materials);
+    for (uint32_t i = 0; i < d->n_materials; i++) {
+        const pt_material& m = d->materials[i];
+        DMaterial o{}; o.kind = m.kind; o.base_color_tex = m.base_color_tex; o.roughness_tex = m.roughness_tex; o.normal_map = m.normal_map;
+        o.mix_a = m.mix_a; o.mix_b = m.mix_b; memcpy(o.p, m.p, sizeof(o.p));
+        materials[i] = o;
+    }
+    std::vector<DRef> lights(d->n_lights);
+    for (uint32_t i = 0; i < d->n_lights; i++) lights[i] = DRef{ref_pack(d->lights[i].kind, d->lights[i].index), 0};
+
+    DScene& D = s->d;
+    if ((rc = U.up(C.nodes, &D.nodes)) || (rc = U.up(C.refs, &D.refs)) || (rc = U.up(spheres, &D.spheres)) || (rc = U.up(quads, &D.quads)) ||
+        (rc = U.up(quad_mat, &D.quad_material)) || (rc = U.up(tris, &D.tris)) || (rc = U.up(tri_normals, &D.tri_normals)) ||
+        (rc = U.up(tri_uvs, &D.tri_uvs)) || (rc = U.up(tri_mesh, &D.tri_mesh)) || (rc = U.up(cuboids, &D.cuboids)) || (rc = U.up(meshes, &D.meshes)) ||
+        (rc = U.up(instances, &D.instances)) || (rc = U.up(textures, &D.textures)) || (rc = U.up(images, &D.images)) ||
+        (rc = U.up(materials, &D.materials)) || (rc = U.up(lights, &D.lights)))
+        return rc;
+    D.image_data = d_img; D.n_lights = d->n_lights; D.root_pair = 0;
+    s->n_materials = d->n_materials; s->n_images = d->n_images; s->images = images;
+    CU(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+    *out = s.release();
+    return PT_OK;
+}
+void pt_scene_destroy(pt_scene* s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    for (void* p : s->allocs) cudaFree(p);
+    delete s;
+}
+uint64_t pt_scene_device_bytes(const pt_scene* s) { return s ? s->bytes : 0; }
+
+// ------------------------------------------------------------------------------------------------ camera
+static d3 dv(const pt_vec3& v) { return mk(v.x, v.y, v.z); }
+uint32_t pt_camera_image_height(const pt_camera* c) { return c ? (uint32_t)((double)c->image_width / c->aspect_ratio) : 0; }  // camera.rs:52
+static int make_camera(const pt_scene* s, const pt_camera* c, DCameraEx* out) {  // Camera::init, camera.rs:51-77
+    if (!c) return fail(PT_ERR_INVALID, "null camera");
+    if (c->image_width == 0 || !(c->aspect_ratio > 0.0)) return fail(PT_ERR_INVALID, "bad camera size");
+    DCameraEx e{}; DCamera& k = e.c;
+    k.width = c->image_width; k.height = pt_camera_image_height(c); k.max_depth = c->max_depth;
+    if (k.height == 0) return fail(PT_ERR_INVALID, "camera image height is zero");
+    k.center = dv(c->look_from);
+    double theta = c->vfov * (kPi / 180.0);  // f64::to_radians
+    double h = std::tan(theta / 2.0);
+    double viewport_height = 2.0 * h * c->focal_length;
+    double viewport_width = viewport_height * ((double)k.width / (double)k.height);
+    d3 forward = normalize(dv(c->look_from) - dv(c->look_at));
+    k.right = normalize(cross(dv(c->vup), forward));
+    k.up = cross(forward, k.right);
+    d3 viewport_u = k.right * viewport_width, viewport_v = k.up * -viewport_height;
+    k.pixel_du = viewport_u / (double)k.width; k.pixel_dv = viewport_v / (double)k.height;
+    d3 upperleft = k.center - (forward * c->focal_length) - (viewport_u / 2.0) - (viewport_v / 2.0);
+    k.pixel00 = upperleft + (k.pixel_du + k.pixel_dv) * 0.5;
+    k.blur_strength = c->blur_strength; k.focal_length = c->focal_length; k.defocus_angle = c->defocus_angle;
+    double radius = std::tan((c->defocus_angle / 2.0) * (kPi / 180.0)) * c->focal_length;  // camera.rs:159
+    e.dof_right = k.right * radius; e.dof_up = k.up * radius;
+    k.env_is_map = c->env_is_map; k.env_color = dv(c->env_color); k.env_image = c->env_image;
+    if (c->env_is_map && (!s || c->env_image >= s->n_images)) return fail(PT_ERR_INVALID, "camera env_image out of range");
+    *out = e;
+    return PT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ render
+static int ensure_pool(pt_ctx* c, uint32_t paths) {
+    if (c->pool >= paths) return PT_OK;
+    free_pool(c);
+    for (int i = 0; i < 2; i++) {
+        CU(cudaMalloc(&c->pool_f[i], (size_t)paths * 10 * sizeof(double)));
+        CU(cudaMalloc(&c->pool_ids[i], (size_t)paths * sizeof(uint4)));
+    }
+    CU(cudaMalloc(&c->hits, (size_t)paths * sizeof(HitRec)));
+    c->pool = paths;
+    return PT_OK;
+}
+static PathBuf path_buf(pt_ctx* c, int which) {
+    PathBuf b;
+    for (int k = 0; k < 10; k++) b.f[k] = c->pool_f[which] + (size_t)k * c->pool;
+    b.ids = c->pool_ids[which];
+    return b;
+}
+
+int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* cam, const pt_render_params* p, float* d_accum, pt_stats* stats) {
+    if (!ctx || !scene || !p || !d_accum) return fail(PT_ERR_INVALID, "pt_render_accumulate: null argument");
+    if (scene->ctx != ctx) return fail(PT_ERR_INVALID, "scene belongs to another context");
+    CU(cudaSetDevice(ctx->device));
+    DCameraEx dcam;
+    int rc = make_camera(scene, cam, &dcam);
+    if (rc) return rc;
+    const uint32_t n_pixels = dcam.c.width * dcam.c.height;
+    const uint64_t total = (uint64_t)n_pixels * p->sample_count;
+    uint32_t pool = p->pool_paths ? p->pool_paths : (4u << 20);
+    if ((uint64_t)pool > total) pool = (uint32_t)std::max<uint64_t>(total, 1);
+    pool = (pool + kBlock - 1) / kBlock * kBlock;
+    if ((rc = ensure_pool(ctx, pool))) return rc;
+    RenderConst rcst{p->seed, p->sample_begin, p->sample_stride ? p->sample_stride : 1u, p->nan_policy, 0};
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemsetAsync(ctx->d_nonfinite, 0, sizeof(unsigned long long), st));
+    pt_stats S{}; S.width = dcam.c.width; S.height = dcam.c.height;
+    float ms_gen = 0, ms_trace = 0, ms_shade = 0;
+    CU(cudaEventRecord(ctx->ev0, st));
+    uint64_t generated = 0; uint32_t live = 0; int cur = 0;
+    while (dcam.c.max_depth > 0 && (live > 0 || generated < total)) {
+        PathBuf in = path_buf(ctx, cur), outb = path_buf(ctx, cur ^ 1);
+        uint32_t n_new = (uint32_t)std::min<uint64_t>(pool - live, total - generated);
+        if (ctx->profiling) CU(cudaEventRecord(ctx->evs[0], st));
+        if (n_new) {
+            k_generate<<<(n_new + kBlock - 1) / kBlock, kBlock, 0, st>>>(in, live, n_new, generated, n_pixels, dcam, rcst);
+            S.kernel_launches++;
+        }
+        const uint32_t n = live + n_new;
+        CU(cudaMemsetAsync(ctx->d_count, 0, sizeof(uint32_t), st));
+        if (ctx->profiling) CU(cudaEventRecord(ctx->evs[1], st));
+        k_trace<<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(in, n, ctx->hits, scene->d);
+        if (ctx->profiling) CU(cudaEventRecord(ctx->evs[2], st));
+        k_shade<<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(in, n, ctx->hits, outb, ctx->d_count, d_accum, ctx->d_nonfinite, scene->d, dcam, rcst);
+        if (ctx->profiling) CU(cudaEventRecord(ctx->evs[3], st));
+        S.kernel_launches += 2;
+        CU(cudaMemcpyAsync(ctx->h_count, ctx->d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (ctx->profiling) {
+            float a = 0, b = 0, c2 = 0;
+            cudaEventElapsedTime(&a, ctx->evs[0], ctx->evs[1]); cudaEventElapsedTime(&b, ctx->evs[1], ctx->evs[2]); cudaEventElapsedTime(&c2, ctx->evs[2], ctx->evs[3]);
+            ms_gen += a; ms_trace += b; ms_shade += c2;
+        }
+        generated += n_new; S.segments += n; S.iterations++;
+        live = ctx->h_count[0];
+        cur ^= 1;
+    }
+    CU(cudaEventRecord(ctx->ev1, st));
+    unsigned long long nf = 0;
+    CU(cudaMemcpyAsync(&nf, ctx->d_nonfinite, sizeof(nf), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    cudaEventElapsedTime(&S.device_ms, ctx->ev0, ctx->ev1);
+    S.paths = generated; S.nonfinite = nf; S.raygen_ms = ms_gen; S.trace_ms = ms_trace; S.shade_ms = ms_shade;
+    if (stats) *stats = S;
+    return PT_OK;
+}
+
+int pt_render(pt_ctx* ctx, const pt_scene* scene, const pt_camera* cam, const pt_render_params* p, float* h_mean, pt_stats* stats) {
+    if (!ctx || !cam || !p || !h_mean) return fail(PT_ERR_INVALID, "pt_render: null argument");
+    if (p->sample_count == 0) return fail(PT_ERR_INVALID, "pt_render: sample_count is zero");
+    CU(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)cam->image_width * pt_camera_image_height(cam) * 3;
+    float* d_accum = nullptr;
+    CU(cudaMalloc(&d_accum, n * sizeof(float)));
+    cudaError_t e = cudaMemsetAsync(d_accum, 0, n * sizeof(float), ctx->stream);
+    int rc = e == cudaSuccess ? pt_render_accumulate(ctx, scene, cam, p, d_accum, stats) : fail(PT_ERR_CUDA, cudaGetErrorString(e));
+    if (rc == PT_OK) {
+        k_scale<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_accum, 1.0f / (float)p->sample_count, (uint32_t)n, d_accum);
+        e = cudaMemcpyAsync(h_mean, d_accum, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fail(PT_ERR_CUDA, cudaGetErrorString(e));
+        if (stats) stats->kernel_launches++;
+    }
+    cudaFree(d_accum);
+    return rc;
+}
+
+int pt_tonemap_rgb8(pt_ctx* ctx, const float* d_accum, double scale, uint32_t n_pixels, uint8_t* h_rgb8) {
+    if (!ctx || !d_accum || !h_rgb8) return fail(PT_ERR_INVALID, "pt_tonemap_rgb8: null argument");
+    CU(cudaSetDevice(ctx->device));
+    uint8_t* d_out = nullptr; const uint32_t n = n_pixels * 3;
+    CU(cudaMalloc(&d_out, n));
+    k_tonemap<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_accum, scale, n, d_out);
+    cudaError_t e = cudaMemcpyAsync(h_rgb8, d_out, n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(PT_ERR_CUDA, cudaGetErrorString(e));
+    return PT_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ parity entry points
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) { CU(cudaMalloc(&p, bytes ? bytes : 1)); return PT_OK; }
+    int from_host(const void* h, size_t bytes, cudaStream_t st) { int rc = alloc(bytes); if (rc) return rc; if (bytes) CU(cudaMemcpyAsync(p, h, bytes, cudaMemcpyHostToDevice, st)); return PT_OK; }
+    int to_host(void* h, size_t bytes, cudaStream_t st) { if (bytes) CU(cudaMemcpyAsync(h, p, bytes, cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st)); CU(cudaGetLastError()); return PT_OK; }
+};
+unsigned grid_for(size_t n) { return (unsigned)((n + 127) / 128); }
+}  // namespace
+
+extern "C" {
+
+int pt_trace_closest(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_ray* rays, double t_min, pt_hit* hits) {
+    if (!ctx || !scene || (n && (!rays || !hits))) return fail(PT_ERR_INVALID, "pt_trace_closest: null argument");
+    if (n == 0) return PT_OK;
+    CU(cudaSetDevice(ctx->device));
+    DevBuf in, out; int rc;
+    if ((rc = in.from_host(rays, n * sizeof(pt_ray), ctx->stream)) || (rc = out.alloc(n * sizeof(pt_hit)))) return rc;
+    k_trace_batch<<<grid_for(n), 128, 0, ctx->stream>>>((const pt_ray*)in.p, n, t_min, (pt_hit*)out.p, scene->d);
+    return out.to_host(hits, n * sizeof(pt_hit), ctx->stream);
+}
+int pt_trace_any(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_ray* rays, double t_min, const double* t_max, uint8_t* occluded) {
+    if (!ctx || !scene || (n && (!rays || !t_max || !occluded))) return fail(PT_ERR_INVALID, "pt_trace_any: null argument");
+    if (n == 0) return PT_OK;
+    CU(cudaSetDevice(ctx->device));
+    DevBuf in, tm, out; int rc;
+    if ((rc = in.from_host(rays, n * sizeof(pt_ray), ctx->stream)) || (rc = tm.from_host(t_max, n * 8, ctx->stream)) || (rc = out.alloc(n))) return rc;
+    k_trace_any_batch<<<grid_for(n), 128, 0, ctx->stream>>>((const pt_ray*)in.p, n, t_min, (const double*)tm.p, (uint8_t*)out.p, scene->d);
+    return out.to_host(occluded, n, ctx->stream);
+}
+int pt_bsdf_eval_pdf(pt_ctx* ctx, const pt_scene* scene, uint32_t material, size_t n, const pt_bsdf_query* q, pt_bsdf_result* o) {
+    if (!ctx || !scene || (n && (!q || !o))) return fail(PT_ERR_INVALID, "pt_bsdf_eval_pdf: null argument");
+    if (material >= scene->n_materials) return fail(PT_ERR_INVALID, "pt_bsdf_eval_pdf: bad material");
+    if (n == 0) return PT_OK;
+    CU(cudaSetDevice(ctx->device));
+    DevBuf in, out; int rc;
+    if ((rc = in.from_host(q, n * sizeof(pt_bsdf_query), ctx->stream)) || (rc = out.alloc(n * sizeof(pt_bsdf_result)))) return rc;
+    k_bsdf_eval<<<grid_for(n), 128, 0, ctx->stream>>>(material, n, (const pt_bsdf_query*)in.p, (pt_bsdf_result*)out.p, scene->d);
+    return out.to_host(o, n * sizeof(pt_bsdf_result), ctx->stream);
+}
+int pt_bsdf_sample(pt_ctx* ctx, const pt_scene* scene, uint32_t material, size_t n, const pt_bsdf_query* q, const double* uniforms8, pt_bsdf_sample_result* o) {
+    if (!ctx || !scene || (n && (!q || !uniforms8 || !o))) return fail(PT_ERR_INVALID, "pt_bsdf_sample: null argument");
+    if (material >= scene->n_materials) return fail(PT_ERR_INVALID, "pt_bsdf_sample: bad material");
+    if (n == 0) return PT_OK;
+    CU(cudaSetDevice(ctx->device));
+    DevBuf in, un, out; int rc;
+    if ((rc = in.from_host(q, n * sizeof(pt_bsdf_query), ctx->stream)) || (rc = un.from_host(uniforms8, n * 64, ctx->stream)) || (rc = out.alloc(n * sizeof(pt_bsdf_sample_result)))) return rc;
+    k_bsdf_sample<<<grid_for(n), 128, 0, ctx->stream>>>(material, n, (const pt_bsdf_query*)in.p, (const double*)un.p, (pt_bsdf_sample_result*)out.p, scene->d);
+    return out.to_host(o, n * sizeof(pt_bsdf_sample_result), ctx->stream);
+}
+int pt_camera_rays(pt_ctx* ctx, const pt_camera* cam, uint64_t seed, size_t n, const uint32_t* row, const uint32_t* col, const uint32_t* sample, pt_ray* o) {
+    if (!ctx || !cam || (n && (!row || !col || !sample || !o))) return fail(PT_ERR_INVALID, "pt_camera_rays: null argument");
+    if (n == 0) return PT_OK;
+    CU(cudaSetDevice(ctx->device));
+    pt_camera c = *cam; c.env_is_map = 0;
+    DCameraEx dcam; int rc = make_camera(nullptr, &c, &dcam);
+    if (rc) return rc;
+    DevBuf r, cc, s, out;
+    if ((rc = r.from_host(row, n * 4, ctx->stream)) || (rc = cc.from_host(col, n * 4, ctx->stream)) || (rc = s.from_host(sample, n * 4, ctx->stream)) || (rc = out.alloc(n * sizeof(pt_ray)))) return rc;
+    k_camera_rays<<<grid_for(n), 128, 0, ctx->stream>>>(dcam, seed, n, (const uint32_t*)r.p, (const uint32_t*)cc.p, (const uint32_t*)s.p, (pt_ray*)out.p);
+    return out.to_host(o, n * sizeof(pt_ray), ctx->stream);
+}
+int pt_lights_sample_pdf(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_vec3* origin, const double* time, const double* uniforms3, pt_vec3* dir, uint32_t* valid, double* pdf) {
+    if (!ctx || !scene || (n && (!origin || !time || !uniforms3 || !dir || !valid || !pdf))) return fail(PT_ERR_INVALID, "pt_lights_sample_pdf: null argument");
+    if (n == 0) return PT_OK;
+    CU(cudaSetDevice(ctx->device));
+    DevBuf o, t, u, dd, vv, pp; int rc;
+    if ((rc = o.from_host(origin, n * 24, ctx->stream)) || (rc = t.from_host(time, n * 8, ctx->stream)) || (rc = u.from_host(uniforms3, n * 24, ctx->stream)) ||
+        (rc = dd.alloc(n * 24)) || (rc = vv.alloc(n * 4)) || (rc = pp.alloc(n * 8))) return rc;
+    k_lights<<<grid_for(n), 128, 0, ctx->stream>>>(n, (const pt_vec3*)o.p, (const double*)t.p, (const double*)u.p, (pt_vec3*)dd.p, (uint32_t*)vv.p, (double*)pp.p, scene->d);
+    if ((rc = dd.to_host(dir, n * 24, ctx->stream)) || (rc = vv.to_host(valid, n * 4, ctx->stream)) || (rc = pp.to_host(pdf, n * 8, ctx->stream))) return rc;
+    return PT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,300 @@
+// Closest-hit traversal and hit reconstruction (device side of src/hittable/*.rs).
+//
+// Traversal: ordered, early-out, two-level walk over the 32-byte node-pair array with a per-thread
+// stack; fp32 conservative slab tests (aabb.rs:31-42) and f64 primitive tests in the reference's exact
+// operation order (sphere.rs:64-100, quad.rs:40-70, mesh.rs:50-112, instance.rs:34-54).  The reference's
+// recursive, un-narrowed traversal (bvh.rs:124-164) is reproduced through the order-independent rule of
+// minimum t wins; an exact tie goes to the larger precomputed tie rank.
+#pragma once
+#include "device_scene.cuh"
+
+namespace ptd {
+
+struct RayD { d3 o, d; double time; };
+PT_D RayD make_ray(d3 o, d3 d, double time) { RayD r; r.o = o; r.d = normalize(d); r.time = time; return r; }  // ray.rs:23-29
+PT_D d3 ray_at(const RayD& r, double t) { return r.o + r.d * t; }                                              // ray.rs:31-33
+
+// ---------------------------------------------------------------- primitive tests: return t or NaN-free "no hit" (-1)
+// Lower bounds follow each primitive's own rule; the upper bound is applied by the caller's candidate logic.
+PT_D bool sphere_t(const DSphere& s, const RayD& r, double t_min, double& t_out) {  // sphere.rs:64-86
+    d3 p1 = mk(s.p1[0], s.p1[1], s.p1[2]), p2 = mk(s.p2[0], s.p2[1], s.p2[2]);
+    d3 c = p1 + (p2 - p1) * r.time;
+    d3 l = c - r.o;
+    double sdot = dot(l, r.d);
+    double l2 = dot(l, l);
+    double rad = fmax(s.radius, 0.0);
+    double r2 = rad * rad;
+    if (sdot < 0.0 && l2 > r2) return false;
+    double d2 = l2 - sdot * sdot;
+    if (d2 > r2) return false;
+    double q = sqrt(r2 - d2);
+    double t = l2 > r2 ? sdot - q : sdot + q;
+    if (t <= t_min) return false;  // exclusive (sphere.rs:84)
+    t_out = t;
+    return true;
+}
+PT_D bool quad_t(const DQuad& qd, const RayD& r, double t_min, double& t_out, double& alpha, double& beta) {  // quad.rs:40-58
+    d3 n = mk(qd.n[0], qd.n[1], qd.n[2]);
+    double nd = dot(n, r.d);
+    if (fabs(nd) < 1e-8) return false;
+    double t = (qd.d - dot(n, r.o)) / nd;
+    if (!(t_min <= t)) return false;  // inclusive lower bound (interval.rs:26-28)
+    d3 p = ray_at(r, t) - mk(qd.q[0], qd.q[1], qd.q[2]);
+    d3 w = mk(qd.w[0], qd.w[1], qd.w[2]);
+    alpha = dot(w, cross(p, mk(qd.v[0], qd.v[1], qd.v[2])));
+    beta = dot(w, cross(mk(qd.u[0], qd.u[1], qd.u[2]), p));
+    if (!(0.0 <= alpha && alpha <= 1.0) || !(0.0 <= beta && beta <= 1.0)) return false;
+    t_out = t;
+    return true;
+}
+PT_D bool tri_t(const DTri& tr, const RayD& r, double t_min, double& t_out, double& u, double& v) {  // mesh.rs:50-82
+    d3 e1 = mk(tr.e1[0], tr.e1[1], tr.e1[2]), e2 = mk(tr.e2[0], tr.e2[1], tr.e2[2]);
+    d3 h = cross(r.d, e2);
+    double a = dot(e1, h);
+    if (fabs(a) < 1e-8) return false;
+    double f = 1.0 / a;
+    d3 s = r.o - mk(tr.v0[0], tr.v0[1], tr.v0[2]);
+    u = f * dot(s, h);
+    if (!(0.0 <= u && u <= 1.0)) return false;
+    d3 q = cross(s, e1);
+    v = f * dot(r.d, q);
+    if (v < 0.0 || u + v > 1.0) return false;
+    double t = f * dot(e2, q);
+    if (!(t_min <= t)) return false;
+    t_out = t;
+    return true;
+}
+PT_D RayD instance_local_ray(const DInstance& in, const RayD& r) {  // instance.rs:36-38
+    d3 lo = xform_point(in.inv, r.o);
+    d3 ld = xform_vector(in.inv, r.d);
+    return make_ray(lo, ld, r.time);
+}
+
+// ---------------------------------------------------------------- fp32 slab test state
+// Conservative by construction: the device boxes are rounded outward and padded by 8 ulp of their largest
+// coordinate on upload (covers the rounding of inv and of the products), and the per-ray slack `e` below
+// covers the rounding of the origin (|o| * 2^-22 per axis, scaled into t).  A NaN plane distance (0 * inf)
+// is dropped by fminf/fmaxf, which only ever widens the accepted interval.
+struct BoxRay { float ix, iy, iz, nx, ny, nz, fx, fy, fz; };  // inv dir; -o*inv -/+ slack for the near / far planes
+PT_D BoxRay make_boxray(const RayD& r) {
+    BoxRay b;
+    const float ox = __double2float_rn(r.o.x), oy = __double2float_rn(r.o.y), oz = __double2float_rn(r.o.z);
+    b.ix = 1.0f / __double2float_rn(r.d.x); b.iy = 1.0f / __double2float_rn(r.d.y); b.iz = 1.0f / __double2float_rn(r.d.z);
+    const float k = 2.384185791015625e-07f;  // 2^-22
+    const float ex = fabsf(ox * b.ix) * k, ey = fabsf(oy * b.iy) * k, ez = fabsf(oz * b.iz) * k;
+    b.nx = -ox * b.ix - ex; b.ny = -oy * b.iy - ey; b.nz = -oz * b.iz - ez;
+    b.fx = -ox * b.ix + ex; b.fy = -oy * b.iy + ey; b.fz = -oz * b.iz + ez;
+    return b;
+}
+// returns entry distance (clamped at t_min) or +inf on miss; t_max is the current closest hit rounded up
+PT_D float slab(const DNode& n, const BoxRay& b, float t_min, float t_max) {
+    const bool sx = b.ix < 0.f, sy = b.iy < 0.f, sz = b.iz < 0.f;
+    float x0 = __fmaf_rn(sx ? n.hi[0] : n.lo[0], b.ix, b.nx), x1 = __fmaf_rn(sx ? n.lo[0] : n.hi[0], b.ix, b.fx);
+    float y0 = __fmaf_rn(sy ? n.hi[1] : n.lo[1], b.iy, b.ny), y1 = __fmaf_rn(sy ? n.lo[1] : n.hi[1], b.iy, b.fy);
+    float z0 = __fmaf_rn(sz ? n.hi[2] : n.lo[2], b.iz, b.nz), z1 = __fmaf_rn(sz ? n.lo[2] : n.hi[2], b.iz, b.fz);
+    float tn = fmaxf(fmaxf(x0, y0), fmaxf(z0, t_min));
+    float tf = fminf(fminf(x1, y1), fminf(z1, t_max));
+    return tn <= tf ? tn : __int_as_float(0x7f800000);
+}
+
+// ---------------------------------------------------------------- traversal
+constexpr int kStack = 64;
+constexpr uint32_t kTagRef = 0x40000000u, kTagSentinel = 0x80000000u, kTagMask = 0xC0000000u;
+
+struct Closest {
+    double t; uint32_t ref, inst, tie_outer, tie_inner; bool is_light;
+};
+PT_D void consider(Closest& c, double t, uint32_t ref, uint32_t inst, uint32_t tie_o, uint32_t tie_i) {
+    if (t < c.t || (t == c.t && (tie_o > c.tie_outer || (tie_o == c.tie_outer && tie_i > c.tie_inner)))) {
+        c.t = t; c.ref = ref; c.inst = inst; c.tie_outer = tie_o; c.tie_inner = tie_i;
+    }
+}
+// A direct (non-BVH) primitive or a cuboid's six quads, in the space of `r`.
+PT_D void test_simple(const DScene& S, uint32_t kind, uint32_t index, const RayD& r, double t_min, Closest& c, uint32_t inst,
+                      uint32_t tie_o, uint32_t tie_i) {
+    double t, a, b;
+    if (kind == PT_PRIM_SPHERE) {
+        // exclusive upper bound against the initial interval (sphere.rs:84); later ties go through the ranks
+        if (sphere_t(S.spheres[index], r, t_min, t) && t <= c.t && !(c.ref == kNone && t == c.t)) consider(c, t, ref_pack(PT_PRIM_SPHERE, index), inst, tie_o, tie_i);
+    } else if (kind == PT_PRIM_QUAD) {
+        if (quad_t(S.quads[index], r, t_min, t, a, b) && t <= c.t) consider(c, t, ref_pack(PT_PRIM_QUAD, index), inst, tie_o, tie_i);
+    } else if (kind == PT_OBJ_CUBOID) {
+        uint32_t fq = S.cuboids[index].first_quad;
+#pragma unroll 1
+        for (uint32_t k = 0; k < 6; k++)  // linear list: later quad wins ties -> inner rank = k (cuboid.rs, list.rs:57-66)
+            if (quad_t(S.quads[fq + k], r, t_min, t, a, b) && t <= c.t) consider(c, t, ref_pack(PT_PRIM_QUAD, fq + k), inst, tie_o, tie_i + k);
+    }
+}
+
+// World::intersect_all(ray, [t_min, inf)) — world.rs:47-62.  any_hit: stop at the first hit with t <= t_max on World.objects.
+template <bool ANY_HIT>
+PT_D bool trace_closest(const DScene& S, const RayD& world_ray, double t_min, double t_max_any, Closest& c) {
+    uint32_t stack[kStack]; float stack_t[kStack];
+    int sp = 0;
+    c.t = ANY_HIT ? t_max_any : __longlong_as_double(0x7ff0000000000000ll);
+    c.ref = kNone; c.inst = kInstNone; c.tie_outer = 0; c.tie_inner = 0; c.is_light = false;
+    RayD r = world_ray;
+    BoxRay br = make_boxray(r);
+    const float tmin_f = __double2float_rd(t_min);
+    uint32_t cur_inst = kInstNone, cur_tie = 0;
+    uint32_t cur = S.root_pair;  // node-pair to visit, or kNone => pop
+    while (true) {
+        if (cur != kNone) {
+            const DNode n0 = S.nodes[cur], n1 = S.nodes[cur + 1];
+            const float tmax_f = __double2float_ru(c.t);
+            float t0 = slab(n0, br, tmin_f, tmax_f), t1 = slab(n1, br, tmin_f, tmax_f);
+            // visit order: nearer child first
+            const bool swap = t1 < t0;
+            const DNode& na = swap ? n1 : n0; const DNode& nb = swap ? n0 : n1;
+            float ta = swap ? t1 : t0, tb = swap ? t0 : t1;
+            uint32_t next = kNone; float next_t = 0.f;
+#pragma unroll
+            for (int side = 0; side < 2; side++) {
+                const DNode& n = side == 0 ? na : nb; const float tn = side == 0 ? ta : tb;
+                if (!(tn <= __double2float_ru(c.t))) continue;  // miss (inf) or beyond the current closest
+                if (n.b == kNone) {  // internal
+                    if (next == kNone) { next = n.a; next_t = tn; }
+                    else if (sp < kStack) { stack[sp] = n.a; stack_t[sp] = tn; sp++; }
+                } else {  // leaf: scan refs
+                    for (uint32_t k = 0; k < n.b; k++) {
+                        const DRef rf = S.refs[n.a + k];
+                        const uint32_t kind = ref_kind(rf.kind_index), index = ref_index(rf.kind_index);
+                        if (kind == PT_PRIM_TRIANGLE) {
+                            double t, u, v;
+                            if (tri_t(S.tris[index], r, t_min, t, u, v) && t <= c.t) consider(c, t, rf.kind_index, cur_inst, cur_tie, rf.tie);
+                        } else {
+                            if (ANY_HIT && !(rf.tie >> 31)) continue;  // shadow rays test World.objects only (world.rs:31-36)
+                            if (kind <= PT_OBJ_CUBOID) test_simple(S, kind, index, r, t_min, c, kInstNone, rf.tie, 0);
+                            else if (sp < kStack) {  // mesh / instance: defer (order does not matter, ties use ranks)
+                                stack[sp] = kTagRef | (n.a + k); stack_t[sp] = tn; sp++;
+                            }
+                        }
+                        if (ANY_HIT && c.ref != kNone) return true;
+                    }
+                }
+            }
+            (void)next_t;
+            cur = next;
+            continue;
+        }
+        // pop
+        if (sp == 0) break;
+        --sp;
+        const uint32_t e = stack[sp];
+        if (e == kTagSentinel) {  // leave the instance / mesh: back to the world ray
+            r = world_ray; br = make_boxray(r); cur_inst = kInstNone; cur_tie = 0;
+            continue;
+        }
+        if (!(stack_t[sp] <= __double2float_ru(c.t))) continue;
+        if ((e & kTagMask) == 0) { cur = e; continue; }
+        // deferred mesh / instance reference
+        const DRef rf = S.refs[e & ~kTagMask];
+        const uint32_t kind = ref_kind(rf.kind_index), index = ref_index(rf.kind_index);
+        uint32_t mesh = kNone;
+        if (kind == PT_OBJ_MESH) { mesh = index; cur_inst = kInstNone; }
+        else {  // PT_OBJ_INSTANCE
+            const DInstance& in = S.instances[index];
+            const RayD lr = instance_local_ray(in, r);
+            if (in.child_kind == PT_OBJ_MESH) { mesh = in.child_index; r = lr; br = make_boxray(r); cur_inst = index; }
+            else {
+                test_simple(S, in.child_kind, in.child_index, lr, t_min, c, index, rf.tie, 0);
+                if (ANY_HIT && c.ref != kNone) return true;
+                continue;
+            }
+        }
+        cur_tie = rf.tie;
+        const DMesh& m = S.meshes[mesh];
+        if (sp < kStack) { stack[sp] = kTagSentinel; stack_t[sp] = 0.f; sp++; }
+        cur = m.root_pair;
+    }
+    c.is_light = c.ref != kNone && !(c.tie_outer >> 31);  // objects carry bit 31 in their outer rank (object beats light, Q31)
+    return c.ref != kNone;
+}
+
+// ---------------------------------------------------------------- hit reconstruction (HitInfo::new, hit_info.rs:16-55)
+struct HitInfoD {
+    d3 point, gn, sn; double t, u, v; bool front_face; uint32_t material;
+};
+PT_D d3 image_value(const DScene& S, uint32_t image, double u, double v) {  // texture.rs:72-91
+    const DImage im = S.images[image];
+    if (im.height == 0) return mk(0.0, 1.0, 1.0);
+    u = clampd(u, 0.0, 1.0);
+    v = 1.0 - clampd(v, 0.0, 1.0);
+    double fi = u * (double)im.width, fj = v * (double)im.height;
+    uint32_t i = fi > 0.0 ? (fi >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)fi) : 0u;  // `as u32` saturates
+    uint32_t j = fj > 0.0 ? (fj >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)fj) : 0u;
+    if (i >= im.width) i = im.width - 1;   // Q22: reference panics here; clamp (documented divergence)
+    if (j >= im.height) j = im.height - 1;
+    const uint8_t* px = S.image_data + im.offset + 3ull * ((uint64_t)j * im.width + i);
+    const double s = 1.0 / 255.0;
+    return mk(s * (double)px[0], s * (double)px[1], s * (double)px[2]);
+}
+PT_D void finish_hit(const DScene& S, const RayD& r, d3 point, d3 normal, double t, uint32_t material, double u, double v, HitInfoD& h) {
+    bool ff = dot(r.d, normal) < 0.0;
+    d3 gn = ff ? normalize(normal) : -normalize(normal);
+    d3 sn = gn;
+    const DMaterial& m = S.materials[material];
+    if (m.kind == PT_MAT_DIFFUSE && m.normal_map != kNone) {  // only DiffuseBRDF overrides normal_map() (diffuse.rs:81-83)
+        d3 c = image_value(S, m.normal_map, u, v);
+        d3 mapped = 2.0 * c - mk(1.0, 1.0, 1.0);
+        d3 a = fabs(gn.x) > 0.9 ? mk(0.0, 1.0, 0.0) : mk(1.0, 0.0, 0.0);  // hit_info.rs:58-67
+        d3 tangent = normalize(cross(gn, a));
+        d3 bitangent = cross(gn, tangent);
+        sn = normalize(mapped.x * tangent + mapped.y * bitangent + mapped.z * gn);
+    }
+    h.point = point; h.gn = gn; h.sn = sn; h.t = t; h.u = u; h.v = v; h.front_face = ff; h.material = material;
+}
+// Recompute the winning primitive's full HitInfo from (ref, instance, t): same formulas, same rounding as the oracle.
+PT_D void reconstruct_hit(const DScene& S, const RayD& world_ray, uint32_t ref, uint32_t inst, double t, HitInfoD& h) {
+    RayD r = world_ray;
+    if (inst != kInstNone) r = instance_local_ray(S.instances[inst], world_ray);
+    const uint32_t kind = ref_kind(ref), index = ref_index(ref);
+    if (kind == PT_PRIM_SPHERE) {  // sphere.rs:88-99
+        const DSphere& s = S.spheres[index];
+        d3 p1 = mk(s.p1[0], s.p1[1], s.p1[2]), p2 = mk(s.p2[0], s.p2[1], s.p2[2]);
+        d3 c = p1 + (p2 - p1) * r.time;
+        d3 point = ray_at(r, t);
+        d3 normal = normalize(point - c);
+        double theta = acos(-normal.y);
+        double phi = atan2(-normal.z, normal.x) + kPi;
+        finish_hit(S, r, point, normal, t, s.material, phi / (2.0 * kPi), theta / kPi, h);
+    } else if (kind == PT_PRIM_QUAD) {  // quad.rs:53-69
+        const DQuad& qd = S.quads[index];
+        d3 p = ray_at(r, t) - mk(qd.q[0], qd.q[1], qd.q[2]);
+        d3 w = mk(qd.w[0], qd.w[1], qd.w[2]);
+        double alpha = dot(w, cross(p, mk(qd.v[0], qd.v[1], qd.v[2])));
+        double beta = dot(w, cross(mk(qd.u[0], qd.u[1], qd.u[2]), p));
+        finish_hit(S, r, ray_at(r, t), mk(qd.n[0], qd.n[1], qd.n[2]), t, S.quad_material[index], alpha, beta, h);
+    } else {  // triangle, mesh.rs:84-111
+        const DTri& tr = S.tris[index];
+        const DMesh& m = S.meshes[S.tri_mesh[index]];
+        d3 e1 = mk(tr.e1[0], tr.e1[1], tr.e1[2]), e2 = mk(tr.e2[0], tr.e2[1], tr.e2[2]);
+        d3 hh = cross(r.d, e2);
+        double a = dot(e1, hh);
+        double f = 1.0 / a;
+        d3 s = r.o - mk(tr.v0[0], tr.v0[1], tr.v0[2]);
+        double u = f * dot(s, hh);
+        d3 q = cross(s, e1);
+        double v = f * dot(r.d, q);
+        double w = 1.0 - u - v;
+        d3 normal;
+        if (m.has_normals) {
+            const double* n = S.tri_normals + 9ull * index;
+            normal = normalize(mk(n[0], n[1], n[2]) * w + mk(n[3], n[4], n[5]) * u + mk(n[6], n[7], n[8]) * v);
+        } else normal = normalize(cross(e1, e2));
+        double ou = u, ov = v;
+        if (m.has_uvs) {
+            const double* t6 = S.tri_uvs + 6ull * index;
+            ou = t6[0] * w + t6[2] * u + t6[4] * v;
+            ov = t6[1] * w + t6[3] * u + t6[5] * v;
+        }
+        finish_hit(S, r, ray_at(r, t), normal, t, m.material, ou, ov, h);
+    }
+    if (inst != kInstNone) {  // instance.rs:43-53: point and geometric normal to world; the rest stays local (Q4)
+        const DInstance& in = S.instances[inst];
+        h.point = xform_point(in.fwd, h.point);
+        h.gn = normalize(xform_vector(in.nrm, h.gn));
+    }
+}
+
+}  // namespace ptd

@@ -1,0 +1,256 @@
+// Wavefront integrator kernels for sm_100a (device side of Camera::trace, src/camera.rs:170-228).
+//
+// Pipeline per iteration over a pool of in-flight paths held as SoA arrays in HBM:
+//   k_generate  — camera rays for freshly started paths (camera.rs:153-168), appended after the survivors
+//   k_trace     — World::intersect_all for every live path (world.rs:47-62) -> 16-byte hit records
+//   k_shade     — miss/environment, emission, Russian roulette, light/BSDF mixture sampling, next ray
+//                 (camera.rs:178-225); survivors are written COMPACTED into the other SoA buffer through a
+//                 warp-ballot + block-prefix + one atomicAdd per block, so every later kernel reads dense,
+//                 coalesced arrays and warps stay full.
+// Radiance contributions go straight to the fp32 accumulators with red.global.add.f32.
+#pragma once
+#include "bsdf.cuh"
+
+namespace ptd {
+
+constexpr int kBlock = 128;
+
+struct PathBuf {
+    double* f[10];  // ox oy oz dx dy dz time thr_r thr_g thr_b
+    uint4* ids;     // pixel, sample, rng_used | bounce << 16, spare
+};
+struct RenderConst {
+    uint64_t seed; uint32_t sample_begin, sample_stride, nan_policy, pad;
+};
+
+// ---------------------------------------------------------------- camera.rs:133-168
+PT_D void random_offsets(Rng& rng, double& x, double& y) {
+    double radius = sqrt(rng.next());
+    double angle = rng.next() * 2.0 * kPi;
+    x = radius * cos(angle); y = radius * sin(angle);
+}
+struct DCameraEx { DCamera c; d3 dof_right, dof_up; };  // dof_* = right/up * lens radius (camera.rs:159-161), host-derived
+PT_D RayD generate_ray(const DCameraEx& cam, uint32_t row, uint32_t col, Rng& rng) {
+    double bx, by; random_offsets(rng, bx, by);
+    bx = bx * cam.c.blur_strength; by = by * cam.c.blur_strength;
+    d3 sample_location = cam.c.pixel00 + (cam.c.pixel_dv * ((double)row + bx)) + (cam.c.pixel_du * ((double)col + by));
+    double px, py; random_offsets(rng, px, py);
+    d3 origin = cam.c.center + (cam.dof_right * px) + (cam.dof_up * py);
+    d3 direction = sample_location - origin;
+    double time = rng.next();
+    return make_ray(origin, direction, time);
+}
+PT_D d3 sample_environment(const DScene& S, const DCamera& cam, d3 dir) {  // camera.rs:140-151
+    if (!cam.env_is_map) return cam.env_color;
+    double theta = acos(dir.y);
+    double phi = atan2(dir.z, dir.x);
+    double u = (phi + kPi) / (2.0 * kPi);
+    double v = 1.0 - theta / kPi;
+    return image_value(S, cam.env_image, u, v);
+}
+
+PT_D void store_path(const PathBuf& b, uint32_t i, const RayD& r, d3 thr, uint4 ids) {
+    b.f[0][i] = r.o.x; b.f[1][i] = r.o.y; b.f[2][i] = r.o.z; b.f[3][i] = r.d.x; b.f[4][i] = r.d.y; b.f[5][i] = r.d.z; b.f[6][i] = r.time;
+    b.f[7][i] = thr.x; b.f[8][i] = thr.y; b.f[9][i] = thr.z; b.ids[i] = ids;
+}
+PT_D RayD load_ray(const PathBuf& b, uint32_t i) {
+    RayD r;
+    r.o = mk(b.f[0][i], b.f[1][i], b.f[2][i]); r.d = mk(b.f[3][i], b.f[4][i], b.f[5][i]); r.time = b.f[6][i];
+    return r;
+}
+
+// g = global index of the path within this render call: sample-major so that consecutive threads take
+// neighbouring pixels of the same sample (coherent primary rays).
+__global__ void __launch_bounds__(kBlock) k_generate(PathBuf out, uint32_t slot0, uint32_t n_new, uint64_t g0, uint32_t n_pixels,
+                                                      DCameraEx cam, RenderConst rc) {
+    uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n_new) return;
+    uint64_t g = g0 + i;
+    uint32_t s_local = (uint32_t)(g / n_pixels), pix = (uint32_t)(g % n_pixels);
+    uint32_t sample = rc.sample_begin + s_local * rc.sample_stride;
+    Rng rng; rng.init(rc.seed, pix, sample, 0);
+    RayD r = generate_ray(cam, pix / cam.c.width, pix % cam.c.width, rng);
+    store_path(out, slot0 + i, r, mk(1, 1, 1), make_uint4(pix, sample, rng.used, 0));
+}
+
+__global__ void __launch_bounds__(kBlock) k_trace(PathBuf in, uint32_t n, HitRec* __restrict__ hits, DScene S) {
+    uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n) return;
+    RayD r = load_ray(in, i);
+    Closest c;
+    trace_closest<false>(S, r, 1e-3, 0.0, c);  // Interval::new(eps, INFINITY), camera.rs:171,179
+    HitRec h; h.t = c.t; h.ref = c.ref; h.inst_light = (c.inst & 0x7FFFFFFFu) | (c.is_light ? 0x80000000u : 0u);
+    hits[i] = h;
+}
+
+PT_D void add_radiance(float* __restrict__ accum, uint32_t pix, d3 v, uint32_t nan_policy, unsigned long long* nonfinite, bool& dead) {
+    if (!finite3(v)) {
+        atomicAdd(nonfinite, 1ull);
+        if (nan_policy == PT_NAN_DROP) { dead = true; return; }  // drop the contribution and end the path
+    }
+    if (v.x != 0.0) atomicAdd(accum + 3ull * pix, (float)v.x);
+    if (v.y != 0.0) atomicAdd(accum + 3ull * pix + 1, (float)v.y);
+    if (v.z != 0.0) atomicAdd(accum + 3ull * pix + 2, (float)v.z);
+}
+
+__global__ void __launch_bounds__(kBlock) k_shade(PathBuf in, uint32_t n, const HitRec* __restrict__ hits, PathBuf out,
+                                                    uint32_t* __restrict__ out_count, float* __restrict__ accum,
+                                                    unsigned long long* __restrict__ nonfinite, DScene S, DCameraEx cam, RenderConst rc) {
+    const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+    bool alive = false;
+    RayD next; d3 thr = mk(0, 0, 0); uint4 ids = make_uint4(0, 0, 0, 0);
+    if (i < n) {
+        RayD ray = load_ray(in, i);
+        thr = mk(in.f[7][i], in.f[8][i], in.f[9][i]);
+        ids = in.ids[i];
+        const HitRec hr = hits[i];
+        const uint32_t pix = ids.x, bounces = ids.z >> 16;
+        Rng rng; rng.init(rc.seed, pix, ids.y, ids.z & 0xFFFFu);
+        bool dead = false;
+        if (hr.ref == kNone) {  // camera.rs:180-183
+            add_radiance(accum, pix, thr * sample_environment(S, cam.c, ray.d), rc.nan_policy, nonfinite, dead);
+        } else {
+            HitInfoD h;
+            const uint32_t inst = hr.inst_light & 0x7FFFFFFFu;
+            reconstruct_hit(S, ray, hr.ref, inst, hr.t, h);
+            const DMaterial& m = S.materials[h.material];
+            // camera.rs:186-187: `radiance += throughput * emitted` runs for every hit; for non-emitters it only
+            // matters when the throughput is already inf/NaN (inf * 0 = NaN poisons the pixel, Q32).
+            if (m.kind == PT_MAT_LIGHT || !finite3(thr)) {
+                d3 em = m.kind == PT_MAT_LIGHT ? texture_value(S, m.base_color_tex, h.u, h.v, h.point) : mk(0, 0, 0);
+                add_radiance(accum, pix, thr * em, rc.nan_policy, nonfinite, dead);
+            }
+            bool go = !dead;
+            if (go && bounces > 5) {  // Russian roulette, camera.rs:190-196
+                double p = clampd(luminance(thr), 0.01, 1.0);
+                if (rng.next() > p) go = false;
+                else thr = thr / p;
+            }
+            if (go) {
+                const double p_light = S.n_lights == 0 ? 0.0 : 0.5, p_bsdf = 1.0 - p_light;  // camera.rs:199-200
+                const double rsel = rng.next();
+                d3 dir;
+                bool ok = rsel < p_light ? lights_sample(S, h.point, ray.time, rng, dir) : bsdf_sample(S, h.material, ray.d, h, rng, dir);
+                if (ok) {  // camera.rs:212-225
+                    d3 f; double bsdf_pdf;
+                    bsdf_eval_pdf(S, h.material, -ray.d, dir, h, f, bsdf_pdf);
+                    double light_pdf = lights_pdf(S, h.point, dir, ray.time);
+                    double pdf = p_bsdf * bsdf_pdf + p_light * light_pdf;
+                    d3 attenuation = f / pdf;
+                    double e = 1e-3 * signum(dot(dir, h.gn));
+                    next = make_ray(h.point + e * h.gn, dir, ray.time);
+                    thr = thr * attenuation;
+                    alive = bounces + 1 < cam.c.max_depth;  // `for bounces in 0..max_depth`, camera.rs:177
+                    if (rc.nan_policy == PT_NAN_DROP && !finite3(thr)) { atomicAdd(nonfinite, 1ull); alive = false; }
+                    ids.z = (rng.used & 0xFFFFu) | ((bounces + 1) << 16);
+                }
+            }
+        }
+    }
+    // ---- compaction: ballot within the warp, prefix across warps, one atomic per block
+    __shared__ uint32_t warp_count[kBlock / 32];
+    __shared__ uint32_t block_base;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, alive);
+    if (lane == 0) warp_count[warp] = __popc(ballot);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+#pragma unroll
+        for (int w = 0; w < kBlock / 32; w++) { uint32_t c = warp_count[w]; warp_count[w] = total; total += c; }
+        block_base = total ? atomicAdd(out_count, total) : 0;
+    }
+    __syncthreads();
+    if (alive) {
+        uint32_t dst = block_base + warp_count[warp] + __popc(ballot & ((1u << lane) - 1u));
+        store_path(out, dst, next, thr, ids);
+    }
+}
+
+// sqrt-gamma + 8-bit quantisation of camera.rs:109-114,128-130 on `scale * accum`
+__global__ void k_tonemap(const float* __restrict__ accum, double scale, uint32_t n_values, uint8_t* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_values) return;
+    double x = (double)accum[i] * scale;
+    double g = sqrt(fmax(x, 0.0));
+    double v = clampd(g, 0.0, 0.999) * 256.0;
+    out[i] = (v != v) ? 0 : (uint8_t)v;
+}
+__global__ void k_scale(const float* __restrict__ accum, float scale, uint32_t n_values, float* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_values) out[i] = accum[i] * scale;
+}
+
+// ---------------------------------------------------------------- parity / test entry kernels
+PT_D pt_vec3 to_abi(d3 v) { pt_vec3 r; r.x = v.x; r.y = v.y; r.z = v.z; return r; }
+PT_D d3 from_abi(pt_vec3 v) { return mk(v.x, v.y, v.z); }
+
+__global__ void k_trace_batch(const pt_ray* __restrict__ rays, size_t n, double t_min, pt_hit* __restrict__ out, DScene S) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    RayD r; r.o = from_abi(rays[i].origin); r.d = from_abi(rays[i].direction); r.time = rays[i].time;
+    Closest c;
+    pt_hit o; memset(&o, 0, sizeof(o)); o.instance = PT_NONE;
+    if (trace_closest<false>(S, r, t_min, 0.0, c)) {
+        HitInfoD h;
+        reconstruct_hit(S, r, c.ref, c.inst, c.t, h);
+        o.hit = 1; o.t = c.t; o.u = h.u; o.v = h.v; o.point = to_abi(h.point); o.geometric_normal = to_abi(h.gn); o.shading_normal = to_abi(h.sn);
+        o.prim_kind = ref_kind(c.ref); o.prim_index = ref_index(c.ref); o.instance = c.inst == kInstNone ? PT_NONE : c.inst;
+        o.material = h.material; o.front_face = h.front_face; o.is_light = c.is_light;
+    }
+    out[i] = o;
+}
+__global__ void k_trace_any_batch(const pt_ray* __restrict__ rays, size_t n, double t_min, const double* __restrict__ t_max,
+                                  uint8_t* __restrict__ out, DScene S) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    RayD r; r.o = from_abi(rays[i].origin); r.d = from_abi(rays[i].direction); r.time = rays[i].time;
+    Closest c;
+    out[i] = trace_closest<true>(S, r, t_min, t_max[i], c) ? 1 : 0;
+}
+PT_D HitInfoD info_from_query(const pt_bsdf_query& q, uint32_t material) {
+    HitInfoD h; h.point = from_abi(q.point); h.gn = from_abi(q.geometric_normal); h.sn = from_abi(q.shading_normal);
+    h.t = 0; h.u = q.u; h.v = q.v; h.front_face = q.front_face != 0; h.material = material;
+    return h;
+}
+__global__ void k_bsdf_eval(uint32_t material, size_t n, const pt_bsdf_query* __restrict__ q, pt_bsdf_result* __restrict__ out, DScene S) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    HitInfoD h = info_from_query(q[i], material);
+    d3 f; double pdf;
+    bsdf_eval_pdf(S, material, from_abi(q[i].view_dir), from_abi(q[i].light_dir), h, f, pdf);
+    pt_bsdf_result r; r.eval = to_abi(f); r.pdf = pdf; r.emitted = to_abi(bsdf_emitted(S, material, h.u, h.v, h.point)); r._pad = 0;
+    out[i] = r;
+}
+__global__ void k_bsdf_sample(uint32_t material, size_t n, const pt_bsdf_query* __restrict__ q, const double* __restrict__ uniforms8,
+                              pt_bsdf_sample_result* __restrict__ out, DScene S) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    HitInfoD h = info_from_query(q[i], material);
+    Rng rng; rng.init_array(uniforms8 + 8 * i, 8);
+    d3 dir = mk(0, 0, 0);
+    bool ok = bsdf_sample(S, material, -from_abi(q[i].view_dir), h, rng, dir);
+    pt_bsdf_sample_result r; r.dir = ok ? to_abi(dir) : to_abi(mk(0, 0, 0)); r.valid = ok; r.n_uniforms = rng.used;
+    out[i] = r;
+}
+__global__ void k_camera_rays(DCameraEx cam, uint64_t seed, size_t n, const uint32_t* __restrict__ row, const uint32_t* __restrict__ col,
+                              const uint32_t* __restrict__ sample, pt_ray* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Rng rng; rng.init(seed, row[i] * cam.c.width + col[i], sample[i], 0);
+    RayD r = generate_ray(cam, row[i], col[i], rng);
+    pt_ray o; o.origin = to_abi(r.o); o.direction = to_abi(r.d); o.time = r.time;
+    out[i] = o;
+}
+__global__ void k_lights(size_t n, const pt_vec3* __restrict__ origin, const double* __restrict__ time, const double* __restrict__ uniforms3,
+                         pt_vec3* __restrict__ dir, uint32_t* __restrict__ valid, double* __restrict__ pdf, DScene S) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Rng rng; rng.init_array(uniforms3 + 3 * i, 3);
+    d3 d = mk(0, 0, 0);
+    bool ok = lights_sample(S, from_abi(origin[i]), time[i], rng, d);
+    valid[i] = ok; dir[i] = to_abi(ok ? d : mk(0, 0, 0));
+    pdf[i] = ok ? lights_pdf(S, from_abi(origin[i]), d, time[i]) : 0.0;
+}
+
+}  // namespace ptd
