@@ -1,0 +1,265 @@
+#!/usr/bin/env python3
+"""Benchmark of the integrator hot path (Camera::render -> Camera::trace, reference src/camera.rs:79-228).
+
+  python bench.py --gpus N --steps K --warmup W            our CUDA path, N ranks (torchrun for N > 1)
+  python bench.py --impl reference --steps K --warmup W     the reference algorithm on the host CPU (oracle port)
+
+Workload (BASELINE.json): scene 6 "everything" at FHD 1920x1080 (reference src/main.rs:371-532, `-q` geometry).
+A step = one pass of the wavefront integrator over one batch of samples: `--spp` samples per pixel PER RANK
+(weak scaling: rank g renders sample indices g, g+N, ... so N ranks deliver N*spp samples per pixel per step), followed
+by the single reduce(sum) of the fp32 accumulators to rank 0.  Throughput does not depend on spp (4000 spp = 4000/spp steps).
+metric: Mrays/s, ray = one World::intersect_all call (camera.rs:179); samples/s is reported alongside.
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+SCENE, WIDTH = 6, 1920
+# device structs (csrc/device_scene.cuh, csrc/kernels.cuh): bytes one segment moves through HBM per stage
+B_RAY, B_HIT, B_STATE = 56, 16, 96   # ray (o,d,time f64), HitRec, full path state (ray + throughput f64x3 + ids uint4)
+B_NODE, B_REF, B_SPHERE, B_QUAD, B_TRI = 32, 8, 64, 128, 80
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_sample(pt, orc, scene, spp, threads=0):
+    """The reference algorithm (C++ restatement, oracle/) on the host CPU over a bounded sample of the workload."""
+    ora = orc.OracleScene(scene.desc, pt)
+    _, st = ora.render(scene.camera, spp, seed=1, nan_policy=pt.PT_NAN_DROP, threads=threads)
+    ora.close()
+    return st
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The Rust binary cannot be built (no cargo/rustc
+    in this image), so this arm times the oracle port with all host threads; each step = FHD x `ref_spp` samples."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pt, orc = ge.load_package(), ge.load_oracle()
+    scene = pt.Scene.build(SCENE, width=WIDTH, spp=args.ref_spp, seed=1)
+    ora = orc.OracleScene(scene.desc, pt)
+    times, segs, paths = [], 0, 0
+    for i in range(args.warmup + args.steps):
+        _, st = ora.render(scene.camera, args.ref_spp, seed=1 + i, nan_policy=pt.PT_NAN_DROP)
+        if i >= args.warmup:
+            times.append(st.seconds); segs += st.segments; paths += st.paths
+    total = sum(times)
+    v = segs / total / 1e6
+    cores = orc.num_threads()
+    line = {"impl": "reference", "metric": "Mrays/s", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "samples_per_s": paths / total,
+            "config": {"workload": f"scene6_everything_{WIDTH}x1080", "spp_per_step": args.ref_spp, "max_depth": 50, "note": "C++ restatement of the reference (oracle/), not the Rust binary"},
+            "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": f"{WIDTH}x1080 x {args.ref_spp} spp per step, {args.steps} steps"},
+            "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--spp", type=int, default=64, help="samples per pixel per rank per step")
+    ap.add_argument("--ref-spp", type=int, default=1, help="samples per pixel per step of the CPU reference arm")
+    ap.add_argument("--pool", type=int, default=0, help="in-flight path pool (0 = library default)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    assert args.warmup >= 3 or os.environ.get("PT_BENCH_ALLOW_SHORT"), "timing rules: at least 3 warm-up steps"
+
+    import torch
+    import torch.distributed as dist
+    pt = ge.load_package()
+    D = __import__("importlib").import_module("pt_b200.distributed")
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    scene = pt.Scene.build(SCENE, width=WIDTH, spp=args.spp, seed=1)
+    cam = scene.camera
+    H = scene.image_height()
+    ctx = pt.Context(local)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    dev = ctx.upload(scene)
+    accum = torch.zeros((H, WIDTH, 3), dtype=torch.float32, device="cuda")
+    host_out = torch.empty((H, WIDTH, 3), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i, dscene):
+        """rank's share of one step: spp samples per pixel (indices rank + k*world, offset by the step), then the reduce."""
+        accum.zero_()
+        st = dscene.render_accumulate(accum.data_ptr(), camera=cam, spp=args.spp, seed=1000 + i, sample_begin=rank, sample_stride=world,
+                                      nan_policy=pt.PT_NAN_DROP, pool_paths=args.pool)
+        D.reduce_accumulators(accum, 0)
+        return st
+
+    def timed(n_steps, first, profiling):
+        ctx.set_profiling(profiling)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        stats = [step(first + i, dev) for i in range(n_steps)]
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        tot = torch.tensor([float(sum(s.segments for s in stats)), float(sum(s.paths for s in stats)), float(sum(s.kernel_launches for s in stats)),
+                            float(sum(s.nonfinite for s in stats))], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)   # max over ranks
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)  # whole-job totals
+        return float(ms.item()), tot.tolist(), stats
+
+    for i in range(args.warmup):
+        step(i, dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, (segs, paths, launches, nonfinite), _ = timed(args.steps, 100, False)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-stage CUDA-event times for the roofline of the dominant kernel (separate pass: the per-stage events
+    #      are recorded on the launching stream around every launch; their overhead is kept out of `value`)
+    ms_p, (segs_p, paths_p, _, _), pstats = timed(args.steps, 100, True)
+    trace_ms, shade_ms, gen_ms = (sum(getattr(s, k) for s in pstats) for k in ("trace_ms", "shade_ms", "raygen_ms"))
+    iters = sum(s.iterations for s in pstats)
+    segs_rank = sum(s.segments for s in pstats); paths_rank = sum(s.paths for s in pstats)
+
+    # ---- end to end through the C ABI with host buffers: scene upload (H2D) + render + reduce + image D2H, every step
+    def e2e_step(i):
+        d2 = ctx.upload(scene)                      # pt_scene_create: H2D of the flattened scene from host memory
+        st = step(i, d2)
+        if rank == 0:
+            host_out.copy_(accum, non_blocking=True)  # D2H of the step's result
+        torch.cuda.synchronize()
+        nbytes = d2.device_bytes
+        d2.close()
+        return st, nbytes
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_stats = [e2e_step(200 + i) for i in range(args.steps)]
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+    e2e_segs = torch.tensor([float(sum(s.segments for s, _ in e2e_stats))], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e_segs, op=dist.ReduceOp.SUM)
+
+    if rank == 0:
+        hbm, peak_src = peaks()
+        # ---- CPU baseline on the box's host cores (bounded sample) + the oracle's work counters for the algorithmic bytes
+        cpu = None
+        n_node = n_sph = n_quad = n_tri = None
+        if not args.no_cpu_baseline:
+            orc = ge.load_oracle()
+            ost = oracle_sample(pt, orc, scene, 2)
+            cpu = {"value": ost.segments / ost.seconds / 1e6, "unit": "Mrays/s", "cores": ost.threads, "kind": "port",
+                   "sample": f"{WIDTH}x{H} x 2 spp of the same scene ({ost.paths} paths, {ost.seconds:.1f} s)", "samples_per_s": ost.paths / ost.seconds}
+            n_node, n_sph, n_quad, n_tri = (getattr(ost, k) / ost.segments for k in ("boxes", "spheres", "quads", "triangles"))
+        else:  # counters measured by the oracle on this scene, used when the CPU leg is skipped
+            n_node, n_sph, n_quad, n_tri = 28.9, 2.84, 2.55, 2.2
+        seg_per_path = segs_rank / max(paths_rank, 1)
+        surv = 1.0 - 1.0 / seg_per_path                     # fraction of segments whose path continues
+        b_trace = B_RAY + B_HIT + n_node * B_NODE + n_sph * B_SPHERE + n_quad * B_QUAD + n_tri * B_TRI + (n_sph + n_quad + n_tri) * B_REF
+        b_shade = B_STATE + B_HIT + surv * B_STATE + 12.0   # read state+hit, write the survivor's state, ~one fp32x3 accumulate per path
+        b_gen = B_STATE / seg_per_path
+        dom = "k_trace" if trace_ms >= shade_ms else "k_shade"
+        dom_ms, dom_b = (trace_ms, b_trace) if dom == "k_trace" else (shade_ms, b_shade)
+        ach = segs_rank * dom_b / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        b_seg = b_trace + b_shade + b_gen
+        step_gbs = (segs / world) * b_seg / (ms * 1e-3) / 1e9
+        line = {
+            "metric": "Mrays/s", "value": segs / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "samples_per_s": paths / (ms * 1e-3),
+            "config": {"workload": f"scene6_everything_{WIDTH}x{H}", "spp_per_step_per_gpu": args.spp, "max_depth": 50, "parallelism": f"spp-split x{world}",
+                       "pool_paths": args.pool or 4 << 20, "triangles": 16628,
+                       "l2": "per-step path-state working set (2 x 4Mi paths x 112 B ~ 0.9 GB) exceeds the 126 MB L2; the 4.2 MB scene (BVH, primitives, envmap) is L2-resident by design"},
+            "gpu_launches": int(launches), "segments_per_path": seg_per_path, "nonfinite_samples": int(nonfinite),
+            "e2e": {"value": e2e_segs.item() / e2e_s.item() / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(e2e_stats[0][1]) * world,
+                    "d2h_bytes_per_step": H * WIDTH * 3 * 4, "ms_per_step": 1e3 * e2e_s.item() / args.steps,
+                    "what": "pt_scene_create (scene H2D) + pt_render_accumulate + reduce + D2H of the fp32 image, every step"},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None, "peak_source": peak_src,
+                         "bytes_per_segment": dom_b, "avg_launch_ms": dom_ms / max(iters, 1), "launches": iters,
+                         "stage_ms_per_step": {"k_generate": gen_ms / args.steps, "k_trace": trace_ms / args.steps, "k_shade": shade_ms / args.steps},
+                         "whole_step": {"bytes_per_segment": b_seg, "achieved": step_gbs, "frac": step_gbs / hbm},
+                         "oracle_counters_per_segment": {"boxes": n_node, "spheres": n_sph, "quads": n_quad, "triangles": n_tri}},
+            "cpu_baseline": cpu, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    dev.close(); ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -241,7 +241,7 @@ typedef struct {
     uint32_t material;
     uint32_t front_face;
     uint32_t is_light;     /* came from World.lights (world.rs:47-62) */
-    uint32_t _pad;
+    uint32_t work;         /* diagnostics: node pairs fetched | primitive tests << 16 (saturating); oracle: 0 */
 } pt_hit;
 /* World::intersect_all(ray, [t_min, inf)) for a batch of host rays. */
 int  pt_trace_closest(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_ray* rays,

@@ -372,5 +372,11 @@ int64_t orc_dump_path_rays(const orc_scene* s, const pt_camera* c, uint64_t seed
     return n;
 }
 int orc_num_threads() { return omp_get_max_threads(); }
+// RNG contract probes (known-answer tests)
+void orc_philox_block(uint32_t k0, uint32_t k1, const uint32_t ctr[4], uint32_t out[4]) { Philox::block(k0, k1, ctr[0], ctr[1], ctr[2], ctr[3], out); }
+void orc_uniforms(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t n, double* out) {
+    Rng rng; rng.seed = seed; rng.pixel = pixel; rng.sample = sample;
+    for (uint32_t i = 0; i < n; i++) out[i] = rng.next();
+}
 
 }  // extern "C"

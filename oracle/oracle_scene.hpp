@@ -261,9 +261,14 @@ struct BVH {
             std::vector<double> pos;
             for (auto& it : items) pos.push_back(it.centroid[axis]);
             std::stable_sort(pos.begin(), pos.end());
-            for (double sp : pos) {
-                double cost = evaluate_sah(axis, sp, parent, items);
-                if (cost < best_cost) { best_cost = cost; best_axis = axis; best_split = sp; }
+            // evaluate_sah is a pure function of (axis, split_pos): evaluate in parallel, then take the
+            // reference's sequential strict-'<' argmin (bvh.rs:68-76) over the same ordered costs.
+            std::vector<double> costs(pos.size());
+            const long n = (long)pos.size();
+#pragma omp parallel for schedule(dynamic, 16) if (n > 256)
+            for (long k = 0; k < n; k++) costs[k] = evaluate_sah(axis, pos[k], parent, items);
+            for (long k = 0; k < n; k++) {
+                if (costs[k] < best_cost) { best_cost = costs[k]; best_axis = axis; best_split = pos[k]; }
             }
         }
         for (auto& it : items) {  // partition keeps list order

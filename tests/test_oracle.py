@@ -1,0 +1,223 @@
+"""CPU tests that PIN THE ORACLE: against the reference's own demo renders (the only result-bearing artefacts
+the reference ships — tests/golden/README.md), and through domain properties of the restated algorithms."""
+import numpy as np
+import pytest
+
+import helpers as H
+
+
+# ---------------------------------------------------------------- reference demo renders (golden fixtures)
+# relRMSE against the reference's 4000-spp render, on 8x8 cells without clipped pixels.  The oracle runs at a few
+# spp per pixel (64 pixels per cell), so the bound is noise floor + systematic error; a wrong camera, BSDF lobe,
+# texture orientation or BVH shows up as > 0.3.  Measured values are in tests/golden/README.md.
+@pytest.mark.parametrize("scene_id,spp,tol", [(4, 4, 0.12), (2, 4, 0.10), (5, 4, 0.10), (6, 3, 0.16)])
+def test_oracle_matches_reference_demo(pt, orc, scene_id, spp, tol):
+    scene = pt.Scene.build(scene_id, width=1920, spp=spp, seed=1)
+    assert scene.image_height() == 1080
+    ora = orc.OracleScene(scene.desc, pt)
+    img, st = ora.render(scene.camera, spp, seed=11, nan_policy=pt.PT_NAN_DROP)
+    err, frac = H.compare_with_demo(img, scene_id)
+    print(f"scene {scene_id}: relRMSE vs reference demo {err:.4f} on {frac:.0%} of cells ({st.seconds:.1f}s, {st.threads} threads)")
+    assert frac > 0.6
+    assert err < tol
+    ora.close()
+
+
+# ---------------------------------------------------------------- exact tie-breaks
+def _ray(pt, o, d, time=0.0):
+    r = np.zeros(1, dtype=pt.RAY_DTYPE)
+    d = np.asarray(d, np.float64)
+    r["origin"], r["direction"], r["time"] = o, d / np.linalg.norm(d), time
+    return r
+
+
+def tie_world(pt, order, bvh=True, n_filler=0):
+    """Coincident primitives at z = -5 hit by the ray (0,0,0)->(0,0,-1) at exactly t = 5 (or 4 for the unit spheres)."""
+    mats = [pt.DiffuseBRDF((0.1 * (i + 1), 0.2, 0.3)) for i in range(len(order))]
+    w = pt.World()
+    for i, kind in enumerate(order):
+        if kind == "quad":
+            w.add_object(pt.Quad((-1, -1, -5), (2, 0, 0), (0, 2, 0), mats[i]))
+        elif kind == "sphere":
+            w.add_object(pt.Sphere.new_still(1.0, (0, 0, -6), mats[i]))
+        elif kind == "cuboid":
+            w.add_object(pt.Cuboid((-1, -1, -7), (1, 1, -5), mats[i]))
+        elif kind == "inst_cuboid":
+            w.add_object(pt.Instance(pt.Cuboid((-1, -1, -7), (1, 1, -5), mats[i]), (0, 1, 0), 0.0, (0, 0, 0)))
+    for k in range(n_filler):  # push the coincident items into different BVH leaves
+        w.add_object(pt.Sphere.new_still(0.1, (10 + 3 * k, 10, -20), mats[0]))
+    if bvh:
+        w.build_bvh()
+    return pt.Scene.from_world(w, pt.make_camera(8))
+
+
+@pytest.mark.parametrize("order,winner", [
+    (["quad", "quad"], 1),              # later quad wins (inclusive contains, quad.rs:49)
+    (["quad", "quad", "quad"], 2),
+    (["sphere", "sphere"], 0),          # later sphere loses (exclusive, sphere.rs:84)
+    (["quad", "cuboid"], 1),            # cuboid front face coincides with the quad; later wins
+    (["cuboid", "quad"], 1),
+    (["quad", "inst_cuboid"], 1),
+    (["inst_cuboid", "quad"], 1),
+])
+@pytest.mark.parametrize("bvh", [True, False])
+def test_oracle_tie_rules(pt, orc, order, winner, bvh):
+    scene = tie_world(pt, order, bvh)
+    ora = orc.OracleScene(scene.desc, pt)
+    h = ora.trace_closest(_ray(pt, (0, 0, 0), (0, 0, -1)))[0]
+    assert h["hit"] == 1 and h["t"] == 5.0
+    assert h["material"] == winner
+    ora.close()
+
+
+def test_oracle_sphere_quad_tie(pt, orc):
+    """[quad, sphere] at the same t: the later sphere loses; [sphere, quad]: the later quad wins."""
+    m0, m1 = pt.DiffuseBRDF((0.1, 0.1, 0.1)), pt.DiffuseBRDF((0.9, 0.9, 0.9))
+    for first_is_quad in (True, False):
+        w = pt.World()
+        quad = lambda m: pt.Quad((-1, -1, -5), (2, 0, 0), (0, 2, 0), m)
+        sph = lambda m: pt.Sphere.new_still(1.0, (0, 0, -6), m)
+        if first_is_quad:
+            w.add_object(quad(m0)); w.add_object(sph(m1))
+        else:
+            w.add_object(sph(m0)); w.add_object(quad(m1))
+        w.build_bvh()
+        scene = pt.Scene.from_world(w, pt.make_camera(8))
+        ora = orc.OracleScene(scene.desc, pt)
+        h = ora.trace_closest(_ray(pt, (0, 0, 0), (0, 0, -1)))[0]
+        assert h["t"] == 5.0
+        assert h["prim_kind"] == pt.PRIM_QUAD  # quad wins both ways
+        ora.close()
+
+
+def test_oracle_light_object_tie(pt, orc):
+    """world.rs:55-59: on an exact tie the object beats the light."""
+    w = pt.World()
+    w.add_light(pt.Quad((-1, -1, -5), (2, 0, 0), (0, 2, 0), pt.DiffuseLight((5, 5, 5))))
+    w.add_object(pt.Quad((-1, -1, -5), (2, 0, 0), (0, 2, 0), pt.DiffuseBRDF((0.5, 0.5, 0.5))))
+    w.build_bvh()
+    scene = pt.Scene.from_world(w, pt.make_camera(8))
+    ora = orc.OracleScene(scene.desc, pt)
+    h = ora.trace_closest(_ray(pt, (0, 0, 0), (0, 0, -1)))[0]
+    assert h["hit"] == 1 and h["is_light"] == 0
+    ora.close()
+
+
+# ---------------------------------------------------------------- textures / tonemap known answers
+def test_oracle_textures_and_tonemap(pt, orc):
+    img = np.zeros((2, 4, 3), np.uint8)
+    img[0, 0] = (255, 0, 0); img[0, 3] = (0, 255, 0); img[1, 0] = (0, 0, 255); img[1, 3] = (10, 20, 30)
+    image = pt.Image(rgb=img)
+    checker = pt.CheckerTexture(0.5, pt.SolidTexture((1, 0, 0)), pt.SolidTexture((0, 1, 0)))
+    w = pt.World()
+    w.add_object(pt.Sphere.new_still(1.0, (0, 0, 0), pt.DiffuseLight(pt.ImageTexture(image))))   # material 0: emitted = texel
+    w.add_object(pt.Sphere.new_still(1.0, (5, 0, 0), pt.DiffuseLight(checker)))                  # material 1
+    scene = pt.Scene.from_world(w, pt.make_camera(8))
+    ora = orc.OracleScene(scene.desc, pt)
+    q = np.zeros(6, dtype=pt.BSDF_QUERY_DTYPE)
+    # texture.rs:78-83: v flips, nearest texel, (u,v) = (0,1) -> top-left, (0.99,0.01) -> bottom-right; u=1 clamps (Q22)
+    q["u"] = [0.0, 0.99, 0.0, 0.99, 1.0, 0.3]
+    q["v"] = [1.0, 1.0, 0.0, 0.01, 1.0, 0.7]
+    e = ora.bsdf_eval_pdf(0, q)["emitted"]
+    assert np.allclose(e[0], [1, 0, 0]) and np.allclose(e[1], [0, 1, 0]) and np.allclose(e[2], [0, 0, 1])
+    assert np.allclose(e[3], np.array([10, 20, 30]) / 255.0) and np.allclose(e[4], [0, 1, 0])
+    # checker: (floor(x/s)+floor(y/s)+floor(z/s)) % 2 == 0 ? tex1 : tex2 with sign-keeping % (texture.rs:44-53, Q23)
+    q = np.zeros(4, dtype=pt.BSDF_QUERY_DTYPE)
+    q["point"] = [(0.1, 0.1, 0.1), (0.6, 0.1, 0.1), (-0.1, 0.1, 0.1), (-0.1, -0.1, 0.1)]
+    e = ora.bsdf_eval_pdf(1, q)["emitted"]
+    assert np.allclose(e[0], [1, 0, 0]) and np.allclose(e[1], [0, 1, 0]) and np.allclose(e[2], [0, 1, 0]) and np.allclose(e[3], [1, 0, 0])
+    # tonemap: camera.rs:109-114,128-130 (NaN -> 0, clamp 0.999, truncating cast)
+    t = orc.tonemap_rgb8(np.array([0.0, 1.0, 4.0, 0.25, -1.0, np.nan, np.inf, 1e-6]))
+    assert list(t) == [0, 255, 255, 128, 0, 0, 255, 0]
+    assert list(pt.tonemap_rgb8(np.array([0.0, 1.0, 4.0, 0.25, -1.0, np.nan, np.inf, 1e-6]))) == list(t)
+    ora.close()
+
+
+# ---------------------------------------------------------------- sampler / pdf consistency (distribution tests)
+def _material_world(pt):
+    mats = [
+        pt.DiffuseBRDF((0.8, 0.6, 0.4)),
+        pt.MetalBRDF((0.9, 0.8, 0.7), 0.4),
+        pt.GlassBSDF((1, 1, 1), 0.3, 1.5),
+        pt.PrincipledBSDF((0.7, 0.5, 0.3), 0.3, 0.5, 0.2, 0.5, 0.3, 1.5, 0.0, 0.4, 0.5, 0.6, 0.7),
+        pt.PrincipledBSDF((0.7, 0.5, 0.3), 0.1, 0.4, 0.2, 0.5, 0.3, 1.5, 0.7, 0.4, 0.5, 0.6, 0.7),
+        pt.DiffuseLight((3, 2, 1)),
+        pt.SheenBRDF((0.6, 0.3, 0.2), 0.5),
+        pt.ClearcoatBRDF(0.4),
+    ]
+    mats.append(pt.MixBxDf(0.3, mats[0], mats[1]))
+    mats.append(pt.MixBxDf(0.6, mats[8], mats[3]))
+    w = pt.World()
+    for i, m in enumerate(mats):
+        w.add_object(pt.Sphere.new_still(0.5, (2.0 * i, 0, 0), m))
+    w.build_bvh()
+    return pt.Scene.from_world(w, pt.make_camera(8)), len(mats)
+
+
+def test_oracle_diffuse_sampler_matches_pdf(pt, orc):
+    """Moment test: for cosine sampling E[1/pdf * f] over samples = albedo (white furnace) and E[cos] = 2/3."""
+    scene, _ = _material_world(pt)
+    ora = orc.OracleScene(scene.desc, pt)
+    rng = np.random.default_rng(5)
+    n = 20000
+    q = np.zeros(n, dtype=pt.BSDF_QUERY_DTYPE)
+    q["geometric_normal"] = (0, 0, 1); q["shading_normal"] = (0, 0, 1); q["view_dir"] = (0.3, 0.2, 0.933); q["front_face"] = 1
+    s = ora.bsdf_sample(0, q, rng.uniform(size=(n, 8)))
+    assert s["valid"].all() and (s["n_uniforms"] == 2).all()
+    q["light_dir"] = s["dir"]
+    r = ora.bsdf_eval_pdf(0, q)
+    w = r["eval"] / r["pdf"][:, None]
+    assert np.allclose(w.mean(axis=0), [0.8, 0.6, 0.4], atol=1e-9)          # eval/pdf == albedo exactly for Lambert
+    assert abs(s["dir"][:, 2].mean() - 2.0 / 3.0) < 0.01
+    ora.close()
+
+
+@pytest.mark.parametrize("material,expect_uniforms", [(1, 2), (2, 3), (7, 2)])
+def test_oracle_specular_samplers_are_consistent(pt, orc, material, expect_uniforms):
+    """The sampled direction must have a positive pdf under the same material and eval/pdf must stay bounded
+    (Monte-Carlo weight sanity); uniform consumption follows SURVEY Appendix B."""
+    scene, _ = _material_world(pt)
+    ora = orc.OracleScene(scene.desc, pt)
+    rng = np.random.default_rng(6)
+    n = 5000
+    q = np.zeros(n, dtype=pt.BSDF_QUERY_DTYPE)
+    q["geometric_normal"] = (0, 0, 1); q["shading_normal"] = (0, 0, 1); q["view_dir"] = (0.3, 0.2, 0.933); q["front_face"] = 1
+    s = ora.bsdf_sample(material, q, rng.uniform(size=(n, 8)))
+    ok = s["valid"] == 1
+    assert ok.mean() > 0.5 and (s["n_uniforms"] == expect_uniforms).all()
+    q["light_dir"] = s["dir"]
+    r = ora.bsdf_eval_pdf(material, q)
+    assert (r["pdf"][ok] > 0).all()
+    wgt = r["eval"][ok, 0] / r["pdf"][ok]
+    assert np.isfinite(wgt).all() and wgt.mean() < 1.5
+    ora.close()
+
+
+def test_oracle_sample_split_is_exact(pt, orc):
+    """spp split across G virtual ranks (sample index = g + k*G) reproduces the 1-rank sum."""
+    scene = pt.Scene.build(3, width=24, spp=8, seed=1)
+    ora = orc.OracleScene(scene.desc, pt)
+    full, _ = ora.render(scene.camera, 8, seed=9, nan_policy=pt.PT_NAN_DROP)
+    parts = [ora.render(scene.camera, 4, seed=9, sample_begin=g, sample_stride=2, nan_policy=pt.PT_NAN_DROP)[0] for g in range(2)]
+    assert np.allclose(full, (parts[0] + parts[1]) / 2.0, rtol=1e-12, atol=1e-12)
+    ora.close()
+
+
+def test_oracle_rng_contract(orc, pt):
+    """Philox4x32-10 known-answer vectors (Random123 kat_vectors) and the uniform construction of the RNG contract:
+    draw k of path (pixel, sample) = lane k%2 of block philox(key=(seed_lo,seed_hi), ctr=(k/2, pixel, sample, 0)),
+    each lane = ((hi << 32 | lo) >> 11) * 2^-53."""
+    import ctypes as C
+    L = orc.lib()
+    kats = [((0, 0), (0, 0, 0, 0), (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
+            ((0xFFFFFFFF, 0xFFFFFFFF), (0xFFFFFFFF,) * 4, (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
+            ((0xA4093822, 0x299F31D0), (0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1))]
+    for key, ctr, want in kats:
+        out = (C.c_uint32 * 4)()
+        L.orc_philox_block(C.c_uint32(key[0]), C.c_uint32(key[1]), (C.c_uint32 * 4)(*ctr), out)
+        assert tuple(out) == want
+    u = np.zeros(4)
+    L.orc_uniforms(C.c_uint64(0), C.c_uint32(0), C.c_uint32(0), C.c_uint32(4), u.ctypes.data_as(C.c_void_p))
+    assert u[0] == float(((0x6627E8D5 << 32) | 0xE169C58D) >> 11) * 2.0 ** -53
+    assert u[1] == float(((0xBC57AC4C << 32) | 0x9B00DBD8) >> 11) * 2.0 ** -53
+    assert ((0 <= u) & (u < 1)).all() and len(set(u)) == 4

@@ -54,7 +54,7 @@ class Stats(C.Structure):  # pt_stats
 RAY_DTYPE = np.dtype([("origin", "<f8", 3), ("direction", "<f8", 3), ("time", "<f8")])
 HIT_DTYPE = np.dtype([("t", "<f8"), ("u", "<f8"), ("v", "<f8"), ("point", "<f8", 3), ("geometric_normal", "<f8", 3),
                       ("shading_normal", "<f8", 3), ("hit", "<u4"), ("prim_kind", "<u4"), ("prim_index", "<u4"),
-                      ("instance", "<u4"), ("material", "<u4"), ("front_face", "<u4"), ("is_light", "<u4"), ("_pad", "<u4")])
+                      ("instance", "<u4"), ("material", "<u4"), ("front_face", "<u4"), ("is_light", "<u4"), ("work", "<u4")])
 BSDF_QUERY_DTYPE = np.dtype([("view_dir", "<f8", 3), ("light_dir", "<f8", 3), ("point", "<f8", 3), ("geometric_normal", "<f8", 3),
                              ("shading_normal", "<f8", 3), ("u", "<f8"), ("v", "<f8"), ("front_face", "<u4"), ("_pad", "<u4")])
 BSDF_RESULT_DTYPE = np.dtype([("eval", "<f8", 3), ("pdf", "<f8"), ("emitted", "<f8", 3), ("_pad", "<f8")])
@@ -401,7 +401,9 @@ class Context:
             raise PtError(f"pt_b200 error {rc}: {self.lib.pt_last_error().decode()}")
 
     def set_stream(self, cuda_stream):
-        self._check(self.lib.pt_ctx_set_stream(self.ptr, C.c_void_p(cuda_stream)))
+        """Launch on an external stream (e.g. torch.cuda.current_stream().cuda_stream).  Handle 0 is the legacy
+        default stream, which the C ABI spells cudaStreamLegacy (0x1) because NULL there means "the ctx's own"."""
+        self._check(self.lib.pt_ctx_set_stream(self.ptr, C.c_void_p(cuda_stream if cuda_stream else 1)))
 
     def set_profiling(self, on):
         self._check(self.lib.pt_ctx_set_profiling(self.ptr, int(on)))

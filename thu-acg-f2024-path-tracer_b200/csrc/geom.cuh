@@ -94,7 +94,7 @@ PT_D float slab(const DNode& n, const BoxRay& b, float t_min, float t_max) {
     float z0 = __fmaf_rn(sz ? n.hi[2] : n.lo[2], b.iz, b.nz), z1 = __fmaf_rn(sz ? n.lo[2] : n.hi[2], b.iz, b.fz);
     float tn = fmaxf(fmaxf(x0, y0), fmaxf(z0, t_min));
     float tf = fminf(fminf(x1, y1), fminf(z1, t_max));
-    return tn <= tf ? tn : __int_as_float(0x7f800000);
+    return tn <= tf ? tn : __int_as_float(0x7fc00000);  // NaN on a miss: fails every `<=` test, even against t_max = +inf
 }
 
 // ---------------------------------------------------------------- traversal
@@ -103,6 +103,7 @@ constexpr uint32_t kTagRef = 0x40000000u, kTagSentinel = 0x80000000u, kTagMask =
 
 struct Closest {
     double t; uint32_t ref, inst, tie_outer, tie_inner; bool is_light;
+    uint32_t n_pairs, n_prims;  // work counters: node pairs fetched, primitive tests
 };
 PT_D void consider(Closest& c, double t, uint32_t ref, uint32_t inst, uint32_t tie_o, uint32_t tie_i) {
     if (t < c.t || (t == c.t && (tie_o > c.tie_outer || (tie_o == c.tie_outer && tie_i > c.tie_inner)))) {
@@ -132,7 +133,7 @@ PT_D bool trace_closest(const DScene& S, const RayD& world_ray, double t_min, do
     uint32_t stack[kStack]; float stack_t[kStack];
     int sp = 0;
     c.t = ANY_HIT ? t_max_any : __longlong_as_double(0x7ff0000000000000ll);
-    c.ref = kNone; c.inst = kInstNone; c.tie_outer = 0; c.tie_inner = 0; c.is_light = false;
+    c.ref = kNone; c.inst = kInstNone; c.tie_outer = 0; c.tie_inner = 0; c.is_light = false; c.n_pairs = 0; c.n_prims = 0;
     RayD r = world_ray;
     BoxRay br = make_boxray(r);
     const float tmin_f = __double2float_rd(t_min);
@@ -141,6 +142,7 @@ PT_D bool trace_closest(const DScene& S, const RayD& world_ray, double t_min, do
     while (true) {
         if (cur != kNone) {
             const DNode n0 = S.nodes[cur], n1 = S.nodes[cur + 1];
+            c.n_pairs++;
             const float tmax_f = __double2float_ru(c.t);
             float t0 = slab(n0, br, tmin_f, tmax_f), t1 = slab(n1, br, tmin_f, tmax_f);
             // visit order: nearer child first
@@ -158,6 +160,7 @@ PT_D bool trace_closest(const DScene& S, const RayD& world_ray, double t_min, do
                 } else {  // leaf: scan refs
                     for (uint32_t k = 0; k < n.b; k++) {
                         const DRef rf = S.refs[n.a + k];
+                        c.n_prims++;
                         const uint32_t kind = ref_kind(rf.kind_index), index = ref_index(rf.kind_index);
                         if (kind == PT_PRIM_TRIANGLE) {
                             double t, u, v;

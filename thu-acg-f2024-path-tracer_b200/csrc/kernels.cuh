@@ -191,7 +191,9 @@ __global__ void k_trace_batch(const pt_ray* __restrict__ rays, size_t n, double 
     RayD r; r.o = from_abi(rays[i].origin); r.d = from_abi(rays[i].direction); r.time = rays[i].time;
     Closest c;
     pt_hit o; memset(&o, 0, sizeof(o)); o.instance = PT_NONE;
-    if (trace_closest<false>(S, r, t_min, 0.0, c)) {
+    const bool hit = trace_closest<false>(S, r, t_min, 0.0, c);
+    o.work = min(c.n_pairs, 0xFFFFu) | (min(c.n_prims, 0xFFFFu) << 16);
+    if (hit) {
         HitInfoD h;
         reconstruct_hit(S, r, c.ref, c.inst, c.t, h);
         o.hit = 1; o.t = c.t; o.u = h.u; o.v = h.v; o.point = to_abi(h.point); o.geometric_normal = to_abi(h.gn); o.shading_normal = to_abi(h.sn);

@@ -1,0 +1,35 @@
+#!/usr/bin/env python3
+"""Developer probe (GPU box): per-scene throughput and per-stage split of the wavefront integrator.
+usage: perf_probe.py scene:width:spp[:pool] ...   e.g. 6:1920:16 3:600:100"""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import __graft_entry__ as ge  # noqa: E402
+
+pt = ge.load_package()
+
+
+def main():
+    ctx = pt.Context(0)
+    for spec in sys.argv[1:]:
+        parts = [int(x) for x in spec.split(":")]
+        sid, width, spp = parts[:3]
+        pool = parts[3] if len(parts) > 3 else 0
+        t0 = time.time(); scene = pt.Scene.build(sid, width=width, spp=spp, seed=1); tb = time.time() - t0
+        t0 = time.time(); dev = ctx.upload(scene); tu = time.time() - t0
+        dev.render(spp=min(spp, 2), seed=1, pool_paths=pool)  # warm-up
+        for prof in (0, 1):
+            ctx.set_profiling(prof)
+            t0 = time.time(); img, st = dev.render(spp=spp, seed=2, nan_policy=pt.PT_NAN_DROP, pool_paths=pool); tw = time.time() - t0
+            print(f"scene {sid} {width}x{st.height} spp {spp} pool {pool or 'default'} prof={prof}: build {tb:.2f}s upload {tu * 1e3:.1f} ms ({dev.device_bytes / 1e6:.1f} MB) | "
+                  f"device {st.device_ms:.1f} ms wall {tw * 1e3:.1f} ms | {st.segments / st.device_ms / 1e3:.1f} Mrays/s {st.paths / st.device_ms * 1e3:.3e} samples/s | "
+                  f"seg/path {st.segments / st.paths:.2f} iters {st.iterations} launches {st.kernel_launches} nonfinite {st.nonfinite} | "
+                  f"gen {st.raygen_ms:.1f} trace {st.trace_ms:.1f} shade {st.shade_ms:.1f} ms", flush=True)
+        dev.close()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
