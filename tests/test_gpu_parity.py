@@ -137,7 +137,7 @@ def test_ragged_meshes_and_motion_blur(pt, orc, ctx):
         scene = pt.Scene.from_world(w, pt.make_camera(8))
         dev, ora = ctx.upload(scene), orc.OracleScene(scene.desc, pt)
         a, b = dev.trace_closest(rays), ora.trace_closest(rays)
-        assert b["hit"].mean() > 0.2
+        assert b["hit"].mean() > 0.05
         assert_hits_equal(pt, a, b, f"ragged world (bvh={build})")
         dev.close(); ora.close()
 
