@@ -29,7 +29,8 @@ struct pt_ctx {
     double* pool_f[2] = {nullptr, nullptr};
     uint4* pool_ids[2] = {nullptr, nullptr};
     HitRec* hits = nullptr;
-    uint32_t* d_count = nullptr;            // [2]: survivors counter, spare
+    uint32_t* d_count = nullptr;            // [16]: [0] survivors counter, [4 .. 4+N_CLS) shade-class queue lengths
+    uint32_t* q_items = nullptr;            // N_CLS queues of `pool` path slots each
     unsigned long long* d_nonfinite = nullptr;
     uint32_t* h_count = nullptr;            // pinned
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs[6] = {nullptr};
@@ -40,6 +41,7 @@ struct pt_scene {
     DScene d{};
     uint64_t bytes = 0;
     uint32_t n_materials = 0, n_images = 0, max_stack = 0;
+    uint32_t class_mask = 1u << CLS_MISS;   // shade classes that can occur in this scene
     std::vector<DImage> images;
 };
 
@@ -57,7 +59,7 @@ int pt_ctx_create(int device, pt_ctx** out) {
     auto* c = new pt_ctx(); c->device = device;
     CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
-    CU(cudaMalloc(&c->d_count, 2 * sizeof(uint32_t)));
+    CU(cudaMalloc(&c->d_count, 16 * sizeof(uint32_t)));
     CU(cudaMalloc(&c->d_nonfinite, sizeof(unsigned long long)));
     CU(cudaMallocHost(&c->h_count, 2 * sizeof(uint32_t)));
     CU(cudaEventCreate(&c->ev0)); CU(cudaEventCreate(&c->ev1));
@@ -67,7 +69,7 @@ int pt_ctx_create(int device, pt_ctx** out) {
 }
 static void free_pool(pt_ctx* c) {
     for (int i = 0; i < 2; i++) { cudaFree(c->pool_f[i]); cudaFree(c->pool_ids[i]); c->pool_f[i] = nullptr; c->pool_ids[i] = nullptr; }
-    cudaFree(c->hits); c->hits = nullptr; c->pool = 0;
+    cudaFree(c->hits); c->hits = nullptr; cudaFree(c->q_items); c->q_items = nullptr; c->pool = 0;
 }
 void pt_ctx_destroy(pt_ctx* c) {
     if (!c) return;
@@ -332,6 +334,8 @@ int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
         DMaterial o{}; o.kind = m.kind; o.base_color_tex = m.base_color_tex; o.roughness_tex = m.roughness_tex; o.normal_map = m.normal_map;
         o.mix_a = m.mix_a; o.mix_b = m.mix_b; memcpy(o.p, m.p, sizeof(o.p));
         materials[i] = o;
+        s->class_mask |= 1u << (m.kind == PT_MAT_LIGHT ? CLS_LIGHT : m.kind == PT_MAT_DIFFUSE ? CLS_DIFFUSE : m.kind == PT_MAT_METAL ? CLS_METAL
+                                : m.kind == PT_MAT_GLASS ? CLS_GLASS : m.kind == PT_MAT_PRINCIPLED ? CLS_PRINCIPLED : CLS_OTHER);
     }
     std::vector<DRef> lights(d->n_lights);
     for (uint32_t i = 0; i < d->n_lights; i++) lights[i] = DRef{ref_pack(d->lights[i].kind, d->lights[i].index), 0};
@@ -396,6 +400,7 @@ static int ensure_pool(pt_ctx* c, uint32_t paths) {
         CU(cudaMalloc(&c->pool_ids[i], (size_t)paths * sizeof(uint4)));
     }
     CU(cudaMalloc(&c->hits, (size_t)paths * sizeof(HitRec)));
+    CU(cudaMalloc(&c->q_items, (size_t)paths * N_CLS * sizeof(uint32_t)));
     c->pool = paths;
     return PT_OK;
 }
@@ -435,13 +440,22 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
             S.kernel_launches++;
         }
         const uint32_t n = live + n_new;
-        CU(cudaMemsetAsync(ctx->d_count, 0, sizeof(uint32_t), st));
+        CU(cudaMemsetAsync(ctx->d_count, 0, 16 * sizeof(uint32_t), st));
+        const Queues q{ctx->q_items, ctx->d_count + 4, ctx->pool};
         if (ctx->profiling) CU(cudaEventRecord(ctx->evs[1], st));
-        k_trace<<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(in, n, ctx->hits, scene->d);
+        k_trace<<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d);
         if (ctx->profiling) CU(cudaEventRecord(ctx->evs[2], st));
-        k_shade<<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(in, n, ctx->hits, outb, ctx->d_count, d_accum, ctx->d_nonfinite, scene->d, dcam, rcst);
+        // one specialised kernel per shade class present in the scene; each walks its queue grid-stride
+        const unsigned sg = std::min<unsigned>((n + kBlock - 1) / kBlock, 148u * 16u);
+#define PT_SHADE(CLS)                                                                                                                    \
+        if (scene->class_mask & (1u << CLS)) {                                                                                           \
+            k_shade<CLS><<<sg, kBlock, 0, st>>>(in, q, ctx->hits, outb, ctx->d_count, d_accum, ctx->d_nonfinite, scene->d, dcam, rcst); \
+            S.kernel_launches++;                                                                                                         \
+        }
+        PT_SHADE(CLS_MISS) PT_SHADE(CLS_LIGHT) PT_SHADE(CLS_DIFFUSE) PT_SHADE(CLS_METAL) PT_SHADE(CLS_GLASS) PT_SHADE(CLS_PRINCIPLED) PT_SHADE(CLS_OTHER)
+#undef PT_SHADE
         if (ctx->profiling) CU(cudaEventRecord(ctx->evs[3], st));
-        S.kernel_launches += 2;
+        S.kernel_launches += 1;
         CU(cudaMemcpyAsync(ctx->h_count, ctx->d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         if (ctx->profiling) {

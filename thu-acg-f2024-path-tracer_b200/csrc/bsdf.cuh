@@ -135,8 +135,10 @@ PT_D PrincipledLobes principled_lobes(const DMaterial& m) {  // principled.rs:79
 PT_D double principled_alpha_g(const DMaterial& m) { double g = m.p[PT_P_CLEARCOAT_GLOSS]; return (1.0 - g) * 0.1 + g * 0.001; }
 
 // BxDFMaterial::sample (leaf materials). ray_dir = incoming ray direction; returns false for None.
+// K >= 0: the material kind is known at compile time (per-class shade kernels) and the switch folds away.
+template <int K = -1>
 PT_D bool bsdf_sample_leaf(const DScene& S, const DMaterial& m, d3 ray_dir, const HitInfoD& h, Rng& rng, d3& out) {
-    switch (m.kind) {
+    switch (K >= 0 ? (uint32_t)K : m.kind) {
         case PT_MAT_DIFFUSE: out = to_world(h.sn, cosine_sample_hemisphere(rng)); return true;  // diffuse.rs:51-54
         case PT_MAT_METAL: {  // metal.rs:39-54
             d3 v = to_local(h.sn, -ray_dir);
@@ -198,8 +200,9 @@ PT_D d3 clearcoat_eval(d3 v, d3 l, d3 h, double alpha_g) {  // extra |l.z| (Q17)
 }
 
 // BxDFMaterial::{pdf, eval} for leaf materials, computed together (they share frames and half vectors).
+template <int K = -1>
 PT_D void bsdf_eval_pdf_leaf(const DScene& S, const DMaterial& m, d3 view_dir, d3 light_dir, const HitInfoD& hi, d3& f_out, double& pdf_out) {
-    switch (m.kind) {
+    switch (K >= 0 ? (uint32_t)K : m.kind) {
         case PT_MAT_DIFFUSE: {  // diffuse.rs:56-65
             d3 color = texture_value(S, m.base_color_tex, hi.u, hi.v, hi.point);
             d3 l = to_local(hi.sn, light_dir);
@@ -303,7 +306,9 @@ PT_D void bsdf_eval_pdf_leaf(const DScene& S, const DMaterial& m, d3 view_dir, d
 
 // MixBxDf (mix.rs:24-45) is a binary tree over leaf materials; walked with a small explicit stack.
 constexpr int kMixDepth = 8;
+template <int K = -1>
 PT_D bool bsdf_sample(const DScene& S, uint32_t mat, d3 ray_dir, const HitInfoD& h, Rng& rng, d3& out) {
+    if (K >= 0) return bsdf_sample_leaf<K>(S, S.materials[mat], ray_dir, h, rng, out);
     for (int d = 0; d < kMixDepth; d++) {
         const DMaterial& m = S.materials[mat];
         if (m.kind != PT_MAT_MIX) return bsdf_sample_leaf(S, m, ray_dir, h, rng, out);
@@ -312,8 +317,10 @@ PT_D bool bsdf_sample(const DScene& S, uint32_t mat, d3 ray_dir, const HitInfoD&
     }
     return false;
 }
+template <int K = -1>
 PT_D void bsdf_eval_pdf(const DScene& S, uint32_t mat, d3 view_dir, d3 light_dir, const HitInfoD& h, d3& f_out, double& pdf_out) {
     const DMaterial& m0 = S.materials[mat];
+    if (K >= 0) { bsdf_eval_pdf_leaf<K>(S, m0, view_dir, light_dir, h, f_out, pdf_out); return; }
     if (m0.kind != PT_MAT_MIX) { bsdf_eval_pdf_leaf(S, m0, view_dir, light_dir, h, f_out, pdf_out); return; }
     // post-order evaluation of w1 = (1-t)*f1, w2 = t*f2, w1 + w2 (mix.rs:34-44)
     struct Frame { uint32_t mat; int state; d3 f1; double p1; };

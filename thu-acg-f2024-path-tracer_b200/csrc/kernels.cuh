@@ -73,14 +73,43 @@ __global__ void __launch_bounds__(kBlock) k_generate(PathBuf out, uint32_t slot0
     store_path(out, slot0 + i, r, mk(1, 1, 1), make_uint4(pix, sample, rng.used, 0));
 }
 
-__global__ void __launch_bounds__(kBlock) k_trace(PathBuf in, uint32_t n, HitRec* __restrict__ hits, DScene S) {
-    uint32_t i = blockIdx.x * kBlock + threadIdx.x;
-    if (i >= n) return;
-    RayD r = load_ray(in, i);
-    Closest c;
-    trace_closest<false>(S, r, 1e-3, 0.0, c);  // Interval::new(eps, INFINITY), camera.rs:171,179
-    HitRec h; h.t = c.t; h.ref = c.ref; h.inst_light = (c.inst & 0x7FFFFFFFu) | (c.is_light ? 0x80000000u : 0u);
-    hits[i] = h;
+// Shade classes: one queue and one specialised shade kernel per class, so warps shade one material kind.
+enum { CLS_MISS = 0, CLS_LIGHT, CLS_DIFFUSE, CLS_METAL, CLS_GLASS, CLS_PRINCIPLED, CLS_OTHER, N_CLS };
+PT_D uint32_t hit_material(const DScene& S, uint32_t ref) {
+    const uint32_t kind = ref_kind(ref), index = ref_index(ref);
+    if (kind == PT_PRIM_SPHERE) return S.spheres[index].material;
+    if (kind == PT_PRIM_QUAD) return S.quad_material[index];
+    return S.meshes[S.tri_mesh[index]].material;
+}
+PT_D uint32_t class_of_kind(uint32_t k) {
+    return k == PT_MAT_LIGHT ? CLS_LIGHT : k == PT_MAT_DIFFUSE ? CLS_DIFFUSE : k == PT_MAT_METAL ? CLS_METAL : k == PT_MAT_GLASS ? CLS_GLASS
+           : k == PT_MAT_PRINCIPLED ? CLS_PRINCIPLED : CLS_OTHER;
+}
+struct Queues { uint32_t* items; uint32_t* count; uint32_t stride; };  // items[cls * stride + k] = path slot
+
+// World::intersect_all for every live path, then the path is appended to the queue of its shade class
+// (warp-aggregated: lanes of the same class share one atomicAdd).
+__global__ void __launch_bounds__(kBlock) k_trace(PathBuf in, uint32_t n, HitRec* __restrict__ hits, Queues q, DScene S) {
+    const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+    uint32_t cls = N_CLS;
+    if (i < n) {
+        RayD r = load_ray(in, i);
+        Closest c;
+        trace_closest<false>(S, r, 1e-3, 0.0, c);  // Interval::new(eps, INFINITY), camera.rs:171,179
+        HitRec h; h.t = c.t; h.ref = c.ref; h.inst_light = (c.inst & 0x7FFFFFFFu) | (c.is_light ? 0x80000000u : 0u);
+        hits[i] = h;
+        cls = c.ref == kNone ? (uint32_t)CLS_MISS : class_of_kind(S.materials[hit_material(S, c.ref)].kind);
+    }
+    __syncwarp();
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, cls);
+    if (cls != N_CLS) {
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if ((int)lane == leader) base = atomicAdd(q.count + cls, __popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        q.items[(size_t)cls * q.stride + base + __popc(peers & ((1u << lane) - 1u))] = i;
+    }
 }
 
 PT_D void add_radiance(float* __restrict__ accum, uint32_t pix, d3 v, uint32_t nan_policy, unsigned long long* nonfinite, bool& dead) {
@@ -93,77 +122,94 @@ PT_D void add_radiance(float* __restrict__ accum, uint32_t pix, d3 v, uint32_t n
     if (v.z != 0.0) atomicAdd(accum + 3ull * pix + 2, (float)v.z);
 }
 
-__global__ void __launch_bounds__(kBlock) k_shade(PathBuf in, uint32_t n, const HitRec* __restrict__ hits, PathBuf out,
+template <int CLS> struct ClassKind { static constexpr int value = -1; };
+template <> struct ClassKind<CLS_LIGHT> { static constexpr int value = PT_MAT_LIGHT; };
+template <> struct ClassKind<CLS_DIFFUSE> { static constexpr int value = PT_MAT_DIFFUSE; };
+template <> struct ClassKind<CLS_METAL> { static constexpr int value = PT_MAT_METAL; };
+template <> struct ClassKind<CLS_GLASS> { static constexpr int value = PT_MAT_GLASS; };
+template <> struct ClassKind<CLS_PRINCIPLED> { static constexpr int value = PT_MAT_PRINCIPLED; };
+
+// One loop iteration of Camera::trace after intersect_all (camera.rs:180-225) for the paths of ONE shade class.
+// Grid-stride over the class queue; survivors are written compacted into `out` (ballot + block prefix + one atomic).
+template <int CLS>
+__global__ void __launch_bounds__(kBlock) k_shade(PathBuf in, Queues q, const HitRec* __restrict__ hits, PathBuf out,
                                                     uint32_t* __restrict__ out_count, float* __restrict__ accum,
                                                     unsigned long long* __restrict__ nonfinite, DScene S, DCameraEx cam, RenderConst rc) {
-    const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
-    bool alive = false;
-    RayD next; d3 thr = mk(0, 0, 0); uint4 ids = make_uint4(0, 0, 0, 0);
-    if (i < n) {
-        RayD ray = load_ray(in, i);
-        thr = mk(in.f[7][i], in.f[8][i], in.f[9][i]);
-        ids = in.ids[i];
-        const HitRec hr = hits[i];
-        const uint32_t pix = ids.x, bounces = ids.z >> 16;
-        Rng rng; rng.init(rc.seed, pix, ids.y, ids.z & 0xFFFFu);
-        bool dead = false;
-        if (hr.ref == kNone) {  // camera.rs:180-183
-            add_radiance(accum, pix, thr * sample_environment(S, cam.c, ray.d), rc.nan_policy, nonfinite, dead);
-        } else {
-            HitInfoD h;
-            const uint32_t inst = hr.inst_light & 0x7FFFFFFFu;
-            reconstruct_hit(S, ray, hr.ref, inst, hr.t, h);
-            const DMaterial& m = S.materials[h.material];
-            // camera.rs:186-187: `radiance += throughput * emitted` runs for every hit; for non-emitters it only
-            // matters when the throughput is already inf/NaN (inf * 0 = NaN poisons the pixel, Q32).
-            if (m.kind == PT_MAT_LIGHT || !finite3(thr)) {
-                d3 em = m.kind == PT_MAT_LIGHT ? texture_value(S, m.base_color_tex, h.u, h.v, h.point) : mk(0, 0, 0);
-                add_radiance(accum, pix, thr * em, rc.nan_policy, nonfinite, dead);
-            }
-            bool go = !dead;
-            if (go && bounces > 5) {  // Russian roulette, camera.rs:190-196
-                double p = clampd(luminance(thr), 0.01, 1.0);
-                if (rng.next() > p) go = false;
-                else thr = thr / p;
-            }
-            if (go) {
-                const double p_light = S.n_lights == 0 ? 0.0 : 0.5, p_bsdf = 1.0 - p_light;  // camera.rs:199-200
-                const double rsel = rng.next();
-                d3 dir;
-                bool ok = rsel < p_light ? lights_sample(S, h.point, ray.time, rng, dir) : bsdf_sample(S, h.material, ray.d, h, rng, dir);
-                if (ok) {  // camera.rs:212-225
-                    d3 f; double bsdf_pdf;
-                    bsdf_eval_pdf(S, h.material, -ray.d, dir, h, f, bsdf_pdf);
-                    double light_pdf = lights_pdf(S, h.point, dir, ray.time);
-                    double pdf = p_bsdf * bsdf_pdf + p_light * light_pdf;
-                    d3 attenuation = f / pdf;
-                    double e = 1e-3 * signum(dot(dir, h.gn));
-                    next = make_ray(h.point + e * h.gn, dir, ray.time);
-                    thr = thr * attenuation;
-                    alive = bounces + 1 < cam.c.max_depth;  // `for bounces in 0..max_depth`, camera.rs:177
-                    if (rc.nan_policy == PT_NAN_DROP && !finite3(thr)) { atomicAdd(nonfinite, 1ull); alive = false; }
-                    ids.z = (rng.used & 0xFFFFu) | ((bounces + 1) << 16);
+    constexpr int K = ClassKind<CLS>::value;
+    const uint32_t count = q.count[CLS];
+    const uint32_t* __restrict__ items = q.items + (size_t)CLS * q.stride;
+    __shared__ uint32_t warp_count[kBlock / 32];
+    __shared__ uint32_t block_base;
+    for (uint32_t base = blockIdx.x * kBlock; base < count; base += gridDim.x * kBlock) {
+        const uint32_t j = base + threadIdx.x;
+        bool alive = false;
+        RayD next; d3 thr = mk(0, 0, 0); uint4 ids = make_uint4(0, 0, 0, 0);
+        if (j < count) {
+            const uint32_t i = items[j];
+            RayD ray = load_ray(in, i);
+            thr = mk(in.f[7][i], in.f[8][i], in.f[9][i]);
+            ids = in.ids[i];
+            const uint32_t pix = ids.x, bounces = ids.z >> 16;
+            bool dead = false;
+            if (CLS == CLS_MISS) {  // camera.rs:180-183
+                add_radiance(accum, pix, thr * sample_environment(S, cam.c, ray.d), rc.nan_policy, nonfinite, dead);
+            } else {
+                const HitRec hr = hits[i];
+                Rng rng; rng.init(rc.seed, pix, ids.y, ids.z & 0xFFFFu);
+                HitInfoD h;
+                reconstruct_hit(S, ray, hr.ref, hr.inst_light & 0x7FFFFFFFu, hr.t, h);
+                const DMaterial& m = S.materials[h.material];
+                // camera.rs:186-187: `radiance += throughput * emitted` runs for every hit; for non-emitters it only
+                // matters when the throughput is already inf/NaN (inf * 0 = NaN poisons the pixel, Q32).
+                if (CLS == CLS_LIGHT || !finite3(thr)) {
+                    d3 em = CLS == CLS_LIGHT ? texture_value(S, m.base_color_tex, h.u, h.v, h.point) : mk(0, 0, 0);
+                    add_radiance(accum, pix, thr * em, rc.nan_policy, nonfinite, dead);
+                }
+                bool go = !dead;
+                if (go && bounces > 5) {  // Russian roulette, camera.rs:190-196
+                    double p = clampd(luminance(thr), 0.01, 1.0);
+                    if (rng.next() > p) go = false;
+                    else thr = thr / p;
+                }
+                if (go) {
+                    const double p_light = S.n_lights == 0 ? 0.0 : 0.5, p_bsdf = 1.0 - p_light;  // camera.rs:199-200
+                    const double rsel = rng.next();
+                    d3 dir;
+                    bool ok = rsel < p_light ? lights_sample(S, h.point, ray.time, rng, dir) : bsdf_sample<K>(S, h.material, ray.d, h, rng, dir);
+                    if (ok) {  // camera.rs:212-225
+                        d3 f; double bsdf_pdf;
+                        bsdf_eval_pdf<K>(S, h.material, -ray.d, dir, h, f, bsdf_pdf);
+                        double light_pdf = lights_pdf(S, h.point, dir, ray.time);
+                        double pdf = p_bsdf * bsdf_pdf + p_light * light_pdf;
+                        d3 attenuation = f / pdf;
+                        double e = 1e-3 * signum(dot(dir, h.gn));
+                        next = make_ray(h.point + e * h.gn, dir, ray.time);
+                        thr = thr * attenuation;
+                        alive = bounces + 1 < cam.c.max_depth;  // `for bounces in 0..max_depth`, camera.rs:177
+                        if (rc.nan_policy == PT_NAN_DROP && !finite3(thr)) { atomicAdd(nonfinite, 1ull); alive = false; }
+                        ids.z = (rng.used & 0xFFFFu) | ((bounces + 1) << 16);
+                    }
                 }
             }
         }
-    }
-    // ---- compaction: ballot within the warp, prefix across warps, one atomic per block
-    __shared__ uint32_t warp_count[kBlock / 32];
-    __shared__ uint32_t block_base;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, alive);
-    if (lane == 0) warp_count[warp] = __popc(ballot);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t total = 0;
+        if (CLS == CLS_MISS) continue;  // a miss ends the path: nothing to compact
+        // ---- compaction: ballot within the warp, prefix across warps, one atomic per block
+        const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, alive);
+        if (lane == 0) warp_count[warp] = __popc(ballot);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t total = 0;
 #pragma unroll
-        for (int w = 0; w < kBlock / 32; w++) { uint32_t c = warp_count[w]; warp_count[w] = total; total += c; }
-        block_base = total ? atomicAdd(out_count, total) : 0;
-    }
-    __syncthreads();
-    if (alive) {
-        uint32_t dst = block_base + warp_count[warp] + __popc(ballot & ((1u << lane) - 1u));
-        store_path(out, dst, next, thr, ids);
+            for (int w = 0; w < kBlock / 32; w++) { uint32_t c = warp_count[w]; warp_count[w] = total; total += c; }
+            block_base = total ? atomicAdd(out_count, total) : 0;
+        }
+        __syncthreads();
+        if (alive) {
+            uint32_t dst = block_base + warp_count[warp] + __popc(ballot & ((1u << lane) - 1u));
+            store_path(out, dst, next, thr, ids);
+        }
+        __syncthreads();  // warp_count / block_base are reused by the next grid-stride iteration
     }
 }
 
