@@ -173,6 +173,7 @@ typedef struct {
 } pt_camera;
 
 /* ---- render control --------------------------------------------------------------- */
+enum { PT_FLAG_PERSISTENT_TRACE = 1 }; /* persistent-lane trace kernel (helps incoherent, mesh-heavy scenes) */
 enum { PT_NAN_REFERENCE = 0, /* non-finite samples poison the pixel like camera.rs:129 */
        PT_NAN_DROP = 1 };    /* drop + count non-finite samples (documented divergence) */
 typedef struct {
@@ -182,7 +183,7 @@ typedef struct {
     uint32_t sample_stride;  /* sample index = sample_begin + i*stride (multi-GPU spp split) */
     uint32_t nan_policy;
     uint32_t pool_paths;     /* in-flight path pool size; 0 = default */
-    uint32_t _pad;
+    uint32_t flags;          /* PT_FLAG_* */
 } pt_render_params;
 
 typedef struct {

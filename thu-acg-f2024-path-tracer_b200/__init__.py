@@ -22,6 +22,7 @@ REPO_ROOT = os.path.dirname(_HERE)
 ASSETS_DIR = os.path.join(REPO_ROOT, "assets")
 PT_NONE = 0xFFFFFFFF
 PT_NAN_REFERENCE, PT_NAN_DROP = 0, 1
+PT_FLAG_PERSISTENT_TRACE = 1
 PRIM_SPHERE, PRIM_QUAD, PRIM_TRIANGLE, OBJ_CUBOID, OBJ_MESH, OBJ_INSTANCE = range(6)
 
 
@@ -39,7 +40,7 @@ class CameraABI(C.Structure):  # pt_camera
 
 class RenderParams(C.Structure):  # pt_render_params
     _fields_ = [("seed", C.c_uint64), ("sample_begin", C.c_uint32), ("sample_count", C.c_uint32),
-                ("sample_stride", C.c_uint32), ("nan_policy", C.c_uint32), ("pool_paths", C.c_uint32), ("_pad", C.c_uint32)]
+                ("sample_stride", C.c_uint32), ("nan_policy", C.c_uint32), ("pool_paths", C.c_uint32), ("flags", C.c_uint32)]
 
 
 class Stats(C.Structure):  # pt_stats
@@ -465,8 +466,8 @@ class DeviceScene:
         self.ctx._check(self.ctx.lib.pt_lights_sample_pdf(self.ctx.ptr, self.ptr, n, _ptr(o), _ptr(t), _ptr(u), _ptr(d), _ptr(valid), _ptr(pdf)))
         return d, valid, pdf
 
-    def params(self, spp, seed=1, sample_begin=0, sample_stride=1, nan_policy=PT_NAN_REFERENCE, pool_paths=0):
-        return RenderParams(seed, sample_begin, spp, sample_stride, nan_policy, pool_paths, 0)
+    def params(self, spp, seed=1, sample_begin=0, sample_stride=1, nan_policy=PT_NAN_REFERENCE, pool_paths=0, flags=0):
+        return RenderParams(seed, sample_begin, spp, sample_stride, nan_policy, pool_paths, flags)
 
     def render(self, camera=None, spp=None, **kw):
         """Camera::render minus the PNG: mean radiance as float32 [H, W, 3] in host memory, plus stats."""

@@ -108,7 +108,7 @@ float round_up(double v) { float f = (float)v; if ((double)f < v) f = std::nexta
 struct Converter {
     const pt_scene_desc* d;
     std::vector<DNode> nodes;
-    std::vector<DRef> refs;
+    std::vector<DNode> refs;  // per-reference fp32 box + (kind|index, tie rank)
     uint32_t tie_counter = 0;
     uint32_t max_depth = 0;
     std::string err;
@@ -116,6 +116,64 @@ struct Converter {
     static bool tie_is_sphere(const pt_scene_desc* d, pt_ref r) {
         if (r.kind == PT_PRIM_SPHERE) return true;
         if (r.kind == PT_OBJ_INSTANCE) return d->instances[r.index].child.kind == PT_PRIM_SPHERE;
+        return false;
+    }
+    // Conservative f64 bounds of one reference (own restatement of the geometry, independent of the host's padded boxes).
+    static void grow(double lo[3], double hi[3], const pt_vec3& p) {
+        lo[0] = std::min(lo[0], p.x); lo[1] = std::min(lo[1], p.y); lo[2] = std::min(lo[2], p.z);
+        hi[0] = std::max(hi[0], p.x); hi[1] = std::max(hi[1], p.y); hi[2] = std::max(hi[2], p.z);
+    }
+    bool ref_box(pt_ref r, double lo[3], double hi[3]) const {
+        for (int k = 0; k < 3; k++) { lo[k] = INFINITY; hi[k] = -INFINITY; }
+        auto add = [](const pt_vec3& a, const pt_vec3& b) { return pt_vec3{a.x + b.x, a.y + b.y, a.z + b.z}; };
+        switch (r.kind) {
+            case PT_PRIM_SPHERE: {
+                const pt_sphere& s = d->spheres[r.index];
+                double rad = std::fabs(s.radius) * (1.0 + 1e-12);
+                for (const pt_vec3* c : {&s.position1, &s.position2}) { grow(lo, hi, pt_vec3{c->x - rad, c->y - rad, c->z - rad}); grow(lo, hi, pt_vec3{c->x + rad, c->y + rad, c->z + rad}); }
+                return true;
+            }
+            case PT_PRIM_QUAD: {
+                const pt_quad& q = d->quads[r.index];
+                grow(lo, hi, q.q); grow(lo, hi, add(q.q, q.u)); grow(lo, hi, add(q.q, q.v)); grow(lo, hi, add(add(q.q, q.u), q.v));
+                return true;
+            }
+            case PT_PRIM_TRIANGLE: {
+                const pt_triangle& t = d->triangles[r.index];
+                grow(lo, hi, t.v0); grow(lo, hi, t.v1); grow(lo, hi, t.v2);
+                return true;
+            }
+            case PT_OBJ_CUBOID: {
+                for (uint32_t k = 0; k < 6; k++) {
+                    double l2[3], h2[3];
+                    ref_box(pt_ref{PT_PRIM_QUAD, d->cuboids[r.index].first_quad + k}, l2, h2);
+                    grow(lo, hi, pt_vec3{l2[0], l2[1], l2[2]}); grow(lo, hi, pt_vec3{h2[0], h2[1], h2[2]});
+                }
+                return true;
+            }
+            case PT_OBJ_MESH: {
+                const pt_mesh& m = d->meshes[r.index];
+                for (uint32_t k = 0; k < m.n_triangles; k++) { const pt_triangle& t = d->triangles[m.first_triangle + k]; grow(lo, hi, t.v0); grow(lo, hi, t.v1); grow(lo, hi, t.v2); }
+                return m.n_triangles > 0;
+            }
+            case PT_OBJ_INSTANCE: {
+                const pt_instance& in = d->instances[r.index];
+                double l2[3], h2[3];
+                if (!ref_box(in.child, l2, h2)) return false;
+                double ext = 0.0;
+                for (int c = 0; c < 8; c++) {  // 8 corners through the rigid transform
+                    double p[3] = {(c & 1) ? h2[0] : l2[0], (c & 2) ? h2[1] : l2[1], (c & 4) ? h2[2] : l2[2]};
+                    pt_vec3 w{in.transform[0] * p[0] + in.transform[4] * p[1] + in.transform[8] * p[2] + in.transform[12],
+                              in.transform[1] * p[0] + in.transform[5] * p[1] + in.transform[9] * p[2] + in.transform[13],
+                              in.transform[2] * p[0] + in.transform[6] * p[1] + in.transform[10] * p[2] + in.transform[14]};
+                    grow(lo, hi, w);
+                    ext = std::max({ext, std::fabs(p[0]), std::fabs(p[1]), std::fabs(p[2])});
+                }
+                double slack = 1e-9 * (ext + 1.0);  // f64 rounding of the forward/inverse transforms
+                for (int k = 0; k < 3; k++) { lo[k] -= slack; hi[k] += slack; }
+                return true;
+            }
+        }
         return false;
     }
     void set_box(DNode& n, const double* lo, const double* hi) {
@@ -133,7 +191,11 @@ struct Converter {
         for (uint32_t p = 0; p < n; p++) {
             // later non-sphere wins a tie; a later sphere loses it
             uint32_t rank = tie_is_sphere(d, items[p]) ? base + n - 1 - p : base + n + p;
-            refs.push_back(DRef{ref_pack(items[p].kind, items[p].index), rank | top_bit});
+            DNode rn{};
+            double lo[3], hi[3];
+            if (ref_box(items[p], lo, hi)) set_box(rn, lo, hi); else { for (int k = 0; k < 3; k++) { rn.lo[k] = -INFINITY; rn.hi[k] = INFINITY; } }
+            rn.a = ref_pack(items[p].kind, items[p].index); rn.b = rank | top_bit;
+            refs.push_back(rn);
         }
     }
     // writes host node hn into nodes[slot]; children become a fresh adjacent pair
@@ -443,7 +505,10 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
         CU(cudaMemsetAsync(ctx->d_count, 0, 16 * sizeof(uint32_t), st));
         const Queues q{ctx->q_items, ctx->d_count + 4, ctx->pool};
         if (ctx->profiling) CU(cudaEventRecord(ctx->evs[1], st));
-        k_trace<<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d);
+        if (p->flags & PT_FLAG_PERSISTENT_TRACE)
+            k_trace_persistent<<<(n + kRaysPerWarp * (kBlock / 32) - 1) / (kRaysPerWarp * (kBlock / 32)), kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d);
+        else
+            k_trace<<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d);
         if (ctx->profiling) CU(cudaEventRecord(ctx->evs[2], st));
         // one specialised kernel per shade class present in the scene; each walks its queue grid-stride
         const unsigned sg = std::min<unsigned>((n + kBlock - 1) / kBlock, 148u * 16u);

@@ -79,7 +79,7 @@ struct BoxRay { float ix, iy, iz, nx, ny, nz, fx, fy, fz; };  // inv dir; -o*inv
 PT_D BoxRay make_boxray(const RayD& r) {
     BoxRay b;
     const float ox = __double2float_rn(r.o.x), oy = __double2float_rn(r.o.y), oz = __double2float_rn(r.o.z);
-    b.ix = 1.0f / __double2float_rn(r.d.x); b.iy = 1.0f / __double2float_rn(r.d.y); b.iz = 1.0f / __double2float_rn(r.d.z);
+    b.ix = __frcp_rn(__double2float_rn(r.d.x)); b.iy = __frcp_rn(__double2float_rn(r.d.y)); b.iz = __frcp_rn(__double2float_rn(r.d.z));
     const float k = 2.384185791015625e-07f;  // 2^-22
     const float ex = fabsf(ox * b.ix) * k, ey = fabsf(oy * b.iy) * k, ez = fabsf(oz * b.iz) * k;
     b.nx = -ox * b.ix - ex; b.ny = -oy * b.iy - ey; b.nz = -oz * b.iz - ez;
@@ -128,6 +128,11 @@ PT_D void test_simple(const DScene& S, uint32_t kind, uint32_t index, const RayD
 }
 
 // World::intersect_all(ray, [t_min, inf)) — world.rs:47-62.  any_hit: stop at the first hit with t <= t_max on World.objects.
+//
+// "while-while" structure: phase 1 walks internal node pairs only (fp32 slab tests, both children per fetch);
+// leaves, deferred mesh/instance references and the instance-exit sentinel are pushed as tagged stack entries and
+// handled in phase 2, so the lanes of a warp run box tests together and f64 primitive tests together.
+constexpr uint32_t kTagLeaf = 0xC0000000u;  // kTagRef = 0x4..., kTagSentinel = 0x8..., internal pair = 0x0...
 template <bool ANY_HIT>
 PT_D bool trace_closest(const DScene& S, const RayD& world_ray, double t_min, double t_max_any, Closest& c) {
     uint32_t stack[kStack]; float stack_t[kStack];
@@ -137,61 +142,70 @@ PT_D bool trace_closest(const DScene& S, const RayD& world_ray, double t_min, do
     RayD r = world_ray;
     BoxRay br = make_boxray(r);
     const float tmin_f = __double2float_rd(t_min);
+    float tmax_f = __double2float_ru(c.t);
     uint32_t cur_inst = kInstNone, cur_tie = 0;
-    uint32_t cur = S.root_pair;  // node-pair to visit, or kNone => pop
+    uint32_t cur = S.root_pair;  // internal node pair to visit next, or kNone
     while (true) {
-        if (cur != kNone) {
+        uint32_t pending = kNone;
+        // ---------------- phase 1: internal pairs until a tagged entry surfaces (or the stack runs dry)
+        while (true) {
+            if (cur == kNone) {
+                while (sp > 0) {
+                    --sp;
+                    const uint32_t e = stack[sp];
+                    if (e != kTagSentinel && !(stack_t[sp] <= tmax_f)) continue;  // beyond the current closest hit
+                    if ((e & kTagMask) == 0) cur = e; else pending = e;
+                    break;
+                }
+                if (cur == kNone) break;  // pending entry, or nothing left
+            }
             const DNode n0 = S.nodes[cur], n1 = S.nodes[cur + 1];
             c.n_pairs++;
-            const float tmax_f = __double2float_ru(c.t);
-            float t0 = slab(n0, br, tmin_f, tmax_f), t1 = slab(n1, br, tmin_f, tmax_f);
-            // visit order: nearer child first
-            const bool swap = t1 < t0;
-            const DNode& na = swap ? n1 : n0; const DNode& nb = swap ? n0 : n1;
-            float ta = swap ? t1 : t0, tb = swap ? t0 : t1;
-            uint32_t next = kNone; float next_t = 0.f;
-#pragma unroll
-            for (int side = 0; side < 2; side++) {
-                const DNode& n = side == 0 ? na : nb; const float tn = side == 0 ? ta : tb;
-                if (!(tn <= __double2float_ru(c.t))) continue;  // miss (inf) or beyond the current closest
-                if (n.b == kNone) {  // internal
-                    if (next == kNone) { next = n.a; next_t = tn; }
-                    else if (sp < kStack) { stack[sp] = n.a; stack_t[sp] = tn; sp++; }
-                } else {  // leaf: scan refs
-                    for (uint32_t k = 0; k < n.b; k++) {
-                        const DRef rf = S.refs[n.a + k];
-                        c.n_prims++;
-                        const uint32_t kind = ref_kind(rf.kind_index), index = ref_index(rf.kind_index);
-                        if (kind == PT_PRIM_TRIANGLE) {
-                            double t, u, v;
-                            if (tri_t(S.tris[index], r, t_min, t, u, v) && t <= c.t) consider(c, t, rf.kind_index, cur_inst, cur_tie, rf.tie);
-                        } else {
-                            if (ANY_HIT && !(rf.tie >> 31)) continue;  // shadow rays test World.objects only (world.rs:31-36)
-                            if (kind <= PT_OBJ_CUBOID) test_simple(S, kind, index, r, t_min, c, kInstNone, rf.tie, 0);
-                            else if (sp < kStack) {  // mesh / instance: defer (order does not matter, ties use ranks)
-                                stack[sp] = kTagRef | (n.a + k); stack_t[sp] = tn; sp++;
-                            }
-                        }
-                        if (ANY_HIT && c.ref != kNone) return true;
-                    }
-                }
+            const float t0 = slab(n0, br, tmin_f, tmax_f), t1 = slab(n1, br, tmin_f, tmax_f);
+            const uint32_t e0 = n0.b == kNone ? n0.a : (kTagLeaf | cur), e1 = n1.b == kNone ? n1.a : (kTagLeaf | (cur + 1));
+            const bool h0 = t0 <= tmax_f, h1 = t1 <= tmax_f;  // NaN (miss) compares false
+            const bool swap = h1 && (!h0 || t1 < t0);        // near child first
+            const uint32_t en = swap ? e1 : e0, ef = swap ? e0 : e1;
+            const float tn = swap ? t1 : t0, tf = swap ? t0 : t1;
+            const bool hn = swap ? h1 : h0, hf = swap ? h0 : h1;
+            cur = kNone;
+            if (hf && sp < kStack) { stack[sp] = ef; stack_t[sp] = tf; sp++; }
+            if (hn) {
+                if ((en & kTagMask) == 0) cur = en;
+                else if (sp < kStack) { stack[sp] = en; stack_t[sp] = tn; sp++; }
             }
-            (void)next_t;
-            cur = next;
-            continue;
         }
-        // pop
-        if (sp == 0) break;
-        --sp;
-        const uint32_t e = stack[sp];
-        if (e == kTagSentinel) {  // leave the instance / mesh: back to the world ray
+        if (pending == kNone) break;  // traversal finished
+        // ---------------- phase 2: one tagged entry
+        if (pending == kTagSentinel) {  // leave the instance / mesh: back to the world ray
             r = world_ray; br = make_boxray(r); cur_inst = kInstNone; cur_tie = 0;
             continue;
         }
-        if (!(stack_t[sp] <= __double2float_ru(c.t))) continue;
-        if ((e & kTagMask) == 0) { cur = e; continue; }
+        if ((pending & kTagMask) == kTagLeaf) {
+            const DNode& n = S.nodes[pending & ~kTagMask];
+            const uint32_t first = n.a, count = n.b;
+            const float leaf_t = stack_t[sp];  // entry distance of this leaf (slot just popped)
+            for (uint32_t k = 0; k < count; k++) {
+                const DNode rb = S.refs[first + k];  // per-reference fp32 box + (kind|index, tie rank)
+                if (!(slab(rb, br, tmin_f, tmax_f) <= tmax_f)) continue;  // most f64 tests would be rejections: cull them in fp32
+                c.n_prims++;
+                const uint32_t kind = ref_kind(rb.a), index = ref_index(rb.a);
+                if (kind == PT_PRIM_TRIANGLE) {
+                    double t, u, v;
+                    if (tri_t(S.tris[index], r, t_min, t, u, v) && t <= c.t) { consider(c, t, rb.a, cur_inst, cur_tie, rb.b); tmax_f = __double2float_ru(c.t); }
+                } else {
+                    if (ANY_HIT && !(rb.b >> 31)) continue;  // shadow rays test World.objects only (world.rs:31-36)
+                    if (kind <= PT_OBJ_CUBOID) { test_simple(S, kind, index, r, t_min, c, kInstNone, rb.b, 0); tmax_f = __double2float_ru(c.t); }
+                    else if (sp < kStack) {  // mesh / instance: defer (order does not matter, ties use ranks)
+                        stack[sp] = kTagRef | (first + k); stack_t[sp] = leaf_t; sp++;
+                    }
+                }
+                if (ANY_HIT && c.ref != kNone) return true;
+            }
+            continue;
+        }
         // deferred mesh / instance reference
-        const DRef rf = S.refs[e & ~kTagMask];
+        const DRef rf{S.refs[pending & ~kTagMask].a, S.refs[pending & ~kTagMask].b};
         const uint32_t kind = ref_kind(rf.kind_index), index = ref_index(rf.kind_index);
         uint32_t mesh = kNone;
         if (kind == PT_OBJ_MESH) { mesh = index; cur_inst = kInstNone; }
@@ -202,16 +216,108 @@ PT_D bool trace_closest(const DScene& S, const RayD& world_ray, double t_min, do
             else {
                 test_simple(S, in.child_kind, in.child_index, lr, t_min, c, index, rf.tie, 0);
                 if (ANY_HIT && c.ref != kNone) return true;
+                tmax_f = __double2float_ru(c.t);
                 continue;
             }
         }
         cur_tie = rf.tie;
-        const DMesh& m = S.meshes[mesh];
         if (sp < kStack) { stack[sp] = kTagSentinel; stack_t[sp] = 0.f; sp++; }
-        cur = m.root_pair;
+        cur = S.meshes[mesh].root_pair;
     }
     c.is_light = c.ref != kNone && !(c.tie_outer >> 31);  // objects carry bit 31 in their outer rank (object beats light, Q31)
     return c.ref != kNone;
+}
+
+// ---------------------------------------------------------------- resumable traversal (persistent-lane trace kernel)
+// Same algorithm as trace_closest<false>, cut into units (phase 1 + one tagged entry) so that a lane whose ray is
+// finished can fetch its next ray while the other lanes of the warp keep traversing.  The world ray is re-read from
+// the path buffer when an instance is left, instead of being held in registers.
+struct Trav {  // scalar state only (stays in registers); the stack arrays are separate locals of the kernel
+    RayD r; BoxRay br; Closest c;
+    int sp; uint32_t cur, cur_inst, cur_tie; float tmax_f;
+};
+PT_D void trav_begin(const DScene& S, Trav& T, const RayD& ray) {
+    T.sp = 0;
+    T.c.t = __longlong_as_double(0x7ff0000000000000ll);
+    T.c.ref = kNone; T.c.inst = kInstNone; T.c.tie_outer = 0; T.c.tie_inner = 0; T.c.is_light = false; T.c.n_pairs = 0; T.c.n_prims = 0;
+    T.r = ray; T.br = make_boxray(ray);
+    T.tmax_f = __int_as_float(0x7f800000);
+    T.cur_inst = kInstNone; T.cur_tie = 0; T.cur = S.root_pair;
+}
+// Runs one unit; returns true when the traversal is complete.  `reload` yields the world ray again.
+template <class ReloadRay>
+PT_D bool trav_unit(const DScene& S, Trav& T, uint32_t* __restrict__ stack, float* __restrict__ stack_t, const double t_min,
+                    const float tmin_f, ReloadRay reload) {
+    uint32_t pending = kNone;
+    while (true) {  // phase 1: internal node pairs
+        if (T.cur == kNone) {
+            while (T.sp > 0) {
+                --T.sp;
+                const uint32_t e = stack[T.sp];
+                if (e != kTagSentinel && !(stack_t[T.sp] <= T.tmax_f)) continue;
+                if ((e & kTagMask) == 0) T.cur = e; else pending = e;
+                break;
+            }
+            if (T.cur == kNone) break;
+        }
+        const uint32_t cur = T.cur;
+        const DNode n0 = S.nodes[cur], n1 = S.nodes[cur + 1];
+        const float t0 = slab(n0, T.br, tmin_f, T.tmax_f), t1 = slab(n1, T.br, tmin_f, T.tmax_f);
+        const uint32_t e0 = n0.b == kNone ? n0.a : (kTagLeaf | cur), e1 = n1.b == kNone ? n1.a : (kTagLeaf | (cur + 1));
+        const bool h0 = t0 <= T.tmax_f, h1 = t1 <= T.tmax_f;
+        const bool swap = h1 && (!h0 || t1 < t0);
+        const uint32_t en = swap ? e1 : e0, ef = swap ? e0 : e1;
+        const float tn = swap ? t1 : t0, tf = swap ? t0 : t1;
+        const bool hn = swap ? h1 : h0, hf = swap ? h0 : h1;
+        T.cur = kNone;
+        if (hf && T.sp < kStack) { stack[T.sp] = ef; stack_t[T.sp] = tf; T.sp++; }
+        if (hn) {
+            if ((en & kTagMask) == 0) T.cur = en;
+            else if (T.sp < kStack) { stack[T.sp] = en; stack_t[T.sp] = tn; T.sp++; }
+        }
+    }
+    if (pending == kNone) {
+        T.c.is_light = T.c.ref != kNone && !(T.c.tie_outer >> 31);
+        return true;
+    }
+    if (pending == kTagSentinel) {
+        T.r = reload(); T.br = make_boxray(T.r); T.cur_inst = kInstNone; T.cur_tie = 0;
+        return false;
+    }
+    if ((pending & kTagMask) == kTagLeaf) {
+        const DNode& n = S.nodes[pending & ~kTagMask];
+        const uint32_t first = n.a, count = n.b;
+        const float leaf_t = stack_t[T.sp];
+        for (uint32_t k = 0; k < count; k++) {
+            const DNode rb = S.refs[first + k];
+            if (!(slab(rb, T.br, tmin_f, T.tmax_f) <= T.tmax_f)) continue;
+            const uint32_t kind = ref_kind(rb.a), index = ref_index(rb.a);
+            if (kind == PT_PRIM_TRIANGLE) {
+                double t, u, v;
+                if (tri_t(S.tris[index], T.r, t_min, t, u, v) && t <= T.c.t) { consider(T.c, t, rb.a, T.cur_inst, T.cur_tie, rb.b); T.tmax_f = __double2float_ru(T.c.t); }
+            } else if (kind <= PT_OBJ_CUBOID) { test_simple(S, kind, index, T.r, t_min, T.c, kInstNone, rb.b, 0); T.tmax_f = __double2float_ru(T.c.t); }
+            else if (T.sp < kStack) { stack[T.sp] = kTagRef | (first + k); stack_t[T.sp] = leaf_t; T.sp++; }
+        }
+        return false;
+    }
+    const DRef rf{S.refs[pending & ~kTagMask].a, S.refs[pending & ~kTagMask].b};
+    const uint32_t kind = ref_kind(rf.kind_index), index = ref_index(rf.kind_index);
+    uint32_t mesh;
+    if (kind == PT_OBJ_MESH) { mesh = index; T.cur_inst = kInstNone; }
+    else {
+        const DInstance& in = S.instances[index];
+        const RayD lr = instance_local_ray(in, T.r);
+        if (in.child_kind != PT_OBJ_MESH) {
+            test_simple(S, in.child_kind, in.child_index, lr, t_min, T.c, index, rf.tie, 0);
+            T.tmax_f = __double2float_ru(T.c.t);
+            return false;
+        }
+        mesh = in.child_index; T.r = lr; T.br = make_boxray(lr); T.cur_inst = index;
+    }
+    T.cur_tie = rf.tie;
+    if (T.sp < kStack) { stack[T.sp] = kTagSentinel; stack_t[T.sp] = 0.f; T.sp++; }
+    T.cur = S.meshes[mesh].root_pair;
+    return false;
 }
 
 // ---------------------------------------------------------------- hit reconstruction (HitInfo::new, hit_info.rs:16-55)
