@@ -81,9 +81,17 @@ class ClockSampler:
 def oracle_sample(pt, orc, scene, spp, threads=0):
     """The reference algorithm (C++ restatement, oracle/) on the host CPU over a bounded sample of the workload."""
     ora = orc.OracleScene(scene.desc, pt)
-    _, st = ora.render(scene.camera, spp, seed=1, nan_policy=pt.PT_NAN_DROP, threads=threads)
+    _, st = ora.render(scene.camera, spp, seed=1, nan_policy=pt.PT_NAN_DROP, threads=threads or host_threads())
     ora.close()
     return st
+
+
+def host_threads():
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1, so ask explicitly)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def run_reference(args):
@@ -97,12 +105,12 @@ def run_reference(args):
     ora = orc.OracleScene(scene.desc, pt)
     times, segs, paths = [], 0, 0
     for i in range(args.warmup + args.steps):
-        _, st = ora.render(scene.camera, args.ref_spp, seed=1 + i, nan_policy=pt.PT_NAN_DROP)
+        _, st = ora.render(scene.camera, args.ref_spp, seed=1 + i, nan_policy=pt.PT_NAN_DROP, threads=host_threads())
         if i >= args.warmup:
             times.append(st.seconds); segs += st.segments; paths += st.paths
     total = sum(times)
     v = segs / total / 1e6
-    cores = orc.num_threads()
+    cores = host_threads()
     line = {"impl": "reference", "metric": "Mrays/s", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "samples_per_s": paths / total,
@@ -219,7 +227,7 @@ def main():
         # ---- CPU baseline on the box's host cores (bounded sample) + the oracle's work counters for the algorithmic bytes
         cpu = None
         n_node = n_sph = n_quad = n_tri = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the CPU baseline leg runs on rank 0 at N=1 only
             orc = ge.load_oracle()
             ost = oracle_sample(pt, orc, scene, 2)
             cpu = {"value": ost.segments / ost.seconds / 1e6, "unit": "Mrays/s", "cores": ost.threads, "kind": "port",

@@ -33,6 +33,7 @@ struct pt_ctx {
     uint32_t* q_items = nullptr;            // N_CLS queues of `pool` path slots each
     unsigned long long* d_nonfinite = nullptr;
     uint32_t* h_count = nullptr;            // pinned
+    void* h_stage = nullptr; size_t stage_bytes = 0;  // pinned staging buffer for scene uploads
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs[6] = {nullptr};
 };
 struct pt_scene {
@@ -76,6 +77,7 @@ void pt_ctx_destroy(pt_ctx* c) {
     cudaSetDevice(c->device);
     free_pool(c);
     cudaFree(c->d_count); cudaFree(c->d_nonfinite); cudaFreeHost(c->h_count);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     for (auto& e : c->evs) cudaEventDestroy(e);
     cudaStreamDestroy(c->own_stream);
@@ -88,17 +90,34 @@ int pt_ctx_set_profiling(pt_ctx* c, int on) { if (!c) return fail(PT_ERR_INVALID
 
 // ------------------------------------------------------------------------------------------------ scene upload
 namespace {
+// One device arena per scene: every table is staged into one pinned host buffer (owned by the ctx, reused across
+// scenes) and moved with a single H2D copy; 256-byte aligned sub-allocations.
 struct Uploader {
     pt_scene* s;
-    template <class T> int up(const std::vector<T>& v, const T** out) {
-        *out = nullptr;
-        if (v.empty()) return PT_OK;
-        void* p = nullptr;
-        CU(cudaMalloc(&p, v.size() * sizeof(T)));
-        s->allocs.push_back(p);
-        CU(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s->ctx->stream));
-        s->bytes += v.size() * sizeof(T);
-        *out = (const T*)p;
+    struct Item { const void* src; size_t bytes; const void** dst; size_t offset; };
+    std::vector<Item> items;
+    size_t total = 0;
+    void add(const void* src, size_t bytes, const void** dst) {
+        *dst = nullptr;
+        if (!bytes) return;
+        items.push_back(Item{src, bytes, dst, total});
+        total += (bytes + 255) / 256 * 256;
+    }
+    template <class T> void up(const std::vector<T>& v, const T** out) { add(v.data(), v.size() * sizeof(T), (const void**)out); }
+    int commit() {
+        if (!total) return PT_OK;
+        pt_ctx* c = s->ctx;
+        if (c->stage_bytes < total) {
+            if (c->h_stage) cudaFreeHost(c->h_stage);
+            c->h_stage = nullptr; c->stage_bytes = 0;
+            CU(cudaMallocHost(&c->h_stage, total));
+            c->stage_bytes = total;
+        }
+        void* base = nullptr;
+        CU(cudaMalloc(&base, total));
+        s->allocs.push_back(base);
+        for (auto& it : items) { memcpy((char*)c->h_stage + it.offset, it.src, it.bytes); *it.dst = (char*)base + it.offset; s->bytes += it.bytes; }
+        CU(cudaMemcpyAsync(base, c->h_stage, total, cudaMemcpyHostToDevice, c->stream));
         return PT_OK;
     }
 };
@@ -403,12 +422,11 @@ int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
     for (uint32_t i = 0; i < d->n_lights; i++) lights[i] = DRef{ref_pack(d->lights[i].kind, d->lights[i].index), 0};
 
     DScene& D = s->d;
-    if ((rc = U.up(C.nodes, &D.nodes)) || (rc = U.up(C.refs, &D.refs)) || (rc = U.up(spheres, &D.spheres)) || (rc = U.up(quads, &D.quads)) ||
-        (rc = U.up(quad_mat, &D.quad_material)) || (rc = U.up(tris, &D.tris)) || (rc = U.up(tri_normals, &D.tri_normals)) ||
-        (rc = U.up(tri_uvs, &D.tri_uvs)) || (rc = U.up(tri_mesh, &D.tri_mesh)) || (rc = U.up(cuboids, &D.cuboids)) || (rc = U.up(meshes, &D.meshes)) ||
-        (rc = U.up(instances, &D.instances)) || (rc = U.up(textures, &D.textures)) || (rc = U.up(images, &D.images)) ||
-        (rc = U.up(materials, &D.materials)) || (rc = U.up(lights, &D.lights)))
-        return rc;
+    U.up(C.nodes, &D.nodes); U.up(C.refs, &D.refs); U.up(spheres, &D.spheres); U.up(quads, &D.quads); U.up(quad_mat, &D.quad_material);
+    U.up(tris, &D.tris); U.up(tri_normals, &D.tri_normals); U.up(tri_uvs, &D.tri_uvs); U.up(tri_mesh, &D.tri_mesh); U.up(cuboids, &D.cuboids);
+    U.up(meshes, &D.meshes); U.up(instances, &D.instances); U.up(textures, &D.textures); U.up(images, &D.images); U.up(materials, &D.materials);
+    U.up(lights, &D.lights);
+    if ((rc = U.commit())) return rc;
     D.image_data = d_img; D.n_lights = d->n_lights; D.root_pair = 0;
     s->n_materials = d->n_materials; s->n_images = d->n_images; s->images = images;
     CU(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
