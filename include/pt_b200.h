@@ -173,7 +173,7 @@ typedef struct {
 } pt_camera;
 
 /* ---- render control --------------------------------------------------------------- */
-enum { PT_FLAG_PERSISTENT_TRACE = 1 }; /* persistent-lane trace kernel (helps incoherent, mesh-heavy scenes) */
+/* flags bits 4-6: k_trace register-cap variant (0 = default 80 regs; 4: 120, 5: 96, 7: 64) — tuning knob */
 enum { PT_NAN_REFERENCE = 0, /* non-finite samples poison the pixel like camera.rs:129 */
        PT_NAN_DROP = 1 };    /* drop + count non-finite samples (documented divergence) */
 typedef struct {

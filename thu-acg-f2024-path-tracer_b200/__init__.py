@@ -22,7 +22,6 @@ REPO_ROOT = os.path.dirname(_HERE)
 ASSETS_DIR = os.path.join(REPO_ROOT, "assets")
 PT_NONE = 0xFFFFFFFF
 PT_NAN_REFERENCE, PT_NAN_DROP = 0, 1
-PT_FLAG_PERSISTENT_TRACE = 1
 PRIM_SPHERE, PRIM_QUAD, PRIM_TRIANGLE, OBJ_CUBOID, OBJ_MESH, OBJ_INSTANCE = range(6)
 
 

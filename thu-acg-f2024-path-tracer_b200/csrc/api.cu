@@ -523,10 +523,12 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
         CU(cudaMemsetAsync(ctx->d_count, 0, 16 * sizeof(uint32_t), st));
         const Queues q{ctx->q_items, ctx->d_count + 4, ctx->pool};
         if (ctx->profiling) CU(cudaEventRecord(ctx->evs[1], st));
-        if (p->flags & PT_FLAG_PERSISTENT_TRACE)
-            k_trace_persistent<<<(n + kRaysPerWarp * (kBlock / 32) - 1) / (kRaysPerWarp * (kBlock / 32)), kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d);
-        else
-            k_trace<<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d);
+            switch ((p->flags >> 4) & 7u) {  // experiment knob: resident blocks per SM the compiler must allow (register cap)
+                case 4: k_trace<4><<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d); break;  // 120 regs
+                case 5: k_trace<5><<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d); break;  // 96 regs
+                case 7: k_trace<8><<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d); break;  // 64 regs, spills
+                default: k_trace<6><<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d);        // 80 regs (measured best overall)
+            }
         if (ctx->profiling) CU(cudaEventRecord(ctx->evs[2], st));
         // one specialised kernel per shade class present in the scene; each walks its queue grid-stride
         const unsigned sg = std::min<unsigned>((n + kBlock - 1) / kBlock, 148u * 16u);

@@ -79,7 +79,13 @@ struct BoxRay { float ix, iy, iz, nx, ny, nz, fx, fy, fz; };  // inv dir; -o*inv
 PT_D BoxRay make_boxray(const RayD& r) {
     BoxRay b;
     const float ox = __double2float_rn(r.o.x), oy = __double2float_rn(r.o.y), oz = __double2float_rn(r.o.z);
-    b.ix = __frcp_rn(__double2float_rn(r.d.x)); b.iy = __frcp_rn(__double2float_rn(r.d.y)); b.iz = __frcp_rn(__double2float_rn(r.d.z));
+    // |1/d| is clamped to 2^100: with an infinite reciprocal the FMA form lo*inv - o*inv would be inf - inf = NaN and the
+    // axis would stop culling (rays exactly parallel to a slab, e.g. light-to-light samples in the Cornell scenes).  With a
+    // huge finite reciprocal the sign of (lo - o) still decides, and the slack below covers the cancellation error.
+    const float big = 1.2676506e30f;
+    b.ix = fminf(fmaxf(__frcp_rn(__double2float_rn(r.d.x)), -big), big);
+    b.iy = fminf(fmaxf(__frcp_rn(__double2float_rn(r.d.y)), -big), big);
+    b.iz = fminf(fmaxf(__frcp_rn(__double2float_rn(r.d.z)), -big), big);
     const float k = 2.384185791015625e-07f;  // 2^-22
     const float ex = fabsf(ox * b.ix) * k, ey = fabsf(oy * b.iy) * k, ez = fabsf(oz * b.iz) * k;
     b.nx = -ox * b.ix - ex; b.ny = -oy * b.iy - ey; b.nz = -oz * b.iz - ez;
@@ -133,13 +139,15 @@ PT_D void test_simple(const DScene& S, uint32_t kind, uint32_t index, const RayD
 // leaves, deferred mesh/instance references and the instance-exit sentinel are pushed as tagged stack entries and
 // handled in phase 2, so the lanes of a warp run box tests together and f64 primitive tests together.
 constexpr uint32_t kTagLeaf = 0xC0000000u;  // kTagRef = 0x4..., kTagSentinel = 0x8..., internal pair = 0x0...
-template <bool ANY_HIT>
-PT_D bool trace_closest(const DScene& S, const RayD& world_ray, double t_min, double t_max_any, Closest& c) {
+// `reload()` returns the world ray again (called when an instance is left), so it need not be kept in registers;
+// COUNT enables the work counters reported by pt_trace_closest.
+template <bool ANY_HIT, bool COUNT, class Reload>
+PT_D bool trace_closest(const DScene& S, Reload reload, double t_min, double t_max_any, Closest& c) {
     uint32_t stack[kStack]; float stack_t[kStack];
     int sp = 0;
     c.t = ANY_HIT ? t_max_any : __longlong_as_double(0x7ff0000000000000ll);
     c.ref = kNone; c.inst = kInstNone; c.tie_outer = 0; c.tie_inner = 0; c.is_light = false; c.n_pairs = 0; c.n_prims = 0;
-    RayD r = world_ray;
+    RayD r = reload();
     BoxRay br = make_boxray(r);
     const float tmin_f = __double2float_rd(t_min);
     float tmax_f = __double2float_ru(c.t);
@@ -160,7 +168,7 @@ PT_D bool trace_closest(const DScene& S, const RayD& world_ray, double t_min, do
                 if (cur == kNone) break;  // pending entry, or nothing left
             }
             const DNode n0 = S.nodes[cur], n1 = S.nodes[cur + 1];
-            c.n_pairs++;
+            if (COUNT) c.n_pairs++;
             const float t0 = slab(n0, br, tmin_f, tmax_f), t1 = slab(n1, br, tmin_f, tmax_f);
             const uint32_t e0 = n0.b == kNone ? n0.a : (kTagLeaf | cur), e1 = n1.b == kNone ? n1.a : (kTagLeaf | (cur + 1));
             const bool h0 = t0 <= tmax_f, h1 = t1 <= tmax_f;  // NaN (miss) compares false
@@ -178,7 +186,7 @@ PT_D bool trace_closest(const DScene& S, const RayD& world_ray, double t_min, do
         if (pending == kNone) break;  // traversal finished
         // ---------------- phase 2: one tagged entry
         if (pending == kTagSentinel) {  // leave the instance / mesh: back to the world ray
-            r = world_ray; br = make_boxray(r); cur_inst = kInstNone; cur_tie = 0;
+            r = reload(); br = make_boxray(r); cur_inst = kInstNone; cur_tie = 0;
             continue;
         }
         if ((pending & kTagMask) == kTagLeaf) {
@@ -188,7 +196,7 @@ PT_D bool trace_closest(const DScene& S, const RayD& world_ray, double t_min, do
             for (uint32_t k = 0; k < count; k++) {
                 const DNode rb = S.refs[first + k];  // per-reference fp32 box + (kind|index, tie rank)
                 if (!(slab(rb, br, tmin_f, tmax_f) <= tmax_f)) continue;  // most f64 tests would be rejections: cull them in fp32
-                c.n_prims++;
+                if (COUNT) c.n_prims++;
                 const uint32_t kind = ref_kind(rb.a), index = ref_index(rb.a);
                 if (kind == PT_PRIM_TRIANGLE) {
                     double t, u, v;
@@ -226,98 +234,6 @@ PT_D bool trace_closest(const DScene& S, const RayD& world_ray, double t_min, do
     }
     c.is_light = c.ref != kNone && !(c.tie_outer >> 31);  // objects carry bit 31 in their outer rank (object beats light, Q31)
     return c.ref != kNone;
-}
-
-// ---------------------------------------------------------------- resumable traversal (persistent-lane trace kernel)
-// Same algorithm as trace_closest<false>, cut into units (phase 1 + one tagged entry) so that a lane whose ray is
-// finished can fetch its next ray while the other lanes of the warp keep traversing.  The world ray is re-read from
-// the path buffer when an instance is left, instead of being held in registers.
-struct Trav {  // scalar state only (stays in registers); the stack arrays are separate locals of the kernel
-    RayD r; BoxRay br; Closest c;
-    int sp; uint32_t cur, cur_inst, cur_tie; float tmax_f;
-};
-PT_D void trav_begin(const DScene& S, Trav& T, const RayD& ray) {
-    T.sp = 0;
-    T.c.t = __longlong_as_double(0x7ff0000000000000ll);
-    T.c.ref = kNone; T.c.inst = kInstNone; T.c.tie_outer = 0; T.c.tie_inner = 0; T.c.is_light = false; T.c.n_pairs = 0; T.c.n_prims = 0;
-    T.r = ray; T.br = make_boxray(ray);
-    T.tmax_f = __int_as_float(0x7f800000);
-    T.cur_inst = kInstNone; T.cur_tie = 0; T.cur = S.root_pair;
-}
-// Runs one unit; returns true when the traversal is complete.  `reload` yields the world ray again.
-template <class ReloadRay>
-PT_D bool trav_unit(const DScene& S, Trav& T, uint32_t* __restrict__ stack, float* __restrict__ stack_t, const double t_min,
-                    const float tmin_f, ReloadRay reload) {
-    uint32_t pending = kNone;
-    while (true) {  // phase 1: internal node pairs
-        if (T.cur == kNone) {
-            while (T.sp > 0) {
-                --T.sp;
-                const uint32_t e = stack[T.sp];
-                if (e != kTagSentinel && !(stack_t[T.sp] <= T.tmax_f)) continue;
-                if ((e & kTagMask) == 0) T.cur = e; else pending = e;
-                break;
-            }
-            if (T.cur == kNone) break;
-        }
-        const uint32_t cur = T.cur;
-        const DNode n0 = S.nodes[cur], n1 = S.nodes[cur + 1];
-        const float t0 = slab(n0, T.br, tmin_f, T.tmax_f), t1 = slab(n1, T.br, tmin_f, T.tmax_f);
-        const uint32_t e0 = n0.b == kNone ? n0.a : (kTagLeaf | cur), e1 = n1.b == kNone ? n1.a : (kTagLeaf | (cur + 1));
-        const bool h0 = t0 <= T.tmax_f, h1 = t1 <= T.tmax_f;
-        const bool swap = h1 && (!h0 || t1 < t0);
-        const uint32_t en = swap ? e1 : e0, ef = swap ? e0 : e1;
-        const float tn = swap ? t1 : t0, tf = swap ? t0 : t1;
-        const bool hn = swap ? h1 : h0, hf = swap ? h0 : h1;
-        T.cur = kNone;
-        if (hf && T.sp < kStack) { stack[T.sp] = ef; stack_t[T.sp] = tf; T.sp++; }
-        if (hn) {
-            if ((en & kTagMask) == 0) T.cur = en;
-            else if (T.sp < kStack) { stack[T.sp] = en; stack_t[T.sp] = tn; T.sp++; }
-        }
-    }
-    if (pending == kNone) {
-        T.c.is_light = T.c.ref != kNone && !(T.c.tie_outer >> 31);
-        return true;
-    }
-    if (pending == kTagSentinel) {
-        T.r = reload(); T.br = make_boxray(T.r); T.cur_inst = kInstNone; T.cur_tie = 0;
-        return false;
-    }
-    if ((pending & kTagMask) == kTagLeaf) {
-        const DNode& n = S.nodes[pending & ~kTagMask];
-        const uint32_t first = n.a, count = n.b;
-        const float leaf_t = stack_t[T.sp];
-        for (uint32_t k = 0; k < count; k++) {
-            const DNode rb = S.refs[first + k];
-            if (!(slab(rb, T.br, tmin_f, T.tmax_f) <= T.tmax_f)) continue;
-            const uint32_t kind = ref_kind(rb.a), index = ref_index(rb.a);
-            if (kind == PT_PRIM_TRIANGLE) {
-                double t, u, v;
-                if (tri_t(S.tris[index], T.r, t_min, t, u, v) && t <= T.c.t) { consider(T.c, t, rb.a, T.cur_inst, T.cur_tie, rb.b); T.tmax_f = __double2float_ru(T.c.t); }
-            } else if (kind <= PT_OBJ_CUBOID) { test_simple(S, kind, index, T.r, t_min, T.c, kInstNone, rb.b, 0); T.tmax_f = __double2float_ru(T.c.t); }
-            else if (T.sp < kStack) { stack[T.sp] = kTagRef | (first + k); stack_t[T.sp] = leaf_t; T.sp++; }
-        }
-        return false;
-    }
-    const DRef rf{S.refs[pending & ~kTagMask].a, S.refs[pending & ~kTagMask].b};
-    const uint32_t kind = ref_kind(rf.kind_index), index = ref_index(rf.kind_index);
-    uint32_t mesh;
-    if (kind == PT_OBJ_MESH) { mesh = index; T.cur_inst = kInstNone; }
-    else {
-        const DInstance& in = S.instances[index];
-        const RayD lr = instance_local_ray(in, T.r);
-        if (in.child_kind != PT_OBJ_MESH) {
-            test_simple(S, in.child_kind, in.child_index, lr, t_min, T.c, index, rf.tie, 0);
-            T.tmax_f = __double2float_ru(T.c.t);
-            return false;
-        }
-        mesh = in.child_index; T.r = lr; T.br = make_boxray(lr); T.cur_inst = index;
-    }
-    T.cur_tie = rf.tie;
-    if (T.sp < kStack) { stack[T.sp] = kTagSentinel; stack_t[T.sp] = 0.f; T.sp++; }
-    T.cur = S.meshes[mesh].root_pair;
-    return false;
 }
 
 // ---------------------------------------------------------------- hit reconstruction (HitInfo::new, hit_info.rs:16-55)

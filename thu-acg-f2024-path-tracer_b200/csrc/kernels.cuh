@@ -106,66 +106,19 @@ PT_D void queue_append(const Queues& q, uint32_t cls, uint32_t i) {
 }
 
 // World::intersect_all for every live path (one ray per thread), then the path joins the queue of its shade class.
-__global__ void __launch_bounds__(kBlock) k_trace(PathBuf in, uint32_t n, HitRec* __restrict__ hits, Queues q, DScene S) {
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(kBlock, MIN_BLOCKS) k_trace(PathBuf in, uint32_t n, HitRec* __restrict__ hits, Queues q, DScene S) {
     const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
     uint32_t cls = N_CLS;
     if (i < n) {
-        RayD r = load_ray(in, i);
         Closest c;
-        trace_closest<false>(S, r, 1e-3, 0.0, c);  // Interval::new(eps, INFINITY), camera.rs:171,179
+        trace_closest<false, false>(S, [&]() { return load_ray(in, i); }, 1e-3, 0.0, c);  // Interval::new(eps, INFINITY), camera.rs:171,179
         HitRec h; h.t = c.t; h.ref = c.ref; h.inst_light = (c.inst & 0x7FFFFFFFu) | (c.is_light ? 0x80000000u : 0u);
         hits[i] = h;
         cls = c.ref == kNone ? (uint32_t)CLS_MISS : class_of_kind(S.materials[hit_material(S, c.ref)].kind);
     }
     __syncwarp();
     queue_append(q, cls, i);
-}
-
-// Optional variant (PT_FLAG_PERSISTENT_TRACE): persistent lanes.  Ray lengths vary a lot (scene 6: mean 9 node pairs,
-// p99 33, max 67), so with one ray per thread a warp idles lanes waiting for its longest ray.  Here every warp owns
-// kRaysPerWarp consecutive rays and idle lanes take the next rays of the chunk (no atomics: the cursor is warp-uniform).
-// Measured: +25% on the mesh-heavy scene 70, -20% on scene 6 whose coherent primary rays prefer k_trace.
-constexpr uint32_t kRaysPerWarp = 128;
-constexpr int kUnitsPerRound = 4;
-constexpr int kRefillIdle = 16;  // refill when this many lanes are idle: coherent warps (primary rays) finish together and stay coherent
-__global__ void __launch_bounds__(kBlock) k_trace_persistent(PathBuf in, uint32_t n, HitRec* __restrict__ hits, Queues q, DScene S) {
-    const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
-    uint32_t next = ((blockIdx.x * kBlock + threadIdx.x) >> 5) * kRaysPerWarp;
-    if (next >= n) return;  // warp-uniform
-    const uint32_t end = min(next + kRaysPerWarp, n);
-    const double t_min = 1e-3;  // Interval::new(eps, INFINITY), camera.rs:171,179
-    const float tmin_f = __double2float_rd(t_min);
-    uint32_t stack[kStack]; float stack_t[kStack];
-    Trav T;
-    bool active = false;
-    uint32_t i = 0;
-    while (true) {
-        const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !active);
-        if (next < end && (__popc(idle) >= kRefillIdle || idle == 0xFFFFFFFFu)) {  // refill the idle lanes from the warp's chunk
-            if (!active) {
-                const uint32_t idx = next + __popc(idle & lt);
-                if (idx < end) { i = idx; trav_begin(S, T, load_ray(in, i)); active = true; }
-            }
-            next += __popc(idle);
-        }
-        if (!__any_sync(0xFFFFFFFFu, active)) break;
-        bool finished = false;
-        if (active) {
-#pragma unroll 1
-            for (int u = 0; u < kUnitsPerRound && !finished; u++)
-                finished = trav_unit(S, T, stack, stack_t, t_min, tmin_f, [&]() { return load_ray(in, i); });
-        }
-        if (__any_sync(0xFFFFFFFFu, finished)) {  // retire: hit record + shade-class queue
-            uint32_t cls = N_CLS;
-            if (finished) {
-                HitRec h; h.t = T.c.t; h.ref = T.c.ref; h.inst_light = (T.c.inst & 0x7FFFFFFFu) | (T.c.is_light ? 0x80000000u : 0u);
-                hits[i] = h;
-                cls = T.c.ref == kNone ? (uint32_t)CLS_MISS : class_of_kind(S.materials[hit_material(S, T.c.ref)].kind);
-                active = false;
-            }
-            queue_append(q, cls, i);
-        }
-    }
 }
 
 PT_D void add_radiance(float* __restrict__ accum, uint32_t pix, d3 v, uint32_t nan_policy, unsigned long long* nonfinite, bool& dead) {
@@ -293,7 +246,7 @@ __global__ void k_trace_batch(const pt_ray* __restrict__ rays, size_t n, double 
     RayD r; r.o = from_abi(rays[i].origin); r.d = from_abi(rays[i].direction); r.time = rays[i].time;
     Closest c;
     pt_hit o; memset(&o, 0, sizeof(o)); o.instance = PT_NONE;
-    const bool hit = trace_closest<false>(S, r, t_min, 0.0, c);
+    const bool hit = trace_closest<false, true>(S, [&]() { return r; }, t_min, 0.0, c);
     o.work = min(c.n_pairs, 0xFFFFu) | (min(c.n_prims, 0xFFFFu) << 16);
     if (hit) {
         HitInfoD h;
@@ -310,7 +263,7 @@ __global__ void k_trace_any_batch(const pt_ray* __restrict__ rays, size_t n, dou
     if (i >= n) return;
     RayD r; r.o = from_abi(rays[i].origin); r.d = from_abi(rays[i].direction); r.time = rays[i].time;
     Closest c;
-    out[i] = trace_closest<true>(S, r, t_min, t_max[i], c) ? 1 : 0;
+    out[i] = trace_closest<true, false>(S, [&]() { return r; }, t_min, t_max[i], c) ? 1 : 0;
 }
 PT_D HitInfoD info_from_query(const pt_bsdf_query& q, uint32_t material) {
     HitInfoD h; h.point = from_abi(q.point); h.gn = from_abi(q.geometric_normal); h.sn = from_abi(q.shading_normal);
