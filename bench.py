@@ -202,13 +202,18 @@ def main():
 
     # ---- end to end through the C ABI with host buffers: scene upload (H2D) + render + reduce + image D2H, every step
     def e2e_step(i):
+        t_a = time.perf_counter()
         d2 = ctx.upload(scene)                      # pt_scene_create: H2D of the flattened scene from host memory
+        t_b = time.perf_counter()
         st = step(i, d2)
+        t_c = time.perf_counter()
         if rank == 0:
             host_out.copy_(accum, non_blocking=True)  # D2H of the step's result
         torch.cuda.synchronize()
         nbytes = d2.device_bytes
         d2.close()
+        if rank == 0 and os.environ.get("PT_BENCH_VERBOSE"):
+            print(f"e2e step {i}: upload {1e3 * (t_b - t_a):.1f} ms, render+reduce {1e3 * (t_c - t_b):.1f} ms, d2h+free {1e3 * (time.perf_counter() - t_c):.1f} ms", file=sys.stderr)
         return st, nbytes
     for i in range(2):
         e2e_step(i)

@@ -34,11 +34,22 @@ struct pt_ctx {
     unsigned long long* d_nonfinite = nullptr;
     uint32_t* h_count = nullptr;            // pinned
     void* h_stage = nullptr; size_t stage_bytes = 0;  // pinned staging buffer for scene uploads
+    std::vector<std::pair<void*, size_t>> free_blocks;  // device blocks of destroyed scenes, reused by the next upload
+    // cudaMalloc/cudaFree cost milliseconds each and synchronise the device; returns the block and its true size
+    int alloc_block(size_t bytes, std::pair<void*, size_t>* out) {
+        size_t best = free_blocks.size();
+        for (size_t i = 0; i < free_blocks.size(); i++)
+            if (free_blocks[i].second >= bytes && free_blocks[i].second <= 2 * bytes + (1 << 20) &&
+                (best == free_blocks.size() || free_blocks[i].second < free_blocks[best].second)) best = i;
+        if (best != free_blocks.size()) { *out = free_blocks[best]; free_blocks.erase(free_blocks.begin() + best); return 0; }
+        out->second = bytes;
+        return cudaMalloc(&out->first, bytes) == cudaSuccess ? 0 : -1;
+    }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs[6] = {nullptr};
 };
 struct pt_scene {
     pt_ctx* ctx = nullptr;
-    std::vector<void*> allocs;
+    std::vector<std::pair<void*, size_t>> allocs;  // device blocks (returned to the ctx's free list on destroy)
     DScene d{};
     uint64_t bytes = 0;
     uint32_t n_materials = 0, n_images = 0, max_stack = 0;
@@ -78,6 +89,7 @@ void pt_ctx_destroy(pt_ctx* c) {
     free_pool(c);
     cudaFree(c->d_count); cudaFree(c->d_nonfinite); cudaFreeHost(c->h_count);
     if (c->h_stage) cudaFreeHost(c->h_stage);
+    for (auto& b : c->free_blocks) cudaFree(b.first);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     for (auto& e : c->evs) cudaEventDestroy(e);
     cudaStreamDestroy(c->own_stream);
@@ -113,9 +125,10 @@ struct Uploader {
             CU(cudaMallocHost(&c->h_stage, total));
             c->stage_bytes = total;
         }
-        void* base = nullptr;
-        CU(cudaMalloc(&base, total));
-        s->allocs.push_back(base);
+        std::pair<void*, size_t> blk{nullptr, 0};
+        if (c->alloc_block(total, &blk)) return fail(PT_ERR_CUDA, "cudaMalloc failed for the scene arena");
+        s->allocs.push_back(blk);
+        void* base = blk.first;
         for (auto& it : items) { memcpy((char*)c->h_stage + it.offset, it.src, it.bytes); *it.dst = (char*)base + it.offset; s->bytes += it.bytes; }
         CU(cudaMemcpyAsync(base, c->h_stage, total, cudaMemcpyHostToDevice, c->stream));
         return PT_OK;
@@ -402,7 +415,10 @@ int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
     }
     uint8_t* d_img = nullptr;
     if (img_bytes) {
-        CU(cudaMalloc(&d_img, img_bytes)); s->allocs.push_back(d_img);
+        std::pair<void*, size_t> blk{nullptr, 0};
+        if (ctx->alloc_block(img_bytes, &blk)) return fail(PT_ERR_CUDA, "cudaMalloc failed for the image block");
+        s->allocs.push_back(blk);
+        d_img = (uint8_t*)blk.first;
         for (uint32_t i = 0; i < d->n_images; i++) {
             size_t nb = 3ull * d->images[i].width * d->images[i].height;
             if (nb) CU(cudaMemcpyAsync(d_img + images[i].offset, d->images[i].rgb, nb, cudaMemcpyHostToDevice, ctx->stream));
@@ -436,7 +452,9 @@ int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
 void pt_scene_destroy(pt_scene* s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
-    for (void* p : s->allocs) cudaFree(p);
+    cudaStreamSynchronize(s->ctx->stream);  // no kernel may still read the tables
+    for (auto& b : s->allocs) s->ctx->free_blocks.push_back(b);
+    while (s->ctx->free_blocks.size() > 8) { cudaFree(s->ctx->free_blocks.front().first); s->ctx->free_blocks.erase(s->ctx->free_blocks.begin()); }
     delete s;
 }
 uint64_t pt_scene_device_bytes(const pt_scene* s) { return s ? s->bytes : 0; }
