@@ -28,7 +28,11 @@ import __graft_entry__ as ge  # noqa: E402
 SCENE, WIDTH = 6, 1920
 # device structs (csrc/device_scene.cuh, csrc/kernels.cuh): bytes one segment moves through HBM per stage
 B_RAY, B_HIT, B_STATE = 56, 16, 96   # ray (o,d,time f64), HitRec, full path state (ray + throughput f64x3 + ids uint4)
-B_NODE, B_REF, B_SPHERE, B_QUAD, B_TRI = 32, 8, 64, 128, 80
+B_NODE, B_REF, B_SPHERE, B_QUAD, B_TRI = 32, 32, 64, 128, 80
+# dram__bytes_read.sum + dram__bytes_write.sum per ray of k_trace from the ncu --set full capture of this workload
+# (profiles/r1_b_k_trace_ncu.md: 146.9 MB + 37.3 MB for 2,539,648 rays): the ray stream and hit records come from HBM,
+# the 4.6 MB scene (BVH, primitives) is served by L2.
+K_TRACE_DRAM_BYTES_PER_RAY = (146.88e6 + 37.25e6) / 2539648
 
 
 def peaks():
@@ -126,7 +130,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--spp", type=int, default=64, help="samples per pixel per rank per step")
+    ap.add_argument("--spp", type=int, default=128, help="samples per pixel per rank per step")
     ap.add_argument("--ref-spp", type=int, default=1, help="samples per pixel per step of the CPU reference arm")
     ap.add_argument("--pool", type=int, default=0, help="in-flight path pool (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -261,8 +265,12 @@ def main():
             "e2e": {"value": e2e_segs.item() / e2e_s.item() / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(e2e_stats[0][1]) * world,
                     "d2h_bytes_per_step": H * WIDTH * 3 * 4, "ms_per_step": 1e3 * e2e_s.item() / args.steps,
                     "what": "pt_scene_create (scene H2D) + pt_render_accumulate + reduce + D2H of the fp32 image, every step"},
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None, "peak_source": peak_src,
-                         "bytes_per_segment": dom_b, "avg_launch_ms": dom_ms / max(iters, 1), "launches": iters,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                         "traffic": (K_TRACE_DRAM_BYTES_PER_RAY * segs_rank / max(iters, 1)) if dom == "k_trace" else None,
+                         "traffic_note": "DRAM bytes per launch = ncu dram read+write per ray (profiles/r1_b_k_trace_ncu.md) x rays per launch; far below the algorithmic bytes because the scene is L2-resident",
+                         "peak_source": peak_src,
+                         "bytes_per_segment": dom_b, "bytes_per_launch": dom_b * segs_rank / max(iters, 1),
+                         "avg_launch_ms": dom_ms / max(iters, 1), "launches": iters,
                          "stage_ms_per_step": {"k_generate": gen_ms / args.steps, "k_trace": trace_ms / args.steps, "k_shade": shade_ms / args.steps},
                          "whole_step": {"bytes_per_segment": b_seg, "achieved": step_gbs, "frac": step_gbs / hbm},
                          "oracle_counters_per_segment": {"boxes": n_node, "spheres": n_sph, "quads": n_quad, "triangles": n_tri}},
