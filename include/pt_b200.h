@@ -195,6 +195,9 @@ typedef struct {
     uint32_t width, height;
     float    device_ms;      /* CUDA-event time of the render loop */
     float    trace_ms, shade_ms, raygen_ms; /* per-stage totals when profiling enabled, else 0 */
+    /* traversal work summed over all segments (profiling mode only, else 0): 64-byte node pairs fetched,
+     * 32-byte reference boxes fetched, f64 primitive tests */
+    uint64_t node_pairs, ref_boxes, prim_tests;
 } pt_stats;
 
 typedef struct pt_ctx pt_ctx;

@@ -45,7 +45,8 @@ class RenderParams(C.Structure):  # pt_render_params
 class Stats(C.Structure):  # pt_stats
     _fields_ = [("paths", C.c_uint64), ("segments", C.c_uint64), ("nonfinite", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("iterations", C.c_uint32), ("width", C.c_uint32), ("height", C.c_uint32), ("device_ms", C.c_float),
-                ("trace_ms", C.c_float), ("shade_ms", C.c_float), ("raygen_ms", C.c_float)]
+                ("trace_ms", C.c_float), ("shade_ms", C.c_float), ("raygen_ms", C.c_float),
+                ("node_pairs", C.c_uint64), ("ref_boxes", C.c_uint64), ("prim_tests", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -72,7 +72,7 @@ int pt_ctx_create(int device, pt_ctx** out) {
     CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CU(cudaMalloc(&c->d_count, 16 * sizeof(uint32_t)));
-    CU(cudaMalloc(&c->d_nonfinite, sizeof(unsigned long long)));
+    CU(cudaMalloc(&c->d_nonfinite, 4 * sizeof(unsigned long long)));  // [0] non-finite samples, [1..3] traversal work counters
     CU(cudaMallocHost(&c->h_count, 2 * sizeof(uint32_t)));
     CU(cudaEventCreate(&c->ev0)); CU(cudaEventCreate(&c->ev1));
     for (auto& e : c->evs) CU(cudaEventCreate(&e));
@@ -524,7 +524,7 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
     if ((rc = ensure_pool(ctx, pool))) return rc;
     RenderConst rcst{p->seed, p->sample_begin, p->sample_stride ? p->sample_stride : 1u, p->nan_policy, 0};
     cudaStream_t st = ctx->stream;
-    CU(cudaMemsetAsync(ctx->d_nonfinite, 0, sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(ctx->d_nonfinite, 0, 4 * sizeof(unsigned long long), st));
     pt_stats S{}; S.width = dcam.c.width; S.height = dcam.c.height;
     float ms_gen = 0, ms_trace = 0, ms_shade = 0;
     CU(cudaEventRecord(ctx->ev0, st));
@@ -541,7 +541,8 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
         CU(cudaMemsetAsync(ctx->d_count, 0, 16 * sizeof(uint32_t), st));
         const Queues q{ctx->q_items, ctx->d_count + 4, ctx->pool};
         if (ctx->profiling) CU(cudaEventRecord(ctx->evs[1], st));
-            switch ((p->flags >> 4) & 7u) {  // experiment knob: resident blocks per SM the compiler must allow (register cap)
+            if (ctx->profiling) k_trace<6, true><<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, ctx->d_nonfinite + 1);
+            else switch ((p->flags >> 4) & 7u) {  // experiment knob: resident blocks per SM the compiler must allow (register cap)
                 case 4: k_trace<4><<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d); break;  // 120 regs
                 case 5: k_trace<5><<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d); break;  // 96 regs
                 case 7: k_trace<8><<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d); break;  // 64 regs, spills
@@ -571,12 +572,13 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
         cur ^= 1;
     }
     CU(cudaEventRecord(ctx->ev1, st));
-    unsigned long long nf = 0;
-    CU(cudaMemcpyAsync(&nf, ctx->d_nonfinite, sizeof(nf), cudaMemcpyDeviceToHost, st));
+    unsigned long long nf[4] = {0, 0, 0, 0};
+    CU(cudaMemcpyAsync(nf, ctx->d_nonfinite, sizeof(nf), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
     cudaEventElapsedTime(&S.device_ms, ctx->ev0, ctx->ev1);
-    S.paths = generated; S.nonfinite = nf; S.raygen_ms = ms_gen; S.trace_ms = ms_trace; S.shade_ms = ms_shade;
+    S.paths = generated; S.nonfinite = nf[0]; S.raygen_ms = ms_gen; S.trace_ms = ms_trace; S.shade_ms = ms_shade;
+    S.node_pairs = nf[1]; S.ref_boxes = nf[2]; S.prim_tests = nf[3];
     if (stats) *stats = S;
     return PT_OK;
 }

@@ -109,7 +109,7 @@ constexpr uint32_t kTagRef = 0x40000000u, kTagSentinel = 0x80000000u, kTagMask =
 
 struct Closest {
     double t; uint32_t ref, inst, tie_outer, tie_inner; bool is_light;
-    uint32_t n_pairs, n_prims;  // work counters: node pairs fetched, primitive tests
+    uint32_t n_pairs, n_refs, n_prims;  // work counters: node pairs fetched (64 B), reference boxes fetched (32 B), f64 primitive tests
 };
 PT_D void consider(Closest& c, double t, uint32_t ref, uint32_t inst, uint32_t tie_o, uint32_t tie_i) {
     if (t < c.t || (t == c.t && (tie_o > c.tie_outer || (tie_o == c.tie_outer && tie_i > c.tie_inner)))) {
@@ -146,7 +146,7 @@ PT_D bool trace_closest(const DScene& S, Reload reload, double t_min, double t_m
     uint32_t stack[kStack]; float stack_t[kStack];
     int sp = 0;
     c.t = ANY_HIT ? t_max_any : __longlong_as_double(0x7ff0000000000000ll);
-    c.ref = kNone; c.inst = kInstNone; c.tie_outer = 0; c.tie_inner = 0; c.is_light = false; c.n_pairs = 0; c.n_prims = 0;
+    c.ref = kNone; c.inst = kInstNone; c.tie_outer = 0; c.tie_inner = 0; c.is_light = false; c.n_pairs = 0; c.n_refs = 0; c.n_prims = 0;
     RayD r = reload();
     BoxRay br = make_boxray(r);
     const float tmin_f = __double2float_rd(t_min);
@@ -195,6 +195,7 @@ PT_D bool trace_closest(const DScene& S, Reload reload, double t_min, double t_m
             const float leaf_t = stack_t[sp];  // entry distance of this leaf (slot just popped)
             for (uint32_t k = 0; k < count; k++) {
                 const DNode rb = S.refs[first + k];  // per-reference fp32 box + (kind|index, tie rank)
+                if (COUNT) c.n_refs++;
                 if (!(slab(rb, br, tmin_f, tmax_f) <= tmax_f)) continue;  // most f64 tests would be rejections: cull them in fp32
                 if (COUNT) c.n_prims++;
                 const uint32_t kind = ref_kind(rb.a), index = ref_index(rb.a);

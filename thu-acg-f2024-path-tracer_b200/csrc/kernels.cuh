@@ -106,19 +106,28 @@ PT_D void queue_append(const Queues& q, uint32_t cls, uint32_t i) {
 }
 
 // World::intersect_all for every live path (one ray per thread), then the path joins the queue of its shade class.
-template <int MIN_BLOCKS>
-__global__ void __launch_bounds__(kBlock, MIN_BLOCKS) k_trace(PathBuf in, uint32_t n, HitRec* __restrict__ hits, Queues q, DScene S) {
+// COUNT (profiling mode only): also sums the traversal work of all rays into work[3] = {node pairs, reference boxes,
+// f64 primitive tests}, from which bench.py derives the bytes the device actually requests per ray.
+template <int MIN_BLOCKS, bool COUNT = false>
+__global__ void __launch_bounds__(kBlock, MIN_BLOCKS) k_trace(PathBuf in, uint32_t n, HitRec* __restrict__ hits, Queues q, DScene S,
+                                                              unsigned long long* __restrict__ work = nullptr) {
     const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
     uint32_t cls = N_CLS;
+    uint32_t w0 = 0, w1 = 0, w2 = 0;
     if (i < n) {
         Closest c;
-        trace_closest<false, false>(S, [&]() { return load_ray(in, i); }, 1e-3, 0.0, c);  // Interval::new(eps, INFINITY), camera.rs:171,179
+        trace_closest<false, COUNT>(S, [&]() { return load_ray(in, i); }, 1e-3, 0.0, c);  // Interval::new(eps, INFINITY), camera.rs:171,179
+        if (COUNT) { w0 = c.n_pairs; w1 = c.n_refs; w2 = c.n_prims; }
         HitRec h; h.t = c.t; h.ref = c.ref; h.inst_light = (c.inst & 0x7FFFFFFFu) | (c.is_light ? 0x80000000u : 0u);
         hits[i] = h;
         cls = c.ref == kNone ? (uint32_t)CLS_MISS : class_of_kind(S.materials[hit_material(S, c.ref)].kind);
     }
     __syncwarp();
     queue_append(q, cls, i);
+    if (COUNT) {
+        w0 = __reduce_add_sync(0xFFFFFFFFu, w0); w1 = __reduce_add_sync(0xFFFFFFFFu, w1); w2 = __reduce_add_sync(0xFFFFFFFFu, w2);
+        if ((threadIdx.x & 31) == 0) { atomicAdd(work, (unsigned long long)w0); atomicAdd(work + 1, (unsigned long long)w1); atomicAdd(work + 2, (unsigned long long)w2); }
+    }
 }
 
 PT_D void add_radiance(float* __restrict__ accum, uint32_t pix, d3 v, uint32_t nan_policy, unsigned long long* nonfinite, bool& dead) {
