@@ -54,6 +54,7 @@ struct pt_scene {
     uint64_t bytes = 0;
     uint32_t n_materials = 0, n_images = 0, max_stack = 0;
     uint32_t class_mask = 1u << CLS_MISS;   // shade classes that can occur in this scene
+    bool wide = false;                      // traversed with 4-wide nodes (some BVH has >= kWideMinItems items) or binary pairs
     std::vector<DImage> images;
 };
 
@@ -136,6 +137,8 @@ struct Uploader {
 };
 float round_down(double v) { float f = (float)v; if ((double)f > v) f = std::nextafterf(f, -INFINITY); return f; }
 float round_up(double v) { float f = (float)v; if ((double)f < v) f = std::nextafterf(f, INFINITY); return f; }
+
+constexpr uint32_t kWideMinItems = 64;  // BVHs over at least this many items are collapsed to 4-wide nodes
 
 struct Converter {
     const pt_scene_desc* d;
@@ -249,6 +252,44 @@ struct Converter {
         return fill(pair, h.left, top_bit, depth + 1) && fill(pair + 1, h.right, top_bit, depth + 1);  // DFS: left before right
     }
     void dummy(uint32_t slot) { DNode n{}; for (int k = 0; k < 3; k++) { n.lo[k] = INFINITY; n.hi[k] = -INFINITY; } n.a = 0; n.b = 0; nodes[slot] = n; }
+
+    // ---- collapse of the binary tree into 4-wide nodes (device_scene.cuh: DWide)
+    std::vector<DWide> wide;
+    uint32_t wide_depth = 0;
+    static float half_area(const DNode& n) {
+        float ex = n.hi[0] - n.lo[0], ey = n.hi[1] - n.lo[1], ez = n.hi[2] - n.lo[2];
+        return ex * ey + ex * ez + ey * ez;
+    }
+    // children: binary node slots.  Internal children are opened, largest box first, until four are held.
+    uint32_t make_wide(std::vector<uint32_t> children, uint32_t depth) {
+        wide_depth = std::max(wide_depth, depth);
+        std::vector<uint32_t> kept;
+        for (uint32_t c : children) if (!(nodes[c].b != kNone && nodes[c].b == 0)) kept.push_back(c);  // drop empty dummy leaves
+        children.swap(kept);
+        while (children.size() < 4) {
+            int best = -1; float best_area = -1.f;
+            for (size_t i = 0; i < children.size(); i++)
+                if (nodes[children[i]].b == kNone && half_area(nodes[children[i]]) > best_area) { best = (int)i; best_area = half_area(nodes[children[i]]); }
+            if (best < 0) break;
+            const uint32_t pair = nodes[children[best]].a;
+            children[best] = pair;
+            children.insert(children.begin() + best + 1, pair + 1);
+        }
+        const uint32_t wi = (uint32_t)wide.size();
+        wide.emplace_back();
+        DWide w{};
+        for (int i = 0; i < 4; i++) {
+            for (int k = 0; k < 3; k++) { w.lo[k][i] = INFINITY; w.hi[k][i] = -INFINITY; }
+            w.child[i] = kNone; w.pad[i] = 0;
+        }
+        for (size_t i = 0; i < children.size(); i++) {
+            const DNode n = nodes[children[i]];
+            for (int k = 0; k < 3; k++) { w.lo[k][i] = n.lo[k]; w.hi[k][i] = n.hi[k]; }
+            w.child[i] = n.b == kNone ? (0x20000000u | make_wide({n.a, n.a + 1}, depth + 1)) : (0xC0000000u | children[i]);
+        }
+        wide[wi] = w;
+        return wi;
+    }
 };
 }  // namespace
 
@@ -330,6 +371,10 @@ int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
     if (!top_list(0, d->objects_bvh_root, d->objects, d->n_objects, 0x80000000u)) return fail(PT_ERR_INVALID, C.err);
     const uint32_t tlas_depth = C.max_depth;
     if (C.tie_counter >= 0x7FFFFFFFu) return fail(PT_ERR_UNSUPPORTED, "too many top-level objects");
+    // one traversal flavour per scene (compile-time in the kernels): 4-wide nodes as soon as any BVH is large
+    bool use_wide = d->n_objects + d->n_lights >= kWideMinItems;
+    for (uint32_t mi = 0; mi < d->n_meshes; mi++) use_wide |= d->meshes[mi].n_triangles >= kWideMinItems;
+    s->wide = use_wide;
     std::vector<DMesh> meshes(d->n_meshes);
     std::vector<uint32_t> tri_mesh(d->n_triangles, 0);
     uint32_t blas_depth = 0;
@@ -347,15 +392,17 @@ int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
             for (uint32_t k = 0; k < m.n_triangles; k++) items[k] = pt_ref{PT_PRIM_TRIANGLE, m.first_triangle + k};
             DNode leaf{}; C.make_leaf(leaf, items.data(), m.n_triangles, 0u, true, nullptr, nullptr); C.nodes[pair] = leaf;
         } else if (!C.fill(pair, m.bvh_root, 0u, 1)) return fail(PT_ERR_INVALID, C.err);
-        blas_depth = std::max(blas_depth, C.max_depth);
-        meshes[mi] = DMesh{pair, m.first_triangle, m.n_triangles, m.material, m.has_normals, m.has_uvs, m.bvh_root == PT_NONE, 0};
+        // large BVHs are collapsed to 4-wide nodes; small ones keep the binary pairs (cheaper when most rays leave at once)
+        uint32_t root_entry = pair, depth_slots = C.max_depth;
+        if (use_wide) { C.wide_depth = 0; root_entry = 0x20000000u | C.make_wide({pair}, 1); depth_slots = 3 * C.wide_depth; }
+        blas_depth = std::max(blas_depth, depth_slots);
+        meshes[mi] = DMesh{root_entry, m.first_triangle, m.n_triangles, m.material, m.has_normals, m.has_uvs, m.bvh_root == PT_NONE, 0};
     }
-    // stack bound: one pending sibling per level + deferred refs of a leaf (<= refs in a TLAS leaf) + sentinel
-    uint32_t max_leaf = 0;
-    for (auto& n : C.nodes) if (n.b != kNone) max_leaf = std::max(max_leaf, n.b);
+    uint32_t world_root = 0, tlas_slots = tlas_depth;
+    if (use_wide) { C.wide_depth = 0; world_root = 0x20000000u | C.make_wide({0u, 1u}, 1); tlas_slots = 3 * C.wide_depth; }
+    // stack bound: one pending sibling per binary level / three per wide level + deferred mesh/instance refs of a TLAS leaf + sentinel
     uint32_t top_leaf = std::max(d->objects_bvh_root == PT_NONE ? d->n_objects : 0u, d->lights_bvh_root == PT_NONE ? d->n_lights : 0u);
-    (void)max_leaf;
-    s->max_stack = tlas_depth + blas_depth + 2 + std::max(top_leaf, 8u);
+    s->max_stack = tlas_slots + blas_depth + 2 + std::max(top_leaf, 8u);
     if (s->max_stack > (uint32_t)kStack) return fail(PT_ERR_UNSUPPORTED, "BVH too deep for the device traversal stack (" + std::to_string(s->max_stack) + " > " + std::to_string(kStack) + ")");
 
     // ---- primitives
@@ -438,12 +485,12 @@ int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
     for (uint32_t i = 0; i < d->n_lights; i++) lights[i] = DRef{ref_pack(d->lights[i].kind, d->lights[i].index), 0};
 
     DScene& D = s->d;
-    U.up(C.nodes, &D.nodes); U.up(C.refs, &D.refs); U.up(spheres, &D.spheres); U.up(quads, &D.quads); U.up(quad_mat, &D.quad_material);
+    U.up(C.wide, &D.wide); U.up(C.nodes, &D.nodes); U.up(C.refs, &D.refs); U.up(spheres, &D.spheres); U.up(quads, &D.quads); U.up(quad_mat, &D.quad_material);
     U.up(tris, &D.tris); U.up(tri_normals, &D.tri_normals); U.up(tri_uvs, &D.tri_uvs); U.up(tri_mesh, &D.tri_mesh); U.up(cuboids, &D.cuboids);
     U.up(meshes, &D.meshes); U.up(instances, &D.instances); U.up(textures, &D.textures); U.up(images, &D.images); U.up(materials, &D.materials);
     U.up(lights, &D.lights);
     if ((rc = U.commit())) return rc;
-    D.image_data = d_img; D.n_lights = d->n_lights; D.root_pair = 0;
+    D.image_data = d_img; D.n_lights = d->n_lights; D.root_entry = world_root;
     s->n_materials = d->n_materials; s->n_images = d->n_images; s->images = images;
     CU(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
     *out = s.release();
@@ -541,12 +588,16 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
         CU(cudaMemsetAsync(ctx->d_count, 0, 16 * sizeof(uint32_t), st));
         const Queues q{ctx->q_items, ctx->d_count + 4, ctx->pool};
         if (ctx->profiling) CU(cudaEventRecord(ctx->evs[1], st));
-            if (ctx->profiling) k_trace<6, true><<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, ctx->d_nonfinite + 1);
+            const unsigned tg = (n + kBlock - 1) / kBlock;
+            if (ctx->profiling) {
+                if (scene->wide) k_trace<6, true, true><<<tg, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, ctx->d_nonfinite + 1);
+                else k_trace<6, false, true><<<tg, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, ctx->d_nonfinite + 1);
+            } else if (!scene->wide) k_trace<6, false><<<tg, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d);
             else switch ((p->flags >> 4) & 7u) {  // experiment knob: resident blocks per SM the compiler must allow (register cap)
-                case 4: k_trace<4><<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d); break;  // 120 regs
-                case 5: k_trace<5><<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d); break;  // 96 regs
-                case 7: k_trace<8><<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d); break;  // 64 regs, spills
-                default: k_trace<6><<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d);        // 80 regs (measured best overall)
+                case 4: k_trace<4, true><<<tg, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d); break;  // 120 regs
+                case 5: k_trace<5, true><<<tg, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d); break;  // 96 regs
+                case 7: k_trace<8, true><<<tg, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d); break;  // 64 regs, spills
+                default: k_trace<6, true><<<tg, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d);        // 80 regs (measured best overall)
             }
         if (ctx->profiling) CU(cudaEventRecord(ctx->evs[2], st));
         // one specialised kernel per shade class present in the scene; each walks its queue grid-stride
@@ -638,7 +689,8 @@ int pt_trace_closest(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_ray*
     CU(cudaSetDevice(ctx->device));
     DevBuf in, out; int rc;
     if ((rc = in.from_host(rays, n * sizeof(pt_ray), ctx->stream)) || (rc = out.alloc(n * sizeof(pt_hit)))) return rc;
-    k_trace_batch<<<grid_for(n), 128, 0, ctx->stream>>>((const pt_ray*)in.p, n, t_min, (pt_hit*)out.p, scene->d);
+    if (scene->wide) k_trace_batch<true><<<grid_for(n), 128, 0, ctx->stream>>>((const pt_ray*)in.p, n, t_min, (pt_hit*)out.p, scene->d);
+    else k_trace_batch<false><<<grid_for(n), 128, 0, ctx->stream>>>((const pt_ray*)in.p, n, t_min, (pt_hit*)out.p, scene->d);
     return out.to_host(hits, n * sizeof(pt_hit), ctx->stream);
 }
 int pt_trace_any(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_ray* rays, double t_min, const double* t_max, uint8_t* occluded) {
@@ -647,7 +699,8 @@ int pt_trace_any(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_ray* ray
     CU(cudaSetDevice(ctx->device));
     DevBuf in, tm, out; int rc;
     if ((rc = in.from_host(rays, n * sizeof(pt_ray), ctx->stream)) || (rc = tm.from_host(t_max, n * 8, ctx->stream)) || (rc = out.alloc(n))) return rc;
-    k_trace_any_batch<<<grid_for(n), 128, 0, ctx->stream>>>((const pt_ray*)in.p, n, t_min, (const double*)tm.p, (uint8_t*)out.p, scene->d);
+    if (scene->wide) k_trace_any_batch<true><<<grid_for(n), 128, 0, ctx->stream>>>((const pt_ray*)in.p, n, t_min, (const double*)tm.p, (uint8_t*)out.p, scene->d);
+    else k_trace_any_batch<false><<<grid_for(n), 128, 0, ctx->stream>>>((const pt_ray*)in.p, n, t_min, (const double*)tm.p, (uint8_t*)out.p, scene->d);
     return out.to_host(occluded, n, ctx->stream);
 }
 int pt_bsdf_eval_pdf(pt_ctx* ctx, const pt_scene* scene, uint32_t material, size_t n, const pt_bsdf_query* q, pt_bsdf_result* o) {

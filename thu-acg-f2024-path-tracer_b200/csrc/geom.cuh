@@ -109,7 +109,7 @@ constexpr uint32_t kTagRef = 0x40000000u, kTagSentinel = 0x80000000u, kTagMask =
 
 struct Closest {
     double t; uint32_t ref, inst, tie_outer, tie_inner; bool is_light;
-    uint32_t n_pairs, n_refs, n_prims;  // work counters: node pairs fetched (64 B), reference boxes fetched (32 B), f64 primitive tests
+    uint32_t n_pairs, n_wide, n_refs, n_prims;  // work counters: binary pairs (64 B) / wide nodes (128 B) fetched, reference boxes (32 B), f64 primitive tests
 };
 PT_D void consider(Closest& c, double t, uint32_t ref, uint32_t inst, uint32_t tie_o, uint32_t tie_i) {
     if (t < c.t || (t == c.t && (tie_o > c.tie_outer || (tie_o == c.tie_outer && tie_i > c.tie_inner)))) {
@@ -135,24 +135,25 @@ PT_D void test_simple(const DScene& S, uint32_t kind, uint32_t index, const RayD
 
 // World::intersect_all(ray, [t_min, inf)) — world.rs:47-62.  any_hit: stop at the first hit with t <= t_max on World.objects.
 //
-// "while-while" structure: phase 1 walks internal node pairs only (fp32 slab tests, both children per fetch);
-// leaves, deferred mesh/instance references and the instance-exit sentinel are pushed as tagged stack entries and
-// handled in phase 2, so the lanes of a warp run box tests together and f64 primitive tests together.
-constexpr uint32_t kTagLeaf = 0xC0000000u;  // kTagRef = 0x4..., kTagSentinel = 0x8..., internal pair = 0x0...
+// "while-while" structure: phase 1 walks 4-wide internal nodes only (fp32 slab tests, four children per 128-byte fetch,
+// sorted near to far); leaves, deferred mesh/instance references and the instance-exit sentinel are pushed as tagged
+// stack entries and handled in phase 2, so the lanes of a warp run box tests together and f64 primitive tests together.
+constexpr uint32_t kTagLeaf = 0xC0000000u;  // kTagRef = 0x4..., kTagSentinel = 0x8..., internal node = 0x0...
+constexpr uint32_t kWideBit = 0x20000000u;  // internal entries: set = index of a 4-wide node, clear = index of a binary node pair
 // `reload()` returns the world ray again (called when an instance is left), so it need not be kept in registers;
 // COUNT enables the work counters reported by pt_trace_closest.
-template <bool ANY_HIT, bool COUNT, class Reload>
+template <bool ANY_HIT, bool COUNT, bool WIDE, class Reload>
 PT_D bool trace_closest(const DScene& S, Reload reload, double t_min, double t_max_any, Closest& c) {
-    uint32_t stack[kStack]; float stack_t[kStack];
+    uint32_t stack[kStack]; float stack_t[kStack + 1];  // +1: slot sp may be written when a leaf is handed to phase 2 directly
     int sp = 0;
     c.t = ANY_HIT ? t_max_any : __longlong_as_double(0x7ff0000000000000ll);
-    c.ref = kNone; c.inst = kInstNone; c.tie_outer = 0; c.tie_inner = 0; c.is_light = false; c.n_pairs = 0; c.n_refs = 0; c.n_prims = 0;
+    c.ref = kNone; c.inst = kInstNone; c.tie_outer = 0; c.tie_inner = 0; c.is_light = false; c.n_pairs = 0; c.n_wide = 0; c.n_refs = 0; c.n_prims = 0;
     RayD r = reload();
     BoxRay br = make_boxray(r);
     const float tmin_f = __double2float_rd(t_min);
     float tmax_f = __double2float_ru(c.t);
     uint32_t cur_inst = kInstNone, cur_tie = 0;
-    uint32_t cur = S.root_pair;  // internal node pair to visit next, or kNone
+    uint32_t cur = S.root_entry;  // internal entry (binary pair or wide node) to visit next, or kNone
     while (true) {
         uint32_t pending = kNone;
         // ---------------- phase 1: internal pairs until a tagged entry surfaces (or the stack runs dry)
@@ -167,20 +168,58 @@ PT_D bool trace_closest(const DScene& S, Reload reload, double t_min, double t_m
                 }
                 if (cur == kNone) break;  // pending entry, or nothing left
             }
-            const DNode n0 = S.nodes[cur], n1 = S.nodes[cur + 1];
-            if (COUNT) c.n_pairs++;
-            const float t0 = slab(n0, br, tmin_f, tmax_f), t1 = slab(n1, br, tmin_f, tmax_f);
-            const uint32_t e0 = n0.b == kNone ? n0.a : (kTagLeaf | cur), e1 = n1.b == kNone ? n1.a : (kTagLeaf | (cur + 1));
-            const bool h0 = t0 <= tmax_f, h1 = t1 <= tmax_f;  // NaN (miss) compares false
-            const bool swap = h1 && (!h0 || t1 < t0);        // near child first
-            const uint32_t en = swap ? e1 : e0, ef = swap ? e0 : e1;
-            const float tn = swap ? t1 : t0, tf = swap ? t0 : t1;
-            const bool hn = swap ? h1 : h0, hf = swap ? h0 : h1;
+            if (!WIDE) {  // compile-time: a scene is traversed entirely with binary pairs or entirely with wide nodes
+                // ---- binary pair (small BVHs: top-level lists of a few objects; most rays leave after one or two fetches)
+                const DNode n0 = S.nodes[cur], n1 = S.nodes[cur + 1];
+                if (COUNT) c.n_pairs++;
+                const float t0 = slab(n0, br, tmin_f, tmax_f), t1 = slab(n1, br, tmin_f, tmax_f);
+                const uint32_t e0 = n0.b == kNone ? n0.a : (kTagLeaf | cur), e1 = n1.b == kNone ? n1.a : (kTagLeaf | (cur + 1));
+                const bool h0 = t0 <= tmax_f, h1 = t1 <= tmax_f;  // NaN (miss) compares false
+                const bool swap = h1 && (!h0 || t1 < t0);        // near child first
+                const uint32_t en = swap ? e1 : e0, ef = swap ? e0 : e1;
+                const float tn = swap ? t1 : t0, tf = swap ? t0 : t1;
+                const bool hn = swap ? h1 : h0, hf = swap ? h0 : h1;
+                cur = kNone;
+                if (hf && sp < kStack) { stack[sp] = ef; stack_t[sp] = tf; sp++; }
+                if (hn) {
+                    if ((en & kTagMask) == 0) cur = en;
+                    else if (sp < kStack) { stack[sp] = en; stack_t[sp] = tn; sp++; }
+                }
+                continue;
+            }
+            // ---- 4-wide node (large BVHs: meshes, big object lists): 7 x 128-bit loads, four slabs, sorted near to far
+            const DWide& w = S.wide[cur & ~kWideBit];
+            const float4 lx = *reinterpret_cast<const float4*>(w.lo[0]), ly = *reinterpret_cast<const float4*>(w.lo[1]),
+                         lz = *reinterpret_cast<const float4*>(w.lo[2]), hx = *reinterpret_cast<const float4*>(w.hi[0]),
+                         hy = *reinterpret_cast<const float4*>(w.hi[1]), hz = *reinterpret_cast<const float4*>(w.hi[2]);
+            const uint4 ch = *reinterpret_cast<const uint4*>(w.child);
+            if (COUNT) c.n_wide++;
+            const float kInf = __int_as_float(0x7f800000);
+            const bool sx = br.ix < 0.f, sy = br.iy < 0.f, sz = br.iz < 0.f;
+#define PT_SLAB4(I)                                                                                                          \
+            float t##I;                                                                                                      \
+            {                                                                                                                \
+                const float x0 = __fmaf_rn(sx ? hx.I : lx.I, br.ix, br.nx), x1 = __fmaf_rn(sx ? lx.I : hx.I, br.ix, br.fx); \
+                const float y0 = __fmaf_rn(sy ? hy.I : ly.I, br.iy, br.ny), y1 = __fmaf_rn(sy ? ly.I : hy.I, br.iy, br.fy); \
+                const float z0 = __fmaf_rn(sz ? hz.I : lz.I, br.iz, br.nz), z1 = __fmaf_rn(sz ? lz.I : hz.I, br.iz, br.fz); \
+                const float tn = fmaxf(fmaxf(x0, y0), fmaxf(z0, tmin_f)), tf = fminf(fminf(x1, y1), fminf(z1, tmax_f));     \
+                t##I = tn <= tf ? tn : kInf; /* NaN planes (0*inf) drop out of fmaxf/fminf: conservative */                  \
+            }
+            PT_SLAB4(x) PT_SLAB4(y) PT_SLAB4(z) PT_SLAB4(w)
+#undef PT_SLAB4
+            uint32_t e0 = ch.x, e1 = ch.y, e2 = ch.z, e3 = ch.w;
+            float t0 = tx, t1 = ty, t2 = tz, t3 = tw;
+#define PT_CSWAP(A, B) { const bool s_ = t##B < t##A; const float tt = s_ ? t##A : t##B; t##A = s_ ? t##B : t##A; t##B = tt; \
+                         const uint32_t ee = s_ ? e##A : e##B; e##A = s_ ? e##B : e##A; e##B = ee; }
+            PT_CSWAP(0, 1) PT_CSWAP(2, 3) PT_CSWAP(0, 2) PT_CSWAP(1, 3) PT_CSWAP(1, 2)  // ascending entry distance
+#undef PT_CSWAP
             cur = kNone;
-            if (hf && sp < kStack) { stack[sp] = ef; stack_t[sp] = tf; sp++; }
-            if (hn) {
-                if ((en & kTagMask) == 0) cur = en;
-                else if (sp < kStack) { stack[sp] = en; stack_t[sp] = tn; sp++; }
+            if (t3 < kInf && sp < kStack) { stack[sp] = e3; stack_t[sp] = t3; sp++; }  // far children first: nearest is popped first
+            if (t2 < kInf && sp < kStack) { stack[sp] = e2; stack_t[sp] = t2; sp++; }
+            if (t1 < kInf && sp < kStack) { stack[sp] = e1; stack_t[sp] = t1; sp++; }
+            if (t0 < kInf) {
+                if ((e0 & kTagMask) == 0) cur = e0;
+                else if (sp < kStack) { stack[sp] = e0; stack_t[sp] = t0; sp++; }
             }
         }
         if (pending == kNone) break;  // traversal finished
@@ -231,7 +270,7 @@ PT_D bool trace_closest(const DScene& S, Reload reload, double t_min, double t_m
         }
         cur_tie = rf.tie;
         if (sp < kStack) { stack[sp] = kTagSentinel; stack_t[sp] = 0.f; sp++; }
-        cur = S.meshes[mesh].root_pair;
+        cur = S.meshes[mesh].root_entry;
     }
     c.is_light = c.ref != kNone && !(c.tie_outer >> 31);  // objects carry bit 31 in their outer rank (object beats light, Q31)
     return c.ref != kNone;

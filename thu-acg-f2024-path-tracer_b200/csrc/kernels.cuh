@@ -108,7 +108,7 @@ PT_D void queue_append(const Queues& q, uint32_t cls, uint32_t i) {
 // World::intersect_all for every live path (one ray per thread), then the path joins the queue of its shade class.
 // COUNT (profiling mode only): also sums the traversal work of all rays into work[3] = {node pairs, reference boxes,
 // f64 primitive tests}, from which bench.py derives the bytes the device actually requests per ray.
-template <int MIN_BLOCKS, bool COUNT = false>
+template <int MIN_BLOCKS, bool WIDE, bool COUNT = false>
 __global__ void __launch_bounds__(kBlock, MIN_BLOCKS) k_trace(PathBuf in, uint32_t n, HitRec* __restrict__ hits, Queues q, DScene S,
                                                               unsigned long long* __restrict__ work = nullptr) {
     const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
@@ -116,8 +116,8 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS) k_trace(PathBuf in, uint32
     uint32_t w0 = 0, w1 = 0, w2 = 0;
     if (i < n) {
         Closest c;
-        trace_closest<false, COUNT>(S, [&]() { return load_ray(in, i); }, 1e-3, 0.0, c);  // Interval::new(eps, INFINITY), camera.rs:171,179
-        if (COUNT) { w0 = c.n_pairs; w1 = c.n_refs; w2 = c.n_prims; }
+        trace_closest<false, COUNT, WIDE>(S, [&]() { return load_ray(in, i); }, 1e-3, 0.0, c);  // Interval::new(eps, INFINITY), camera.rs:171,179
+        if (COUNT) { w0 = c.n_pairs + 2 * c.n_wide; w1 = c.n_refs; w2 = c.n_prims; }  // in 64-byte units
         HitRec h; h.t = c.t; h.ref = c.ref; h.inst_light = (c.inst & 0x7FFFFFFFu) | (c.is_light ? 0x80000000u : 0u);
         hits[i] = h;
         cls = c.ref == kNone ? (uint32_t)CLS_MISS : class_of_kind(S.materials[hit_material(S, c.ref)].kind);
@@ -249,14 +249,15 @@ __global__ void k_scale(const float* __restrict__ accum, float scale, uint32_t n
 PT_D pt_vec3 to_abi(d3 v) { pt_vec3 r; r.x = v.x; r.y = v.y; r.z = v.z; return r; }
 PT_D d3 from_abi(pt_vec3 v) { return mk(v.x, v.y, v.z); }
 
+template <bool WIDE>
 __global__ void k_trace_batch(const pt_ray* __restrict__ rays, size_t n, double t_min, pt_hit* __restrict__ out, DScene S) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     RayD r; r.o = from_abi(rays[i].origin); r.d = from_abi(rays[i].direction); r.time = rays[i].time;
     Closest c;
     pt_hit o; memset(&o, 0, sizeof(o)); o.instance = PT_NONE;
-    const bool hit = trace_closest<false, true>(S, [&]() { return r; }, t_min, 0.0, c);
-    o.work = min(c.n_pairs, 0xFFFFu) | (min(c.n_prims, 0xFFFFu) << 16);
+    const bool hit = trace_closest<false, true, WIDE>(S, [&]() { return r; }, t_min, 0.0, c);
+    o.work = min(c.n_pairs + c.n_wide, 0xFFFFu) | (min(c.n_prims, 0xFFFFu) << 16);
     if (hit) {
         HitInfoD h;
         reconstruct_hit(S, r, c.ref, c.inst, c.t, h);
@@ -266,13 +267,14 @@ __global__ void k_trace_batch(const pt_ray* __restrict__ rays, size_t n, double 
     }
     out[i] = o;
 }
+template <bool WIDE>
 __global__ void k_trace_any_batch(const pt_ray* __restrict__ rays, size_t n, double t_min, const double* __restrict__ t_max,
                                   uint8_t* __restrict__ out, DScene S) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     RayD r; r.o = from_abi(rays[i].origin); r.d = from_abi(rays[i].direction); r.time = rays[i].time;
     Closest c;
-    out[i] = trace_closest<true, false>(S, [&]() { return r; }, t_min, t_max[i], c) ? 1 : 0;
+    out[i] = trace_closest<true, false, WIDE>(S, [&]() { return r; }, t_min, t_max[i], c) ? 1 : 0;
 }
 PT_D HitInfoD info_from_query(const pt_bsdf_query& q, uint32_t material) {
     HitInfoD h; h.point = from_abi(q.point); h.gn = from_abi(q.geometric_normal); h.sn = from_abi(q.shading_normal);
