@@ -279,7 +279,7 @@ def main():
                          "avg_launch_ms": dom_ms / max(iters, 1), "launches": iters,
                          "stage_ms_per_step": {"k_generate": gen_ms / args.steps, "k_trace": trace_ms / args.steps, "k_shade": shade_ms / args.steps},
                          "whole_step": {"bytes_per_segment": b_seg, "achieved": step_gbs, "frac": step_gbs / hbm},
-                         "k_trace_device_counters": {"node_pairs_per_segment": d_pairs, "ref_boxes_per_segment": d_refs, "f64_prim_tests_per_segment": d_prims,
+                         "k_trace_device_counters": {"node_fetch_64B_units_per_segment": d_pairs,  # binary pair = 1 unit, 4-wide node = 2 units "ref_boxes_per_segment": d_refs, "f64_prim_tests_per_segment": d_prims,
                                                      "bytes_per_segment": b_trace_dev, "achieved": ach_dev, "frac": ach_dev / hbm,
                                                      "note": "bytes the device actually requests (mostly served by L2, the scene is 4.6 MB)"},
                          "oracle_counters_per_segment": {"boxes": n_node, "spheres": n_sph, "quads": n_quad, "triangles": n_tri}},

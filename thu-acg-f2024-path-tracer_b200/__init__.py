@@ -83,12 +83,15 @@ _dev = None
 _host = None
 
 
+_LIBDIR = os.environ.get("PT_B200_LIBDIR", os.path.join(_HERE, "lib"))  # override: A/B builds while tuning
+
+
 def device_lib_path():
-    return os.path.join(_HERE, "lib", "libptb200.so")
+    return os.path.join(_LIBDIR, "libptb200.so")
 
 
 def host_lib_path():
-    return os.path.join(_HERE, "lib", "libptb200_host.so")
+    return os.path.join(_LIBDIR, "libptb200_host.so")
 
 
 def device_lib():

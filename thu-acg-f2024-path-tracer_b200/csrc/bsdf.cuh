@@ -308,14 +308,17 @@ PT_D void bsdf_eval_pdf_leaf(const DScene& S, const DMaterial& m, d3 view_dir, d
 constexpr int kMixDepth = 8;
 template <int K = -1>
 PT_D bool bsdf_sample(const DScene& S, uint32_t mat, d3 ray_dir, const HitInfoD& h, Rng& rng, d3& out) {
-    if (K >= 0) return bsdf_sample_leaf<K>(S, S.materials[mat], ray_dir, h, rng, out);
-    for (int d = 0; d < kMixDepth; d++) {
-        const DMaterial& m = S.materials[mat];
-        if (m.kind != PT_MAT_MIX) return bsdf_sample_leaf(S, m, ray_dir, h, rng, out);
-        double p = rng.next();
-        mat = (m.p[PT_P_MIX_T] < p) ? m.mix_a : m.mix_b;  // mix.rs:26-31
+    if constexpr (K >= 0) {
+        return bsdf_sample_leaf<K>(S, S.materials[mat], ray_dir, h, rng, out);
+    } else {
+        for (int d = 0; d < kMixDepth; d++) {
+            const DMaterial& m = S.materials[mat];
+            if (m.kind != PT_MAT_MIX) return bsdf_sample_leaf(S, m, ray_dir, h, rng, out);
+            double p = rng.next();
+            mat = (m.p[PT_P_MIX_T] < p) ? m.mix_a : m.mix_b;  // mix.rs:26-31
+        }
+        return false;
     }
-    return false;
 }
 template <int K = -1>
 PT_D void bsdf_eval_pdf(const DScene& S, uint32_t mat, d3 view_dir, d3 light_dir, const HitInfoD& h, d3& f_out, double& pdf_out) {

@@ -14,6 +14,9 @@
 namespace ptd {
 
 constexpr int kBlock = 128;
+#ifndef PT_SHADE_MIN_BLOCKS
+#define PT_SHADE_MIN_BLOCKS 4  // resident blocks per SM the shade kernels must allow (register cap 128)
+#endif
 
 struct PathBuf {
     double* f[10];  // ox oy oz dx dy dz time thr_r thr_g thr_b
@@ -150,7 +153,7 @@ template <> struct ClassKind<CLS_PRINCIPLED> { static constexpr int value = PT_M
 // One loop iteration of Camera::trace after intersect_all (camera.rs:180-225) for the paths of ONE shade class.
 // Grid-stride over the class queue; survivors are written compacted into `out` (ballot + block prefix + one atomic).
 template <int CLS>
-__global__ void __launch_bounds__(kBlock) k_shade(PathBuf in, Queues q, const HitRec* __restrict__ hits, PathBuf out,
+__global__ void __launch_bounds__(kBlock, PT_SHADE_MIN_BLOCKS) k_shade(PathBuf in, Queues q, const HitRec* __restrict__ hits, PathBuf out,
                                                     uint32_t* __restrict__ out_count, float* __restrict__ accum,
                                                     unsigned long long* __restrict__ nonfinite, DScene S, DCameraEx cam, RenderConst rc) {
     constexpr int K = ClassKind<CLS>::value;
