@@ -265,8 +265,8 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "samples_per_s": paths / (ms * 1e-3),
             "config": {"workload": f"scene6_everything_{WIDTH}x{H}", "spp_per_step_per_gpu": args.spp, "max_depth": 50, "parallelism": f"spp-split x{world}",
-                       "pool_paths": args.pool or 4 << 20, "triangles": 16628,
-                       "l2": "per-step path-state working set (2 x 4Mi paths x 112 B ~ 0.9 GB) exceeds the 126 MB L2; the 4.2 MB scene (BVH, primitives, envmap) is L2-resident by design"},
+                       "pool_paths": args.pool or 16 << 20, "triangles": 16628,
+                       "l2": "per-step path-state working set (2 x 16Mi paths x 112 B ~ 3.8 GB) exceeds the 126 MB L2; the 4.6 MB scene (BVH, primitives, envmap) is L2-resident by design"},
             "gpu_launches": int(launches), "segments_per_path": seg_per_path, "nonfinite_samples": int(nonfinite),
             "e2e": {"value": e2e_segs.item() / e2e_s.item() / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(e2e_stats[0][1]) * world,
                     "d2h_bytes_per_step": H * WIDTH * 3 * 4, "ms_per_step": 1e3 * e2e_s.item() / args.steps,

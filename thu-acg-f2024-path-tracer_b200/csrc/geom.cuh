@@ -310,6 +310,9 @@ PT_D void finish_hit(const DScene& S, const RayD& r, d3 point, d3 normal, double
     h.point = point; h.gn = gn; h.sn = sn; h.t = t; h.u = u; h.v = v; h.front_face = ff; h.material = material;
 }
 // Recompute the winning primitive's full HitInfo from (ref, instance, t): same formulas, same rounding as the oracle.
+// FULL_UV = false (shading): a sphere's (u, v) — an f64 acos + atan2 — is skipped when no texture of the hit material
+// reads it (DMaterial::uses_uv, resolved on upload); the parity entry points always compute it.
+template <bool FULL_UV = true>
 PT_D void reconstruct_hit(const DScene& S, const RayD& world_ray, uint32_t ref, uint32_t inst, double t, HitInfoD& h) {
     RayD r = world_ray;
     if (inst != kInstNone) r = instance_local_ray(S.instances[inst], world_ray);
@@ -320,9 +323,13 @@ PT_D void reconstruct_hit(const DScene& S, const RayD& world_ray, uint32_t ref, 
         d3 c = p1 + (p2 - p1) * r.time;
         d3 point = ray_at(r, t);
         d3 normal = normalize(point - c);
-        double theta = acos(-normal.y);
-        double phi = atan2(-normal.z, normal.x) + kPi;
-        finish_hit(S, r, point, normal, t, s.material, phi / (2.0 * kPi), theta / kPi, h);
+        double su = 0.0, sv = 0.0;
+        if (FULL_UV || S.materials[s.material].uses_uv) {  // sphere.rs:52-56
+            double theta = acos(-normal.y);
+            double phi = atan2(-normal.z, normal.x) + kPi;
+            su = phi / (2.0 * kPi); sv = theta / kPi;
+        }
+        finish_hit(S, r, point, normal, t, s.material, su, sv, h);
     } else if (kind == PT_PRIM_QUAD) {  // quad.rs:53-69
         const DQuad& qd = S.quads[index];
         d3 p = ray_at(r, t) - mk(qd.q[0], qd.q[1], qd.q[2]);

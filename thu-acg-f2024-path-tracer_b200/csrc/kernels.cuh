@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(kBlock, PT_SHADE_MIN_BLOCKS) k_shade(PathBuf i
                 const HitRec hr = hits[i];
                 Rng rng; rng.init(rc.seed, pix, ids.y, ids.z & 0xFFFFu);
                 HitInfoD h;
-                reconstruct_hit(S, ray, hr.ref, hr.inst_light & 0x7FFFFFFFu, hr.t, h);
+                reconstruct_hit<false>(S, ray, hr.ref, hr.inst_light & 0x7FFFFFFFu, hr.t, h);
                 const DMaterial& m = S.materials[h.material];
                 // camera.rs:186-187: `radiance += throughput * emitted` runs for every hit; for non-emitters it only
                 // matters when the throughput is already inf/NaN (inf * 0 = NaN poisons the pixel, Q32).
