@@ -175,7 +175,9 @@ typedef struct {
 /* ---- render control --------------------------------------------------------------- */
 /* flags bits 4-6: k_trace register-cap variant (0 = default 80 regs; 4: 120, 5: 96, 7: 64) — tuning knob */
 enum { PT_NAN_REFERENCE = 0, /* non-finite samples poison the pixel like camera.rs:129 */
-       PT_NAN_DROP = 1 };    /* drop + count non-finite samples (documented divergence) */
+       PT_NAN_DROP = 1 };    /* documented divergence: a non-finite contribution is skipped and a non-finite
+                                throughput ends the path (each counted once in pt_stats.nonfinite); finite
+                                contributions that sample made earlier — e.g. a directly seen light — stay */
 typedef struct {
     uint64_t seed;
     uint32_t sample_begin;   /* first sample index of this call (per pixel) */
@@ -273,9 +275,9 @@ int  pt_bsdf_sample(pt_ctx* ctx, const pt_scene* scene, uint32_t material, size_
 int  pt_camera_rays(pt_ctx* ctx, const pt_camera* cam, uint64_t seed, size_t n,
                     const uint32_t* row, const uint32_t* col, const uint32_t* sample,
                     pt_ray* out);
-/* World.lights.{sample,pdf} (list.rs:78-96): sample uses 3 uniforms per query. */
+/* World.lights.{sample,pdf} (list.rs:78-96): sample uses up to 4 uniforms per query (light pick, side/triangle pick, 2 on the surface). */
 int  pt_lights_sample_pdf(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_vec3* origin,
-                          const double* time, const double* uniforms3, pt_vec3* dir,
+                          const double* time, const double* uniforms4, pt_vec3* dir,
                           uint32_t* valid, double* pdf);
 
 #ifdef __cplusplus

@@ -60,7 +60,11 @@ struct Camera {
         return Ray::make(origin, direction, time);
     }
     // camera.rs:170-228.  `record`, when non-null, receives every ray handed to intersect_all.
-    Vec3 trace(uint32_t r, uint32_t c, const World& world, Rng& rng, std::vector<Ray>* record = nullptr) const {
+    // `dropped`, when non-null, selects PT_NAN_DROP (include/pt_b200.h; NOT reference behaviour): a non-finite
+    // contribution is skipped and a non-finite throughput ends the path, each counted once in *dropped; finite
+    // contributions the sample made before that stay.  With dropped == nullptr this is the reference's loop verbatim.
+    Vec3 trace(uint32_t r, uint32_t c, const World& world, Rng& rng, std::vector<Ray>* record = nullptr, uint64_t* dropped = nullptr) const {
+        auto fin3 = [](const Vec3& v) { return std::isfinite(v.x) && std::isfinite(v.y) && std::isfinite(v.z); };
         const double eps = 1e-3;
         const uint32_t min_bounces = 5;
         Vec3 radiance(0, 0, 0), throughput(1, 1, 1);
@@ -70,11 +74,14 @@ struct Camera {
             if (record) record->push_back(ray);
             auto hit = world.intersect_all(ray, Interval{eps, INF});
             if (!hit) {
-                radiance += throughput * sample_environment(ray);
+                Vec3 env = throughput * sample_environment(ray);
+                if (dropped && !fin3(env)) { ++*dropped; break; }
+                radiance += env;
                 break;
             }
             const HitInfo& info = hit->first;
             Vec3 emission = info.mat->emitted(info.u, info.v, info.point);
+            if (dropped && !fin3(throughput * emission)) { ++*dropped; break; }
             radiance += throughput * emission;
             if (bounces > min_bounces) {  // Russian roulette, camera.rs:190-196
                 double p = clamp_(luminance(throughput), 0.01, 1.0);
@@ -96,6 +103,7 @@ struct Camera {
             double e = 1e-3 * signum_(dot(*dir, info.geometric_normal));  // bsdf::EPS, camera.rs:217
             Ray next = Ray::make(info.point + e * info.geometric_normal, *dir, ray.time);
             throughput *= attenuation;
+            if (dropped && !fin3(throughput)) { ++*dropped; break; }
             ray = next;
         }
         return radiance;

@@ -293,10 +293,10 @@ int orc_bsdf_sample(const orc_scene* s, uint32_t material, size_t n, const pt_bs
     }
     return 0;
 }
-int orc_lights_sample_pdf(const orc_scene* s, size_t n, const pt_vec3* origin, const double* time, const double* uniforms3,
+int orc_lights_sample_pdf(const orc_scene* s, size_t n, const pt_vec3* origin, const double* time, const double* uniforms4,
                           pt_vec3* dir, uint32_t* valid, double* pdf) {
     for (size_t i = 0; i < n; i++) {
-        Rng rng; rng.arr = uniforms3 + 3 * i; rng.arr_n = 3;
+        Rng rng; rng.arr = uniforms4 + 4 * i; rng.arr_n = 4;
         auto d = s->world.lights.sample(V(origin[i]), time[i], rng);
         valid[i] = d.has_value(); dir[i] = d ? P(*d) : pt_vec3{0, 0, 0};
         pdf[i] = d ? s->world.lights.pdf(V(origin[i]), *d, time[i]) : 0.0;
@@ -325,9 +325,9 @@ int orc_render(const orc_scene* s, const pt_camera* c, const pt_render_params* p
             Vec3 color(0, 0, 0);
             for (uint32_t k = 0; k < p->sample_count; k++) {
                 Rng rng; rng.seed = p->seed; rng.pixel = (uint32_t)px; rng.sample = p->sample_begin + k * p->sample_stride;
-                Vec3 rad = cam.trace(r, col, s->world, rng);
+                Vec3 rad = cam.trace(r, col, s->world, rng, nullptr, p->nan_policy == PT_NAN_DROP ? &nf : nullptr);
                 bool fin = std::isfinite(rad.x) && std::isfinite(rad.y) && std::isfinite(rad.z);
-                if (!fin) { nf++; if (p->nan_policy == PT_NAN_DROP) continue; }
+                if (!fin) nf++;  // PT_NAN_REFERENCE only: the sample poisons its pixel (camera.rs:129)
                 color += rad;
             }
             color *= 1.0 / (double)p->sample_count;

@@ -193,6 +193,54 @@ def test_oracle_specular_samplers_are_consistent(pt, orc, material, expect_unifo
     ora.close()
 
 
+def mixed_lights_world(pt, width=48):
+    """Every Hittable kind in World.lights: sphere, quad, cuboid (cuboid.rs:74-80), triangle mesh (mesh.rs:213-219),
+    and instances of a quad, a cuboid and a mesh (instance.rs:64-75), over a diffuse floor and a glossy ball."""
+    rng = np.random.default_rng(12)
+    pos = np.array([[-0.5, 0, -0.5], [0.5, 0, -0.5], [0.5, 0, 0.5], [-0.5, 0, 0.5], [0, 0.6, 0]], dtype=np.float32)
+    idx = np.array([[0, 1, 4], [1, 2, 4], [2, 3, 4], [3, 0, 4], [0, 2, 1], [0, 3, 2]], dtype=np.uint32)
+    nrm = (pos + rng.normal(scale=0.05, size=pos.shape)).astype(np.float32)
+    glow = [pt.DiffuseLight(c) for c in ((4, 4, 4), (3, 2, 1), (1, 2, 3), (2, 3, 1), (3, 1, 2), (1, 3, 3), (2, 2, 4))]
+    w = pt.World()
+    w.add_light(pt.Sphere.new_still(0.4, (-2.5, 2.5, 0), glow[0]))
+    w.add_light(pt.Quad((-0.5, 3.5, -0.5), (1, 0, 0), (0, 0, 1), glow[1]))
+    w.add_light(pt.Cuboid((1.8, 2.0, -0.4), (2.6, 2.5, 0.4), glow[2]))
+    w.add_light(pt.TriangleMesh.from_arrays(0.8, pos + np.float32([-1.2, 2.4, 1.0]), idx, glow[3], None, nrm))
+    w.add_light(pt.Instance(pt.Quad((-0.4, 0, -0.4), (0.8, 0, 0), (0, 0, 0.8), glow[4]), (1, 0.2, 0), 0.6, (1.0, 2.8, 1.4)))
+    w.add_light(pt.Instance(pt.Cuboid((-0.3, -0.2, -0.3), (0.3, 0.2, 0.3), glow[5]), (0, 1, 0.3), 1.1, (-1.5, 2.0, -1.6)))
+    w.add_light(pt.Instance(pt.TriangleMesh.from_arrays(0.7, pos, idx, glow[6]), (0.3, 0.1, 1), -0.8, (0.9, 2.2, -1.5)))
+    w.add_object(pt.Quad((-6, 0, -6), (12, 0, 0), (0, 0, 12), pt.DiffuseBRDF((0.6, 0.6, 0.6))))
+    w.add_object(pt.Sphere.new_still(0.7, (0, 0.7, 0), pt.MetalBRDF((0.9, 0.8, 0.7), 0.3)))
+    w.build_bvh()
+    cam = pt.make_camera(width, aspect_ratio=1.0, samples_per_pixel=4, max_depth=8, vfov=55.0, look_from=(0, 2.2, 7.5), look_at=(0, 1.6, 0))
+    return pt.Scene.from_world(w, cam)
+
+
+def test_oracle_every_light_kind_samples_what_its_pdf_sees(pt, orc):
+    """list.rs:78-96 over sphere / quad / cuboid / mesh / instance lights: a sampled direction hits the light it was
+    drawn from, so the mixture pdf along it is positive; uniform consumption is 3 (sphere, quad) or 4 (lists inside)."""
+    scene = mixed_lights_world(pt)
+    ora = orc.OracleScene(scene.desc, pt)
+    rng = np.random.default_rng(13)
+    n = 6000
+    o = rng.uniform(-2, 2, size=(n, 3)) * [1, 0.1, 1] + [0, 0.5, 0]
+    t = np.zeros(n); u = rng.uniform(size=(n, 4))
+    d, valid, pdf = ora.lights_sample_pdf(o, t, u)
+    pick = np.minimum((u[:, 0] * 7).astype(int), 6)
+    # instance.rs:21 feeds the caller's axis to Quat::from_axis_angle un-normalised, so instanced lights return
+    # directions scaled by the (non-unit) quaternion — kept as the reference has it
+    assert valid.all() and np.allclose(np.linalg.norm(d[pick < 4], axis=1), 1.0, atol=1e-12)
+    for k in range(7):
+        sel = pick == k
+        # mesh.rs:122-129 samples outside the triangle when a + b > 1 (kept as the reference has it): those may miss
+        floor = 0.45 if k in (3, 6) else 0.98
+        assert sel.sum() > 500 and (pdf[sel] > 0).mean() > floor, f"light {k}: {(pdf[sel] > 0).mean():.3f}"
+    u2 = u.copy(); u2[:, 3] = rng.uniform(size=n)               # sphere and quad picks never read the 4th uniform
+    d2, _, _ = ora.lights_sample_pdf(o, t, u2)
+    assert np.array_equal(d[pick < 2], d2[pick < 2]) and not np.array_equal(d[pick >= 2], d2[pick >= 2])
+    ora.close()
+
+
 def test_oracle_sample_split_is_exact(pt, orc):
     """spp split across G virtual ranks (sample index = g + k*G) reproduces the 1-rank sum."""
     scene = pt.Scene.build(3, width=24, spp=8, seed=1)

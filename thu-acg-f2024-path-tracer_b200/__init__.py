@@ -460,11 +460,11 @@ class DeviceScene:
         self.ctx._check(self.ctx.lib.pt_bsdf_sample(self.ctx.ptr, self.ptr, material, q.shape[0], _ptr(q), _ptr(u), _ptr(out)))
         return out
 
-    def lights_sample_pdf(self, origins, times, uniforms3):
+    def lights_sample_pdf(self, origins, times, uniforms4):
         o = np.ascontiguousarray(origins, dtype=np.float64).reshape(-1, 3)
         n = o.shape[0]
         t = np.ascontiguousarray(times, dtype=np.float64)
-        u = np.ascontiguousarray(uniforms3, dtype=np.float64).reshape(n, 3)
+        u = np.ascontiguousarray(uniforms4, dtype=np.float64).reshape(n, 4)
         d, valid, pdf = np.zeros((n, 3)), np.zeros(n, np.uint32), np.zeros(n)
         self.ctx._check(self.ctx.lib.pt_lights_sample_pdf(self.ctx.ptr, self.ptr, n, _ptr(o), _ptr(t), _ptr(u), _ptr(d), _ptr(valid), _ptr(pdf)))
         return d, valid, pdf

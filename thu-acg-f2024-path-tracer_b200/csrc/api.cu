@@ -321,9 +321,6 @@ static int check_desc(const pt_scene_desc* d) {
         pt_ref c = d->instances[i].child;
         if (c.kind == PT_OBJ_INSTANCE || c.kind == PT_PRIM_TRIANGLE || !ref_ok(c, false)) return fail(PT_ERR_UNSUPPORTED, "instance child must be a sphere, quad, cuboid or mesh");
     }
-    for (uint32_t i = 0; i < d->n_lights; i++)
-        if (d->lights[i].kind != PT_PRIM_QUAD && d->lights[i].kind != PT_PRIM_SPHERE)
-            return fail(PT_ERR_UNSUPPORTED, "World.lights may hold quads and spheres only on the device (sample/pdf subset)");
     for (uint32_t i = 0; i < d->n_materials; i++) {
         const pt_material& m = d->materials[i];
         auto tex_ok = [&](uint32_t t) { return t < d->n_textures; };
@@ -495,13 +492,20 @@ int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
                                 : m.kind == PT_MAT_GLASS ? CLS_GLASS : m.kind == PT_MAT_PRINCIPLED ? CLS_PRINCIPLED : CLS_OTHER);
     }
     std::vector<DRef> lights(d->n_lights);
-    for (uint32_t i = 0; i < d->n_lights; i++) lights[i] = DRef{ref_pack(d->lights[i].kind, d->lights[i].index), 0};
+    bool mesh_light = false;  // Triangle::sample needs the original vertices (mesh.rs:126), which the traversal layout does not keep
+    for (uint32_t i = 0; i < d->n_lights; i++) {
+        lights[i] = DRef{ref_pack(d->lights[i].kind, d->lights[i].index), 0};
+        const pt_ref r = d->lights[i].kind == PT_OBJ_INSTANCE ? d->instances[d->lights[i].index].child : d->lights[i];
+        mesh_light |= r.kind == PT_OBJ_MESH;
+    }
+    std::vector<double> tri_verts;
+    if (mesh_light) { tri_verts.resize(9ull * d->n_triangles); memcpy(tri_verts.data(), d->triangles, tri_verts.size() * sizeof(double)); }
 
     DScene& D = s->d;
     U.up(C.wide, &D.wide); U.up(C.nodes, &D.nodes); U.up(C.refs, &D.refs); U.up(spheres, &D.spheres); U.up(quads, &D.quads); U.up(quad_mat, &D.quad_material);
     U.up(tris, &D.tris); U.up(tri_normals, &D.tri_normals); U.up(tri_uvs, &D.tri_uvs); U.up(tri_mesh, &D.tri_mesh); U.up(cuboids, &D.cuboids);
     U.up(meshes, &D.meshes); U.up(instances, &D.instances); U.up(textures, &D.textures); U.up(images, &D.images); U.up(materials, &D.materials);
-    U.up(lights, &D.lights);
+    U.up(lights, &D.lights); U.up(tri_verts, &D.tri_verts);
     if ((rc = U.commit())) return rc;
     D.image_data = d_img; D.n_lights = d->n_lights; D.root_entry = world_root;
     s->n_materials = d->n_materials; s->n_images = d->n_images; s->images = images;
@@ -750,12 +754,12 @@ int pt_camera_rays(pt_ctx* ctx, const pt_camera* cam, uint64_t seed, size_t n, c
     k_camera_rays<<<grid_for(n), 128, 0, ctx->stream>>>(dcam, seed, n, (const uint32_t*)r.p, (const uint32_t*)cc.p, (const uint32_t*)s.p, (pt_ray*)out.p);
     return out.to_host(o, n * sizeof(pt_ray), ctx->stream);
 }
-int pt_lights_sample_pdf(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_vec3* origin, const double* time, const double* uniforms3, pt_vec3* dir, uint32_t* valid, double* pdf) {
-    if (!ctx || !scene || (n && (!origin || !time || !uniforms3 || !dir || !valid || !pdf))) return fail(PT_ERR_INVALID, "pt_lights_sample_pdf: null argument");
+int pt_lights_sample_pdf(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_vec3* origin, const double* time, const double* uniforms4, pt_vec3* dir, uint32_t* valid, double* pdf) {
+    if (!ctx || !scene || (n && (!origin || !time || !uniforms4 || !dir || !valid || !pdf))) return fail(PT_ERR_INVALID, "pt_lights_sample_pdf: null argument");
     if (n == 0) return PT_OK;
     CU(cudaSetDevice(ctx->device));
     DevBuf o, t, u, dd, vv, pp; int rc;
-    if ((rc = o.from_host(origin, n * 24, ctx->stream)) || (rc = t.from_host(time, n * 8, ctx->stream)) || (rc = u.from_host(uniforms3, n * 24, ctx->stream)) ||
+    if ((rc = o.from_host(origin, n * 24, ctx->stream)) || (rc = t.from_host(time, n * 8, ctx->stream)) || (rc = u.from_host(uniforms4, n * 32, ctx->stream)) ||
         (rc = dd.alloc(n * 24)) || (rc = vv.alloc(n * 4)) || (rc = pp.alloc(n * 8))) return rc;
     k_lights<<<grid_for(n), 128, 0, ctx->stream>>>(n, (const pt_vec3*)o.p, (const double*)t.p, (const double*)u.p, (pt_vec3*)dd.p, (uint32_t*)vv.p, (double*)pp.p, scene->d);
     if ((rc = dd.to_host(dir, n * 24, ctx->stream)) || (rc = vv.to_host(valid, n * 4, ctx->stream)) || (rc = pp.to_host(pdf, n * 8, ctx->stream))) return rc;

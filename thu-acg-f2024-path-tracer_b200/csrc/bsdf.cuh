@@ -351,16 +351,21 @@ PT_D d3 bsdf_emitted(const DScene& S, uint32_t mat, double u, double v, d3 p) { 
 }
 
 // ---------------------------------------------------------------- World.lights.{sample,pdf} (list.rs:78-96)
-PT_D bool light_sample_one(const DScene& S, DRef rf, d3 origin, double time, Rng& rng, d3& dir) {
-    const uint32_t kind = ref_kind(rf.kind_index), index = ref_index(rf.kind_index);
-    if (kind == PT_PRIM_QUAD) {  // quad.rs:80-86
+// Hittable::sample for one non-instance object (sphere.rs:110-121, quad.rs:80-86, cuboid.rs:74-76 -> list.rs:78-84,
+// mesh.rs:122-129,213-215).  Uniform picks follow the RNG contract: index = min(floor(U*n), n-1).
+PT_D bool light_sample_object(const DScene& S, uint32_t kind, uint32_t index, d3 origin, double time, Rng& rng, d3& dir) {
+    if (kind == PT_OBJ_CUBOID) {  // sides.sample: one of the six quads
+        uint32_t i = (uint32_t)(rng.next() * 6.0); if (i > 5) i = 5;
+        kind = PT_PRIM_QUAD; index = S.cuboids[index].first_quad + i;
+    }
+    if (kind == PT_PRIM_QUAD) {
         const DQuad& q = S.quads[index];
         double a = rng.next(), b = rng.next();
         d3 point = mk(q.q[0], q.q[1], q.q[2]) + mk(q.u[0], q.u[1], q.u[2]) * a + mk(q.v[0], q.v[1], q.v[2]) * b;
         dir = normalize(point - origin);
         return true;
     }
-    if (kind == PT_PRIM_SPHERE) {  // sphere.rs:110-121
+    if (kind == PT_PRIM_SPHERE) {
         const DSphere& s = S.spheres[index];
         double u = rng.next(), v = rng.next();
         double theta = 2.0 * kPi * u;
@@ -371,12 +376,23 @@ PT_D bool light_sample_one(const DScene& S, DRef rf, d3 origin, double time, Rng
         dir = normalize(point - origin);
         return true;
     }
+    if (kind == PT_OBJ_MESH) {  // triangles.sample: a uniformly chosen triangle, then mesh.rs:122-129
+        const DMesh& m = S.meshes[index];
+        if (m.n_tri == 0 || !S.tri_verts) return false;
+        uint32_t i = (uint32_t)(rng.next() * (double)m.n_tri); if (i >= m.n_tri) i = m.n_tri - 1;
+        const double* tv = S.tri_verts + 9ull * (m.first_tri + i);
+        double u = rng.next(), v = rng.next();
+        double w = 1.0 - u - v;  // not area-uniform (w may be negative): kept as the reference has it
+        d3 point = mk(tv[0], tv[1], tv[2]) * w + mk(tv[3], tv[4], tv[5]) * u + mk(tv[6], tv[7], tv[8]) * v;
+        dir = normalize(point - origin);
+        return true;
+    }
     return false;
 }
-PT_D double light_pdf_one(const DScene& S, DRef rf, d3 origin, d3 direction, double time) {
-    const uint32_t kind = ref_kind(rf.kind_index), index = ref_index(rf.kind_index);
-    RayD ray = make_ray(origin, direction, time);  // Ray::new re-normalises (quad.rs:89, sphere.rs:125)
-    if (kind == PT_PRIM_QUAD) {  // quad.rs:88-98
+// Hittable::pdf for one non-instance object (sphere.rs:123-135, quad.rs:88-98, mesh.rs:131-141; lists average, list.rs:86-96).
+PT_D double light_pdf_prim(const DScene& S, uint32_t kind, uint32_t index, d3 origin, d3 direction, double time) {
+    RayD ray = make_ray(origin, direction, time);  // Ray::new re-normalises (quad.rs:89, sphere.rs:125, mesh.rs:132)
+    if (kind == PT_PRIM_QUAD) {
         const DQuad& q = S.quads[index];
         double t, a, b;
         if (!quad_t(q, ray, 0.0, t, a, b)) return 0.0;
@@ -386,7 +402,7 @@ PT_D double light_pdf_one(const DScene& S, DRef rf, d3 origin, d3 direction, dou
         double cos_theta = fabs(dot(ray.d, h.sn));  // shading normal (Q9)
         return (t * t) / (cos_theta * area);
     }
-    if (kind == PT_PRIM_SPHERE) {  // sphere.rs:123-135
+    if (kind == PT_PRIM_SPHERE) {
         const DSphere& s = S.spheres[index];
         double t;
         if (!sphere_t(s, ray, 0.0, t) || !(t < __longlong_as_double(0x7ff0000000000000ll))) return 0.0;
@@ -398,7 +414,48 @@ PT_D double light_pdf_one(const DScene& S, DRef rf, d3 origin, d3 direction, dou
         double solid_angle = 2.0 * kPi * sqrt(1.0 - r2 / dot(dc, dc));
         return 1.0 / solid_angle;
     }
+    if (kind == PT_PRIM_TRIANGLE) {
+        const DTri& tr = S.tris[index];
+        double t, u, v;
+        if (!tri_t(tr, ray, 0.0, t, u, v)) return 0.0;
+        HitInfoD h;
+        reconstruct_hit<true>(S, ray, ref_pack(PT_PRIM_TRIANGLE, index), kInstNone, t, h);
+        double area = 0.5 * length(cross(mk(tr.e1[0], tr.e1[1], tr.e1[2]), mk(tr.e2[0], tr.e2[1], tr.e2[2])));  // mesh.rs:42-46
+        double cos_theta = fabs(dot(direction, h.sn));  // the un-normalised `direction` (mesh.rs:136)
+        return t * t / (cos_theta * area);
+    }
     return 0.0;
+}
+PT_D double light_pdf_object(const DScene& S, uint32_t kind, uint32_t index, d3 origin, d3 direction, double time) {
+    if (kind == PT_OBJ_CUBOID) {
+        const uint32_t fq = S.cuboids[index].first_quad;
+        double s = 0.0;
+        for (uint32_t k = 0; k < 6; k++) s += light_pdf_prim(S, PT_PRIM_QUAD, fq + k, origin, direction, time);
+        return s / 6.0;
+    }
+    if (kind == PT_OBJ_MESH) {  // O(triangles) per evaluation, exactly like the reference's list average
+        const DMesh& m = S.meshes[index];
+        if (m.n_tri == 0) return 0.0;
+        double s = 0.0;
+        for (uint32_t k = 0; k < m.n_tri; k++) s += light_pdf_prim(S, PT_PRIM_TRIANGLE, m.first_tri + k, origin, direction, time);
+        return s / (double)m.n_tri;
+    }
+    return light_pdf_prim(S, kind, index, origin, direction, time);
+}
+PT_D bool light_sample_one(const DScene& S, DRef rf, d3 origin, double time, Rng& rng, d3& dir) {
+    const uint32_t kind = ref_kind(rf.kind_index), index = ref_index(rf.kind_index);
+    if (kind != PT_OBJ_INSTANCE) return light_sample_object(S, kind, index, origin, time, rng, dir);
+    const DInstance& in = S.instances[index];  // instance.rs:64-69
+    d3 local;
+    if (!light_sample_object(S, in.child_kind, in.child_index, xform_point(in.inv, origin), time, rng, local)) return false;
+    dir = xform_vector(in.fwd, local);
+    return true;
+}
+PT_D double light_pdf_one(const DScene& S, DRef rf, d3 origin, d3 direction, double time) {
+    const uint32_t kind = ref_kind(rf.kind_index), index = ref_index(rf.kind_index);
+    if (kind != PT_OBJ_INSTANCE) return light_pdf_object(S, kind, index, origin, direction, time);
+    const DInstance& in = S.instances[index];  // instance.rs:71-75
+    return light_pdf_object(S, in.child_kind, in.child_index, xform_point(in.inv, origin), xform_vector(in.inv, direction), time);
 }
 PT_D bool lights_sample(const DScene& S, d3 origin, double time, Rng& rng, d3& dir) {  // list.rs:78-84
     if (S.n_lights == 0) return false;

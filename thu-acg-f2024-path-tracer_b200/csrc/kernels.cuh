@@ -313,11 +313,11 @@ __global__ void k_camera_rays(DCameraEx cam, uint64_t seed, size_t n, const uint
     pt_ray o; o.origin = to_abi(r.o); o.direction = to_abi(r.d); o.time = r.time;
     out[i] = o;
 }
-__global__ void k_lights(size_t n, const pt_vec3* __restrict__ origin, const double* __restrict__ time, const double* __restrict__ uniforms3,
+__global__ void k_lights(size_t n, const pt_vec3* __restrict__ origin, const double* __restrict__ time, const double* __restrict__ uniforms4,
                          pt_vec3* __restrict__ dir, uint32_t* __restrict__ valid, double* __restrict__ pdf, DScene S) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    Rng rng; rng.init_array(uniforms3 + 3 * i, 3);
+    Rng rng; rng.init_array(uniforms4 + 4 * i, 4);
     d3 d = mk(0, 0, 0);
     bool ok = lights_sample(S, from_abi(origin[i]), time[i], rng, d);
     valid[i] = ok; dir[i] = to_abi(ok ? d : mk(0, 0, 0));
