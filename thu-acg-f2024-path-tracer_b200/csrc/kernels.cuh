@@ -128,6 +128,9 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS) k_trace(PathBuf in, uint32
     __syncwarp();
     queue_append(q, cls, i);
     if (COUNT) {
+#ifdef PT_DIAG_WARP  // diagnostic build: ref_boxes := sum of per-ray cost, prim_tests := sum of the warp's maximum cost per lane
+        w1 = 3 * w0 + w1 + 4 * w2 + 1; w2 = __reduce_max_sync(0xFFFFFFFFu, w1);
+#endif
         w0 = __reduce_add_sync(0xFFFFFFFFu, w0); w1 = __reduce_add_sync(0xFFFFFFFFu, w1); w2 = __reduce_add_sync(0xFFFFFFFFu, w2);
         if ((threadIdx.x & 31) == 0) { atomicAdd(work, (unsigned long long)w0); atomicAdd(work + 1, (unsigned long long)w1); atomicAdd(work + 2, (unsigned long long)w2); }
     }

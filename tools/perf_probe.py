@@ -27,7 +27,9 @@ def main():
             print(f"scene {sid} {width}x{st.height} spp {spp} pool {pool or 'default'} flags {flags} prof={prof}:build {tb:.2f}s upload {tu * 1e3:.1f} ms ({dev.device_bytes / 1e6:.1f} MB) | "
                   f"device {st.device_ms:.1f} ms wall {tw * 1e3:.1f} ms | {st.segments / st.device_ms / 1e3:.1f} Mrays/s {st.paths / st.device_ms * 1e3:.3e} samples/s | "
                   f"seg/path {st.segments / st.paths:.2f} iters {st.iterations} launches {st.kernel_launches} nonfinite {st.nonfinite} | "
-                  f"gen {st.raygen_ms:.1f} trace {st.trace_ms:.1f} shade {st.shade_ms:.1f} ms", flush=True)
+                  f"gen {st.raygen_ms:.1f} trace {st.trace_ms:.1f} shade {st.shade_ms:.1f} ms"
+                  + (f" | per ray: {st.node_pairs / st.segments:.2f} x64B nodes, {st.ref_boxes / st.segments:.2f} ref boxes, {st.prim_tests / st.segments:.2f} f64 tests"
+                     if prof else ""), flush=True)
         dev.close()
     ctx.close()
 
