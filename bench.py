@@ -25,7 +25,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as ge  # noqa: E402
 
-SCENE, WIDTH = 6, 1920
+SCENE, WIDTH = 6, 1920   # the headline workload; --scene / --width select the other BASELINE.json configs
+SCENE_NAMES = {3: "scene3_cornell_box", 1: "scene1_bouncing_balls", 5: "scene5_principled_grid_envmap", 7: "scene7_normal_mapped_cornell",
+               70: "scene7m_cornell_bunny_teapot", 6: "scene6_everything", 2: "scene2_earth", 4: "scene4_lights"}
 # device structs (csrc/device_scene.cuh, csrc/kernels.cuh): bytes one segment moves through HBM per stage
 B_RAY, B_HIT, B_STATE = 56, 16, 96   # ray (o,d,time f64), HitRec, full path state (ray + throughput f64x3 + ids uint4)
 B_NODE, B_REF, B_SPHERE, B_QUAD, B_TRI = 32, 32, 64, 128, 80
@@ -82,12 +84,17 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def oracle_sample(pt, orc, scene, spp, threads=0):
-    """The reference algorithm (C++ restatement, oracle/) on the host CPU over a bounded sample of the workload."""
+def oracle_sample(pt, orc, scene, seconds, threads=0):
+    """The reference algorithm (C++ restatement, oracle/) on the host CPU over a bounded sample of the workload: one
+    sample per pixel to learn the speed, then as many as fit in about `seconds` (at most 64), timed in one call."""
     ora = orc.OracleScene(scene.desc, pt)
-    _, st = ora.render(scene.camera, spp, seed=1, nan_policy=pt.PT_NAN_DROP, threads=threads or host_threads())
+    threads = threads or host_threads()
+    _, st = ora.render(scene.camera, 1, seed=1, nan_policy=pt.PT_NAN_DROP, threads=threads)
+    spp = int(max(1, min(64, seconds / max(st.seconds, 1e-3))))
+    if spp > 1:
+        _, st = ora.render(scene.camera, spp, seed=2, nan_policy=pt.PT_NAN_DROP, threads=threads)
     ora.close()
-    return st
+    return st, spp
 
 
 def host_threads():
@@ -105,7 +112,8 @@ def run_reference(args):
     if rank != 0:
         return
     pt, orc = ge.load_package(), ge.load_oracle()
-    scene = pt.Scene.build(SCENE, width=WIDTH, spp=args.ref_spp, seed=1)
+    scene = pt.Scene.build(args.scene, width=args.width, spp=args.ref_spp, seed=1)
+    H = scene.image_height()
     ora = orc.OracleScene(scene.desc, pt)
     times, segs, paths = [], 0, 0
     for i in range(args.warmup + args.steps):
@@ -118,8 +126,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "Mrays/s", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "samples_per_s": paths / total,
-            "config": {"workload": f"scene6_everything_{WIDTH}x1080", "spp_per_step": args.ref_spp, "max_depth": 50, "note": "C++ restatement of the reference (oracle/), not the Rust binary"},
-            "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": f"{WIDTH}x1080 x {args.ref_spp} spp per step, {args.steps} steps"},
+            "config": {"workload": f"{SCENE_NAMES.get(args.scene, args.scene)}_{args.width}x{H}", "spp_per_step": args.ref_spp, "max_depth": 50,
+                       "note": "C++ restatement of the reference (oracle/), not the Rust binary"},
+            "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": f"{args.width}x{H} x {args.ref_spp} spp per step, {args.steps} steps"},
             "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -131,10 +140,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--spp", type=int, default=128, help="samples per pixel per rank per step")
-    ap.add_argument("--ref-spp", type=int, default=1, help="samples per pixel per step of the CPU reference arm")
+    ap.add_argument("--ref-spp", type=int, default=4, help="samples per pixel per step of the CPU reference arm")
     ap.add_argument("--pool", type=int, default=0, help="in-flight path pool (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scene", type=int, default=SCENE, help="reference scene id (main.rs -s N; 70 = scene 7 + bunny + teapot)")
+    ap.add_argument("--width", type=int, default=0, help="image width (default: 1920 for scene 6 like `-q`, else the reference's 600)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work of the cpu_baseline sample")
     args = ap.parse_args()
+    args.width = args.width or (1920 if args.scene == SCENE else 600)
     if args.impl == "reference":
         return run_reference(args)
     assert args.warmup >= 3 or os.environ.get("PT_BENCH_ALLOW_SHORT"), "timing rules: at least 3 warm-up steps"
@@ -150,7 +163,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    scene = pt.Scene.build(SCENE, width=WIDTH, spp=args.spp, seed=1)
+    WIDTH = args.width
+    scene = pt.Scene.build(args.scene, width=WIDTH, spp=args.spp, seed=1)
     cam = scene.camera
     H = scene.image_height()
     ctx = pt.Context(local)
@@ -236,14 +250,15 @@ def main():
         # ---- CPU baseline on the box's host cores (bounded sample) + the oracle's work counters for the algorithmic bytes
         cpu = None
         n_node = n_sph = n_quad = n_tri = None
+        orc = ge.load_oracle()
         if not args.no_cpu_baseline and world == 1:  # the CPU baseline leg runs on rank 0 at N=1 only
-            orc = ge.load_oracle()
-            ost = oracle_sample(pt, orc, scene, 2)
+            ost, cpu_spp = oracle_sample(pt, orc, scene, args.cpu_seconds)
             cpu = {"value": ost.segments / ost.seconds / 1e6, "unit": "Mrays/s", "cores": ost.threads, "kind": "port",
-                   "sample": f"{WIDTH}x{H} x 2 spp of the same scene ({ost.paths} paths, {ost.seconds:.1f} s)", "samples_per_s": ost.paths / ost.seconds}
-            n_node, n_sph, n_quad, n_tri = (getattr(ost, k) / ost.segments for k in ("boxes", "spheres", "quads", "triangles"))
-        else:  # counters measured by the oracle on this scene, used when the CPU leg is skipped
-            n_node, n_sph, n_quad, n_tri = 28.9, 2.84, 2.55, 2.2
+                   "sample": f"{WIDTH}x{H} x {cpu_spp} spp of the same scene ({ost.paths} paths, {ost.seconds:.1f} s)", "samples_per_s": ost.paths / ost.seconds}
+        else:  # no timed CPU leg: the oracle only counts the reference's work per segment, on a small image of the same scene
+            small = pt.Scene.build(args.scene, width=min(WIDTH, 240), spp=1, seed=1)
+            ost, _ = oracle_sample(pt, orc, small, 0.0)
+        n_node, n_sph, n_quad, n_tri = (getattr(ost, k) / ost.segments for k in ("boxes", "spheres", "quads", "triangles"))
         seg_per_path = segs_rank / max(paths_rank, 1)
         surv = 1.0 - 1.0 / seg_per_path                     # fraction of segments whose path continues
         b_trace = B_RAY + B_HIT + n_node * B_NODE + n_sph * B_SPHERE + n_quad * B_QUAD + n_tri * B_TRI + (n_sph + n_quad + n_tri) * B_REF
@@ -264,24 +279,26 @@ def main():
             "metric": "Mrays/s", "value": segs / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "samples_per_s": paths / (ms * 1e-3),
-            "config": {"workload": f"scene6_everything_{WIDTH}x{H}", "spp_per_step_per_gpu": args.spp, "max_depth": 50, "parallelism": f"spp-split x{world}",
-                       "pool_paths": args.pool or 16 << 20, "triangles": 16628,
-                       "l2": "per-step path-state working set (2 x 16Mi paths x 112 B ~ 3.8 GB) exceeds the 126 MB L2; the 4.6 MB scene (BVH, primitives, envmap) is L2-resident by design"},
+            "config": {"workload": f"{SCENE_NAMES.get(args.scene, args.scene)}_{WIDTH}x{H}", "spp_per_step_per_gpu": args.spp, "max_depth": cam.max_depth,
+                       "parallelism": f"spp-split x{world}", "pool_paths": args.pool or 16 << 20, "scene_device_bytes": int(dev.device_bytes),
+                       "l2": f"per-step path-state working set (2 x min(16Mi, {WIDTH * H * args.spp}) paths x 112 B) exceeds the 126 MB L2 "
+                             f"unless the step is tiny; the {dev.device_bytes / 1e6:.1f} MB scene (BVH, primitives, textures) is read through L2 by design"},
             "gpu_launches": int(launches), "segments_per_path": seg_per_path, "nonfinite_samples": int(nonfinite),
             "e2e": {"value": e2e_segs.item() / e2e_s.item() / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(e2e_stats[0][1]) * world,
                     "d2h_bytes_per_step": H * WIDTH * 3 * 4, "ms_per_step": 1e3 * e2e_s.item() / args.steps,
                     "what": "pt_scene_create (scene H2D) + pt_render_accumulate + reduce + D2H of the fp32 image, every step"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                         "traffic": (K_TRACE_DRAM_BYTES_PER_RAY * segs_rank / max(iters, 1)) if dom == "k_trace" else None,
+                         "traffic": (K_TRACE_DRAM_BYTES_PER_RAY * segs_rank / max(iters, 1)) if dom == "k_trace" and args.scene == SCENE else None,
                          "traffic_note": "DRAM bytes per launch = ncu dram read+write per ray (profiles/r1_b_k_trace_ncu.md) x rays per launch; far below the algorithmic bytes because the scene is L2-resident",
                          "peak_source": peak_src,
                          "bytes_per_segment": dom_b, "bytes_per_launch": dom_b * segs_rank / max(iters, 1),
                          "avg_launch_ms": dom_ms / max(iters, 1), "launches": iters,
                          "stage_ms_per_step": {"k_generate": gen_ms / args.steps, "k_trace": trace_ms / args.steps, "k_shade": shade_ms / args.steps},
                          "whole_step": {"bytes_per_segment": b_seg, "achieved": step_gbs, "frac": step_gbs / hbm},
-                         "k_trace_device_counters": {"node_fetch_64B_units_per_segment": d_pairs,  # binary pair = 1 unit, 4-wide node = 2 units "ref_boxes_per_segment": d_refs, "f64_prim_tests_per_segment": d_prims,
+                         # node fetches in 64-byte units: a binary pair = 1 unit, a 4-wide node = 2 units
+                         "k_trace_device_counters": {"node_fetch_64B_units_per_segment": d_pairs, "ref_boxes_per_segment": d_refs, "f64_prim_tests_per_segment": d_prims,
                                                      "bytes_per_segment": b_trace_dev, "achieved": ach_dev, "frac": ach_dev / hbm,
-                                                     "note": "bytes the device actually requests (mostly served by L2, the scene is 4.6 MB)"},
+                                                     "note": "bytes the device actually requests (mostly served by L1/L2: see config.scene_device_bytes)"},
                          "oracle_counters_per_segment": {"boxes": n_node, "spheres": n_sph, "quads": n_quad, "triangles": n_tri}},
             "cpu_baseline": cpu, "clocks": clocks,
         }
