@@ -174,6 +174,12 @@ typedef struct {
 
 /* ---- render control --------------------------------------------------------------- */
 /* flags bits 4-6: k_trace register-cap variant (0 = default 80 regs; 4: 120, 5: 96, 7: 64) — tuning knob */
+/* PT_RENDER_ENV_IMPORTANCE (NOT reference behaviour): when the camera's environment is a map, the
+ * direction mixture of camera.rs:199-215 gains a third sampler that draws from the map's luminance (built by
+ * pt_scene_build_env_sampler): p_bsdf = 0.5, p_env = 0.5 without lights, p_light = p_env = 0.25 with lights; the
+ * combined pdf gains p_env * pdf_env.  Same expectation as the reference's estimator, lower variance under
+ * concentrated skylight.  Per-sample results differ from the reference's, so it is off by default. */
+#define PT_RENDER_ENV_IMPORTANCE 0x1u
 enum { PT_NAN_REFERENCE = 0, /* non-finite samples poison the pixel like camera.rs:129 */
        PT_NAN_DROP = 1 };    /* documented divergence: a non-finite contribution is skipped and a non-finite
                                 throughput ends the path (each counted once in pt_stats.nonfinite); finite
@@ -218,6 +224,10 @@ int  pt_scene_create(pt_ctx* ctx, const pt_scene_desc* desc, pt_scene** out);
 void pt_scene_destroy(pt_scene* scene);
 /* bytes uploaded host->device by pt_scene_create */
 uint64_t pt_scene_device_bytes(const pt_scene* scene);
+/* Builds the importance sampler of environment image `image` (a lat-long map read as camera.rs:140-151 reads it):
+ * a piecewise-constant density over min(height, max_rows) x min(width, max_cols) cells (0 = 512 x 1024), cell weight =
+ * sum of texel luminance * sin(theta) + a 5 % uniform floor.  Required before rendering with PT_RENDER_ENV_IMPORTANCE. */
+int  pt_scene_build_env_sampler(pt_scene* scene, uint32_t image, uint32_t max_rows, uint32_t max_cols);
 
 /* ---- Camera::render replacement (camera.rs:79-126 minus the PNG encode) ------------ */
 /* image height as Camera::init computes it (camera.rs:52) */
@@ -279,6 +289,8 @@ int  pt_camera_rays(pt_ctx* ctx, const pt_camera* cam, uint64_t seed, size_t n,
 int  pt_lights_sample_pdf(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_vec3* origin,
                           const double* time, const double* uniforms4, pt_vec3* dir,
                           uint32_t* valid, double* pdf);
+/* The environment sampler of pt_scene_build_env_sampler: direction from 2 uniforms per query and its solid-angle pdf. */
+int  pt_env_sample_pdf(pt_ctx* ctx, const pt_scene* scene, size_t n, const double* uniforms2, pt_vec3* dir, double* pdf);
 
 #ifdef __cplusplus
 }

@@ -6,7 +6,76 @@
 
 namespace orc {
 
+// Environment importance sampler — NOT in the reference (PT_RENDER_ENV_IMPORTANCE, include/pt_b200.h).
+// The oracle restates the product's definition so device and CPU can be compared sample for sample: a
+// piecewise-constant density over rows x cols cells of the lat-long map, weight = sum over the cell's texels of
+// luminance * sin(theta of the texel row) + a uniform floor of 5 % of the mean weight; sequential f64 sums.
+struct EnvDist {
+    std::vector<double> marginal, cond;  // CDFs: [rows + 1], [rows][cols + 1]
+    uint32_t rows = 0, cols = 0;
+    void build(const ImageData& img, uint32_t max_rows, uint32_t max_cols) {
+        const uint32_t W = img.width, H = img.height;
+        rows = std::min<uint32_t>(H, max_rows ? max_rows : 512u); cols = std::min<uint32_t>(W, max_cols ? max_cols : 1024u);
+        std::vector<double> w((size_t)rows * cols, 0.0);
+        for (uint32_t j = 0; j < H; j++) {
+            double st = std::sin(((double)j + 0.5) / (double)H * PI);
+            size_t r = (size_t)((uint64_t)j * rows / H);
+            for (uint32_t i = 0; i < W; i++) {
+                const uint8_t* p = img.rgb + ((size_t)j * W + i) * 3;
+                double lum = luminance(Vec3((double)p[0] / 255.0, (double)p[1] / 255.0, (double)p[2] / 255.0));
+                w[r * cols + (size_t)((uint64_t)i * cols / W)] += lum * st;
+            }
+        }
+        double total = 0.0;
+        for (double v : w) total += v;
+        double floor_w = total > 0.0 ? 0.05 * total / ((double)rows * (double)cols) : 1.0;
+        marginal.assign(rows + 1, 0.0); cond.assign((size_t)rows * (cols + 1), 0.0);
+        std::vector<double> row_sum(rows);
+        double all = 0.0;
+        for (uint32_t r = 0; r < rows; r++) {
+            double rs = 0.0;
+            for (uint32_t c = 0; c < cols; c++) { w[(size_t)r * cols + c] += floor_w; rs += w[(size_t)r * cols + c]; }
+            row_sum[r] = rs; all += rs;
+            double* cr = cond.data() + (size_t)r * (cols + 1);
+            for (uint32_t c = 0; c < cols; c++) cr[c + 1] = cr[c] + w[(size_t)r * cols + c] / rs;
+            cr[cols] = 1.0;
+        }
+        for (uint32_t r = 0; r < rows; r++) marginal[r + 1] = marginal[r] + row_sum[r] / all;
+        marginal[rows] = 1.0;
+    }
+    static uint32_t find(const double* cdf, uint32_t n, double u) {  // largest i in [0, n) with cdf[i] <= u
+        uint32_t lo = 0, hi = n;
+        while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (cdf[mid] <= u) lo = mid; else hi = mid; }
+        return lo;
+    }
+    Vec3 sample(double u1, double u2) const {
+        uint32_t r = find(marginal.data(), rows, u1);
+        double m0 = marginal[r], m1 = marginal[r + 1];
+        const double* row = cond.data() + (size_t)r * (cols + 1);
+        uint32_t c = find(row, cols, u2);
+        double c0 = row[c], c1 = row[c + 1];
+        double fr = m1 > m0 ? (u1 - m0) / (m1 - m0) : 0.5, fc = c1 > c0 ? (u2 - c0) / (c1 - c0) : 0.5;
+        double theta = (((double)r + fr) / (double)rows) * PI;
+        double phi = (((double)c + fc) / (double)cols) * (2.0 * PI) - PI;
+        double st = std::sin(theta);
+        return Vec3(st * std::cos(phi), std::cos(theta), st * std::sin(phi));
+    }
+    double pdf(Vec3 dir) const {
+        double theta = std::acos(dir.y), phi = std::atan2(dir.z, dir.x);
+        double st = std::sin(theta);
+        if (!(st > 0.0)) return 0.0;
+        double fu = (phi + PI) / (2.0 * PI) * (double)cols, fv = theta / PI * (double)rows;
+        uint32_t c = fu > 0.0 ? (uint32_t)fu : 0u, r = fv > 0.0 ? (uint32_t)fv : 0u;
+        if (c >= cols) c = cols - 1;
+        if (r >= rows) r = rows - 1;
+        const double* row = cond.data() + (size_t)r * (cols + 1);
+        double cell = (marginal[r + 1] - marginal[r]) * (row[c + 1] - row[c]);
+        return cell * (double)rows * (double)cols / (2.0 * PI * PI * st);
+    }
+};
+
 struct Camera {
+    const EnvDist* env_dist = nullptr;  // non-null: PT_RENDER_ENV_IMPORTANCE (ours, not the reference's)
     // public fields, camera.rs:23-36
     double aspect_ratio = 1.0; uint32_t image_width = 0, samples_per_pixel = 0, max_depth = 0;
     double vfov = 0; Vec3 look_from, look_at, vup;
@@ -90,14 +159,22 @@ struct Camera {
             }
             double p_light = world.lights.is_empty() ? 0.0 : 0.5;  // camera.rs:199
             double p_bsdf = 1.0 - p_light;
+            double p_env = 0.0;
+            if (env_dist) {  // ours (PT_RENDER_ENV_IMPORTANCE): the environment map joins the mixture as a third sampler
+                p_env = world.lights.is_empty() ? 0.5 : 0.25;
+                p_light = world.lights.is_empty() ? 0.0 : 0.5 - p_env;
+                p_bsdf = 0.5;
+            }
             double rr = rng.next();
             std::optional<Vec3> dir;
             if (rr < p_light) dir = world.lights.sample(info.point, ray.time, rng);
+            else if (env_dist && rr < p_light + p_env) { double u1 = rng.next(), u2 = rng.next(); dir = env_dist->sample(u1, u2); }
             else dir = info.mat->sample(ray, info, rng);
             if (!dir) break;
             double bsdf_pdf = info.mat->pdf(-ray.direction, *dir, info);
             double light_pdf = world.lights.pdf(info.point, *dir, ray.time);
             double pdf = p_bsdf * bsdf_pdf + p_light * light_pdf;
+            if (env_dist) pdf = pdf + p_env * env_dist->pdf(*dir);
             Vec3 brdf = info.mat->eval(-ray.direction, *dir, info);
             Vec3 attenuation = brdf / pdf;
             double e = 1e-3 * signum_(dot(*dir, info.geometric_normal));  // bsdf::EPS, camera.rs:217

@@ -23,6 +23,7 @@ struct orc_scene {
     std::vector<std::vector<uint8_t>> image_store;
     World world;
     std::string error;
+    EnvDist env; uint32_t env_image = UINT32_MAX;  // orc_scene_build_env_sampler
 };
 
 static Vec3 V(const pt_vec3& v) { return Vec3(v.x, v.y, v.z); }
@@ -304,6 +305,22 @@ int orc_lights_sample_pdf(const orc_scene* s, size_t n, const pt_vec3* origin, c
     return 0;
 }
 
+// ---- environment importance sampler (ours, not the reference's: see EnvDist) --------------------------
+int orc_scene_build_env_sampler(orc_scene* s, uint32_t image, uint32_t max_rows, uint32_t max_cols) {
+    if (image >= s->image_tex.size() || s->image_tex[image]->img.width == 0 || s->image_tex[image]->img.height == 0) { g_err = "bad env image"; return 1; }
+    s->env.build(s->image_tex[image]->img, max_rows, max_cols);
+    s->env_image = image;
+    return 0;
+}
+int orc_env_sample_pdf(const orc_scene* s, size_t n, const double* uniforms2, pt_vec3* dir, double* pdf) {
+    if (s->env_image == UINT32_MAX) { g_err = "no env sampler"; return 1; }
+    for (size_t i = 0; i < n; i++) {
+        Vec3 d = s->env.sample(uniforms2[2 * i], uniforms2[2 * i + 1]);
+        dir[i] = P(d); pdf[i] = s->env.pdf(d);
+    }
+    return 0;
+}
+
 // ---- render (Camera::render, camera.rs:79-126, minus PNG) ---------------------------------------
 struct orc_stats { uint64_t paths, segments, boxes, spheres, quads, triangles, instances, nonfinite; double seconds; int threads; };
 
@@ -311,6 +328,10 @@ struct orc_stats { uint64_t paths, segments, boxes, spheres, quads, triangles, i
 int orc_render(const orc_scene* s, const pt_camera* c, const pt_render_params* p, int threads, double* out_mean,
                orc_stats* st) {
     Camera cam = make_camera(s, c);
+    if ((p->flags & PT_RENDER_ENV_IMPORTANCE) && c->env_is_map) {
+        if (s->env_image != c->env_image) { g_err = "orc_render: build the env sampler first"; return 1; }
+        cam.env_dist = &s->env;
+    }
     const uint32_t W = cam.image_width, H = cam.image_height;
     if (threads <= 0) threads = omp_get_max_threads();
     Counters total; uint64_t nonfinite = 0;

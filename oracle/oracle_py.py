@@ -52,6 +52,8 @@ def lib():
         L.orc_camera_rays.argtypes = [C.c_void_p, C.c_uint64, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(OrcStats)]
         L.orc_tonemap_rgb8.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        L.orc_scene_build_env_sampler.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.orc_env_sample_pdf.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_item_bbox.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p]
         L.orc_quad_derived.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p]
         L.orc_instance_matrices.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p]
@@ -113,13 +115,22 @@ class OracleScene:
         self.L.orc_lights_sample_pdf(self.ptr, n, _ptr(o), _ptr(t), _ptr(u), _ptr(d), _ptr(valid), _ptr(pdf))
         return d, valid, pdf
 
-    def render(self, camera, spp, seed=1, sample_begin=0, sample_stride=1, nan_policy=0, threads=0):
+    def build_env_sampler(self, image, max_rows=0, max_cols=0):
+        assert self.L.orc_scene_build_env_sampler(self.ptr, image, max_rows, max_cols) == 0, self.L.orc_last_error().decode()
+
+    def env_sample_pdf(self, uniforms2):
+        u = np.ascontiguousarray(uniforms2, dtype=np.float64).reshape(-1, 2)
+        d, pdf = np.zeros((u.shape[0], 3)), np.zeros(u.shape[0])
+        assert self.L.orc_env_sample_pdf(self.ptr, u.shape[0], _ptr(u), _ptr(d), _ptr(pdf)) == 0
+        return d, pdf
+
+    def render(self, camera, spp, seed=1, sample_begin=0, sample_stride=1, nan_policy=0, threads=0, flags=0):
         """Camera::render minus the PNG.  Returns (mean radiance float64 [H,W,3], OrcStats)."""
-        params = self.dt.RenderParams(seed, sample_begin, spp, sample_stride, nan_policy, 0, 0)
+        params = self.dt.RenderParams(seed, sample_begin, spp, sample_stride, nan_policy, 0, flags)
         h = self.L.orc_camera_image_height(C.byref(camera))
         out = np.zeros((h, camera.image_width, 3), dtype=np.float64)
         st = OrcStats()
-        self.L.orc_render(self.ptr, C.byref(camera), C.byref(params), threads, _ptr(out), C.byref(st))
+        assert self.L.orc_render(self.ptr, C.byref(camera), C.byref(params), threads, _ptr(out), C.byref(st)) == 0, self.L.orc_last_error().decode()
         return out, st
 
     def dump_path_rays(self, camera, seed, pixel_step, spp, min_bounce, cap):

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 import helpers as H
-from test_oracle import _material_world, _ray, mixed_lights_world, tie_world
+from test_oracle import _material_world, _ray, mixed_lights_world, sun_world, tie_world
 
 pytestmark = pytest.mark.gpu
 
@@ -234,6 +234,49 @@ def test_every_light_kind_matches_oracle(pt, orc, ctx):
     assert abs(int(st.nonfinite) - int(ost.nonfinite)) <= 8 and abs(int(st.segments) - int(ost.segments)) <= 64
     assert (d > 1e-4 * np.maximum(ref.max(axis=2), 1.0)).mean() < 0.02 and H.rel_rmse(img, ref) < 0.05
     dev.close(); ora.close()
+
+
+# ---------------------------------------------------------------- environment importance sampling (ours)
+@pytest.mark.parametrize("with_light", [False, True])
+def test_env_importance_sampling_matches_oracle(pt, orc, ctx, with_light):
+    """PT_RENDER_ENV_IMPORTANCE is not reference behaviour (flag-gated, off by default); the oracle restates the same
+    sampler, so the device is checked sample for sample, and against the reference estimator's expectation."""
+    scene = sun_world(pt, 64, with_light)
+    dev, ora = ctx.upload(scene), orc.OracleScene(scene.desc, pt)
+    with pytest.raises(pt.PtError):                                       # the sampler has to be built first
+        dev.render(spp=1, flags=pt.PT_RENDER_ENV_IMPORTANCE)
+    dev.build_env_sampler(); ora.build_env_sampler(scene.camera.env_image)
+    u = np.random.default_rng(22).uniform(size=(50000, 2))
+    (da, pa), (db, pb) = dev.env_sample_pdf(u), ora.env_sample_pdf(u)
+    assert np.abs(da - db).max() < 1e-12 and H.max_rel_err(pa, pb) < 1e-9
+    img, st = dev.render(spp=16, seed=23, nan_policy=pt.PT_NAN_DROP, flags=pt.PT_RENDER_ENV_IMPORTANCE)
+    ref, ost = ora.render(scene.camera, 16, seed=23, nan_policy=pt.PT_NAN_DROP, flags=pt.PT_RENDER_ENV_IMPORTANCE)
+    assert st.paths == ost.paths and abs(int(st.segments) - int(ost.segments)) <= 64
+    d = np.abs(img - ref).max(axis=2)
+    assert (d > 1e-4 * np.maximum(ref.max(axis=2), 1.0)).mean() < 0.02 and H.rel_rmse(img, ref) < 0.05
+    # same expectation as the reference's estimator, much less noise (400 spp each, two seeds)
+    base = [dev.render(spp=400, seed=s, nan_policy=pt.PT_NAN_DROP)[0] for s in (1, 2)]
+    envs = [dev.render(spp=400, seed=s, nan_policy=pt.PT_NAN_DROP, flags=pt.PT_RENDER_ENV_IMPORTANCE)[0] for s in (1, 2)]
+    n_base, n_env = H.rel_rmse(base[0], base[1]), H.rel_rmse(envs[0], envs[1])
+    print(f"lights={with_light}: noise at 400 spp: reference estimator {n_base:.4f}, env importance sampling {n_env:.4f}")
+    assert n_env < (0.9 if with_light else 0.5) * n_base                   # with the quad light on, its own noise remains
+    assert abs((base[0] + base[1]).mean() - (envs[0] + envs[1]).mean()) < 0.03 * (base[0] + base[1]).mean()
+    dev.close(); ora.close()
+
+
+def test_env_importance_sampling_scene5_and_default_unchanged(pt, orc, pairs):
+    """Scene 5 (87 MB sky): device vs oracle sample for sample with the sampler on; with the flag off the result does not
+    depend on whether a sampler was built."""
+    p = pairs(5, 96)
+    before, _ = p.dev.render(spp=4, seed=9, nan_policy=pt.PT_NAN_DROP)
+    p.dev.build_env_sampler(); p.ora.build_env_sampler(p.scene.camera.env_image)
+    after, _ = p.dev.render(spp=4, seed=9, nan_policy=pt.PT_NAN_DROP)
+    assert np.allclose(before, after, rtol=1e-6, atol=1e-7)
+    img, st = p.dev.render(spp=8, seed=9, nan_policy=pt.PT_NAN_DROP, flags=pt.PT_RENDER_ENV_IMPORTANCE)
+    ref, ost = p.ora.render(p.scene.camera, 8, seed=9, nan_policy=pt.PT_NAN_DROP, flags=pt.PT_RENDER_ENV_IMPORTANCE)
+    assert abs(int(st.segments) - int(ost.segments)) <= max(64, ost.segments // 2000)
+    d = np.abs(img - ref).max(axis=2)
+    assert (d > 1e-4 * np.maximum(ref.max(axis=2), 1.0)).mean() < 0.02 and H.rel_rmse(img, ref) < 0.05
 
 
 # ---------------------------------------------------------------- renders

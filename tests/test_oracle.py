@@ -241,6 +241,48 @@ def test_oracle_every_light_kind_samples_what_its_pdf_sees(pt, orc):
     ora.close()
 
 
+def sun_world(pt, width=48, with_light=False):
+    """A dim lat-long sky with a small bright sun over a diffuse floor, a glossy and a principled ball: the case
+    environment importance sampling (PT_RENDER_ENV_IMPORTANCE, ours) exists for."""
+    sky = np.full((64, 128, 3), 1, dtype=np.uint8)
+    sky[40:, :, :] = 0                      # below the horizon
+    sky[12:15, 40:48, :] = (255, 240, 200)  # the sun: 24 texels of 8192
+    w = pt.World()
+    w.add_object(pt.Quad((-6, 0, -6), (12, 0, 0), (0, 0, 12), pt.DiffuseBRDF((0.7, 0.7, 0.7))))
+    w.add_object(pt.Sphere.new_still(0.8, (-1.0, 0.8, 0), pt.MetalBRDF((0.9, 0.8, 0.7), 0.4)))
+    w.add_object(pt.Sphere.new_still(0.8, (1.0, 0.8, 0), pt.PrincipledBSDF((0.7, 0.3, 0.3), 0.0, 0.5, 0.0, 0.5, 0.0, 1.5, 0.0, 0.0, 0.5, 0.0, 0.0)))
+    if with_light:
+        w.add_light(pt.Quad((-0.5, 3.0, -0.5), (1, 0, 0), (0, 0, 1), pt.DiffuseLight((3, 3, 3))))
+    w.build_bvh()
+    cam = pt.make_camera(width, aspect_ratio=1.0, samples_per_pixel=4, max_depth=12, vfov=50.0, look_from=(0, 2.0, 6.0), look_at=(0, 0.8, 0), env_is_map=True)
+    return pt.Scene.from_world(w, cam, pt.Image(rgb=sky))
+
+
+def test_oracle_env_sampler_is_a_density_and_keeps_the_expectation(pt, orc):
+    """EnvDist (ours): sample() and pdf() agree (sampled directions have the pdf of their cell, the pdf integrates to 1
+    over the sphere), the sun gets most of the samples, and rendering with the sampler in the mixture converges to the
+    same image as the reference's estimator with less noise."""
+    scene = sun_world(pt, 24)
+    ora = orc.OracleScene(scene.desc, pt)
+    ora.build_env_sampler(scene.camera.env_image)
+    rng = np.random.default_rng(21)
+    d, pdf = ora.env_sample_pdf(rng.uniform(size=(40000, 2)))
+    assert np.allclose(np.linalg.norm(d, axis=1), 1.0, atol=1e-12) and (pdf > 0).all()
+    theta, phi = np.arccos(d[:, 1]), np.arctan2(d[:, 2], d[:, 0])
+    row, col = (theta / np.pi * 64).astype(int), ((phi + np.pi) / (2 * np.pi) * 128).astype(int)
+    in_sun = (row >= 12) & (row < 15) & (col >= 40) & (col < 48)
+    assert 0.3 < in_sun.mean() < 0.9                                  # 24 of 8192 texels draw a large share of the samples
+    assert abs((1.0 / pdf).mean() - 4 * np.pi) < 0.25                  # E_{d ~ pdf}[1 / pdf(d)] = area of the support = the whole sphere
+    base = [ora.render(scene.camera, 200, seed=s, nan_policy=pt.PT_NAN_DROP)[0] for s in (1, 2)]
+    envs = [ora.render(scene.camera, 200, seed=s, nan_policy=pt.PT_NAN_DROP, flags=pt.PT_RENDER_ENV_IMPORTANCE)[0] for s in (1, 2)]
+    noise_base, noise_env = H.rel_rmse(base[0], base[1]), H.rel_rmse(envs[0], envs[1])
+    print(f"noise (relRMSE between two 200-spp renders): reference estimator {noise_base:.3f}, with env importance sampling {noise_env:.3f}")
+    assert noise_env < 0.6 * noise_base
+    a, b = (base[0] + base[1]) / 2, (envs[0] + envs[1]) / 2
+    assert abs(a.mean() - b.mean()) < 0.05 * a.mean()                   # same expectation
+    ora.close()
+
+
 def test_oracle_sample_split_is_exact(pt, orc):
     """spp split across G virtual ranks (sample index = g + k*G) reproduces the 1-rank sum."""
     scene = pt.Scene.build(3, width=24, spp=8, seed=1)

@@ -22,6 +22,7 @@ REPO_ROOT = os.path.dirname(_HERE)
 ASSETS_DIR = os.path.join(REPO_ROOT, "assets")
 PT_NONE = 0xFFFFFFFF
 PT_NAN_REFERENCE, PT_NAN_DROP = 0, 1
+PT_RENDER_ENV_IMPORTANCE = 0x1  # pt_render_params.flags: environment-map importance sampling (not reference behaviour)
 PRIM_SPHERE, PRIM_QUAD, PRIM_TRIANGLE, OBJ_CUBOID, OBJ_MESH, OBJ_INSTANCE = range(6)
 
 
@@ -67,7 +68,7 @@ assert BSDF_RESULT_DTYPE.itemsize == 64 and BSDF_SAMPLE_DTYPE.itemsize == 32
 ABI_SYMBOLS = ["pt_ctx_create", "pt_ctx_destroy", "pt_ctx_set_stream", "pt_ctx_set_profiling", "pt_last_error", "pt_device_count",
                "pt_scene_create", "pt_scene_destroy", "pt_scene_device_bytes", "pt_camera_image_height", "pt_render_accumulate",
                "pt_render", "pt_tonemap_rgb8", "pt_trace_closest", "pt_trace_any", "pt_bsdf_eval_pdf", "pt_bsdf_sample",
-               "pt_camera_rays", "pt_lights_sample_pdf"]
+               "pt_camera_rays", "pt_lights_sample_pdf", "pt_scene_build_env_sampler", "pt_env_sample_pdf"]
 
 
 class PtError(RuntimeError):
@@ -122,6 +123,8 @@ def device_lib():
         lib.pt_bsdf_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.pt_camera_rays.argtypes = [C.c_void_p, C.POINTER(CameraABI), C.c_uint64, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.pt_lights_sample_pdf.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.pt_scene_build_env_sampler.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
+        lib.pt_env_sample_pdf.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
         _dev = lib
     return _dev
 
@@ -468,6 +471,17 @@ class DeviceScene:
         d, valid, pdf = np.zeros((n, 3)), np.zeros(n, np.uint32), np.zeros(n)
         self.ctx._check(self.ctx.lib.pt_lights_sample_pdf(self.ctx.ptr, self.ptr, n, _ptr(o), _ptr(t), _ptr(u), _ptr(d), _ptr(valid), _ptr(pdf)))
         return d, valid, pdf
+
+    def build_env_sampler(self, image=None, max_rows=0, max_cols=0):
+        """pt_scene_build_env_sampler for `image` (default: the camera's environment map); needed by PT_RENDER_ENV_IMPORTANCE."""
+        image = self.host_scene.camera.env_image if image is None else image
+        self.ctx._check(self.ctx.lib.pt_scene_build_env_sampler(self.ptr, image, max_rows, max_cols))
+
+    def env_sample_pdf(self, uniforms2):
+        u = np.ascontiguousarray(uniforms2, dtype=np.float64).reshape(-1, 2)
+        d, pdf = np.zeros((u.shape[0], 3)), np.zeros(u.shape[0])
+        self.ctx._check(self.ctx.lib.pt_env_sample_pdf(self.ctx.ptr, self.ptr, u.shape[0], _ptr(u), _ptr(d), _ptr(pdf)))
+        return d, pdf
 
     def params(self, spp, seed=1, sample_begin=0, sample_stride=1, nan_policy=PT_NAN_REFERENCE, pool_paths=0, flags=0):
         return RenderParams(seed, sample_begin, spp, sample_stride, nan_policy, pool_paths, flags)

@@ -56,6 +56,10 @@ struct pt_scene {
     uint32_t class_mask = 1u << CLS_MISS;   // shade classes that can occur in this scene
     bool wide = false;                      // traversed with 4-wide nodes (some BVH has >= kWideMinItems items) or binary pairs
     std::vector<DImage> images;
+    bool general_lights = false;            // World.lights holds something other than quads and spheres (shade kernel variant)
+    DEnvDist env{};                         // pt_scene_build_env_sampler: importance sampler of image `env_image`
+    uint32_t env_image = 0xFFFFFFFFu;
+    void* env_block = nullptr;
 };
 
 extern "C" {
@@ -497,6 +501,7 @@ int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
         lights[i] = DRef{ref_pack(d->lights[i].kind, d->lights[i].index), 0};
         const pt_ref r = d->lights[i].kind == PT_OBJ_INSTANCE ? d->instances[d->lights[i].index].child : d->lights[i];
         mesh_light |= r.kind == PT_OBJ_MESH;
+        s->general_lights |= d->lights[i].kind != PT_PRIM_QUAD && d->lights[i].kind != PT_PRIM_SPHERE;
     }
     std::vector<double> tri_verts;
     if (mesh_light) { tri_verts.resize(9ull * d->n_triangles); memcpy(tri_verts.data(), d->triangles, tri_verts.size() * sizeof(double)); }
@@ -519,9 +524,64 @@ void pt_scene_destroy(pt_scene* s) {
     cudaStreamSynchronize(s->ctx->stream);  // no kernel may still read the tables
     for (auto& b : s->allocs) s->ctx->free_blocks.push_back(b);
     while (s->ctx->free_blocks.size() > 8) { cudaFree(s->ctx->free_blocks.front().first); s->ctx->free_blocks.erase(s->ctx->free_blocks.begin()); }
+    if (s->env_block) cudaFree(s->env_block);
     delete s;
 }
 uint64_t pt_scene_device_bytes(const pt_scene* s) { return s ? s->bytes : 0; }
+
+// Importance sampler of a lat-long environment image (NOT reference behaviour, used only with
+// PT_RENDER_ENV_IMPORTANCE).  Cell weight = sum over the cell's texels of luminance * sin(theta of the texel row), plus
+// a uniform floor of 5 % of the mean so that every direction keeps a positive density; rows and columns follow
+// ImageTexture::value's texel mapping (texture.rs:72-91: row 0 = theta 0).  Built on the host in f64, sequential sums.
+int pt_scene_build_env_sampler(pt_scene* s, uint32_t image, uint32_t max_rows, uint32_t max_cols) {
+    if (!s || image >= s->n_images) return fail(PT_ERR_INVALID, "pt_scene_build_env_sampler: bad scene or image index");
+    const DImage im = s->images[image];
+    if (im.width == 0 || im.height == 0) return fail(PT_ERR_INVALID, "pt_scene_build_env_sampler: empty image");
+    CU(cudaSetDevice(s->ctx->device));
+    const uint32_t W = im.width, H = im.height;
+    const uint32_t rows = std::min<uint32_t>(H, max_rows ? max_rows : 512u), cols = std::min<uint32_t>(W, max_cols ? max_cols : 1024u);
+    std::vector<uint8_t> px((size_t)W * H * 3);
+    CU(cudaMemcpyAsync(px.data(), s->d.image_data + im.offset, px.size(), cudaMemcpyDeviceToHost, s->ctx->stream));
+    CU(cudaStreamSynchronize(s->ctx->stream));
+    std::vector<double> w((size_t)rows * cols, 0.0);
+    for (uint32_t j = 0; j < H; j++) {
+        const double st = sin(((double)j + 0.5) / (double)H * kPi);
+        double* wr = w.data() + (size_t)((uint64_t)j * rows / H) * cols;
+        const uint8_t* p = px.data() + (size_t)j * W * 3;
+        for (uint32_t i = 0; i < W; i++) {
+            const double lum = luminance(mk((double)p[3 * i] / 255.0, (double)p[3 * i + 1] / 255.0, (double)p[3 * i + 2] / 255.0));
+            wr[(uint64_t)i * cols / W] += lum * st;
+        }
+    }
+    double total = 0.0;
+    for (double v : w) total += v;
+    const double floor_w = total > 0.0 ? 0.05 * total / ((double)rows * (double)cols) : 1.0;
+    std::vector<double> table((size_t)rows + 1 + (size_t)rows * (cols + 1));
+    double* marginal = table.data();
+    double* cond = table.data() + rows + 1;
+    std::vector<double> row_sum(rows);
+    double all = 0.0;
+    for (uint32_t r = 0; r < rows; r++) {
+        double rs = 0.0;
+        for (uint32_t c = 0; c < cols; c++) { w[(size_t)r * cols + c] += floor_w; rs += w[(size_t)r * cols + c]; }
+        row_sum[r] = rs; all += rs;
+        double* cr = cond + (size_t)r * (cols + 1);
+        cr[0] = 0.0;
+        for (uint32_t c = 0; c < cols; c++) cr[c + 1] = cr[c] + w[(size_t)r * cols + c] / rs;
+        cr[cols] = 1.0;
+    }
+    marginal[0] = 0.0;
+    for (uint32_t r = 0; r < rows; r++) marginal[r + 1] = marginal[r] + row_sum[r] / all;
+    marginal[rows] = 1.0;
+    if (s->env_block) { CU(cudaStreamSynchronize(s->ctx->stream)); cudaFree(s->env_block); s->env_block = nullptr; s->env_image = 0xFFFFFFFFu; }
+    CU(cudaMalloc(&s->env_block, table.size() * sizeof(double)));
+    CU(cudaMemcpyAsync(s->env_block, table.data(), table.size() * sizeof(double), cudaMemcpyHostToDevice, s->ctx->stream));
+    CU(cudaStreamSynchronize(s->ctx->stream));
+    s->env = DEnvDist{(const double*)s->env_block, (const double*)s->env_block + rows + 1, rows, cols};
+    s->env_image = image;
+    s->bytes += table.size() * sizeof(double);
+    return PT_OK;
+}
 
 // ------------------------------------------------------------------------------------------------ camera
 static d3 dv(const pt_vec3& v) { return mk(v.x, v.y, v.z); }
@@ -588,7 +648,11 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
     if ((uint64_t)pool > total) pool = (uint32_t)std::max<uint64_t>(total, 1);
     pool = (pool + kBlock - 1) / kBlock * kBlock;
     if ((rc = ensure_pool(ctx, pool))) return rc;
-    RenderConst rcst{p->seed, p->sample_begin, p->sample_stride ? p->sample_stride : 1u, p->nan_policy, 0};
+    RenderConst rcst{p->seed, p->sample_begin, p->sample_stride ? p->sample_stride : 1u, p->nan_policy, 0, DEnvDist{nullptr, nullptr, 0, 0}};
+    if ((p->flags & PT_RENDER_ENV_IMPORTANCE) && cam->env_is_map) {  // a constant-colour environment needs no importance sampling
+        if (scene->env_image != cam->env_image) return fail(PT_ERR_INVALID, "PT_RENDER_ENV_IMPORTANCE: call pt_scene_build_env_sampler for the camera's env_image first");
+        rcst.env_importance = 1; rcst.env = scene->env;
+    }
     cudaStream_t st = ctx->stream;
     CU(cudaMemsetAsync(ctx->d_nonfinite, 0, 4 * sizeof(unsigned long long), st));
     pt_stats S{}; S.width = dcam.c.width; S.height = dcam.c.height;
@@ -623,7 +687,9 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
         const unsigned sg = std::min<unsigned>((n + kBlock - 1) / kBlock, 148u * 16u);
 #define PT_SHADE(CLS)                                                                                                                    \
         if (scene->class_mask & (1u << CLS)) {                                                                                           \
-            k_shade<CLS><<<sg, kBlock, 0, st>>>(in, q, ctx->hits, outb, ctx->d_count, d_accum, ctx->d_nonfinite, scene->d, dcam, rcst); \
+            if (rcst.env_importance) k_shade<CLS, 3><<<sg, kBlock, 0, st>>>(in, q, ctx->hits, outb, ctx->d_count, d_accum, ctx->d_nonfinite, scene->d, dcam, rcst);  \
+            else if (scene->general_lights) k_shade<CLS, 2><<<sg, kBlock, 0, st>>>(in, q, ctx->hits, outb, ctx->d_count, d_accum, ctx->d_nonfinite, scene->d, dcam, rcst); \
+            else k_shade<CLS, 0><<<sg, kBlock, 0, st>>>(in, q, ctx->hits, outb, ctx->d_count, d_accum, ctx->d_nonfinite, scene->d, dcam, rcst); \
             S.kernel_launches++;                                                                                                         \
         }
         PT_SHADE(CLS_MISS) PT_SHADE(CLS_LIGHT) PT_SHADE(CLS_DIFFUSE) PT_SHADE(CLS_METAL) PT_SHADE(CLS_GLASS) PT_SHADE(CLS_PRINCIPLED) PT_SHADE(CLS_OTHER)
@@ -763,6 +829,17 @@ int pt_lights_sample_pdf(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_
         (rc = dd.alloc(n * 24)) || (rc = vv.alloc(n * 4)) || (rc = pp.alloc(n * 8))) return rc;
     k_lights<<<grid_for(n), 128, 0, ctx->stream>>>(n, (const pt_vec3*)o.p, (const double*)t.p, (const double*)u.p, (pt_vec3*)dd.p, (uint32_t*)vv.p, (double*)pp.p, scene->d);
     if ((rc = dd.to_host(dir, n * 24, ctx->stream)) || (rc = vv.to_host(valid, n * 4, ctx->stream)) || (rc = pp.to_host(pdf, n * 8, ctx->stream))) return rc;
+    return PT_OK;
+}
+int pt_env_sample_pdf(pt_ctx* ctx, const pt_scene* scene, size_t n, const double* uniforms2, pt_vec3* dir, double* pdf) {
+    if (!ctx || !scene || (n && (!uniforms2 || !dir || !pdf))) return fail(PT_ERR_INVALID, "pt_env_sample_pdf: null argument");
+    if (scene->env_image == 0xFFFFFFFFu) return fail(PT_ERR_INVALID, "pt_env_sample_pdf: no sampler built (pt_scene_build_env_sampler)");
+    if (n == 0) return PT_OK;
+    CU(cudaSetDevice(ctx->device));
+    DevBuf u, dd, pp; int rc;
+    if ((rc = u.from_host(uniforms2, n * 16, ctx->stream)) || (rc = dd.alloc(n * 24)) || (rc = pp.alloc(n * 8))) return rc;
+    k_env<<<grid_for(n), 128, 0, ctx->stream>>>(n, (const double*)u.p, (pt_vec3*)dd.p, (double*)pp.p, scene->env);
+    if ((rc = dd.to_host(dir, n * 24, ctx->stream)) || (rc = pp.to_host(pdf, n * 8, ctx->stream))) return rc;
     return PT_OK;
 }
 

@@ -353,8 +353,8 @@ PT_D d3 bsdf_emitted(const DScene& S, uint32_t mat, double u, double v, d3 p) { 
 // ---------------------------------------------------------------- World.lights.{sample,pdf} (list.rs:78-96)
 // Hittable::sample for one non-instance object (sphere.rs:110-121, quad.rs:80-86, cuboid.rs:74-76 -> list.rs:78-84,
 // mesh.rs:122-129,213-215).  Uniform picks follow the RNG contract: index = min(floor(U*n), n-1).
-PT_D bool light_sample_object(const DScene& S, uint32_t kind, uint32_t index, d3 origin, double time, Rng& rng, d3& dir) {
-    if (kind == PT_OBJ_CUBOID) {  // sides.sample: one of the six quads
+template <bool GENERAL> PT_D bool light_sample_object(const DScene& S, uint32_t kind, uint32_t index, d3 origin, double time, Rng& rng, d3& dir) {
+    if (GENERAL && kind == PT_OBJ_CUBOID) {  // sides.sample: one of the six quads
         uint32_t i = (uint32_t)(rng.next() * 6.0); if (i > 5) i = 5;
         kind = PT_PRIM_QUAD; index = S.cuboids[index].first_quad + i;
     }
@@ -376,7 +376,7 @@ PT_D bool light_sample_object(const DScene& S, uint32_t kind, uint32_t index, d3
         dir = normalize(point - origin);
         return true;
     }
-    if (kind == PT_OBJ_MESH) {  // triangles.sample: a uniformly chosen triangle, then mesh.rs:122-129
+    if (GENERAL && kind == PT_OBJ_MESH) {  // triangles.sample: a uniformly chosen triangle, then mesh.rs:122-129
         const DMesh& m = S.meshes[index];
         if (m.n_tri == 0 || !S.tri_verts) return false;
         uint32_t i = (uint32_t)(rng.next() * (double)m.n_tri); if (i >= m.n_tri) i = m.n_tri - 1;
@@ -390,7 +390,7 @@ PT_D bool light_sample_object(const DScene& S, uint32_t kind, uint32_t index, d3
     return false;
 }
 // Hittable::pdf for one non-instance object (sphere.rs:123-135, quad.rs:88-98, mesh.rs:131-141; lists average, list.rs:86-96).
-PT_D double light_pdf_prim(const DScene& S, uint32_t kind, uint32_t index, d3 origin, d3 direction, double time) {
+template <bool GENERAL> PT_D double light_pdf_prim(const DScene& S, uint32_t kind, uint32_t index, d3 origin, d3 direction, double time) {
     RayD ray = make_ray(origin, direction, time);  // Ray::new re-normalises (quad.rs:89, sphere.rs:125, mesh.rs:132)
     if (kind == PT_PRIM_QUAD) {
         const DQuad& q = S.quads[index];
@@ -414,7 +414,7 @@ PT_D double light_pdf_prim(const DScene& S, uint32_t kind, uint32_t index, d3 or
         double solid_angle = 2.0 * kPi * sqrt(1.0 - r2 / dot(dc, dc));
         return 1.0 / solid_angle;
     }
-    if (kind == PT_PRIM_TRIANGLE) {
+    if (GENERAL && kind == PT_PRIM_TRIANGLE) {
         const DTri& tr = S.tris[index];
         double t, u, v;
         if (!tri_t(tr, ray, 0.0, t, u, v)) return 0.0;
@@ -426,48 +426,48 @@ PT_D double light_pdf_prim(const DScene& S, uint32_t kind, uint32_t index, d3 or
     }
     return 0.0;
 }
-PT_D double light_pdf_object(const DScene& S, uint32_t kind, uint32_t index, d3 origin, d3 direction, double time) {
-    if (kind == PT_OBJ_CUBOID) {
+template <bool GENERAL> PT_D double light_pdf_object(const DScene& S, uint32_t kind, uint32_t index, d3 origin, d3 direction, double time) {
+    if (GENERAL && kind == PT_OBJ_CUBOID) {
         const uint32_t fq = S.cuboids[index].first_quad;
         double s = 0.0;
-        for (uint32_t k = 0; k < 6; k++) s += light_pdf_prim(S, PT_PRIM_QUAD, fq + k, origin, direction, time);
+        for (uint32_t k = 0; k < 6; k++) s += light_pdf_prim<GENERAL>(S, PT_PRIM_QUAD, fq + k, origin, direction, time);
         return s / 6.0;
     }
-    if (kind == PT_OBJ_MESH) {  // O(triangles) per evaluation, exactly like the reference's list average
+    if (GENERAL && kind == PT_OBJ_MESH) {  // O(triangles) per evaluation, exactly like the reference's list average
         const DMesh& m = S.meshes[index];
         if (m.n_tri == 0) return 0.0;
         double s = 0.0;
-        for (uint32_t k = 0; k < m.n_tri; k++) s += light_pdf_prim(S, PT_PRIM_TRIANGLE, m.first_tri + k, origin, direction, time);
+        for (uint32_t k = 0; k < m.n_tri; k++) s += light_pdf_prim<GENERAL>(S, PT_PRIM_TRIANGLE, m.first_tri + k, origin, direction, time);
         return s / (double)m.n_tri;
     }
-    return light_pdf_prim(S, kind, index, origin, direction, time);
+    return light_pdf_prim<GENERAL>(S, kind, index, origin, direction, time);
 }
-PT_D bool light_sample_one(const DScene& S, DRef rf, d3 origin, double time, Rng& rng, d3& dir) {
+template <bool GENERAL> PT_D bool light_sample_one(const DScene& S, DRef rf, d3 origin, double time, Rng& rng, d3& dir) {
     const uint32_t kind = ref_kind(rf.kind_index), index = ref_index(rf.kind_index);
-    if (kind != PT_OBJ_INSTANCE) return light_sample_object(S, kind, index, origin, time, rng, dir);
+    if (!GENERAL || kind != PT_OBJ_INSTANCE) return light_sample_object<GENERAL>(S, kind, index, origin, time, rng, dir);
     const DInstance& in = S.instances[index];  // instance.rs:64-69
     d3 local;
-    if (!light_sample_object(S, in.child_kind, in.child_index, xform_point(in.inv, origin), time, rng, local)) return false;
+    if (!light_sample_object<GENERAL>(S, in.child_kind, in.child_index, xform_point(in.inv, origin), time, rng, local)) return false;
     dir = xform_vector(in.fwd, local);
     return true;
 }
-PT_D double light_pdf_one(const DScene& S, DRef rf, d3 origin, d3 direction, double time) {
+template <bool GENERAL> PT_D double light_pdf_one(const DScene& S, DRef rf, d3 origin, d3 direction, double time) {
     const uint32_t kind = ref_kind(rf.kind_index), index = ref_index(rf.kind_index);
-    if (kind != PT_OBJ_INSTANCE) return light_pdf_object(S, kind, index, origin, direction, time);
+    if (!GENERAL || kind != PT_OBJ_INSTANCE) return light_pdf_object<GENERAL>(S, kind, index, origin, direction, time);
     const DInstance& in = S.instances[index];  // instance.rs:71-75
-    return light_pdf_object(S, in.child_kind, in.child_index, xform_point(in.inv, origin), xform_vector(in.inv, direction), time);
+    return light_pdf_object<GENERAL>(S, in.child_kind, in.child_index, xform_point(in.inv, origin), xform_vector(in.inv, direction), time);
 }
-PT_D bool lights_sample(const DScene& S, d3 origin, double time, Rng& rng, d3& dir) {  // list.rs:78-84
+template <bool GENERAL = true> PT_D bool lights_sample(const DScene& S, d3 origin, double time, Rng& rng, d3& dir) {  // list.rs:78-84
     if (S.n_lights == 0) return false;
     uint32_t n = S.n_lights;
     uint32_t i = (uint32_t)(rng.next() * (double)n);  // RNG contract: index = min(floor(U*n), n-1)
     if (i >= n) i = n - 1;
-    return light_sample_one(S, S.lights[i], origin, time, rng, dir);
+    return light_sample_one<GENERAL>(S, S.lights[i], origin, time, rng, dir);
 }
-PT_D double lights_pdf(const DScene& S, d3 origin, d3 direction, double time) {  // list.rs:86-96
+template <bool GENERAL = true> PT_D double lights_pdf(const DScene& S, d3 origin, d3 direction, double time) {  // list.rs:86-96
     if (S.n_lights == 0) return 0.0;
     double s = 0.0;
-    for (uint32_t i = 0; i < S.n_lights; i++) s += light_pdf_one(S, S.lights[i], origin, direction, time);
+    for (uint32_t i = 0; i < S.n_lights; i++) s += light_pdf_one<GENERAL>(S, S.lights[i], origin, direction, time);
     return s / (double)S.n_lights;
 }
 

@@ -22,8 +22,14 @@ struct PathBuf {
     double* f[10];  // ox oy oz dx dy dz time thr_r thr_g thr_b
     uint4* ids;     // pixel, sample, rng_used | bounce << 16, spare
 };
+// Importance sampler of a lat-long environment map (PT_RENDER_ENV_IMPORTANCE; not reference behaviour):
+// a piecewise-constant density over rows x cols cells of the (u, theta/pi) unit square, built on the host in f64 by
+// pt_scene_build_env_sampler.  marginal[rows + 1] is the CDF over rows (row 0 = theta 0 = +y), cond[r * (cols + 1) ...]
+// the CDF over the columns of row r; both start at 0 and end at 1.
+struct DEnvDist { const double* marginal; const double* cond; uint32_t rows, cols; };
 struct RenderConst {
-    uint64_t seed; uint32_t sample_begin, sample_stride, nan_policy, pad;
+    uint64_t seed; uint32_t sample_begin, sample_stride, nan_policy, env_importance;
+    DEnvDist env;
 };
 
 // ---------------------------------------------------------------- camera.rs:133-168
@@ -50,6 +56,37 @@ PT_D d3 sample_environment(const DScene& S, const DCamera& cam, d3 dir) {  // ca
     double u = (phi + kPi) / (2.0 * kPi);
     double v = 1.0 - theta / kPi;
     return image_value(S, cam.env_image, u, v);
+}
+// largest i in [0, n) with cdf[i] <= u  (cdf[0] = 0, cdf[n] = 1)
+PT_D uint32_t cdf_find(const double* __restrict__ cdf, uint32_t n, double u) {
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (cdf[mid] <= u) lo = mid; else hi = mid; }
+    return lo;
+}
+// direction ~ the cell density; inverse of sample_environment's mapping (theta = acos(d.y), phi = atan2(d.z, d.x))
+PT_D d3 env_sample(const DEnvDist& E, double u1, double u2) {
+    const uint32_t r = cdf_find(E.marginal, E.rows, u1);
+    const double m0 = E.marginal[r], m1 = E.marginal[r + 1];
+    const double* __restrict__ row = E.cond + (size_t)r * (E.cols + 1);
+    const uint32_t c = cdf_find(row, E.cols, u2);
+    const double c0 = row[c], c1 = row[c + 1];
+    const double fr = m1 > m0 ? (u1 - m0) / (m1 - m0) : 0.5, fc = c1 > c0 ? (u2 - c0) / (c1 - c0) : 0.5;
+    const double theta = (((double)r + fr) / (double)E.rows) * kPi;
+    const double phi = (((double)c + fc) / (double)E.cols) * (2.0 * kPi) - kPi;
+    const double st = sin(theta);
+    return mk(st * cos(phi), cos(theta), st * sin(phi));
+}
+PT_D double env_pdf(const DEnvDist& E, d3 dir) {  // solid-angle density of env_sample
+    const double theta = acos(dir.y), phi = atan2(dir.z, dir.x);
+    const double st = sin(theta);
+    if (!(st > 0.0)) return 0.0;
+    const double fu = (phi + kPi) / (2.0 * kPi) * (double)E.cols, fv = theta / kPi * (double)E.rows;
+    uint32_t c = fu > 0.0 ? (uint32_t)fu : 0u, r = fv > 0.0 ? (uint32_t)fv : 0u;
+    if (c >= E.cols) c = E.cols - 1;
+    if (r >= E.rows) r = E.rows - 1;
+    const double* __restrict__ row = E.cond + (size_t)r * (E.cols + 1);
+    const double cell = (E.marginal[r + 1] - E.marginal[r]) * (row[c + 1] - row[c]);
+    return cell * (double)E.rows * (double)E.cols / (2.0 * kPi * kPi * st);
 }
 
 PT_D void store_path(const PathBuf& b, uint32_t i, const RayD& r, d3 thr, uint4 ids) {
@@ -155,7 +192,9 @@ template <> struct ClassKind<CLS_PRINCIPLED> { static constexpr int value = PT_M
 
 // One loop iteration of Camera::trace after intersect_all (camera.rs:180-225) for the paths of ONE shade class.
 // Grid-stride over the class queue; survivors are written compacted into `out` (ballot + block prefix + one atomic).
-template <int CLS>
+// VAR bit 0: environment importance sampling joins the mixture; bit 1: World.lights holds more than quads and spheres
+// (cuboid / mesh / instance lights).  The reference's shipped scenes need neither, and their kernels carry none of that code.
+template <int CLS, int VAR = 0>
 __global__ void __launch_bounds__(kBlock, PT_SHADE_MIN_BLOCKS) k_shade(PathBuf in, Queues q, const HitRec* __restrict__ hits, PathBuf out,
                                                     uint32_t* __restrict__ out_count, float* __restrict__ accum,
                                                     unsigned long long* __restrict__ nonfinite, DScene S, DCameraEx cam, RenderConst rc) {
@@ -196,15 +235,23 @@ __global__ void __launch_bounds__(kBlock, PT_SHADE_MIN_BLOCKS) k_shade(PathBuf i
                     else thr = thr / p;
                 }
                 if (go) {
-                    const double p_light = S.n_lights == 0 ? 0.0 : 0.5, p_bsdf = 1.0 - p_light;  // camera.rs:199-200
+                    // camera.rs:199-200: p_light = 0.5 iff lights exist.  With PT_RENDER_ENV_IMPORTANCE (ours) the environment map
+                    // joins the mixture as a third sampler: p_bsdf = 0.5, the other half is split between lights and environment.
+                    constexpr bool env_is = (VAR & 1) != 0, GEN = (VAR & 2) != 0;
+                    const double p_env = env_is ? (S.n_lights == 0 ? 0.5 : 0.25) : 0.0;
+                    const double p_light = S.n_lights == 0 ? 0.0 : 0.5 - p_env, p_bsdf = env_is ? 0.5 : 1.0 - p_light;
                     const double rsel = rng.next();
                     d3 dir;
-                    bool ok = rsel < p_light ? lights_sample(S, h.point, ray.time, rng, dir) : bsdf_sample<K>(S, h.material, ray.d, h, rng, dir);
+                    bool ok;
+                    if (rsel < p_light) ok = lights_sample<GEN>(S, h.point, ray.time, rng, dir);
+                    else if (env_is && rsel < p_light + p_env) { const double u1 = rng.next(), u2 = rng.next(); dir = env_sample(rc.env, u1, u2); ok = true; }
+                    else ok = bsdf_sample<K>(S, h.material, ray.d, h, rng, dir);
                     if (ok) {  // camera.rs:212-225
                         d3 f; double bsdf_pdf;
                         bsdf_eval_pdf<K>(S, h.material, -ray.d, dir, h, f, bsdf_pdf);
-                        double light_pdf = lights_pdf(S, h.point, dir, ray.time);
+                        double light_pdf = lights_pdf<GEN>(S, h.point, dir, ray.time);
                         double pdf = p_bsdf * bsdf_pdf + p_light * light_pdf;
+                        if (env_is) pdf = pdf + p_env * env_pdf(rc.env, dir);
                         d3 attenuation = f / pdf;
                         double e = 1e-3 * signum(dot(dir, h.gn));
                         next = make_ray(h.point + e * h.gn, dir, ray.time);
@@ -325,6 +372,14 @@ __global__ void k_lights(size_t n, const pt_vec3* __restrict__ origin, const dou
     bool ok = lights_sample(S, from_abi(origin[i]), time[i], rng, d);
     valid[i] = ok; dir[i] = to_abi(ok ? d : mk(0, 0, 0));
     pdf[i] = ok ? lights_pdf(S, from_abi(origin[i]), d, time[i]) : 0.0;
+}
+
+__global__ void k_env(size_t n, const double* __restrict__ uniforms2, pt_vec3* __restrict__ dir, double* __restrict__ pdf, DEnvDist E) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const d3 d = env_sample(E, uniforms2[2 * i], uniforms2[2 * i + 1]);
+    dir[i] = to_abi(d);
+    pdf[i] = env_pdf(E, d);
 }
 
 }  // namespace ptd

@@ -12,7 +12,7 @@
 
 int main(int argc, char** argv) {
     int scene = 1; bool quality = false; long spp = -1, width = -1; unsigned long long seed = 1; int device = 0;
-    std::string assets = "assets", outdir = "demo"; bool drop = false;
+    std::string assets = "assets", outdir = "demo"; bool drop = false, env_is = false;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() -> const char* { if (i + 1 >= argc) { fprintf(stderr, "missing value for %s\n", a.c_str()); exit(2); } return argv[++i]; };
@@ -25,14 +25,15 @@ int main(int argc, char** argv) {
         else if (a == "--assets") assets = next();
         else if (a == "--out") outdir = next();
         else if (a == "--drop-nonfinite") drop = true;
-        else { fprintf(stderr, "usage: ptb200 [-s N] [-q] [--spp N] [--width N] [--seed N] [--device N] [--assets DIR] [--out DIR]\n"); return 2; }
+        else if (a == "--env-importance") env_is = true;
+        else { fprintf(stderr, "usage: ptb200 [-s N] [-q] [--spp N] [--width N] [--seed N] [--device N] [--assets DIR] [--out DIR] [--drop-nonfinite] [--env-importance]\n"); return 2; }
     }
     uint32_t w = quality ? 1920 : 600, s = quality ? 4000 : 100;  // main.rs:633
     if (width > 0) w = (uint32_t)width;
     if (spp > 0) s = (uint32_t)spp;
     try {
         auto b = pt::build_scene(scene, w, s, seed, assets);
-        pt::RenderOptions o; o.seed = seed; o.device = device; o.nan_policy = drop ? PT_NAN_DROP : PT_NAN_REFERENCE;
+        pt::RenderOptions o; o.seed = seed; o.device = device; o.nan_policy = drop ? PT_NAN_DROP : PT_NAN_REFERENCE; o.env_importance = env_is;
         return b->camera.render(b->world, outdir + "/" + b->output_name, o) ? 1 : 0;
     } catch (const std::exception& e) {
         fprintf(stderr, "error: %s\n", e.what());

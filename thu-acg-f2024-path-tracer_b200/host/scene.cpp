@@ -367,6 +367,11 @@ int render_flat(const pt_scene_desc& desc, const pt_camera& cam, const std::stri
     uint32_t H = pt_camera_image_height(&cam), W = cam.image_width;
     std::vector<float> mean((size_t)W * H * 3);
     pt_render_params p{}; p.seed = opt.seed; p.sample_begin = 0; p.sample_count = samples_per_pixel; p.sample_stride = 1; p.nan_policy = opt.nan_policy;
+    if (opt.env_importance && cam.env_is_map) {
+        rc = pt_scene_build_env_sampler(scene, cam.env_image, 0, 0);
+        if (rc) { fprintf(stderr, "pt_scene_build_env_sampler: %s\n", pt_last_error()); pt_scene_destroy(scene); pt_ctx_destroy(ctx); return rc; }
+        p.flags |= PT_RENDER_ENV_IMPORTANCE;
+    }
     pt_stats st{};
     if (opt.verbose) printf("rendering production\n");  // camera.rs:101
     rc = pt_render(ctx, scene, &cam, &p, mean.data(), &st);
