@@ -311,6 +311,35 @@ def test_virtual_rank_split_equals_single_rank(pt, pairs):
     assert np.allclose(full, small_pool, rtol=2e-5, atol=2e-6)
 
 
+def test_progressive_checkpoint_resume_and_noise_floor(pt, ctx, tmp_path):
+    """batches + checkpoint/resume give the image of one pt_render call; the A/B half estimate of the noise
+    predicts the relRMSE actually measured against a converged render."""
+    P = __import__("importlib").import_module("pt_b200.progressive")
+    scene = pt.Scene.build(3, width=96, spp=64, seed=1)
+    dev = ctx.upload(scene)
+    one_shot, st = dev.render(spp=64, seed=5, nan_policy=pt.PT_NAN_DROP)
+    ck = str(tmp_path / "ck.npz")
+    pr = P.ProgressiveRender(dev, seed=5, nan_policy=pt.PT_NAN_DROP)
+    pr.advance(16).advance(16); pr.save(ck)
+    pr2 = P.ProgressiveRender(dev, seed=5, nan_policy=pt.PT_NAN_DROP).load(ck)     # "after the crash"
+    assert pr2.spp == 32
+    pr2.advance(32)
+    mean, se = pr2.result()
+    assert pr2.spp == 64 and pr2.paths == st.paths
+    assert np.allclose(mean, one_shot, rtol=2e-5, atol=2e-6)
+    with pytest.raises(ValueError):
+        P.ProgressiveRender(dev, seed=6, nan_policy=pt.PT_NAN_DROP).load(ck)         # another seed: not this render's checkpoint
+    converged, _ = dev.render(spp=4096, seed=99, nan_policy=pt.PT_NAN_DROP)
+    measured, predicted = H.rel_rmse(mean, converged), pr2.noise_floor()
+    print(f"64 spp: relRMSE vs 4096-spp render {measured:.4f}, predicted from the A/B halves {predicted:.4f}")
+    assert 0.6 * measured < predicted < 1.6 * measured
+    pr2.advance(960)
+    later = pr2.noise_floor()
+    print(f"1024 spp: predicted {later:.4f}")
+    assert pr2.spp == 1024 and later < 0.6 * predicted                              # 16x the samples (1/4 for Gaussian noise; fireflies decay slower)
+    dev.close()
+
+
 def test_tonemap_matches_reference_formula(pt, orc, ctx):
     import torch
     x = np.array([0.0, 1.0, 4.0, 0.25, -1.0, np.nan, np.inf, 1e-6, 0.5, 0.9981], dtype=np.float32)

@@ -50,6 +50,21 @@ def test_partition_covers_every_sample_once(pt):
             assert sorted(seen) == list(range(spp))
 
 
+def test_progressive_halves_cover_every_sample_once(pt):
+    """progressive.py: batches x halves (A even / B odd) x ranks enumerate each sample index exactly once."""
+    P = __import__("importlib").import_module("pt_b200.progressive")
+    for world in (1, 2, 8):
+        seen, done = [], 0
+        for batch in (3, 1, 4):                      # samples per half per rank in successive batches
+            for r in range(world):
+                for b, c, s in P.half_ranges(done, batch, r, world):
+                    seen += [b + k * s for k in range(c)]
+            done += batch
+        assert sorted(seen) == list(range(2 * 8 * world))
+        halves = [P.half_ranges(0, 8, r, world) for r in range(world)]
+        assert all((b + k * s) // world % 2 == h for rr in halves for h, (b, c, s) in enumerate(rr) for k in range(c))
+
+
 def test_two_rank_reduce_equals_single_rank(pt, orc, tmp_path):
     out = str(tmp_path / "r.npy")
     mp.spawn(_worker, args=(2, _free_port(), 5, out), nprocs=2, join=True)  # odd spp: ragged split 3 + 2
