@@ -25,7 +25,7 @@ extern "C" {
 #endif
 
 #define PT_NONE 0xFFFFFFFFu
-#define PT_ABI_VERSION 1
+#define PT_ABI_VERSION 2
 
 typedef enum {
     PT_OK = 0,
@@ -59,7 +59,8 @@ enum {
     PT_MAT_LIGHT = 4,      /* material.rs DiffuseLight */
     PT_MAT_SHEEN = 5,      /* bsdf/sheen.rs     */
     PT_MAT_CLEARCOAT = 6,  /* bsdf/clearcoat.rs */
-    PT_MAT_MIX = 7         /* bsdf/mix.rs       */
+    PT_MAT_MIX = 7,        /* bsdf/mix.rs       */
+    PT_MAT_ISOTROPIC = 8   /* volume.rs:18 phase_function (IsotropicMaterial, stub only): uniform sphere, albedo = base colour */
 };
 /* indices into pt_material.p */
 enum {
@@ -82,9 +83,29 @@ typedef struct {
 /* ---- hittables: src/hittable/*.rs ---------------------------------------------------- */
 enum {
     PT_PRIM_SPHERE = 0, PT_PRIM_QUAD = 1, PT_PRIM_TRIANGLE = 2,
-    PT_OBJ_CUBOID = 3, PT_OBJ_MESH = 4, PT_OBJ_INSTANCE = 5
+    PT_OBJ_CUBOID = 3, PT_OBJ_MESH = 4, PT_OBJ_INSTANCE = 5, PT_OBJ_VOLUME = 6
 };
 typedef struct { uint32_t kind, index; } pt_ref;
+
+/* Constant-density medium — the reference's src/volume.rs:15-41 is a commented-out stub (`HomogeneousVolume { boundary,
+ * negative_inv_density, phase_function }` with `intersects` = todo!()), so the behaviour below is OURS (SURVEY §8(f)-4;
+ * oracle-only parity).  For a ray (unit direction) and interval [t_min, inf):
+ *   h1 = boundary.intersects(ray, [t_min, inf));  none -> no hit
+ *   h1.front_face (entering):  t_in = h1.t;  from just inside, ray' = (ray.at(t_in + 1e-4), same direction):
+ *                              h2 = boundary.intersects(ray', [0, inf)),  none -> no hit,  t_out = t_in + 1e-4 + h2.t
+ *                              (sphere.rs:80 returns only the near root to an outside origin, hence the re-origin)
+ *   otherwise (origin inside): t_in = t_min, t_out = h1.t
+ *   s = -ln(U) / density;  s > t_out - t_in -> no hit;  else hit at t = t_in + s, normal (1,0,0), u = v = 0.
+ * U is NOT drawn from the path's sequential stream (traversal order must not matter): it is uniform #0 of
+ * philox4x32-10(key = seed, counter = (bounce, pixel, sample, 1 + volume index)); pt_trace_closest / pt_trace_any use
+ * seed 0, pixel = ray index, sample = bounce = 0.  The phase function is a PT_MAT_ISOTROPIC material: direction uniform
+ * on the sphere from 2 uniforms (z = 1 - 2 u1, phi = 2 pi u2), pdf = 1/(4 pi), eval = albedo/(4 pi). */
+typedef struct {
+    pt_ref boundary;        /* PT_PRIM_SPHERE or PT_OBJ_CUBOID: closed and convex */
+    double density;
+    uint32_t material;      /* PT_MAT_ISOTROPIC */
+    uint32_t _pad;
+} pt_volume;
 
 typedef struct {            /* sphere.rs:13-19 */
     pt_vec3 position1, position2;
@@ -116,7 +137,7 @@ typedef struct {            /* mesh.rs:144-198 */
 } pt_mesh;
 
 typedef struct {            /* instance.rs:12-31; column-major 4x4 like glam::DMat4 */
-    pt_ref child;           /* SPHERE, QUAD, CUBOID or MESH (no nesting) */
+    pt_ref child;           /* SPHERE, QUAD, CUBOID, MESH or VOLUME (no nested instances) */
     pt_vec3 axis;           /* arguments of Instance::new (instance.rs:20), informational: */
     double angle;           /*   the device consumes only the three matrices below        */
     pt_vec3 translation;
@@ -154,6 +175,8 @@ typedef struct {
     const pt_ref*      lights;       /* World.lights in insertion order (world.rs:7) */
     uint32_t objects_bvh_root;       /* PT_NONE => linear scan */
     uint32_t lights_bvh_root;        /* PT_NONE => linear scan / empty */
+    uint32_t n_volumes, _pad;        /* ABI version 2 */
+    const pt_volume* volumes;
 } pt_scene_desc;
 
 /* ---- camera: public fields of src/camera.rs:23-36; init() (camera.rs:51-77) is

@@ -324,6 +324,22 @@ struct DiffuseLight : BxDF {
     Vec3 emitted(double u, double v, Vec3 p) const override { return emission->value(u, v, p); }
 };
 
+// ---------------------------------------------------------------- volume.rs:18 phase_function (stub in the reference)
+// NOT reference behaviour (include/pt_b200.h, PT_MAT_ISOTROPIC): direction uniform on the sphere, albedo from a texture.
+struct IsotropicMaterial : BxDF {
+    const Texture* albedo;
+    explicit IsotropicMaterial(const Texture* a) : albedo(a) {}
+    std::optional<Vec3> sample(const Ray&, const HitInfo&, Rng& rng) const override {
+        double u1 = rng.next(), u2 = rng.next();
+        double z = 1.0 - 2.0 * u1;
+        double r = std::sqrt(fmax_(0.0, 1.0 - z * z));
+        double phi = 2.0 * PI * u2;
+        return Vec3(r * std::cos(phi), r * std::sin(phi), z);
+    }
+    double pdf(Vec3, Vec3, const HitInfo&) const override { return 1.0 / (4.0 * PI); }
+    Vec3 eval(Vec3, Vec3, const HitInfo& info) const override { return albedo->value(info.u, info.v, info.point) * (1.0 / (4.0 * PI)); }
+};
+
 // ---------------------------------------------------------------- bsdf/sheen.rs
 struct SheenBRDF : BxDF {
     Vec3 base_color; double sheen_tint;

@@ -141,6 +141,7 @@ struct Camera {
         g_cnt.paths++;
         for (uint32_t bounces = 0; bounces < max_depth; bounces++) {
             if (record) record->push_back(ray);
+            g_path_key = PathKey{rng.seed, rng.pixel, rng.sample, bounces};  // only volumes (ours) read it
             auto hit = world.intersect_all(ray, Interval{eps, INF});
             if (!hit) {
                 Vec3 env = throughput * sample_environment(ray);

@@ -58,6 +58,14 @@ static HitPtr build_ref(orc_scene* s, const pt_scene_desc* d, pt_ref r, bool all
             if (!child) return nullptr;
             return std::make_shared<Instance>(child, V(in.axis), in.angle, V(in.translation), r.index);
         }
+        case PT_OBJ_VOLUME: {
+            if (d->abi_version < 2 || r.index >= d->n_volumes) return nullptr;
+            const pt_volume& v = d->volumes[r.index];
+            if (v.boundary.kind != PT_PRIM_SPHERE && v.boundary.kind != PT_OBJ_CUBOID) return nullptr;
+            HitPtr boundary = build_ref(s, d, v.boundary, false);
+            if (!boundary) return nullptr;
+            return std::make_shared<HomogeneousVolume>(boundary, v.density, s->materials[v.material].get(), r.index);
+        }
         default:
             return nullptr;
     }
@@ -123,6 +131,7 @@ int orc_scene_create(const pt_scene_desc* d, orc_scene** out) {
                         b = std::make_unique<SheenBRDF>(Vec3(m.p[PT_P_COLOR_R], m.p[PT_P_COLOR_G], m.p[PT_P_COLOR_B]), m.p[PT_P_SHEEN_TINT]);
                         break;
                     case PT_MAT_CLEARCOAT: b = std::make_unique<ClearcoatBRDF>(m.p[PT_P_ALPHA_G]); break;
+                    case PT_MAT_ISOTROPIC: b = std::make_unique<IsotropicMaterial>(tex(m.base_color_tex)); break;
                     case PT_MAT_MIX: break;
                     default: g_err = "unknown material kind"; return -1;
                 }
@@ -250,6 +259,7 @@ int orc_trace_closest(const orc_scene* s, size_t n, const pt_ray* rays, double t
 #pragma omp parallel for schedule(dynamic, 256)
     for (size_t i = 0; i < n; i++) {
         Ray r{V(rays[i].origin), V(rays[i].direction), rays[i].time};
+        g_path_key = PathKey{0, (uint32_t)i, 0, 0};  // keyed uniforms of ray batches (include/pt_b200.h, pt_volume)
         fill_hit(s->world, s->world.intersect_all(r, Interval{t_min, INF}), &hits[i]);
     }
     return 0;
@@ -258,6 +268,7 @@ int orc_trace_any(const orc_scene* s, size_t n, const pt_ray* rays, double t_min
 #pragma omp parallel for schedule(dynamic, 256)
     for (size_t i = 0; i < n; i++) {
         Ray r{V(rays[i].origin), V(rays[i].direction), rays[i].time};
+        g_path_key = PathKey{0, (uint32_t)i, 0, 0};
         occluded[i] = s->world.occluded(r, Interval{t_min, t_max[i]}) ? 1 : 0;
     }
     return 0;

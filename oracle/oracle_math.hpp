@@ -248,4 +248,16 @@ struct Rng {
     }
 };
 
+// Keyed uniforms for decisions taken INSIDE an intersection test (the constant-density medium of include/pt_b200.h —
+// ours, the reference's volume.rs is a stub): they must not depend on traversal order, so they are addressed by
+// (path, bounce, stream) instead of being drawn sequentially: uniform #0 of philox(key = seed, counter = (bounce, pixel,
+// sample, 1 + stream)).  The integrator sets the key before each intersect_all; ray batches use (0, ray index, 0, 0).
+struct PathKey { uint64_t seed = 0; uint32_t pixel = 0, sample = 0, bounce = 0; };
+inline thread_local PathKey g_path_key;
+inline double keyed_uniform(uint32_t stream) {
+    uint32_t o[4];
+    Philox::block((uint32_t)g_path_key.seed, (uint32_t)(g_path_key.seed >> 32), g_path_key.bounce, g_path_key.pixel, g_path_key.sample, 1u + stream, o);
+    return (double)((((uint64_t)o[0] << 32) | o[1]) >> 11) * (1.0 / 9007199254740992.0);
+}
+
 }  // namespace orc

@@ -528,6 +528,39 @@ struct Instance : Hittable {
     }
 };
 
+// ---------------------------------------------------------------- HomogeneousVolume (src/volume.rs:15-41 is a stub)
+// NOT reference behaviour: the reference never finished this type (`intersects` is todo!()).  The semantics are the
+// ones include/pt_b200.h documents for pt_volume; this is the CPU statement of them the device is checked against.
+struct HomogeneousVolume : Hittable {
+    HitPtr boundary; double negative_inv_density; const BxDF* phase_function; uint32_t id;
+    HomogeneousVolume(HitPtr b, double density, const BxDF* phase, uint32_t id_)
+        : boundary(std::move(b)), negative_inv_density(-1.0 / density), phase_function(phase), id(id_) {}
+    std::optional<HitInfo> intersects(const Ray& ray, Interval ray_t) const override {
+        auto h1 = boundary->intersects(ray, Interval{ray_t.min, INF});
+        if (!h1) return std::nullopt;
+        double t_in, t_out;
+        if (h1->front_face) {
+            t_in = h1->dist;
+            // the exit is found from just inside: sphere.rs:80 only ever returns the near root to an outside origin
+            double step = t_in + 1e-4;
+            Ray inner{ray.at(step), ray.direction, ray.time};
+            auto h2 = boundary->intersects(inner, Interval{0.0, INF});
+            if (!h2) return std::nullopt;
+            t_out = step + h2->dist;
+        } else { t_in = ray_t.min; t_out = h1->dist; }
+        double s = negative_inv_density * std::log(keyed_uniform(id));
+        if (s > t_out - t_in) return std::nullopt;
+        double t = t_in + s;
+        if (!ray_t.contains(t)) return std::nullopt;
+        HitInfo h = make_hit_info(ray, ray.at(t), Vec3(1, 0, 0), t, phase_function, 0.0, 0.0);
+        h.prim_kind = 6; h.prim_index = id;
+        return h;
+    }
+    AABB bounding_box() const override { return boundary->bounding_box(); }
+    std::optional<Vec3> sample(Vec3, double, Rng&) const override { return std::nullopt; }
+    double pdf(Vec3, Vec3, double) const override { return 0.0; }
+};
+
 // ---------------------------------------------------------------- World (src/hittable/world.rs)
 struct World {
     HittableList objects, lights;

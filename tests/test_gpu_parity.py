@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 import helpers as H
-from test_oracle import _material_world, _ray, mixed_lights_world, sun_world, tie_world
+from test_oracle import _material_world, _ray, fog_world, mixed_lights_world, sun_world, tie_world
 
 pytestmark = pytest.mark.gpu
 
@@ -277,6 +277,37 @@ def test_env_importance_sampling_scene5_and_default_unchanged(pt, orc, pairs):
     assert abs(int(st.segments) - int(ost.segments)) <= max(64, ost.segments // 2000)
     d = np.abs(img - ref).max(axis=2)
     assert (d > 1e-4 * np.maximum(ref.max(axis=2), 1.0)).mean() < 0.02 and H.rel_rmse(img, ref) < 0.05
+
+
+# ---------------------------------------------------------------- constant-density media (ours)
+def test_volumes_match_oracle(pt, orc, ctx):
+    """pt_volume (the reference's volume.rs is a stub, so parity is against the oracle's statement of include/pt_b200.h):
+    scatter distances of ray batches, closest / any hits in a world with fog spheres, smoke cuboids and an instanced
+    medium, Beer-Lambert transmittance on the device, and a render that follows the oracle sample for sample."""
+    scene = fog_world(pt, 64)
+    dev, ora = ctx.upload(scene), orc.OracleScene(scene.desc, pt)
+    cam = scene.camera
+    rows, cols = np.divmod(np.arange(64 * 64, dtype=np.uint32), 64)
+    rays = orc.camera_rays(cam, 3, rows, cols, np.zeros_like(rows), pt)
+    a, b = dev.trace_closest(rays), ora.trace_closest(rays)
+    assert (b["prim_kind"][b["hit"] == 1] == 6).mean() > 0.05            # a good share of the camera rays scatter in a medium
+    assert_hits_equal(pt, a, b, "fog world camera rays")
+    bounce = ora.dump_path_rays(cam, 5, 1, 2, 1, 60000)
+    assert len(bounce) > 5000
+    assert_hits_equal(pt, dev.trace_closest(bounce), ora.trace_closest(bounce), "fog world bounce rays")
+    t_max = np.random.default_rng(31).uniform(0.2, 8.0, size=len(bounce))
+    assert np.array_equal(dev.trace_any(bounce, t_max), ora.trace_any(bounce, t_max))
+    n = 200000                                                            # Beer-Lambert on the device itself
+    probe = np.zeros(n, dtype=pt.RAY_DTYPE)
+    probe["origin"] = (-1.2, 1.0, 5.0); probe["direction"] = (0, 0, -1)   # through the centre of the fog sphere: chord 2, density 0.8
+    h = dev.trace_closest(probe)
+    assert abs((h["prim_kind"] == 6).mean() - (1 - np.exp(-0.8 * 2.0))) < 0.004
+    img, st = dev.render(spp=8, seed=33, nan_policy=pt.PT_NAN_DROP)
+    ref, ost = ora.render(cam, 8, seed=33, nan_policy=pt.PT_NAN_DROP)
+    assert st.paths == ost.paths and abs(int(st.segments) - int(ost.segments)) <= max(64, ost.segments // 2000)
+    d = np.abs(img - ref).max(axis=2)
+    assert (d > 1e-4 * np.maximum(ref.max(axis=2), 1.0)).mean() < 0.02 and H.rel_rmse(img, ref) < 0.05
+    dev.close(); ora.close()
 
 
 # ---------------------------------------------------------------- renders

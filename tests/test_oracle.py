@@ -283,6 +283,52 @@ def test_oracle_env_sampler_is_a_density_and_keeps_the_expectation(pt, orc):
     ora.close()
 
 
+def fog_world(pt, width=48):
+    """Constant-density media (ours; the reference's volume.rs is a stub): a fog sphere, a smoke cuboid, an instanced fog
+    cuboid and a dense ball inside a Cornell-like set with a quad light."""
+    grey = pt.DiffuseBRDF((0.6, 0.6, 0.6))
+    w = pt.World()
+    w.add_light(pt.Quad((-1, 3.99, -1), (2, 0, 0), (0, 0, 2), pt.DiffuseLight((12, 12, 12))))
+    w.add_object(pt.Quad((-4, 0, -4), (8, 0, 0), (0, 0, 8), grey))
+    w.add_object(pt.Quad((-4, 0, -4), (8, 0, 0), (0, 4, 0), pt.DiffuseBRDF((0.6, 0.2, 0.2))))
+    w.add_object(pt.Sphere.new_still(0.6, (1.6, 0.6, -1.0), pt.MetalBRDF((0.9, 0.9, 0.9), 0.2)))
+    w.add_object(pt.HomogeneousVolume(pt.Sphere.new_still(1.0, (-1.2, 1.0, 0.0), grey), 0.8, (0.9, 0.9, 0.9)))
+    w.add_object(pt.HomogeneousVolume(pt.Cuboid((0.2, 0.0, 0.4), (1.4, 1.6, 1.6), grey), 2.5, (0.2, 0.2, 0.25)))
+    w.add_object(pt.Instance(pt.HomogeneousVolume(pt.Cuboid((-0.5, -0.5, -0.5), (0.5, 0.5, 0.5), grey), 1.5, (0.7, 0.8, 0.9)),
+                             (0, 1, 0), 0.6, (0.0, 2.6, -1.5)))
+    w.add_object(pt.HomogeneousVolume(pt.Sphere.new_still(0.4, (2.6, 0.4, 1.2), grey), 40.0, (0.3, 0.7, 0.3)))
+    w.build_bvh()
+    cam = pt.make_camera(width, aspect_ratio=1.0, samples_per_pixel=4, max_depth=20, vfov=45.0, look_from=(0, 2.0, 9.0), look_at=(0, 1.5, 0),
+                         env_color=(0.05, 0.06, 0.08))
+    return pt.Scene.from_world(w, cam)
+
+
+def test_oracle_volume_follows_beer_lambert(pt, orc):
+    """pt_volume semantics (include/pt_b200.h): the chance to cross a medium unscattered is exp(-density * chord), scatter
+    distances are exponential, a ray starting inside sees only the rest of the chord, and each ray has its own keyed uniform."""
+    w = pt.World()
+    w.add_object(pt.HomogeneousVolume(pt.Sphere.new_still(1.0, (0, 0, -5), pt.DiffuseBRDF((0.5, 0.5, 0.5))), 0.7, (1, 1, 1)))
+    scene = pt.Scene.from_world(w, pt.make_camera(8))
+    ora = orc.OracleScene(scene.desc, pt)
+    n = 200000
+    rays = np.zeros(n, dtype=pt.RAY_DTYPE)
+    rays["direction"] = (0, 0, -1)
+    h = ora.trace_closest(rays)                                           # along the diameter: chord 2
+    assert abs((h["hit"] == 0).mean() - np.exp(-0.7 * 2.0)) < 0.004
+    hit = h["hit"] == 1
+    s = h["t"][hit] - 4.0                                                 # distance travelled inside
+    assert (h["prim_kind"][hit] == 6).all() and s.min() > 0 and s.max() <= 2.0
+    assert abs(s.mean() - (1 / 0.7 - 2.0 * np.exp(-1.4) / (1 - np.exp(-1.4)))) < 0.01   # mean of a truncated exponential
+    assert np.allclose(h["geometric_normal"][hit], (1, 0, 0)) or np.allclose(np.abs(h["geometric_normal"][hit]), (1, 0, 0))
+    rays["origin"] = (0, 0, -5)                                           # from the centre: chord 1
+    h2 = ora.trace_closest(rays)
+    assert abs((h2["hit"] == 0).mean() - np.exp(-0.7)) < 0.004
+    assert np.array_equal(ora.trace_closest(rays[:1000]), h2[:1000])       # keyed by the ray index: reproducible
+    rays["origin"] = (0, 2.0, 0)                                          # misses the sphere
+    assert ora.trace_closest(rays[:1000])["hit"].sum() == 0
+    ora.close()
+
+
 def test_oracle_sample_split_is_exact(pt, orc):
     """spp split across G virtual ranks (sample index = g + k*G) reproduces the 1-rank sum."""
     scene = pt.Scene.build(3, width=24, spp=8, seed=1)

@@ -148,7 +148,8 @@ def host_lib():
             "pth_sphere_still": [C.c_double, d3, vp], "pth_sphere_moving": [C.c_double, d3, d3, vp], "pth_quad": [d3, d3, d3, vp],
             "pth_cuboid": [d3, d3, vp], "pth_mesh_load": [C.c_char_p, C.c_double, vp],
             "pth_mesh_from_arrays": [C.c_double, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp],
-            "pth_instance": [vp, d3, C.c_double, d3], "pth_world_new": [], "pth_scene_from_world": [vp, C.POINTER(CameraABI), vp],
+            "pth_instance": [vp, d3, C.c_double, d3], "pth_volume": [vp, C.c_double, vp],
+            "pth_world_new": [], "pth_scene_from_world": [vp, C.POINTER(CameraABI), vp],
             "pth_scene_build": [C.c_int, C.c_uint32, C.c_uint32, C.c_uint64, C.c_char_p, vp, C.c_uint32, C.c_uint32],
             "pth_scene_desc": [vp], "pth_scene_camera": [vp],
         }
@@ -323,6 +324,18 @@ class TriangleMesh(_Handle):
 class Instance(_Handle):
     def __init__(self, obj, axis, angle, translation):
         super().__init__(host_lib().pth_instance(obj.ptr, _d3(axis), float(angle), _d3(translation)), (obj,))
+
+
+class HomogeneousVolume(_Handle):
+    """volume.rs:15-41 (a stub in the reference; semantics in include/pt_b200.h): constant-density medium inside a sphere
+    or cuboid boundary with an isotropic phase function of the given albedo (colour or texture)."""
+
+    def __init__(self, boundary, density, albedo):
+        t = _tex(albedo)
+        p = host_lib().pth_volume(boundary.ptr, float(density), t.ptr)
+        if not p:
+            raise PtError(host_lib().pth_last_error().decode())
+        super().__init__(p, (boundary, t))
 
 
 class World(_Handle):

@@ -57,6 +57,7 @@ struct pt_scene {
     bool wide = false;                      // traversed with 4-wide nodes (some BVH has >= kWideMinItems items) or binary pairs
     std::vector<DImage> images;
     bool general_lights = false;            // World.lights holds something other than quads and spheres (shade kernel variant)
+    bool has_volumes = false;               // constant-density media present (trace kernel variant with keyed uniforms)
     DEnvDist env{};                         // pt_scene_build_env_sampler: importance sampler of image `env_image`
     uint32_t env_image = 0xFFFFFFFFu;
     void* env_block = nullptr;
@@ -212,6 +213,7 @@ struct Converter {
                 for (int k = 0; k < 3; k++) { lo[k] -= slack; hi[k] += slack; }
                 return true;
             }
+            case PT_OBJ_VOLUME: return ref_box(d->volumes[r.index].boundary, lo, hi);  // a scatter point lies inside the boundary
         }
         return false;
     }
@@ -315,9 +317,22 @@ static int check_desc(const pt_scene_desc* d) {
             case PT_OBJ_CUBOID: return r.index < d->n_cuboids;
             case PT_OBJ_MESH: return r.index < d->n_meshes;
             case PT_OBJ_INSTANCE: return top && r.index < d->n_instances;
+            case PT_OBJ_VOLUME: return r.index < d->n_volumes;
             default: return false;
         }
     };
+    if (d->n_volumes && !d->volumes) return fail(PT_ERR_INVALID, "scene description has a null array with a non-zero count");
+    for (uint32_t i = 0; i < d->n_volumes; i++) {
+        const pt_volume& v = d->volumes[i];
+        if ((v.boundary.kind != PT_PRIM_SPHERE && v.boundary.kind != PT_OBJ_CUBOID) || !ref_ok(v.boundary, false))
+            return fail(PT_ERR_UNSUPPORTED, "volume boundary must be a sphere or a cuboid");
+        if (!(v.density > 0.0) || v.material >= d->n_materials || d->materials[v.material].kind != PT_MAT_ISOTROPIC)
+            return fail(PT_ERR_INVALID, "volume needs a positive density and a PT_MAT_ISOTROPIC phase function");
+    }
+    for (uint32_t i = 0; i < d->n_lights; i++) {
+        const pt_ref r = d->lights[i].kind == PT_OBJ_INSTANCE && d->lights[i].index < d->n_instances ? d->instances[d->lights[i].index].child : d->lights[i];
+        if (r.kind == PT_OBJ_VOLUME) return fail(PT_ERR_UNSUPPORTED, "a volume cannot be a light");
+    }
     for (uint32_t i = 0; i < d->n_objects; i++) if (!ref_ok(d->objects[i], true)) return fail(PT_ERR_INVALID, "bad ref in objects");
     for (uint32_t i = 0; i < d->n_lights; i++) if (!ref_ok(d->lights[i], true)) return fail(PT_ERR_INVALID, "bad ref in lights");
     for (uint32_t i = 0; i < d->n_leaf_refs; i++) if (!ref_ok(d->leaf_refs[i], false) && !ref_ok(d->leaf_refs[i], true)) return fail(PT_ERR_INVALID, "bad leaf ref");
@@ -332,7 +347,7 @@ static int check_desc(const pt_scene_desc* d) {
         switch (m.kind) {
             case PT_MAT_DIFFUSE: ok = tex_ok(m.base_color_tex) && (m.normal_map == PT_NONE || m.normal_map < d->n_images); break;
             case PT_MAT_METAL: case PT_MAT_GLASS: ok = tex_ok(m.base_color_tex) && tex_ok(m.roughness_tex); break;
-            case PT_MAT_PRINCIPLED: case PT_MAT_LIGHT: ok = tex_ok(m.base_color_tex); break;
+            case PT_MAT_PRINCIPLED: case PT_MAT_LIGHT: case PT_MAT_ISOTROPIC: ok = tex_ok(m.base_color_tex); break;
             case PT_MAT_SHEEN: case PT_MAT_CLEARCOAT: break;
             case PT_MAT_MIX: ok = m.mix_a < i && m.mix_b < i; break;
             default: ok = false;
@@ -448,6 +463,10 @@ int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
         o.child_kind = p.child.kind; o.child_index = p.child.index; o.tie_is_sphere = p.child.kind == PT_PRIM_SPHERE;
         instances[i] = o;
     }
+    std::vector<DVolume> volumes(d->n_volumes);
+    for (uint32_t i = 0; i < d->n_volumes; i++)
+        volumes[i] = DVolume{d->volumes[i].boundary.kind, d->volumes[i].boundary.index, d->volumes[i].material, 0, -1.0 / d->volumes[i].density, 0.0};
+    s->has_volumes = d->n_volumes > 0;
     // ---- textures, images, materials
     std::vector<DTexture> textures(d->n_textures);
     for (uint32_t i = 0; i < d->n_textures; i++) {
@@ -510,7 +529,7 @@ int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
     U.up(C.wide, &D.wide); U.up(C.nodes, &D.nodes); U.up(C.refs, &D.refs); U.up(spheres, &D.spheres); U.up(quads, &D.quads); U.up(quad_mat, &D.quad_material);
     U.up(tris, &D.tris); U.up(tri_normals, &D.tri_normals); U.up(tri_uvs, &D.tri_uvs); U.up(tri_mesh, &D.tri_mesh); U.up(cuboids, &D.cuboids);
     U.up(meshes, &D.meshes); U.up(instances, &D.instances); U.up(textures, &D.textures); U.up(images, &D.images); U.up(materials, &D.materials);
-    U.up(lights, &D.lights); U.up(tri_verts, &D.tri_verts);
+    U.up(lights, &D.lights); U.up(tri_verts, &D.tri_verts); U.up(volumes, &D.volumes);
     if ((rc = U.commit())) return rc;
     D.image_data = d_img; D.n_lights = d->n_lights; D.root_entry = world_root;
     s->n_materials = d->n_materials; s->n_images = d->n_images; s->images = images;
@@ -672,6 +691,11 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
         const Queues q{ctx->q_items, ctx->d_count + 4, ctx->pool};
         if (ctx->profiling) CU(cudaEventRecord(ctx->evs[1], st));
             const unsigned tg = (n + kBlock - 1) / kBlock;
+            if (scene->has_volumes) {  // media: the trace kernel variant that draws keyed free-flight uniforms
+                unsigned long long* wk = ctx->profiling ? ctx->d_nonfinite + 1 : nullptr;
+                if (scene->wide) { if (wk) k_trace<6, true, true, true><<<tg, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, p->seed); else k_trace<6, true, false, true><<<tg, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, p->seed); }
+                else { if (wk) k_trace<6, false, true, true><<<tg, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, p->seed); else k_trace<6, false, false, true><<<tg, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, p->seed); }
+            } else
             if (ctx->profiling) {
                 if (scene->wide) k_trace<6, true, true><<<tg, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, ctx->d_nonfinite + 1);
                 else k_trace<6, false, true><<<tg, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, ctx->d_nonfinite + 1);

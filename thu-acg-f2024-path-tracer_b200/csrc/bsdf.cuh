@@ -184,6 +184,14 @@ PT_D bool bsdf_sample_leaf(const DScene& S, const DMaterial& m, d3 ray_dir, cons
             out = to_world(h.sn, reflect(-v, hh));
             return !(dot(out, h.sn) <= 0.0);
         }
+        case PT_MAT_ISOTROPIC: {  // phase function of a medium (pt_volume; ours): uniform on the sphere
+            const double u1 = rng.next(), u2 = rng.next();
+            const double z = 1.0 - 2.0 * u1;
+            const double r = sqrt(fmax(0.0, 1.0 - z * z));
+            const double phi = 2.0 * kPi * u2;
+            out = mk(r * cos(phi), r * sin(phi), z);
+            return true;
+        }
         default: return false;  // DiffuseLight::sample -> None (material.rs:168-170)
     }
 }
@@ -300,6 +308,10 @@ PT_D void bsdf_eval_pdf_leaf(const DScene& S, const DMaterial& m, d3 view_dir, d
             f_out = clearcoat_eval(v, l, h, m.p[PT_P_ALPHA_G]);
             return;
         }
+        case PT_MAT_ISOTROPIC:
+            pdf_out = 1.0 / (4.0 * kPi);
+            f_out = texture_value(S, m.base_color_tex, hi.u, hi.v, hi.point) * (1.0 / (4.0 * kPi));
+            return;
         default: pdf_out = 0.0; f_out = mk(0, 0, 0); return;
     }
 }

@@ -133,6 +133,55 @@ PT_D void test_simple(const DScene& S, uint32_t kind, uint32_t index, const RayD
     }
 }
 
+// ---------------------------------------------------------------- constant-density media (include/pt_b200.h, pt_volume; ours)
+// Nearest crossing of a volume boundary (sphere or cuboid) at t > / >= t_lo as the primitive's own rule has it, plus the
+// HitInfo::new front_face of that crossing (hit_info.rs:27: direction . outward normal < 0).
+PT_D bool boundary_hit(const DScene& S, uint32_t kind, uint32_t index, const RayD& r, double t_lo, double& t_out, bool& front_face) {
+    if (kind == PT_PRIM_SPHERE) {
+        const DSphere& s = S.spheres[index];
+        double t;
+        if (!sphere_t(s, r, t_lo, t) || !(t < __longlong_as_double(0x7ff0000000000000ll))) return false;
+        d3 p1 = mk(s.p1[0], s.p1[1], s.p1[2]), p2 = mk(s.p2[0], s.p2[1], s.p2[2]);
+        d3 normal = normalize(ray_at(r, t) - (p1 + (p2 - p1) * r.time));
+        t_out = t; front_face = dot(r.d, normal) < 0.0;
+        return true;
+    }
+    const uint32_t fq = S.cuboids[index].first_quad;  // six quads, linear list: a later quad wins an equal t (list.rs:57-66)
+    bool any = false; double best = __longlong_as_double(0x7ff0000000000000ll);
+#pragma unroll 1
+    for (uint32_t k = 0; k < 6; k++) {
+        double t, a, b;
+        if (quad_t(S.quads[fq + k], r, t_lo, t, a, b) && t <= best) {
+            best = t; any = true;
+            front_face = dot(r.d, mk(S.quads[fq + k].n[0], S.quads[fq + k].n[1], S.quads[fq + k].n[2])) < 0.0;
+        }
+    }
+    t_out = best;
+    return any;
+}
+// Scatter distance inside volume `vi` for ray r on [t_min, inf), given the ray's keyed uniform u.
+PT_D bool volume_t(const DScene& S, uint32_t vi, const RayD& r, double t_min, double u, double& t_out) {
+    const DVolume v = S.volumes[vi];
+    double t1; bool ff;
+    if (!boundary_hit(S, v.child_kind, v.child_index, r, t_min, t1, ff)) return false;
+    double t_in, t_exit;
+    if (ff) {  // entering: find the exit from just inside (sphere.rs:80 never returns the far root to an outside origin)
+        t_in = t1;
+        const double step = t_in + 1e-4;
+        RayD inner; inner.o = ray_at(r, step); inner.d = r.d; inner.time = r.time;
+        double t2; bool ff2;
+        if (!boundary_hit(S, v.child_kind, v.child_index, inner, 0.0, t2, ff2)) return false;
+        t_exit = step + t2;
+    } else { t_in = t_min; t_exit = t1; }
+    const double s = v.neg_inv_density * log(u);
+    if (s > t_exit - t_in) return false;
+    const double t = t_in + s;
+    if (!(t_min <= t)) return false;
+    t_out = t;
+    return true;
+}
+struct NoVol { static constexpr bool kEnabled = false; PT_D double operator()(uint32_t) const { return 1.0; } };
+
 // World::intersect_all(ray, [t_min, inf)) — world.rs:47-62.  any_hit: stop at the first hit with t <= t_max on World.objects.
 //
 // "while-while" structure: phase 1 walks 4-wide internal nodes only (fp32 slab tests, four children per 128-byte fetch,
@@ -142,8 +191,10 @@ constexpr uint32_t kTagLeaf = 0xC0000000u;  // kTagRef = 0x4..., kTagSentinel = 
 constexpr uint32_t kWideBit = 0x20000000u;  // internal entries: set = index of a 4-wide node, clear = index of a binary node pair
 // `reload()` returns the world ray again (called when an instance is left), so it need not be kept in registers;
 // COUNT enables the work counters reported by pt_trace_closest.
-template <bool ANY_HIT, bool COUNT, bool WIDE, class Reload>
-PT_D bool trace_closest(const DScene& S, Reload reload, double t_min, double t_max_any, Closest& c) {
+// `vol_u(volume index)` returns the ray's keyed uniform for that medium; VolU::kEnabled is false for scenes without media,
+// whose kernels then carry none of the medium code.
+template <bool ANY_HIT, bool COUNT, bool WIDE, class Reload, class VolU = NoVol>
+PT_D bool trace_closest(const DScene& S, Reload reload, double t_min, double t_max_any, Closest& c, VolU vol_u = VolU()) {
     uint32_t stack[kStack]; float stack_t[kStack + 1];  // +1: slot sp may be written when a leaf is handed to phase 2 directly
     int sp = 0;
     c.t = ANY_HIT ? t_max_any : __longlong_as_double(0x7ff0000000000000ll);
@@ -257,11 +308,24 @@ PT_D bool trace_closest(const DScene& S, Reload reload, double t_min, double t_m
         const uint32_t kind = ref_kind(rf.kind_index), index = ref_index(rf.kind_index);
         uint32_t mesh = kNone;
         if (kind == PT_OBJ_MESH) { mesh = index; cur_inst = kInstNone; }
-        else {  // PT_OBJ_INSTANCE
+        else if (VolU::kEnabled && kind == PT_OBJ_VOLUME) {
+            double t;
+            if (volume_t(S, index, r, t_min, vol_u(index), t) && t <= c.t) consider(c, t, rf.kind_index, kInstNone, rf.tie, 0);
+            if (ANY_HIT && c.ref != kNone) return true;
+            tmax_f = __double2float_ru(c.t);
+            continue;
+        } else {  // PT_OBJ_INSTANCE
             const DInstance& in = S.instances[index];
             const RayD lr = instance_local_ray(in, r);
             if (in.child_kind == PT_OBJ_MESH) { mesh = in.child_index; r = lr; br = make_boxray(r); cur_inst = index; }
-            else {
+            else if (VolU::kEnabled && in.child_kind == PT_OBJ_VOLUME) {
+                double t;
+                if (volume_t(S, in.child_index, lr, t_min, vol_u(in.child_index), t) && t <= c.t)
+                    consider(c, t, ref_pack(PT_OBJ_VOLUME, in.child_index), index, rf.tie, 0);
+                if (ANY_HIT && c.ref != kNone) return true;
+                tmax_f = __double2float_ru(c.t);
+                continue;
+            } else {
                 test_simple(S, in.child_kind, in.child_index, lr, t_min, c, index, rf.tie, 0);
                 if (ANY_HIT && c.ref != kNone) return true;
                 tmax_f = __double2float_ru(c.t);
@@ -337,6 +401,8 @@ PT_D void reconstruct_hit(const DScene& S, const RayD& world_ray, uint32_t ref, 
         double alpha = dot(w, cross(p, mk(qd.v[0], qd.v[1], qd.v[2])));
         double beta = dot(w, cross(mk(qd.u[0], qd.u[1], qd.u[2]), p));
         finish_hit(S, r, ray_at(r, t), mk(qd.n[0], qd.n[1], qd.n[2]), t, S.quad_material[index], alpha, beta, h);
+    } else if (kind == PT_OBJ_VOLUME) {  // scatter point inside a medium: arbitrary normal (1,0,0), u = v = 0 (pt_volume)
+        finish_hit(S, r, ray_at(r, t), mk(1.0, 0.0, 0.0), t, S.volumes[index].material, 0.0, 0.0, h);
     } else {  // triangle, mesh.rs:84-111
         const DTri& tr = S.tris[index];
         const DMesh& m = S.meshes[S.tri_mesh[index]];

@@ -123,6 +123,7 @@ PT_D uint32_t hit_material(const DScene& S, uint32_t ref) {
     const uint32_t kind = ref_kind(ref), index = ref_index(ref);
     if (kind == PT_PRIM_SPHERE) return S.spheres[index].material;
     if (kind == PT_PRIM_QUAD) return S.quad_material[index];
+    if (kind == PT_OBJ_VOLUME) return S.volumes[index].material;
     return S.meshes[S.tri_mesh[index]].material;
 }
 PT_D uint32_t class_of_kind(uint32_t k) {
@@ -148,15 +149,23 @@ PT_D void queue_append(const Queues& q, uint32_t cls, uint32_t i) {
 // World::intersect_all for every live path (one ray per thread), then the path joins the queue of its shade class.
 // COUNT (profiling mode only): also sums the traversal work of all rays into work[3] = {node pairs, reference boxes,
 // f64 primitive tests}, from which bench.py derives the bytes the device actually requests per ray.
-template <int MIN_BLOCKS, bool WIDE, bool COUNT = false>
+// VOL: the scene holds constant-density media; their free-flight uniforms are keyed by (seed, pixel, sample, bounce).
+struct PathVol {
+    static constexpr bool kEnabled = true;
+    uint64_t seed; const uint4* __restrict__ ids; uint32_t i;
+    PT_D double operator()(uint32_t v) const { const uint4 id = ids[i]; return keyed_uniform(seed, id.x, id.y, id.z >> 16, v); }
+};
+template <int MIN_BLOCKS, bool WIDE, bool COUNT = false, bool VOL = false>
 __global__ void __launch_bounds__(kBlock, MIN_BLOCKS) k_trace(PathBuf in, uint32_t n, HitRec* __restrict__ hits, Queues q, DScene S,
-                                                              unsigned long long* __restrict__ work = nullptr) {
+                                                              unsigned long long* __restrict__ work = nullptr, uint64_t seed = 0) {
     const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
     uint32_t cls = N_CLS;
     uint32_t w0 = 0, w1 = 0, w2 = 0;
     if (i < n) {
         Closest c;
-        trace_closest<false, COUNT, WIDE>(S, [&]() { return load_ray(in, i); }, 1e-3, 0.0, c);  // Interval::new(eps, INFINITY), camera.rs:171,179
+        // Interval::new(eps, INFINITY), camera.rs:171,179
+        if constexpr (VOL) trace_closest<false, COUNT, WIDE>(S, [&]() { return load_ray(in, i); }, 1e-3, 0.0, c, PathVol{seed, in.ids, i});
+        else trace_closest<false, COUNT, WIDE>(S, [&]() { return load_ray(in, i); }, 1e-3, 0.0, c);
         if (COUNT) { w0 = c.n_pairs + 2 * c.n_wide; w1 = c.n_refs; w2 = c.n_prims; }  // in 64-byte units
         HitRec h; h.t = c.t; h.ref = c.ref; h.inst_light = (c.inst & 0x7FFFFFFFu) | (c.is_light ? 0x80000000u : 0u);
         hits[i] = h;
@@ -302,6 +311,8 @@ __global__ void k_scale(const float* __restrict__ accum, float scale, uint32_t n
 PT_D pt_vec3 to_abi(d3 v) { pt_vec3 r; r.x = v.x; r.y = v.y; r.z = v.z; return r; }
 PT_D d3 from_abi(pt_vec3 v) { return mk(v.x, v.y, v.z); }
 
+// keyed uniforms of ray batches (pt_volume): seed 0, pixel = ray index, sample = bounce = 0
+struct BatchVol { static constexpr bool kEnabled = true; uint32_t i; PT_D double operator()(uint32_t v) const { return keyed_uniform(0, i, 0, 0, v); } };
 template <bool WIDE>
 __global__ void k_trace_batch(const pt_ray* __restrict__ rays, size_t n, double t_min, pt_hit* __restrict__ out, DScene S) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -309,7 +320,7 @@ __global__ void k_trace_batch(const pt_ray* __restrict__ rays, size_t n, double 
     RayD r; r.o = from_abi(rays[i].origin); r.d = from_abi(rays[i].direction); r.time = rays[i].time;
     Closest c;
     pt_hit o; memset(&o, 0, sizeof(o)); o.instance = PT_NONE;
-    const bool hit = trace_closest<false, true, WIDE>(S, [&]() { return r; }, t_min, 0.0, c);
+    const bool hit = trace_closest<false, true, WIDE>(S, [&]() { return r; }, t_min, 0.0, c, BatchVol{(uint32_t)i});
     o.work = min(c.n_pairs + c.n_wide, 0xFFFFu) | (min(c.n_prims, 0xFFFFu) << 16);
     if (hit) {
         HitInfoD h;
@@ -327,7 +338,7 @@ __global__ void k_trace_any_batch(const pt_ray* __restrict__ rays, size_t n, dou
     if (i >= n) return;
     RayD r; r.o = from_abi(rays[i].origin); r.d = from_abi(rays[i].direction); r.time = rays[i].time;
     Closest c;
-    out[i] = trace_closest<true, false, WIDE>(S, [&]() { return r; }, t_min, t_max[i], c) ? 1 : 0;
+    out[i] = trace_closest<true, false, WIDE>(S, [&]() { return r; }, t_min, t_max[i], c, BatchVol{(uint32_t)i}) ? 1 : 0;
 }
 PT_D HitInfoD info_from_query(const pt_bsdf_query& q, uint32_t material) {
     HitInfoD h; h.point = from_abi(q.point); h.gn = from_abi(q.geometric_normal); h.sn = from_abi(q.shading_normal);

@@ -62,6 +62,9 @@ void* pth_mesh_from_arrays(double scale, const float* pos, uint32_t n_pos_floats
 void* pth_instance(void* child, const double* axis, double angle, const double* translation) {
     PTH_TRY(return box<Hittable>(Instance::make(unbox<Hittable>(child), V(axis), angle, V(translation))));
 }
+void* pth_volume(void* boundary, double density, void* albedo_tex) {
+    PTH_TRY(return box<Hittable>(HomogeneousVolume::from_texture(unbox<Hittable>(boundary), density, unbox<Texture>(albedo_tex))));
+}
 // ---- world ----
 void* pth_world_new() { return new World(); }
 void pth_world_free(void* w) { delete static_cast<World*>(w); }

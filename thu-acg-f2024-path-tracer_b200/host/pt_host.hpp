@@ -89,6 +89,7 @@ struct DiffuseLight { static MatPtr make(TexPtr emission); static MatPtr from_rg
 struct SheenBRDF { static MatPtr make(Vec3 base_color, double sheen_tint); };
 struct ClearcoatBRDF { static MatPtr make(double clearcoat_gloss); };
 struct MixBxDf { static MatPtr make(double t, MatPtr a, MatPtr b); };
+struct IsotropicMaterial { static MatPtr from_texture(TexPtr albedo); static MatPtr from_albedo(Vec3 albedo); };  // volume.rs:18 (stub)
 
 // ---- hittables (src/hittable/*.rs) ----------------------------------------------------------------
 struct BvhTree {  // host form of bvh.rs:6-16 over the items of one list
@@ -113,8 +114,14 @@ struct Hittable {
     Vec3 a, b; HittableList sides;
     std::vector<pt_triangle> triangles; std::vector<pt_vec3> tri_normals; std::vector<double> tri_uvs;
     std::vector<Box> tri_boxes; std::shared_ptr<BvhTree> mesh_bvh;
-    // instance
+    // instance (child = the transformed object) / volume (child = the boundary)
     HitPtr child; Vec3 axis, translation; double angle = 0; double transform[16], inverse[16], normal_matrix[16];
+    double density = 0;
+};
+// volume.rs:15-41 (a commented-out stub in the reference; semantics: include/pt_b200.h, pt_volume)
+struct HomogeneousVolume {
+    static HitPtr from_texture(HitPtr boundary, double density, TexPtr texture);
+    static HitPtr from_albedo(HitPtr boundary, double density, Vec3 albedo);
 };
 struct Sphere {
     static HitPtr new_still(double radius, Vec3 position, MatPtr m);
@@ -146,6 +153,7 @@ struct FlatScene {
     std::vector<pt_triangle> triangles; std::vector<pt_vec3> tri_normals; std::vector<double> tri_uvs;
     std::vector<pt_cuboid> cuboids; std::vector<pt_mesh> meshes; std::vector<pt_instance> instances;
     std::vector<pt_bvh_node> nodes; std::vector<pt_ref> leaf_refs, objects, lights;
+    std::vector<pt_volume> volumes;
     pt_scene_desc desc{};
     // identity maps (pointer -> index) so shared Arc<> objects flatten once
     std::vector<const Texture*> tex_keys; std::vector<const Image*> img_keys; std::vector<const Material*> mat_keys;

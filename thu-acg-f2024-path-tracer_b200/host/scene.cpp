@@ -91,6 +91,8 @@ MatPtr SheenBRDF::make(Vec3 c, double tint) {
     auto m = new_mat(PT_MAT_SHEEN); m->p[PT_P_COLOR_R] = c.x; m->p[PT_P_COLOR_G] = c.y; m->p[PT_P_COLOR_B] = c.z; m->p[PT_P_SHEEN_TINT] = tint; return m;
 }
 MatPtr ClearcoatBRDF::make(double gloss) { auto m = new_mat(PT_MAT_CLEARCOAT); m->p[PT_P_ALPHA_G] = (1.0 - gloss) * 0.1 + gloss * 0.001; return m; }  // clearcoat.rs:16-18
+MatPtr IsotropicMaterial::from_texture(TexPtr albedo) { auto m = new_mat(PT_MAT_ISOTROPIC); m->base_color = std::move(albedo); return m; }
+MatPtr IsotropicMaterial::from_albedo(Vec3 albedo) { return from_texture(SolidTexture::make(albedo)); }
 MatPtr MixBxDf::make(double t, MatPtr a, MatPtr b) {
     auto m = new_mat(PT_MAT_MIX); m->p[PT_P_MIX_T] = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t); m->mix_a = std::move(a); m->mix_b = std::move(b); return m;  // mix.rs:17
 }
@@ -146,6 +148,15 @@ HitPtr Instance::make(HitPtr object, Vec3 axis, double angle, Vec3 translation) 
     h->material = object->material;
     return h;
 }
+HitPtr HomogeneousVolume::from_texture(HitPtr boundary, double density, TexPtr texture) {  // volume.rs:22-34 (stub)
+    if (boundary->kind != PT_PRIM_SPHERE && boundary->kind != PT_OBJ_CUBOID) throw std::runtime_error("volume boundary must be a sphere or a cuboid");
+    if (!(density > 0.0)) throw std::runtime_error("volume density must be positive");
+    auto h = std::make_shared<Hittable>(); h->kind = PT_OBJ_VOLUME; h->child = std::move(boundary); h->density = density;
+    h->material = IsotropicMaterial::from_texture(std::move(texture));
+    h->bbox = h->child->bbox;  // volume.rs:48-50: the boundary's box, as is
+    return h;
+}
+HitPtr HomogeneousVolume::from_albedo(HitPtr boundary, double density, Vec3 albedo) { return from_texture(std::move(boundary), density, SolidTexture::make(albedo)); }
 HitPtr TriangleMesh::from_obj(double scale, const ObjMesh& mesh, MatPtr m) {  // mesh.rs:149-197
     auto h = std::make_shared<Hittable>(); h->kind = PT_OBJ_MESH; h->material = std::move(m);
     size_t nv = mesh.positions.size() / 3, nn = mesh.normals.size() / 3, nt = mesh.texcoords.size() / 2;
@@ -314,6 +325,11 @@ pt_ref FlatScene::add_hittable(const HitPtr& h, bool allow_instance) {
             instances.push_back(in);
             return pt_ref{PT_OBJ_INSTANCE, (uint32_t)instances.size() - 1};
         }
+        case PT_OBJ_VOLUME: {
+            pt_volume v{}; v.boundary = add_hittable(h->child, false); v.density = h->density; v.material = add_material(h->material);
+            volumes.push_back(v);
+            return pt_ref{PT_OBJ_VOLUME, (uint32_t)volumes.size() - 1};
+        }
     }
     throw std::runtime_error("unknown hittable kind");
 }
@@ -330,6 +346,7 @@ void FlatScene::finish() {
     desc.quads = quads.data(); desc.triangles = triangles.data(); desc.tri_normals = tri_normals.data(); desc.tri_uvs = tri_uvs.data();
     desc.cuboids = cuboids.data(); desc.meshes = meshes.data(); desc.instances = instances.data(); desc.nodes = nodes.data();
     desc.leaf_refs = leaf_refs.data(); desc.objects = objects.data(); desc.lights = lights.data();
+    desc.n_volumes = (uint32_t)volumes.size(); desc.volumes = volumes.data();
 }
 std::unique_ptr<FlatScene> flatten(const World& world) {
     auto f = std::make_unique<FlatScene>();
