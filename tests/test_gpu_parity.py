@@ -371,6 +371,54 @@ def test_progressive_checkpoint_resume_and_noise_floor(pt, ctx, tmp_path):
     dev.close()
 
 
+def test_edge_sizes_and_error_codes(pt, orc, ctx):
+    """Empty / ragged / extreme arguments of the C ABI: zero samples, a 1x1 and an odd-sized image (the 8x4 tile order does
+    not apply), a pool smaller than one warp's worth of pixels, max_depth 0 and 1, empty ray batches, and the error codes
+    of a corrupted scene description (no exception crosses the ABI)."""
+    import ctypes as C
+    scene = pt.Scene.build(3, width=37, spp=4, seed=1)                     # 37 x 37: not a multiple of 8 x 4
+    dev, ora = ctx.upload(scene), orc.OracleScene(scene.desc, pt)
+    with pytest.raises(pt.PtError, match="sample_count"):                  # the mean of zero samples is undefined
+        dev.render(spp=0)
+    img, st = dev.render(spp=5, seed=3, nan_policy=pt.PT_NAN_DROP)
+    ref, ost = ora.render(scene.camera, 5, seed=3, nan_policy=pt.PT_NAN_DROP)
+    assert img.shape == (37, 37, 3) and st.paths == 37 * 37 * 5 and abs(int(st.segments) - int(ost.segments)) <= 64
+    assert H.rel_rmse(img, ref) < 0.05
+    tiny, st2 = dev.render(spp=5, seed=3, nan_policy=pt.PT_NAN_DROP, pool_paths=100)   # rounded up to one block of 128 paths
+    assert np.allclose(tiny, img, rtol=2e-5, atol=2e-6) and st2.segments == st.segments and st2.iterations > 100
+    for depth, bound in ((0, 0.0), (1, None)):
+        cam = scene.camera_copy(max_depth=depth)
+        im, s = dev.render(camera=cam, spp=2, seed=3)
+        assert s.segments == (0 if depth == 0 else s.paths)
+        if bound is not None:
+            assert not im.any()                                             # no bounce: nothing is ever added (camera.rs:177)
+    one = scene.camera_copy(image_width=1)
+    im, s = dev.render(camera=one, spp=3, seed=3, nan_policy=pt.PT_NAN_DROP)
+    assert im.shape == (1, 1, 3) and s.paths == 3
+    assert len(dev.trace_closest(np.zeros(0, dtype=pt.RAY_DTYPE))) == 0
+    assert len(dev.trace_any(np.zeros(0, dtype=pt.RAY_DTYPE), np.zeros(0))) == 0
+    # corrupted descriptions: a copy of the 200-byte pt_scene_desc with one field broken
+    raw = C.string_at(scene.desc, 200)
+    def create(mutate):
+        buf = C.create_string_buffer(raw, 200)
+        mutate(buf)
+        out = C.c_void_p()
+        rc = ctx.lib.pt_scene_create(ctx.ptr, C.cast(buf, C.c_void_p), C.byref(out))
+        msg = ctx.lib.pt_last_error().decode()
+        if rc == 0:
+            ctx.lib.pt_scene_destroy(out)
+        return rc, msg
+    rc, msg = create(lambda b: C.memmove(b, (C.c_uint32 * 1)(99), 4))                       # abi_version
+    assert rc == pt.PT_ERR_INVALID and "abi_version" in msg
+    rc, msg = create(lambda b: C.memmove(C.addressof(b) + 56, (C.c_uint64 * 1)(0), 8))      # textures = NULL with n_textures > 0
+    assert rc == pt.PT_ERR_INVALID and "null array" in msg
+    rc, msg = create(lambda b: C.memmove(C.addressof(b) + 176, (C.c_uint32 * 1)(0x7FFFFFF0), 4))  # objects_bvh_root out of range
+    assert rc != 0 and msg
+    rc, _ = create(lambda b: None)                                                           # the untouched copy is fine
+    assert rc == 0
+    dev.close(); ora.close()
+
+
 def test_tonemap_matches_reference_formula(pt, orc, ctx):
     import torch
     x = np.array([0.0, 1.0, 4.0, 0.25, -1.0, np.nan, np.inf, 1e-6, 0.5, 0.9981], dtype=np.float32)
