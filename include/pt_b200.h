@@ -196,7 +196,7 @@ typedef struct {
 } pt_camera;
 
 /* ---- render control --------------------------------------------------------------- */
-/* flags bits 4-6: k_trace register-cap variant (0 = default 80 regs; 4: 120, 5: 96, 7: 64) — tuning knob */
+/* flags bits 4-6: k_trace register-cap variant for 4-wide scenes (0 = default 72 regs; 4: 120, 5: 96, 6: 80, 7: 64) — tuning knob */
 /* PT_RENDER_ENV_IMPORTANCE (NOT reference behaviour): when the camera's environment is a map, the
  * direction mixture of camera.rs:199-215 gains a third sampler that draws from the map's luminance (built by
  * pt_scene_build_env_sampler): p_bsdf = 0.5, p_env = 0.5 without lights, p_light = p_env = 0.25 with lights; the

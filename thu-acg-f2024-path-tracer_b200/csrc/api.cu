@@ -690,21 +690,22 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
         CU(cudaMemsetAsync(ctx->d_count, 0, 16 * sizeof(uint32_t), st));
         const Queues q{ctx->q_items, ctx->d_count + 4, ctx->pool};
         if (ctx->profiling) CU(cudaEventRecord(ctx->evs[1], st));
-            const unsigned tg = (n + kBlock - 1) / kBlock;
+            const unsigned tg = (n + kTraceBlock - 1) / kTraceBlock;
             if (scene->has_volumes) {  // media: the trace kernel variant that draws keyed free-flight uniforms
                 unsigned long long* wk = ctx->profiling ? ctx->d_nonfinite + 1 : nullptr;
-                if (scene->wide) { if (wk) k_trace<6, true, true, true><<<tg, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, p->seed); else k_trace<6, true, false, true><<<tg, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, p->seed); }
-                else { if (wk) k_trace<6, false, true, true><<<tg, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, p->seed); else k_trace<6, false, false, true><<<tg, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, p->seed); }
+                if (scene->wide) { if (wk) k_trace<6, true, true, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, p->seed); else k_trace<6, true, false, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, p->seed); }
+                else { if (wk) k_trace<6, false, true, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, p->seed); else k_trace<6, false, false, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, p->seed); }
             } else
             if (ctx->profiling) {
-                if (scene->wide) k_trace<6, true, true><<<tg, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, ctx->d_nonfinite + 1);
-                else k_trace<6, false, true><<<tg, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, ctx->d_nonfinite + 1);
-            } else if (!scene->wide) k_trace<6, false><<<tg, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d);
+                if (scene->wide) k_trace<6, true, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, ctx->d_nonfinite + 1);
+                else k_trace<6, false, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, ctx->d_nonfinite + 1);
+            } else if (!scene->wide) k_trace<6, false><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d);  // 80 regs (72: -2 % .. +1.5 %)
             else switch ((p->flags >> 4) & 7u) {  // experiment knob: resident blocks per SM the compiler must allow (register cap)
-                case 4: k_trace<4, true><<<tg, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d); break;  // 120 regs
-                case 5: k_trace<5, true><<<tg, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d); break;  // 96 regs
-                case 7: k_trace<8, true><<<tg, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d); break;  // 64 regs, spills
-                default: k_trace<6, true><<<tg, kBlock, 0, st>>>(in, n, ctx->hits, q, scene->d);        // 80 regs (measured best overall)
+                case 4: k_trace<4, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d); break;  // 120 regs
+                case 5: k_trace<5, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d); break;  // 96 regs
+                case 6: k_trace<6, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d); break;  // 80 regs
+                case 7: k_trace<8, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d); break;  // 64 regs, spills
+                default: k_trace<7, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d);        // 72 regs, 28 warps/SM (measured best: +2 % over 80)
             }
         if (ctx->profiling) CU(cudaEventRecord(ctx->evs[2], st));
         // one specialised kernel per shade class present in the scene; each walks its queue grid-stride
