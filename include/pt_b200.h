@@ -203,6 +203,14 @@ typedef struct {
  * combined pdf gains p_env * pdf_env.  Same expectation as the reference's estimator, lower variance under
  * concentrated skylight.  Per-sample results differ from the reference's, so it is off by default. */
 #define PT_RENDER_ENV_IMPORTANCE 0x1u
+/* PT_RENDER_NEE (NOT reference behaviour): next-event estimation with multiple importance sampling instead
+ * of the one-sample mixture of camera.rs:199-215.  At every non-emissive hit a direction from World.lights.sample is
+ * tested with a shadow ray (a closest-hit ray: it contributes throughput * f * emitted / (pdf_light + pdf_bsdf) if the
+ * first thing it meets is an emitter), and the path continues by BSDF sampling alone; emission found by the continued
+ * path is weighted pdf_bsdf / (pdf_bsdf + pdf_light) (balance heuristic; 1 for camera rays and for emitters outside
+ * World.lights).  Environment hits keep weight 1.  Shadow rays count as segments in pt_stats.  Same expectation as the
+ * reference's estimator up to its quirks Q8/Q11; cannot be combined with PT_RENDER_ENV_IMPORTANCE yet. */
+#define PT_RENDER_NEE 0x2u
 enum { PT_NAN_REFERENCE = 0, /* non-finite samples poison the pixel like camera.rs:129 */
        PT_NAN_DROP = 1 };    /* documented divergence: a non-finite contribution is skipped and a non-finite
                                 throughput ends the path (each counted once in pt_stats.nonfinite); finite

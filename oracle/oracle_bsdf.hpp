@@ -322,6 +322,7 @@ struct DiffuseLight : BxDF {
     double pdf(Vec3, Vec3, const HitInfo&) const override { return 1.0; }
     Vec3 eval(Vec3, Vec3, const HitInfo&) const override { return Vec3(1, 1, 1); }
     Vec3 emitted(double u, double v, Vec3 p) const override { return emission->value(u, v, p); }
+    bool is_emitter() const override { return true; }
 };
 
 // ---------------------------------------------------------------- volume.rs:18 phase_function (stub in the reference)

@@ -186,6 +186,69 @@ struct Camera {
         }
         return radiance;
     }
+
+    // PT_RENDER_NEE (include/pt_b200.h) — NOT the reference's integrator: next-event estimation with the balance heuristic.
+    // Same hit handling, Russian roulette, offsets and sampling routines as trace(); the difference is how directions are
+    // chosen and weighted.  The device spawns the shadow ray as a child path and resolves it one iteration later; here it
+    // is resolved on the spot, which adds the same terms.
+    Vec3 trace_nee(uint32_t r, uint32_t c, const World& world, Rng& rng, uint64_t* dropped = nullptr) const {
+        auto fin3 = [](const Vec3& v) { return std::isfinite(v.x) && std::isfinite(v.y) && std::isfinite(v.z); };
+        auto add = [&](Vec3& radiance, const Vec3& v) {  // false: the contribution was dropped (PT_NAN_DROP)
+            if (!fin3(v)) { if (dropped) { ++*dropped; return false; } }
+            radiance += v;
+            return true;
+        };
+        const double eps = 1e-3;
+        Vec3 radiance(0, 0, 0), throughput(1, 1, 1);
+        Ray ray = generate_ray(r, c, rng);
+        g_cnt.paths++;
+        double w_prev = 1.0;  // MIS weight of the BSDF strategy for the direction that produced `ray`
+        for (uint32_t bounces = 0; bounces < max_depth; bounces++) {
+            g_path_key = PathKey{rng.seed, rng.pixel, rng.sample, bounces};
+            auto hit = world.intersect_all(ray, Interval{eps, INF});
+            if (!hit) { add(radiance, throughput * sample_environment(ray)); break; }
+            const HitInfo& info = hit->first;
+            if (info.mat->is_emitter()) {  // emitters end the path (DiffuseLight::sample -> None)
+                add(radiance, throughput * info.mat->emitted(info.u, info.v, info.point) * (bounces == 0 ? 1.0 : w_prev));
+                break;
+            }
+            if (!fin3(throughput) && !add(radiance, throughput * 0.0)) break;
+            if (bounces > 5) {
+                double p = clamp_(luminance(throughput), 0.01, 1.0);
+                if (rng.next() > p) break;
+                throughput /= p;
+            }
+            const bool deeper = bounces + 1 < max_depth;
+            if (!world.lights.is_empty()) {
+                if (auto ld = world.lights.sample(info.point, ray.time, rng)) {
+                    double pl = world.lights.pdf(info.point, *ld, ray.time);
+                    double pb = info.mat->pdf(-ray.direction, *ld, info);
+                    Vec3 fl = info.mat->eval(-ray.direction, *ld, info);
+                    Vec3 W = throughput * (fl / (pl + pb));
+                    if (deeper && pl > 0.0 && (W.x != 0.0 || W.y != 0.0 || W.z != 0.0)) {
+                        double e = 1e-3 * signum_(dot(*ld, info.geometric_normal));
+                        Ray shadow = Ray::make(info.point + e * info.geometric_normal, *ld, ray.time);
+                        g_path_key.bounce = bounces + 1;
+                        auto sh = world.intersect_all(shadow, Interval{eps, INF});
+                        if (sh && sh->first.mat->is_emitter()) add(radiance, W * sh->first.mat->emitted(sh->first.u, sh->first.v, sh->first.point));
+                    }
+                }
+            }
+            auto dir = info.mat->sample(ray, info, rng);
+            if (!dir) break;
+            double pb = info.mat->pdf(-ray.direction, *dir, info);
+            Vec3 f = info.mat->eval(-ray.direction, *dir, info);
+            double pl = world.lights.is_empty() ? 0.0 : world.lights.pdf(info.point, *dir, ray.time);
+            w_prev = pl > 0.0 ? (double)(float)(pb / (pb + pl)) : 1.0;  // carried as fp32 by the device
+            double e = 1e-3 * signum_(dot(*dir, info.geometric_normal));
+            Ray next = Ray::make(info.point + e * info.geometric_normal, *dir, ray.time);
+            throughput *= f / pb;
+            if (dropped && !fin3(throughput)) { ++*dropped; break; }
+            if (!deeper) break;
+            ray = next;
+        }
+        return radiance;
+    }
 };
 
 }  // namespace orc

@@ -357,7 +357,8 @@ int orc_render(const orc_scene* s, const pt_camera* c, const pt_render_params* p
             Vec3 color(0, 0, 0);
             for (uint32_t k = 0; k < p->sample_count; k++) {
                 Rng rng; rng.seed = p->seed; rng.pixel = (uint32_t)px; rng.sample = p->sample_begin + k * p->sample_stride;
-                Vec3 rad = cam.trace(r, col, s->world, rng, nullptr, p->nan_policy == PT_NAN_DROP ? &nf : nullptr);
+                uint64_t* drop = p->nan_policy == PT_NAN_DROP ? &nf : nullptr;
+                Vec3 rad = (p->flags & PT_RENDER_NEE) ? cam.trace_nee(r, col, s->world, rng, drop) : cam.trace(r, col, s->world, rng, nullptr, drop);
                 bool fin = std::isfinite(rad.x) && std::isfinite(rad.y) && std::isfinite(rad.z);
                 if (!fin) nf++;  // PT_NAN_REFERENCE only: the sample poisons its pixel (camera.rs:129)
                 color += rad;

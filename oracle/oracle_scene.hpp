@@ -95,6 +95,7 @@ struct BxDF {  // bsdf/mod.rs:21-57
     virtual double pdf(Vec3 view_dir, Vec3 light_dir, const HitInfo& info) const = 0;
     virtual Vec3 eval(Vec3 view_dir, Vec3 light_dir, const HitInfo& info) const = 0;
     virtual Vec3 emitted(double, double, Vec3) const { return Vec3(0, 0, 0); }
+    virtual bool is_emitter() const { return false; }  // DiffuseLight only (used by the NEE integrator, ours)
     virtual const ImageTexture* normal_map() const { return nullptr; }
 };
 

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 import helpers as H
-from test_oracle import _material_world, _ray, fog_world, mixed_lights_world, sun_world, tie_world
+from test_oracle import _material_world, _ray, fog_world, mixed_lights_world, small_light_world, sun_world, tie_world
 
 pytestmark = pytest.mark.gpu
 
@@ -277,6 +277,41 @@ def test_env_importance_sampling_scene5_and_default_unchanged(pt, orc, pairs):
     assert abs(int(st.segments) - int(ost.segments)) <= max(64, ost.segments // 2000)
     d = np.abs(img - ref).max(axis=2)
     assert (d > 1e-4 * np.maximum(ref.max(axis=2), 1.0)).mean() < 0.02 and H.rel_rmse(img, ref) < 0.05
+
+
+# ---------------------------------------------------------------- next-event estimation (ours)
+def test_nee_matches_oracle(pt, orc, ctx, pairs):
+    """PT_RENDER_NEE: shadow paths ride the ordinary wavefront pool.  The oracle resolves each shadow ray on the spot;
+    the sums must agree sample for sample — also when the pool is so small that spawning paths are throttled — and the
+    NEE image must converge to the reference estimator's with less noise."""
+    scene = small_light_world(pt, 64, sphere_light=True)
+    dev, ora = ctx.upload(scene), orc.OracleScene(scene.desc, pt)
+    for policy in (pt.PT_NAN_DROP, pt.PT_NAN_REFERENCE):
+        img, st = dev.render(spp=8, seed=41, nan_policy=policy, flags=pt.PT_RENDER_NEE)
+        ref, ost = ora.render(scene.camera, 8, seed=41, nan_policy=policy, flags=pt.PT_RENDER_NEE)
+        assert st.paths == ost.paths and abs(int(st.segments) - int(ost.segments)) <= max(64, ost.segments // 2000)
+        fin = np.isfinite(ref).all(axis=2) & np.isfinite(img).all(axis=2)
+        assert fin.mean() > 0.99
+        d = np.abs(img - ref)[fin].max(axis=1)
+        assert (d > 1e-4 * np.maximum(ref[fin].max(axis=1), 1.0)).mean() < 0.02
+    assert st.segments > 1.5 * dev.render(spp=8, seed=41)[1].segments        # the shadow rays are traced and counted
+    small, st_small = dev.render(spp=8, seed=41, nan_policy=pt.PT_NAN_REFERENCE, flags=pt.PT_RENDER_NEE, pool_paths=3000)
+    assert st_small.segments == st.segments and np.allclose(np.nan_to_num(small), np.nan_to_num(img), rtol=2e-5, atol=2e-6)
+    dev.close(); ora.close()
+    # convergence on the consistent (quad-light) variant: same mean as the reference estimator, less noise
+    scene = small_light_world(pt, 64)
+    dev = ctx.upload(scene)
+    base = [dev.render(spp=512, seed=s, nan_policy=pt.PT_NAN_DROP)[0] for s in (1, 2)]
+    nee = [dev.render(spp=512, seed=s, nan_policy=pt.PT_NAN_DROP, flags=pt.PT_RENDER_NEE)[0] for s in (1, 2)]
+    n_base, n_nee = H.rel_rmse(base[0], base[1]), H.rel_rmse(nee[0], nee[1])
+    a, b = np.clip((base[0] + base[1]) / 2, 0, 0.999), np.clip((nee[0] + nee[1]) / 2, 0, 0.999)
+    print(f"noise at 512 spp: reference estimator {n_base:.3f}, NEE {n_nee:.3f}; clipped means {a.mean():.4f} vs {b.mean():.4f}")
+    assert n_nee < 0.7 * n_base and abs(a.mean() - b.mean()) < 0.05 * a.mean()
+    dev.close()
+    p = pairs(3, 96)                                                            # the Cornell box of the reference
+    img, st = p.dev.render(spp=8, seed=43, nan_policy=pt.PT_NAN_DROP, flags=pt.PT_RENDER_NEE)
+    ref, ost = p.ora.render(p.scene.camera, 8, seed=43, nan_policy=pt.PT_NAN_DROP, flags=pt.PT_RENDER_NEE)
+    assert abs(int(st.segments) - int(ost.segments)) <= max(64, ost.segments // 2000) and H.rel_rmse(img, ref) < 0.05
 
 
 # ---------------------------------------------------------------- constant-density media (ours; SURVEY §8(f)-4)

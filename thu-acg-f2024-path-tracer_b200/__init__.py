@@ -24,6 +24,7 @@ PT_NONE = 0xFFFFFFFF
 PT_OK, PT_ERR_INVALID, PT_ERR_CUDA, PT_ERR_UNSUPPORTED, PT_ERR_NO_DEVICE = 0, -1, -2, -3, -4  # pt_status
 PT_NAN_REFERENCE, PT_NAN_DROP = 0, 1
 PT_RENDER_ENV_IMPORTANCE = 0x1  # pt_render_params.flags: environment-map importance sampling (not reference behaviour)
+PT_RENDER_NEE = 0x2             # next-event estimation with MIS and shadow rays (not reference behaviour)
 PRIM_SPHERE, PRIM_QUAD, PRIM_TRIANGLE, OBJ_CUBOID, OBJ_MESH, OBJ_INSTANCE = range(6)
 
 

@@ -677,10 +677,14 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
     pt_stats S{}; S.width = dcam.c.width; S.height = dcam.c.height;
     float ms_gen = 0, ms_trace = 0, ms_shade = 0;
     CU(cudaEventRecord(ctx->ev0, st));
-    uint64_t generated = 0; uint32_t live = 0; int cur = 0;
+    uint64_t generated = 0; uint32_t live = 0, live_spawning = 0; int cur = 0;
+    const bool nee = (p->flags & PT_RENDER_NEE) != 0;
+    if (nee && rcst.env_importance) return fail(PT_ERR_UNSUPPORTED, "PT_RENDER_NEE and PT_RENDER_ENV_IMPORTANCE cannot be combined yet");
     while (dcam.c.max_depth > 0 && (live > 0 || generated < total)) {
         PathBuf in = path_buf(ctx, cur), outb = path_buf(ctx, cur ^ 1);
         uint32_t n_new = (uint32_t)std::min<uint64_t>(pool - live, total - generated);
+        // NEE: a path may spawn a shadow path, so at most pool / 2 spawning (non-shadow) paths enter an iteration
+        if (nee) n_new = std::min<uint32_t>(n_new, pool / 2 > live_spawning ? pool / 2 - live_spawning : 0u);
         if (ctx->profiling) CU(cudaEventRecord(ctx->evs[0], st));
         if (n_new) {
             k_generate<<<(n_new + kBlock - 1) / kBlock, kBlock, 0, st>>>(in, live, n_new, generated, n_pixels, dcam, rcst);
@@ -712,7 +716,8 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
         const unsigned sg = std::min<unsigned>((n + kBlock - 1) / kBlock, 148u * 16u);
 #define PT_SHADE(CLS)                                                                                                                    \
         if (scene->class_mask & (1u << CLS)) {                                                                                           \
-            if (rcst.env_importance) k_shade<CLS, 3><<<sg, kBlock, 0, st>>>(in, q, ctx->hits, outb, ctx->d_count, d_accum, ctx->d_nonfinite, scene->d, dcam, rcst);  \
+            if (nee) k_shade_nee<CLS><<<sg, kBlock, 0, st>>>(in, q, ctx->hits, outb, ctx->d_count, d_accum, ctx->d_nonfinite, scene->d, dcam, rcst);    \
+            else if (rcst.env_importance) k_shade<CLS, 3><<<sg, kBlock, 0, st>>>(in, q, ctx->hits, outb, ctx->d_count, d_accum, ctx->d_nonfinite, scene->d, dcam, rcst);  \
             else if (scene->general_lights) k_shade<CLS, 2><<<sg, kBlock, 0, st>>>(in, q, ctx->hits, outb, ctx->d_count, d_accum, ctx->d_nonfinite, scene->d, dcam, rcst); \
             else k_shade<CLS, 0><<<sg, kBlock, 0, st>>>(in, q, ctx->hits, outb, ctx->d_count, d_accum, ctx->d_nonfinite, scene->d, dcam, rcst); \
             S.kernel_launches++;                                                                                                         \
@@ -721,7 +726,7 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
 #undef PT_SHADE
         if (ctx->profiling) CU(cudaEventRecord(ctx->evs[3], st));
         S.kernel_launches += 1;
-        CU(cudaMemcpyAsync(ctx->h_count, ctx->d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ctx->h_count, ctx->d_count, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         if (ctx->profiling) {
             float a = 0, b = 0, c2 = 0;
@@ -729,7 +734,7 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
             ms_gen += a; ms_trace += b; ms_shade += c2;
         }
         generated += n_new; S.segments += n; S.iterations++;
-        live = ctx->h_count[0];
+        live = ctx->h_count[0]; live_spawning = ctx->h_count[1];
         cur ^= 1;
     }
     CU(cudaEventRecord(ctx->ev1, st));

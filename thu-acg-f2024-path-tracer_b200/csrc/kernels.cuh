@@ -300,6 +300,105 @@ __global__ void __launch_bounds__(kBlock, PT_SHADE_MIN_BLOCKS) k_shade(PathBuf i
     }
 }
 
+// ---- PT_RENDER_NEE (ours): next-event estimation with MIS instead of the reference's one-sample mixture.
+// At every non-emissive hit: (1) a light direction from World.lights.sample spawns a SHADOW PATH — an ordinary pool entry
+// marked kShadowMark that carries W = throughput * f / (pdf_light + pdf_bsdf) (balance heuristic folded in); it is traced
+// by k_trace like any ray and only ever adds W * emitted if its closest hit is an emitter; (2) the path continues by BSDF
+// sampling alone and remembers w = pdf_bsdf / (pdf_bsdf + pdf_light(dir)) (as fp32 in ids.w) to weight the emission it may
+// run into next.  Environment hits keep weight 1 (the environment is not a NEE light).  Two outputs per input at most:
+// out_count[0] counts all outputs, out_count[1] the non-shadow ones (the host keeps those <= pool / 2).
+constexpr uint32_t kShadowMark = 0xFFFFFFFFu;
+template <int CLS>
+__global__ void __launch_bounds__(kBlock, PT_SHADE_MIN_BLOCKS) k_shade_nee(PathBuf in, Queues q, const HitRec* __restrict__ hits, PathBuf out,
+                                                        uint32_t* __restrict__ out_count, float* __restrict__ accum,
+                                                        unsigned long long* __restrict__ nonfinite, DScene S, DCameraEx cam, RenderConst rc) {
+    constexpr int K = ClassKind<CLS>::value;
+    const uint32_t count = q.count[CLS];
+    const uint32_t* __restrict__ items = q.items + (size_t)CLS * q.stride;
+    __shared__ uint32_t warp_count[kBlock / 32], warp_alive[kBlock / 32];
+    __shared__ uint32_t block_base;
+    for (uint32_t base = blockIdx.x * kBlock; base < count; base += gridDim.x * kBlock) {
+        const uint32_t j = base + threadIdx.x;
+        bool alive = false, shadow = false;
+        RayD next, sray; d3 thr = mk(0, 0, 0), sthr = mk(0, 0, 0); uint4 ids = make_uint4(0, 0, 0, 0);
+        if (j < count) {
+            const uint32_t i = items[j];
+            RayD ray = load_ray(in, i);
+            thr = mk(in.f[7][i], in.f[8][i], in.f[9][i]);
+            ids = in.ids[i];
+            const uint32_t pix = ids.x, bounces = ids.z >> 16;
+            const bool is_shadow = ids.w == kShadowMark;
+            bool dead = false;
+            if (CLS == CLS_MISS) {
+                if (!is_shadow) add_radiance(accum, pix, thr * sample_environment(S, cam.c, ray.d), rc.nan_policy, nonfinite, dead);
+            } else {
+                const HitRec hr = hits[i];
+                HitInfoD h;
+                reconstruct_hit<false>(S, ray, hr.ref, hr.inst_light & 0x7FFFFFFFu, hr.t, h);
+                const DMaterial& m = S.materials[h.material];
+                if (CLS == CLS_LIGHT) {  // emitters end the path (DiffuseLight::sample -> None); MIS weight of the strategy that got here
+                    const double w = (is_shadow || bounces == 0) ? 1.0 : (double)__uint_as_float(ids.w);
+                    add_radiance(accum, pix, thr * texture_value(S, m.base_color_tex, h.u, h.v, h.point) * w, rc.nan_policy, nonfinite, dead);
+                } else if (!is_shadow) {
+                    Rng rng; rng.init(rc.seed, pix, ids.y, ids.z & 0xFFFFu);
+                    if (!finite3(thr)) add_radiance(accum, pix, thr * 0.0, rc.nan_policy, nonfinite, dead);  // poisons like camera.rs:186-187 (Q32)
+                    bool go = !dead;
+                    if (go && bounces > 5) {  // Russian roulette, camera.rs:190-196
+                        double p = clampd(luminance(thr), 0.01, 1.0);
+                        if (rng.next() > p) go = false;
+                        else thr = thr / p;
+                    }
+                    if (go) {
+                        const bool deeper = bounces + 1 < cam.c.max_depth;
+                        d3 dir;
+                        if (S.n_lights != 0 && lights_sample<true>(S, h.point, ray.time, rng, dir)) {
+                            const double pl = lights_pdf<true>(S, h.point, dir, ray.time);
+                            d3 fl; double pb;
+                            bsdf_eval_pdf<K>(S, h.material, -ray.d, dir, h, fl, pb);
+                            const d3 W = thr * (fl / (pl + pb));
+                            if (deeper && pl > 0.0 && (W.x != 0.0 || W.y != 0.0 || W.z != 0.0)) {
+                                shadow = true; sthr = W;
+                                sray = make_ray(h.point + (1e-3 * signum(dot(dir, h.gn))) * h.gn, dir, ray.time);
+                            }
+                        }
+                        if (bsdf_sample<K>(S, h.material, ray.d, h, rng, dir)) {
+                            d3 f; double pb;
+                            bsdf_eval_pdf<K>(S, h.material, -ray.d, dir, h, f, pb);
+                            const double pl = S.n_lights != 0 ? lights_pdf<true>(S, h.point, dir, ray.time) : 0.0;
+                            const float w = pl > 0.0 ? (float)(pb / (pb + pl)) : 1.0f;
+                            next = make_ray(h.point + (1e-3 * signum(dot(dir, h.gn))) * h.gn, dir, ray.time);
+                            thr = thr * (f / pb);
+                            alive = deeper;
+                            if (rc.nan_policy == PT_NAN_DROP && !finite3(thr)) { atomicAdd(nonfinite, 1ull); alive = false; }
+                            ids.w = __float_as_uint(w);
+                        }
+                        ids.z = (rng.used & 0xFFFFu) | ((bounces + 1) << 16);
+                    }
+                }
+            }
+        }
+        if (CLS == CLS_MISS || CLS == CLS_LIGHT) continue;  // nothing survives a miss or an emitter
+        // ---- compaction of up to two outputs per lane
+        const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const uint32_t b_alive = __ballot_sync(0xFFFFFFFFu, alive), b_shadow = __ballot_sync(0xFFFFFFFFu, shadow);
+        if (lane == 0) { warp_count[warp] = __popc(b_alive) + __popc(b_shadow); warp_alive[warp] = __popc(b_alive); }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t total = 0, total_alive = 0;
+#pragma unroll
+            for (int w = 0; w < kBlock / 32; w++) { uint32_t c = warp_count[w]; warp_count[w] = total; total += c; total_alive += warp_alive[w]; }
+            block_base = total ? atomicAdd(out_count, total) : 0;
+            if (total_alive) atomicAdd(out_count + 1, total_alive);
+        }
+        __syncthreads();
+        const uint32_t below = (1u << lane) - 1u;
+        const uint32_t wbase = block_base + warp_count[warp];
+        if (alive) store_path(out, wbase + __popc(b_alive & below), next, thr, ids);
+        if (shadow) store_path(out, wbase + __popc(b_alive) + __popc(b_shadow & below), sray, sthr, make_uint4(ids.x, ids.y, ids.z, kShadowMark));
+        __syncthreads();
+    }
+}
+
 // sqrt-gamma + 8-bit quantisation of camera.rs:109-114,128-130 on `scale * accum`
 __global__ void k_tonemap(const float* __restrict__ accum, double scale, uint32_t n_values, uint8_t* __restrict__ out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
