@@ -12,7 +12,7 @@
 
 int main(int argc, char** argv) {
     int scene = 1; bool quality = false; long spp = -1, width = -1; unsigned long long seed = 1; int device = 0;
-    std::string assets = "assets", outdir = "demo"; bool drop = false, env_is = false;
+    std::string assets = "assets", outdir = "demo"; bool drop = false, env_is = false, nee = false;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() -> const char* { if (i + 1 >= argc) { fprintf(stderr, "missing value for %s\n", a.c_str()); exit(2); } return argv[++i]; };
@@ -26,14 +26,15 @@ int main(int argc, char** argv) {
         else if (a == "--out") outdir = next();
         else if (a == "--drop-nonfinite") drop = true;
         else if (a == "--env-importance") env_is = true;
-        else { fprintf(stderr, "usage: ptb200 [-s N] [-q] [--spp N] [--width N] [--seed N] [--device N] [--assets DIR] [--out DIR] [--drop-nonfinite] [--env-importance]\n"); return 2; }
+        else if (a == "--nee") nee = true;
+        else { fprintf(stderr, "usage: ptb200 [-s N] [-q] [--spp N] [--width N] [--seed N] [--device N] [--assets DIR] [--out DIR] [--drop-nonfinite] [--env-importance] [--nee]\n"); return 2; }
     }
     uint32_t w = quality ? 1920 : 600, s = quality ? 4000 : 100;  // main.rs:633
     if (width > 0) w = (uint32_t)width;
     if (spp > 0) s = (uint32_t)spp;
     try {
         auto b = pt::build_scene(scene, w, s, seed, assets);
-        pt::RenderOptions o; o.seed = seed; o.device = device; o.nan_policy = drop ? PT_NAN_DROP : PT_NAN_REFERENCE; o.env_importance = env_is;
+        pt::RenderOptions o; o.seed = seed; o.device = device; o.nan_policy = drop ? PT_NAN_DROP : PT_NAN_REFERENCE; o.env_importance = env_is; o.nee = nee;
         return b->camera.render(b->world, outdir + "/" + b->output_name, o) ? 1 : 0;
     } catch (const std::exception& e) {
         fprintf(stderr, "error: %s\n", e.what());

@@ -389,6 +389,7 @@ int render_flat(const pt_scene_desc& desc, const pt_camera& cam, const std::stri
         if (rc) { fprintf(stderr, "pt_scene_build_env_sampler: %s\n", pt_last_error()); pt_scene_destroy(scene); pt_ctx_destroy(ctx); return rc; }
         p.flags |= PT_RENDER_ENV_IMPORTANCE;
     }
+    if (opt.nee) p.flags |= PT_RENDER_NEE;
     pt_stats st{};
     if (opt.verbose) printf("rendering production\n");  // camera.rs:101
     rc = pt_render(ctx, scene, &cam, &p, mean.data(), &st);
