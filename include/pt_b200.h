@@ -320,6 +320,12 @@ int  pt_camera_rays(pt_ctx* ctx, const pt_camera* cam, uint64_t seed, size_t n,
 int  pt_lights_sample_pdf(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_vec3* origin,
                           const double* time, const double* uniforms4, pt_vec3* dir,
                           uint32_t* valid, double* pdf);
+/* The step before the path: the exact SAH sweep of bvh.rs:54-120 for ONE node on the device.  For the
+ * n items of the node in list order (boxes6 = lo xyz, hi xyz per item, padded as AABB::new leaves them) and every axis a,
+ * cost3n[a * n + k] = BVH::evaluate_sah at item k's centroid[a] — the same sequential padded unions as the reference
+ * (aabb.rs:16-25), so costs are bit-identical to the host's — or +inf where the reference rejects the split.  The host
+ * keeps the recursion, the strict-'<' choice and the partition (bvh.rs:28-84); this only removes the O(n^2) part. */
+int  pt_sah_sweep(pt_ctx* ctx, uint32_t n, const double* boxes6, const double* parent6, double* cost3n);
 /* The environment sampler of pt_scene_build_env_sampler: direction from 2 uniforms per query and its solid-angle pdf. */
 int  pt_env_sample_pdf(pt_ctx* ctx, const pt_scene* scene, size_t n, const double* uniforms2, pt_vec3* dir, double* pdf);
 

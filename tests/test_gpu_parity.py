@@ -454,6 +454,30 @@ def test_edge_sizes_and_error_codes(pt, orc, ctx):
     dev.close(); ora.close()
 
 
+def test_device_sah_sweep_builds_the_same_trees(pt, ctx):
+    """SURVEY §8(f)-1: with a build context the O(n^2) SAH sweep of bvh.rs:54-120 runs on the device (pt_sah_sweep);
+    costs are bit-identical to the host's, so the flattened BVH (nodes + leaf order) is the same byte for byte."""
+    import ctypes as C
+    import time
+
+    def tree_bytes(scene):
+        raw = C.string_at(scene.desc, 200)
+        n_nodes, n_refs = np.frombuffer(raw, np.uint32, 2, 40)
+        nodes_ptr, refs_ptr = np.frombuffer(raw, np.uint64, 2, 144)
+        return C.string_at(int(nodes_ptr), int(n_nodes) * 64), C.string_at(int(refs_ptr), int(n_refs) * 8), int(n_nodes)
+
+    for sid in (6, 70, 1):
+        t0 = time.time(); host = pt.Scene.build(sid, width=64, spp=1, seed=1); t_host = time.time() - t0
+        pt.set_build_context(ctx)
+        try:
+            t0 = time.time(); devb = pt.Scene.build(sid, width=64, spp=1, seed=1); t_dev = time.time() - t0
+        finally:
+            pt.set_build_context(None)
+        a, b = tree_bytes(host), tree_bytes(devb)
+        print(f"scene {sid}: {a[2]} BVH nodes, scene build {t_host:.2f} s on the host, {t_dev:.2f} s with the device sweep")
+        assert a[0] == b[0] and a[1] == b[1]
+
+
 def test_tonemap_matches_reference_formula(pt, orc, ctx):
     import torch
     x = np.array([0.0, 1.0, 4.0, 0.25, -1.0, np.nan, np.inf, 1e-6, 0.5, 0.9981], dtype=np.float32)

@@ -70,7 +70,7 @@ assert BSDF_RESULT_DTYPE.itemsize == 64 and BSDF_SAMPLE_DTYPE.itemsize == 32
 ABI_SYMBOLS = ["pt_ctx_create", "pt_ctx_destroy", "pt_ctx_set_stream", "pt_ctx_set_profiling", "pt_last_error", "pt_device_count",
                "pt_scene_create", "pt_scene_destroy", "pt_scene_device_bytes", "pt_camera_image_height", "pt_render_accumulate",
                "pt_render", "pt_tonemap_rgb8", "pt_trace_closest", "pt_trace_any", "pt_bsdf_eval_pdf", "pt_bsdf_sample",
-               "pt_camera_rays", "pt_lights_sample_pdf", "pt_scene_build_env_sampler", "pt_env_sample_pdf"]
+               "pt_camera_rays", "pt_lights_sample_pdf", "pt_scene_build_env_sampler", "pt_env_sample_pdf", "pt_sah_sweep"]
 
 
 class PtError(RuntimeError):
@@ -127,6 +127,7 @@ def device_lib():
         lib.pt_lights_sample_pdf.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.pt_scene_build_env_sampler.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
         lib.pt_env_sample_pdf.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.pt_sah_sweep.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         _dev = lib
     return _dev
 
@@ -165,7 +166,7 @@ def host_lib():
         for name in ["pth_world_add_object", "pth_world_add_light"]:
             getattr(lib, name).argtypes = [vp, vp]
             getattr(lib, name).restype = None
-        for name in ["pth_world_build_bvh", "pth_world_free", "pth_scene_free"]:
+        for name in ["pth_world_build_bvh", "pth_world_free", "pth_scene_free", "pth_set_build_context"]:
             getattr(lib, name).argtypes = [vp]
             getattr(lib, name).restype = None
         lib.pth_scene_render.argtypes = [vp, C.c_char_p, C.c_uint64, C.c_int, C.c_uint32, C.c_int, C.POINTER(Stats)]
@@ -355,6 +356,12 @@ class World(_Handle):
 
     def build_bvh(self):
         host_lib().pth_world_build_bvh(self.ptr)
+
+
+def set_build_context(ctx):
+    """BVH builds of this thread price the splits of large nodes on the device (pt_sah_sweep): same trees, much faster.
+    Pass None to go back to the host-only build."""
+    host_lib().pth_set_build_context(ctx.ptr if ctx is not None else None)
 
 
 def make_camera(image_width, aspect_ratio=1.0, samples_per_pixel=1, max_depth=50, vfov=40.0, look_from=(0, 0, 0), look_at=(0, 0, -1),

@@ -861,6 +861,17 @@ int pt_lights_sample_pdf(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_
     if ((rc = dd.to_host(dir, n * 24, ctx->stream)) || (rc = vv.to_host(valid, n * 4, ctx->stream)) || (rc = pp.to_host(pdf, n * 8, ctx->stream))) return rc;
     return PT_OK;
 }
+int pt_sah_sweep(pt_ctx* ctx, uint32_t n, const double* boxes6, const double* parent6, double* cost3n) {
+    if (!ctx || (n && (!boxes6 || !parent6 || !cost3n))) return fail(PT_ERR_INVALID, "pt_sah_sweep: null argument");
+    if (n == 0) return PT_OK;
+    if (n > (1u << 26)) return fail(PT_ERR_UNSUPPORTED, "pt_sah_sweep: too many items");
+    CU(cudaSetDevice(ctx->device));
+    DevBuf b, c; int rc;
+    if ((rc = b.from_host(boxes6, (size_t)n * sizeof(SahBox), ctx->stream)) || (rc = c.alloc((size_t)n * 3 * sizeof(double)))) return rc;
+    SahBox parent; memcpy(&parent, parent6, sizeof(parent));
+    k_sah_sweep<<<(3u * n + kSahTile - 1) / kSahTile, kSahTile, 0, ctx->stream>>>(n, (const SahBox*)b.p, parent, (double*)c.p);
+    return c.to_host(cost3n, (size_t)n * 3 * sizeof(double), ctx->stream);
+}
 int pt_env_sample_pdf(pt_ctx* ctx, const pt_scene* scene, size_t n, const double* uniforms2, pt_vec3* dir, double* pdf) {
     if (!ctx || !scene || (n && (!uniforms2 || !dir || !pdf))) return fail(PT_ERR_INVALID, "pt_env_sample_pdf: null argument");
     if (scene->env_image == 0xFFFFFFFFu) return fail(PT_ERR_INVALID, "pt_env_sample_pdf: no sampler built (pt_scene_build_env_sampler)");

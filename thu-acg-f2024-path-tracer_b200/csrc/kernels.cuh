@@ -494,6 +494,52 @@ __global__ void k_lights(size_t n, const pt_vec3* __restrict__ origin, const dou
     pdf[i] = ok ? lights_pdf(S, from_abi(origin[i]), d, time[i]) : 0.0;
 }
 
+// ---- exact SAH sweep of bvh.rs:54-120 for one node (the step before the path).  Thread (axis, k) folds all
+// n items in list order into a left / right box exactly as BVH::evaluate_sah does (AABB::union pads 1e-3 on EVERY union,
+// aabb.rs:16-25, so the fold order is part of the result) and prices the split at item k's centroid.  O(n^2) work like the
+// reference, but 3n folds run at once; items are staged through shared memory, every thread reads the same item (broadcast).
+struct SahBox { double lo[3], hi[3]; };
+PT_D void sah_merge(SahBox& b, const SahBox& o) {  // AABB::union -> AABB::new(min, max) with its padding
+    for (int a = 0; a < 3; a++) {
+        const double mn = fmin(b.lo[a], o.lo[a]), mx = fmax(b.hi[a], o.hi[a]);
+        b.lo[a] = fmin(mn, mx) - 1e-3; b.hi[a] = fmax(mn, mx) + 1e-3;
+    }
+}
+PT_D double sah_half_area(const SahBox& b) {
+    const double ex = b.hi[0] - b.lo[0], ey = b.hi[1] - b.lo[1], ez = b.hi[2] - b.lo[2];
+    return ex * ey + ex * ez + ey * ez;
+}
+constexpr int kSahTile = 128;
+__global__ void __launch_bounds__(kSahTile) k_sah_sweep(uint32_t n, const SahBox* __restrict__ boxes, SahBox parent, double* __restrict__ cost) {
+    __shared__ SahBox tile[kSahTile];
+    const uint32_t t = blockIdx.x * kSahTile + threadIdx.x;
+    const bool active = t < 3u * n;
+    const uint32_t axis = active ? t / n : 0u, k = active ? t % n : 0u;
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    const double split = 0.5 * (boxes[k].lo[axis] + boxes[k].hi[axis]);  // AABB::centroid
+    SahBox lb, rb;
+    for (int a = 0; a < 3; a++) { lb.lo[a] = rb.lo[a] = inf; lb.hi[a] = rb.hi[a] = -inf; }
+    uint32_t lc = 0, rc = 0;
+    for (uint32_t base = 0; base < n; base += kSahTile) {
+        const uint32_t m = min((uint32_t)kSahTile, n - base);
+        __syncthreads();
+        if (threadIdx.x < m) tile[threadIdx.x] = boxes[base + threadIdx.x];
+        __syncthreads();
+        for (uint32_t i = 0; i < m; i++) {
+            const SahBox& o = tile[i];
+            if (0.5 * (o.lo[axis] + o.hi[axis]) < split) { sah_merge(lb, o); lc++; } else { sah_merge(rb, o); rc++; }
+        }
+    }
+    if (!active) return;
+    double c = inf;
+    if (lc != 0 && rc != 0) {
+        const double v = sah_half_area(lb) * (double)lc + sah_half_area(rb) * (double)rc;
+        const double parent_cost = sah_half_area(parent) * (double)n;
+        if (v > 0.0 && v < parent_cost) c = v;
+    }
+    cost[t] = c;
+}
+
 __global__ void k_env(size_t n, const double* __restrict__ uniforms2, pt_vec3* __restrict__ dir, double* __restrict__ pdf, DEnvDist E) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

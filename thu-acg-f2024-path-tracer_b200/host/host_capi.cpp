@@ -65,6 +65,7 @@ void* pth_instance(void* child, const double* axis, double angle, const double* 
 void* pth_volume(void* boundary, double density, void* albedo_tex) {
     PTH_TRY(return box<Hittable>(HomogeneousVolume::from_texture(unbox<Hittable>(boundary), density, unbox<Texture>(albedo_tex))));
 }
+void pth_set_build_context(void* ctx) { set_build_context(static_cast<pt_ctx*>(ctx)); }
 // ---- world ----
 void* pth_world_new() { return new World(); }
 void pth_world_free(void* w) { delete static_cast<World*>(w); }

@@ -145,6 +145,9 @@ struct World {  // world.rs
 
 // SAH builder restating bvh.rs:24-120 (full sweep, strict '<', stable partition, Q3 fallbacks).
 std::shared_ptr<BvhTree> build_bvh(const std::vector<Box>& boxes);
+// Optional: with a device context set (per thread), nodes of 256+ items price their splits through pt_sah_sweep — the same
+// tree, bit for bit, without the O(n^2) host loop.  nullptr (default) = host only, e.g. on a machine without a GPU.
+void set_build_context(pt_ctx* ctx);
 
 // ---- flattening to the C ABI ----------------------------------------------------------------------
 struct FlatScene {

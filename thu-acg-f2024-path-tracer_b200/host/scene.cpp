@@ -187,9 +187,11 @@ HitPtr TriangleMesh::from_obj(double scale, const ObjMesh& mesh, MatPtr m) {  //
 }
 
 // ---- SAH build, bvh.rs:24-120 --------------------------------------------------------------------
+static thread_local pt_ctx* g_build_ctx = nullptr;  // set_build_context: sweep large nodes on the device (same tree, faster)
+void set_build_context(pt_ctx* ctx) { g_build_ctx = ctx; }
 namespace {
 struct Builder {
-    const std::vector<Box>& boxes; std::vector<Vec3> cent; BvhTree& tree;
+    const std::vector<Box>& boxes; std::vector<Vec3> cent; BvhTree& tree; pt_ctx* ctx = nullptr;
     Box fold(const std::vector<uint32_t>& items) const { Box b; for (uint32_t i : items) b = b.merged(boxes[i]); return b; }
     double sah(int axis, double split, const Box& parent, const std::vector<uint32_t>& items) const {  // bvh.rs:86-120
         Box lb, rb; size_t lc = 0, rc = 0;
@@ -209,6 +211,22 @@ struct Builder {
         Box parent = fold(items);
         double best_cost = kInf, best_split = 0.0; int best_axis = 0;
         std::vector<double> pos(items.size()), cost(items.size());
+        if (ctx && items.size() >= 256) {  // the O(n^2) sweep on the device (pt_sah_sweep): bit-identical costs, same choice
+            const size_t n = items.size();
+            std::vector<Box> ib(n); for (size_t k = 0; k < n; k++) ib[k] = boxes[items[k]];
+            std::vector<double> dc(3 * n);
+            if (pt_sah_sweep(ctx, (uint32_t)n, reinterpret_cast<const double*>(ib.data()), reinterpret_cast<const double*>(&parent), dc.data()) != PT_OK)
+                throw std::runtime_error(std::string("pt_sah_sweep: ") + pt_last_error());
+            std::vector<std::pair<double, double>> pc(n);
+            for (int axis = 0; axis < 3; axis++) {
+                for (size_t k = 0; k < n; k++) pc[k] = {cent[items[k]][axis], dc[axis * n + k]};
+                std::stable_sort(pc.begin(), pc.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+                for (size_t k = 0; k < n; k++) {
+                    if (k > 0 && pc[k].first == pc[k - 1].first) continue;  // duplicate split position
+                    if (pc[k].second < best_cost) { best_cost = pc[k].second; best_axis = axis; best_split = pc[k].first; }
+                }
+            }
+        } else
         for (int axis = 0; axis < 3; axis++) {  // bvh.rs:62-77
             for (size_t k = 0; k < items.size(); k++) pos[k] = cent[items[k]][axis];
             std::stable_sort(pos.begin(), pos.end());
@@ -235,7 +253,7 @@ struct Builder {
 }  // namespace
 std::shared_ptr<BvhTree> build_bvh(const std::vector<Box>& boxes) {
     auto tree = std::make_shared<BvhTree>();
-    Builder b{boxes, {}, *tree};
+    Builder b{boxes, {}, *tree, g_build_ctx};
     for (auto& bx : boxes) b.cent.push_back(bx.centroid());
     std::vector<uint32_t> all(boxes.size()); for (uint32_t i = 0; i < boxes.size(); i++) all[i] = i;
     b.build(all);
