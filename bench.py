@@ -32,9 +32,9 @@ SCENE_NAMES = {3: "scene3_cornell_box", 1: "scene1_bouncing_balls", 5: "scene5_p
 B_RAY, B_HIT, B_STATE = 56, 16, 96   # ray (o,d,time f64), HitRec, full path state (ray + throughput f64x3 + ids uint4)
 B_NODE, B_REF, B_SPHERE, B_QUAD, B_TRI = 32, 32, 64, 128, 80
 # dram__bytes_read.sum + dram__bytes_write.sum per ray of k_trace from the ncu --set full capture of this workload
-# (profiles/r1_b_k_trace_ncu.md: 146.9 MB + 37.3 MB for 2,539,648 rays): the ray stream and hit records come from HBM,
-# the 4.6 MB scene (BVH, primitives) is served by L2.
-K_TRACE_DRAM_BYTES_PER_RAY = (146.88e6 + 37.25e6) / 2539648
+# (profiles/r1_h_k_trace_ncu.md: 64.1 MB + 17.8 MB for one launch of 26 999 x 32 rays; the earlier r1_b capture of a
+# 2.5 M-ray launch gave 72.5 B/ray): the ray stream, hit records and stack spills come from HBM, the 4.6 MB scene from L2.
+K_TRACE_DRAM_BYTES_PER_RAY = (64.13e6 + 17.79e6) / (26999 * 32)  # profiles/r1_h_k_trace_ncu.md (a bounce-ray launch of 864 k rays)
 
 
 def peaks():
@@ -289,7 +289,7 @@ def main():
                     "what": "pt_scene_create (scene H2D) + pt_render_accumulate + reduce + D2H of the fp32 image, every step"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
                          "traffic": (K_TRACE_DRAM_BYTES_PER_RAY * segs_rank / max(iters, 1)) if dom == "k_trace" and args.scene == SCENE else None,
-                         "traffic_note": "DRAM bytes per launch = ncu dram read+write per ray (profiles/r1_b_k_trace_ncu.md) x rays per launch; far below the algorithmic bytes because the scene is L2-resident",
+                         "traffic_note": "DRAM bytes per launch = ncu dram read+write per ray (profiles/r1_h_k_trace_ncu.md) x rays per launch; far below the algorithmic bytes because the scene is L2-resident",
                          "peak_source": peak_src,
                          "bytes_per_segment": dom_b, "bytes_per_launch": dom_b * segs_rank / max(iters, 1),
                          "avg_launch_ms": dom_ms / max(iters, 1), "launches": iters,
