@@ -280,8 +280,8 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "samples_per_s": paths / (ms * 1e-3),
             "config": {"workload": f"{SCENE_NAMES.get(args.scene, args.scene)}_{WIDTH}x{H}", "spp_per_step_per_gpu": args.spp, "max_depth": cam.max_depth,
-                       "parallelism": f"spp-split x{world}", "pool_paths": args.pool or 16 << 20, "scene_device_bytes": int(dev.device_bytes),
-                       "l2": f"per-step path-state working set (2 x min(16Mi, {WIDTH * H * args.spp}) paths x 112 B) exceeds the 126 MB L2 "
+                       "parallelism": f"spp-split x{world}", "pool_paths": args.pool or 32 << 20, "scene_device_bytes": int(dev.device_bytes),
+                       "l2": f"per-step path-state working set (2 x min(32Mi, {WIDTH * H * args.spp}) paths x 112 B) exceeds the 126 MB L2 "
                              f"unless the step is tiny; the {dev.device_bytes / 1e6:.1f} MB scene (BVH, primitives, textures) is read through L2 by design"},
             "gpu_launches": int(launches), "segments_per_path": seg_per_path, "nonfinite_samples": int(nonfinite),
             "e2e": {"value": e2e_segs.item() / e2e_s.item() / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(e2e_stats[0][1]) * world,

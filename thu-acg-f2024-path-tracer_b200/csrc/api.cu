@@ -661,9 +661,10 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
     if (rc) return rc;
     const uint32_t n_pixels = dcam.c.width * dcam.c.height;
     const uint64_t total = (uint64_t)n_pixels * p->sample_count;
-    // default 16 Mi paths in flight (3.8 GB of state): each wavefront iteration costs one host round trip, so large
-    // iterations amortise it (measured on scene 6 FHD: 4 Mi 2681, 8 Mi 2827, 16 Mi 2913 Mrays/s)
-    uint32_t pool = p->pool_paths ? p->pool_paths : (16u << 20);
+    // default 32 Mi paths in flight (7.9 GB of state): each wavefront iteration costs one host round trip (~0.2 ms with its
+    // small-launch tail), so large iterations amortise it (scene 6 FHD: 4 Mi 2681, 8 Mi 2827, 16 Mi 2913 Mrays/s at the
+    // time; with the final kernels 16 Mi 3113, 32 Mi 3170, 64 Mi 3204); never more than the render needs
+    uint32_t pool = p->pool_paths ? p->pool_paths : (32u << 20);
     if ((uint64_t)pool > total) pool = (uint32_t)std::max<uint64_t>(total, 1);
     pool = (pool + kBlock - 1) / kBlock * kBlock;
     if ((rc = ensure_pool(ctx, pool))) return rc;
