@@ -754,6 +754,7 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
         }
         generated += n_new; S.segments += n; S.iterations++;
         live = ctx->h_count[0]; live_spawning = ctx->h_count[1];
+        if (live > pool) return fail(PT_ERR_CUDA, "internal error: the shade stage produced more paths than the pool holds");
         cur ^= 1;
     }
     CU(cudaEventRecord(ctx->ev1, st));
