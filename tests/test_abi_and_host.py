@@ -121,6 +121,39 @@ def test_png_roundtrip(pt, tmp_path):
     assert back.ptr
 
 
+def test_jpeg_decoder_matches_libjpeg(pt, tmp_path):
+    """host/jpeg.cpp (no Python bake for the reference's .jpg assets): baseline and progressive Huffman
+    JPEG, 4:4:4 / 4:2:2 / 4:2:0 / grey, odd sizes, optimised tables, restart intervals — byte-identical to PIL (libjpeg:
+    islow IDCT, fancy upsampling), and the reference's 7616x3808 progressive assets/envmap.jpg of scene 5."""
+    import io
+    from PIL import Image
+    Image.MAX_IMAGE_PIXELS = None
+    rng = np.random.default_rng(1)
+    img = (rng.uniform(size=(45, 67, 3)) * 255).astype(np.uint8)
+    img[10:30, 5:50] = (200, 30, 90)
+    cases = [dict(subsampling=0), dict(subsampling=0, progressive=True), dict(subsampling=1), dict(subsampling=2),
+             dict(subsampling=2, progressive=True), dict(subsampling=0, quality=30, optimize=True), dict(grey=True),
+             dict(subsampling=2, restart_marker_blocks=3), dict(subsampling=0, progressive=True, restart_marker_rows=1)]
+    for kw in cases:
+        kw = dict(kw)
+        src = Image.fromarray(img[:, :, 0] if kw.pop("grey", False) else img)
+        buf = io.BytesIO()
+        try:
+            src.save(buf, "JPEG", quality=kw.pop("quality", 85), **kw)
+        except TypeError:
+            continue                                                    # an older Pillow without restart-marker options
+        p = str(tmp_path / "t.jpg")
+        open(p, "wb").write(buf.getvalue())
+        ours = pt.Image(path=p).pixels()
+        theirs = np.asarray(Image.open(p).convert("RGB"))
+        assert np.array_equal(ours, theirs), kw
+    env = os.path.join(pt.ASSETS_DIR, "envmap.jpg")
+    assert np.array_equal(pt.Image(path=env).pixels(), pt.load_rgb8(env))
+    with pytest.raises(pt.PtError):
+        open(str(tmp_path / "bad.jpg"), "wb").write(b"\xff\xd8\xff\xc3\x00\x04")   # lossless SOF3: unsupported, must say so
+        pt.Image(path=str(tmp_path / "bad.jpg"))
+
+
 def test_unsupported_constructs_are_rejected(pt):
     mat = pt.DiffuseBRDF((0.5, 0.5, 0.5))
     inner = pt.Instance(pt.Sphere.new_still(1.0, (0, 0, 0), mat), (0, 1, 0), 0.3, (1, 0, 0))

@@ -217,10 +217,21 @@ class Image(_Handle):
             a = np.ascontiguousarray(rgb, dtype=np.uint8)
             assert a.ndim == 3 and a.shape[2] == 3
             super().__init__(L.pth_image(_ptr(a), a.shape[1], a.shape[0]))
+        if not self.ptr:
+            raise PtError(L.pth_last_error().decode())
+
+    def pixels(self):
+        """The decoded RGB8 pixels as a numpy array [H, W, 3] (a copy)."""
+        L = host_lib()
+        w, h = C.c_uint32(), C.c_uint32()
+        L.pth_image_pixels.restype = C.POINTER(C.c_uint8)
+        L.pth_image_pixels.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        p = L.pth_image_pixels(self.ptr, C.byref(w), C.byref(h))
+        return np.ctypeslib.as_array(p, shape=(h.value, w.value, 3)).copy()
 
 
 def load_rgb8(path):
-    """Decode an asset to RGB8 with PIL (the C++ host reads only .png/.rgb8; envmap.jpg is a JPEG)."""
+    """Decode an asset to RGB8 with PIL (independent of the C++ host's own PNG / JPEG decoders; used by tests and bakes)."""
     from PIL import Image as PILImage
     PILImage.MAX_IMAGE_PIXELS = None
     return np.asarray(PILImage.open(path).convert("RGB"), dtype=np.uint8)
@@ -392,9 +403,7 @@ class Scene:
     @staticmethod
     def build(scene_id, width=600, spp=100, seed=1, assets_dir=ASSETS_DIR):
         """One of the reference's scenes (src/main.rs:635-644); 70 = our mesh variant of scene 7."""
-        env = None
-        if scene_id == 5:  # assets/envmap.jpg has no C++ decoder: hand the pixels in
-            env = np.ascontiguousarray(load_rgb8(os.path.join(assets_dir, "envmap.jpg")))
+        env = None  # an RGB8 array here would override scene 5's assets/envmap.jpg (decoded natively by host/jpeg.cpp)
         ptr = host_lib().pth_scene_build(scene_id, width, spp, seed, assets_dir.encode(), _ptr(env) if env is not None else None,
                                          0 if env is None else env.shape[1], 0 if env is None else env.shape[0])
         return Scene(ptr)

@@ -113,6 +113,7 @@ static ImagePtr decode_png(const std::vector<uint8_t>& buf, const std::string& p
 ImagePtr ImageTexture::load(const std::string& path) {
     auto buf = read_file(path);
     if (ends_with(path, ".png")) return decode_png(buf, path);
+    if (ends_with(path, ".jpg") || ends_with(path, ".jpeg")) return decode_jpeg(buf);  // host/jpeg.cpp
     if (ends_with(path, ".rgb8")) {  // 'PTI1', u32 w, u32 h, raw RGB (tools/bake_assets.py --raw)
         if (buf.size() < 12 || memcmp(buf.data(), "PTI1", 4) != 0) throw std::runtime_error("bad .rgb8 file " + path);
         uint32_t w, h; memcpy(&w, &buf[4], 4); memcpy(&h, &buf[8], 4);

@@ -34,6 +34,12 @@ void* pth_checker_texture(double scale, void* t1, void* t2) { return box<Texture
 void* pth_image(const uint8_t* rgb, uint32_t w, uint32_t h) { return box<Image>(ImageTexture::from_rgb8(rgb, w, h)); }
 void* pth_image_load(const char* path) { PTH_TRY(return box<Image>(ImageTexture::load(path))); }
 void* pth_image_texture(void* image) { return box<Texture>(ImageTexture::make(unbox<Image>(image))); }
+// decoded pixels of an image handle: returns the RGB8 bytes (row-major, top row first) and its size
+const uint8_t* pth_image_pixels(void* image, uint32_t* w, uint32_t* h) {
+    auto im = unbox<Image>(image);
+    *w = im->width; *h = im->height;
+    return im->rgb.data();
+}
 // ---- materials ----
 void* pth_diffuse(void* tex, void* normal_image) { return box<Material>(DiffuseBRDF::from_textures(unbox<Texture>(tex), unbox<Image>(normal_image))); }
 void* pth_metal(void* tex, void* rough) { return box<Material>(MetalBRDF::make(unbox<Texture>(tex), unbox<Texture>(rough))); }

@@ -199,6 +199,8 @@ struct SceneBundle { World world; Camera camera; std::string output_name; };
 // Throws std::runtime_error on a missing asset.
 std::unique_ptr<SceneBundle> build_scene(int scene, uint32_t width, uint32_t spp, uint64_t seed, const std::string& assets_dir);
 
+// Baseline / progressive Huffman JPEG -> RGB8 (jpeg.cpp); throws std::runtime_error on anything else
+ImagePtr decode_jpeg(const std::vector<uint8_t>& file);
 // PNG I/O (assets.cpp)
 bool write_png_rgb8(const std::string& path, const uint8_t* rgb, uint32_t w, uint32_t h);
 

@@ -138,7 +138,7 @@ void bsdf_demo_scene(SceneBundle& b, uint32_t width, uint32_t spp, const std::st
     Vec3 from(-2.0, 2.0, -1.0);
     set_camera(b.camera, 16.0 / 9.0, width, spp, 60.0, from, from + Vec3(0.0, 0.0, -1000.0), 5.0, 0.0);
     b.camera.environment.is_map = true;
-    b.camera.environment.map = g_envmap_override ? g_envmap_override : ImageTexture::load(assets + "/baked/envmap.rgb8");
+    b.camera.environment.map = g_envmap_override ? g_envmap_override : ImageTexture::load(assets + "/envmap.jpg");  // main.rs:365
     b.output_name = "bsdf.png";
 }
 
