@@ -57,6 +57,16 @@ def desc_array(scene, name, dtype, count):
     return raw.view(dtype).copy()
 
 
+def desc_images(scene):
+    """The decoded RGB8 images of a flattened scene (pt_image: pointer, width, height)."""
+    n = desc_header(scene)["n_images"]
+    out = []
+    for im in desc_array(scene, "images", np.dtype([("rgb", "<u8"), ("w", "<u4"), ("h", "<u4")]), n):
+        raw = np.ctypeslib.as_array(C.cast(C.c_void_p(int(im["rgb"])), C.POINTER(C.c_uint8)), shape=(int(im["h"]), int(im["w"]), 3))
+        out.append(raw.copy())
+    return out
+
+
 def desc_roots(scene):
     """(objects_bvh_root, lights_bvh_root) — the two uint32 after the 15 pointers."""
     u32 = C.cast(C.c_void_p(scene.desc + 56 + 15 * 8), C.POINTER(C.c_uint32))

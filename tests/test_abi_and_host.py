@@ -154,6 +154,80 @@ def test_jpeg_decoder_matches_libjpeg(pt, tmp_path):
         pt.Image(path=str(tmp_path / "bad.jpg"))
 
 
+def test_reference_asset_files_load_natively(pt, tmp_path):
+    """the host reads the reference's own asset files.  host/hdr.cpp (Radiance RGBE with the reference's
+    clamp-and-round `to_rgb8`, src/texture.rs:62-69, Q22) must give the bytes of the shipped bake, which was made by an
+    independent decoder (cv2, tools/bake_assets.py); synthetic files cover flat pixels, both RLE flavours and the
+    rounding.  When the reference's assets directory is present (this container; not the GPU box), every scene built
+    from it (.obj, .jpg, .hdr, bricks/*.png) must flatten to the same bytes as the scene built from the bakes."""
+    import struct
+    w, h = 16, 3
+    rng = np.random.default_rng(3)
+    rgbe = rng.integers(0, 256, size=(h, w, 4), dtype=np.uint8)
+    rgbe[..., 3] = rng.integers(120, 140, size=(h, w))
+    rgbe[0, 0] = (200, 1, 0, 135)                                        # 0.5 -> 127.5 -> 128 (round half away from zero)
+    rgbe[0, 1] = (255, 255, 255, 0)                                      # e == 0 -> black
+    rgbe[1, 4:12] = rgbe[1, 3]                                           # a run for the RLE encoders below
+    want = np.where(rgbe[..., 3:4] == 0, 0.0, rgbe[..., :3].astype(np.float32) * np.exp2(rgbe[..., 3:4].astype(np.float32) - 136))
+    want = np.floor(np.clip(want, 0, 1).astype(np.float32) * np.float32(255) + np.float32(0.5)).astype(np.uint8)
+    head = b"#?RADIANCE\n# made by a test\nFORMAT=32-bit_rle_rgbe\nEXPOSURE=1.0\n\n-Y %d +X %d\n" % (h, w)
+    flat = head + rgbe.tobytes()
+    rle = head
+    for y in range(h):
+        rle += bytes([2, 2, w >> 8, w & 255])
+        for ch in range(4):
+            row, x = rgbe[y, :, ch], 0
+            while x < w:
+                n = 1
+                while x + n < w and row[x + n] == row[x] and n < 127:
+                    n += 1
+                if n >= 3:
+                    rle += bytes([128 + n, row[x]]); x += n
+                else:
+                    m = min(5, w - x)
+                    rle += bytes([m]) + row[x:x + m].tobytes(); x += m
+    old = head
+    for y in range(h):
+        x = 0
+        while x < w:
+            n = 1
+            while x + n < w and (rgbe[y, x + n] == rgbe[y, x]).all():
+                n += 1
+            old += rgbe[y, x].tobytes() + (bytes([1, 1, 1, n - 1]) if n > 1 else b"")
+            x += n
+    for name, blob in [("flat", flat), ("rle", rle), ("old", old)]:
+        p = str(tmp_path / (name + ".hdr"))
+        open(p, "wb").write(blob)
+        assert np.array_equal(pt.Image(path=p).pixels(), want), name
+    for bad in [b"P6\n", head[:30], head + b"\x02\x02\x00\x11", b"#?RADIANCE\nFORMAT=32-bit_rle_xyze\n\n-Y 1 +X 1\n\0\0\0\0",
+                b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n+Y 1 +X 1\n\0\0\0\0"]:
+        p = str(tmp_path / "bad.hdr")
+        open(p, "wb").write(bad)
+        with pytest.raises(pt.PtError):
+            pt.Image(path=p)
+    shipped = os.path.join(pt.ASSETS_DIR, "grace_probe_latlong.hdr")
+    assert np.array_equal(pt.Image(path=shipped).pixels(), pt.Image(path=os.path.join(pt.ASSETS_DIR, "grace_probe_latlong.png")).pixels())
+    assert np.array_equal(pt.Image(path=os.path.join(pt.ASSETS_DIR, "earthmap.jpg")).pixels(),
+                          pt.Image(path=os.path.join(pt.ASSETS_DIR, "earthmap.png")).pixels())
+    ref_assets = "/root/reference/assets"
+    if not os.path.isdir(ref_assets):
+        return
+    baked = str(tmp_path / "baked")                                      # only the bakes: forces the fallback names
+    os.makedirs(baked)
+    for f in os.listdir(pt.ASSETS_DIR):
+        if f.endswith((".mesh", ".png")) or f == "envmap.jpg":
+            os.symlink(os.path.join(pt.ASSETS_DIR, f), os.path.join(baked, f))
+    for scene_id in (2, 4, 6, 7, 70):
+        a, b = pt.Scene.build(scene_id, 64, 1, 1, assets_dir=ref_assets), pt.Scene.build(scene_id, 64, 1, 1, assets_dir=baked)
+        ha, hb = H.desc_header(a), H.desc_header(b)
+        assert ha == hb, scene_id
+        for name, dt, n in [("nodes", H.NODE_DT, ha["n_nodes"]), ("leaf_refs", H.REF_DT, ha["n_leaf_refs"]),
+                            ("triangles", np.dtype([("v", "<f8", 9)]), ha["n_triangles"]), ("quads", H.QUAD_DT, ha["n_quads"])]:
+            assert H.desc_array(a, name, dt, n).tobytes() == H.desc_array(b, name, dt, n).tobytes(), (scene_id, name)
+        ia, ib = H.desc_images(a), H.desc_images(b)
+        assert len(ia) == len(ib) == ha["n_images"] and all(np.array_equal(x, y) for x, y in zip(ia, ib)), scene_id
+
+
 def test_unsupported_constructs_are_rejected(pt):
     mat = pt.DiffuseBRDF((0.5, 0.5, 0.5))
     inner = pt.Instance(pt.Sphere.new_still(1.0, (0, 0, 0), mat), (0, 1, 0), 0.3, (1, 0, 0))

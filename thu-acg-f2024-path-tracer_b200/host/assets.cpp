@@ -114,13 +114,14 @@ ImagePtr ImageTexture::load(const std::string& path) {
     auto buf = read_file(path);
     if (ends_with(path, ".png")) return decode_png(buf, path);
     if (ends_with(path, ".jpg") || ends_with(path, ".jpeg")) return decode_jpeg(buf);  // host/jpeg.cpp
+    if (ends_with(path, ".hdr") || ends_with(path, ".pic")) return decode_hdr(buf);     // host/hdr.cpp
     if (ends_with(path, ".rgb8")) {  // 'PTI1', u32 w, u32 h, raw RGB (tools/bake_assets.py --raw)
         if (buf.size() < 12 || memcmp(buf.data(), "PTI1", 4) != 0) throw std::runtime_error("bad .rgb8 file " + path);
         uint32_t w, h; memcpy(&w, &buf[4], 4); memcpy(&h, &buf[8], 4);
         if (buf.size() != 12 + (size_t)3 * w * h) throw std::runtime_error("truncated .rgb8 file " + path);
         return from_rgb8(buf.data() + 12, w, h);
     }
-    throw std::runtime_error("unsupported image format (use .png or a baked .rgb8; see tools/bake_assets.py): " + path);
+    throw std::runtime_error("unsupported image format (.png, .jpg, .hdr or a baked .rgb8): " + path);
 }
 
 // ---- PNG encode (RGB8, filter 0) --------------------------------------------------------------------

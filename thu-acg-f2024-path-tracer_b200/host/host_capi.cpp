@@ -93,7 +93,7 @@ pth_scene* pth_scene_from_world(void* world, const pt_camera* cam, void* env_ima
     } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
 }
 // One of the reference's scenes (1..7; 70 = our mesh variant of scene 7).  env_rgb: optional decoded
-// assets/envmap.jpg for scene 5 (the C++ side has no JPEG decoder).
+// assets/envmap.jpg for scene 5 (skips the native decode when the caller already holds the pixels).
 pth_scene* pth_scene_build(int scene, uint32_t width, uint32_t spp, uint64_t seed, const char* assets_dir, const uint8_t* env_rgb,
                            uint32_t env_w, uint32_t env_h) {
     try {

@@ -62,7 +62,7 @@ using TexPtr = std::shared_ptr<const Texture>;
 struct SolidTexture { static TexPtr make(Vec3 v); static TexPtr scalar(double v); };
 struct CheckerTexture { static TexPtr make(double scale, TexPtr a, TexPtr b); };
 struct ImageTexture {
-    static ImagePtr load(const std::string& path);        // .png / .rgb8 (see assets.cpp)
+    static ImagePtr load(const std::string& path);        // .png / .jpg / .hdr / .rgb8 (see assets.cpp)
     static ImagePtr from_rgb8(const uint8_t* rgb, uint32_t w, uint32_t h);
     static TexPtr make(ImagePtr img);
 };
@@ -201,6 +201,8 @@ std::unique_ptr<SceneBundle> build_scene(int scene, uint32_t width, uint32_t spp
 
 // Baseline / progressive Huffman JPEG -> RGB8 (jpeg.cpp); throws std::runtime_error on anything else
 ImagePtr decode_jpeg(const std::vector<uint8_t>& file);
+// Radiance RGBE (.hdr) -> RGB8 with the reference's clamp-and-round `to_rgb8` (hdr.cpp); throws on anything else
+ImagePtr decode_hdr(const std::vector<uint8_t>& file);
 // PNG I/O (assets.cpp)
 bool write_png_rgb8(const std::string& path, const uint8_t* rgb, uint32_t w, uint32_t h);
 

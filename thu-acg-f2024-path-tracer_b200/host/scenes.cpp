@@ -1,6 +1,7 @@
 // The seven scene builders of the reference (src/main.rs:14-618), restated against the host mirror.
 // Geometry, materials and camera values are the reference's; only scene 1's random layout differs in
 // that it is seeded (the reference draws from an unseeded thread_rng, main.rs:38-59).
+#include <cstdio>
 #include <stdexcept>
 
 #include "pt_host.hpp"
@@ -8,6 +9,15 @@
 namespace pt {
 
 ImagePtr g_envmap_override;  // scene 5: a pre-decoded assets/envmap.jpg handed in by the caller (host_capi.cpp)
+
+// An assets directory may be the reference's own `assets/` (bunny.obj, earthmap.jpg, grace_probe_latlong.hdr,
+// bricks/color.png: all decoded natively by host/assets.cpp, jpeg.cpp, hdr.cpp) or this repo's `assets/`, which also
+// holds bakes made by tools/bake_assets.py (.mesh, .png).  The reference's file name wins when it is there.
+static std::string asset(const std::string& dir, const char* original, const char* baked) {
+    std::string p = dir + "/" + original;
+    if (FILE* f = fopen(p.c_str(), "rb")) { fclose(f); return p; }
+    return dir + "/" + baked;
+}
 
 namespace {
 struct SplitMix {  // seeded stand-in for rand::thread_rng() during scene construction
@@ -65,7 +75,7 @@ void balls_scene(SceneBundle& b, uint32_t width, uint32_t spp, uint64_t seed) { 
 
 void earth_scene(SceneBundle& b, uint32_t width, uint32_t spp, const std::string& assets) {  // main.rs:84-132
     World& world = b.world;
-    auto earth = ImageTexture::make(ImageTexture::load(assets + "/earthmap.png"));
+    auto earth = ImageTexture::make(ImageTexture::load(asset(assets, "earthmap.jpg", "earthmap.png")));
     world.add_object(Sphere::new_still(1.0, Vec3(4.9, 1.0, 3.0), DiffuseBRDF::make(earth)));
     world.add_object(Sphere::new_still(1.0, Vec3(0.0, 1.0, 0.0), DiffuseBRDF::from_rgb(Vec3(0.4, 0.2, 0.1))));
     world.add_object(Sphere::new_still(1.0, Vec3(4.0, 1.0, 0.0), MetalBRDF::from_rgb(Vec3(0.7, 0.6, 0.5), 0.1)));
@@ -113,7 +123,7 @@ void environment_map_scene(SceneBundle& b, uint32_t width, uint32_t spp, const s
     world.build_bvh();
     set_camera(b.camera, 16.0 / 9.0, width, spp, 90.0, Vec3(0.0, 3.0, 17.0), Vec3(0.0, 2.0, 0.0), 17.0, 1.5);
     b.camera.environment.is_map = true;
-    b.camera.environment.map = ImageTexture::load(assets + "/grace_probe_latlong.png");
+    b.camera.environment.map = ImageTexture::load(asset(assets, "grace_probe_latlong.hdr", "grace_probe_latlong.png"));
     b.output_name = "lights.png";
 }
 
@@ -150,13 +160,13 @@ void everything_scene(SceneBundle& b, uint32_t width, uint32_t spp, const std::s
     world.add_object(Sphere::new_still(1.0, Vec3(4.0, 1.0, 6.0), GlassBSDF::basic(1.5)));
     auto box1 = Cuboid::make(Vec3(0, 0, 0), Vec3(1.0, 2.0, 1.0), DiffuseBRDF::from_rgb(Vec3(0.0, 0.5, 1.0)));
     world.add_object(Instance::make(box1, Vec3(0, 1, 0), 0.5, Vec3(1.2, 0.0, 6.0)));
-    auto bunny = TriangleMesh::from_obj(10.0, ObjMesh::load(assets + "/bunny.mesh"),
+    auto bunny = TriangleMesh::from_obj(10.0, ObjMesh::load(asset(assets, "bunny.obj", "bunny.mesh")),
                                         principled(Vec3(1, 1, 1), 0.91, 0.01, 0.01, 0.01, 0.91, 1.5, 0.01, 0.91, 0.91, 0.91, 0.01));
     world.add_object(Instance::make(bunny, Vec3(0, 1, 0), 3.14, Vec3(0.1, -0.327, 5.0)));
-    auto spot = TriangleMesh::from_obj(0.65, ObjMesh::load(assets + "/spot.mesh"),
+    auto spot = TriangleMesh::from_obj(0.65, ObjMesh::load(asset(assets, "spot.obj", "spot.mesh")),
                                        principled(Vec3(0.65, 0.05, 0.05), 0.01, 0.01, 0.91, 0.01, 0.01, 1.5, 0.01, 0.91, 0.91, 0.91, 0.01));
     world.add_object(Instance::make(spot, Vec3(0, 1, 0), 0.87, Vec3(-1.5, 2.8, 4.3)));
-    auto cow = TriangleMesh::from_obj(0.75, ObjMesh::load(assets + "/cow.mesh"),
+    auto cow = TriangleMesh::from_obj(0.75, ObjMesh::load(asset(assets, "cow.obj", "cow.mesh")),
                                       principled(Vec3(0.05, 0.65, 0.05), 0.91, 0.21, 0.91, 0.01, 0.01, 1.5, 0.01, 0.91, 0.91, 0.91, 0.01));
     world.add_object(Instance::make(cow, Vec3(0, 1, 0), 0.93, Vec3(2.5, 3.8, 12.0)));
     world.add_object(Sphere::new_still(0.1, Vec3(1.0, 0.1, 3.0), DiffuseLight::from_rgb(Vec3(20.0, 20.0, 10.0))));
@@ -165,14 +175,14 @@ void everything_scene(SceneBundle& b, uint32_t width, uint32_t spp, const std::s
     world.build_bvh();
     set_camera(b.camera, 16.0 / 9.0, width, spp, 60.0, Vec3(0.0, 1.5, 0.0), Vec3(0.0, 1.5, 100000.0), 6.0, 1.0);
     b.camera.environment.is_map = true;
-    b.camera.environment.map = ImageTexture::load(assets + "/grace_probe_latlong.png");
+    b.camera.environment.map = ImageTexture::load(asset(assets, "grace_probe_latlong.hdr", "grace_probe_latlong.png"));
     b.output_name = "scene6.png";
 }
 
 void normal_demo_scene(SceneBundle& b, uint32_t width, uint32_t spp, const std::string& assets) {  // main.rs:534-618
     World& world = b.world;
-    auto albedo = ImageTexture::make(ImageTexture::load(assets + "/bricks_color.png"));
-    auto normal = ImageTexture::load(assets + "/bricks_normal.png");
+    auto albedo = ImageTexture::make(ImageTexture::load(asset(assets, "bricks/color.png", "bricks_color.png")));
+    auto normal = ImageTexture::load(asset(assets, "bricks/normal.png", "bricks_normal.png"));
     auto with_normal = DiffuseBRDF::from_textures(albedo, normal);
     auto without_normal = DiffuseBRDF::from_textures(albedo, nullptr);
     auto white = DiffuseBRDF::from_rgb(Vec3(0.73, 0.73, 0.73));
@@ -191,10 +201,10 @@ void normal_demo_scene(SceneBundle& b, uint32_t width, uint32_t spp, const std::
 void normal_demo_mesh_scene(SceneBundle& b, uint32_t width, uint32_t spp, const std::string& assets) {
     normal_demo_scene(b, width, spp, assets);
     World& world = b.world;
-    auto bunny = TriangleMesh::from_obj(1400.0, ObjMesh::load(assets + "/bunny.mesh"),
+    auto bunny = TriangleMesh::from_obj(1400.0, ObjMesh::load(asset(assets, "bunny.obj", "bunny.mesh")),
                                         principled(Vec3(0.9, 0.7, 0.3), 0.91, 0.2, 0.01, 0.5, 0.01, 1.5, 0.01, 0.01, 0.01, 0.5, 0.5));
     world.add_object(Instance::make(bunny, Vec3(0, 1, 0), 3.3, Vec3(400.0, 280.0, 330.0)));
-    auto teapot = TriangleMesh::from_obj(28.0, ObjMesh::load(assets + "/teapot.mesh"), DiffuseBRDF::from_rgb(Vec3(0.3, 0.4, 0.8)));
+    auto teapot = TriangleMesh::from_obj(28.0, ObjMesh::load(asset(assets, "teapot.obj", "teapot.mesh")), DiffuseBRDF::from_rgb(Vec3(0.3, 0.4, 0.8)));
     world.add_object(Instance::make(teapot, Vec3(0, 1, 0), 0.6, Vec3(380.0, 0.0, 120.0)));
     world.build_bvh();
     b.output_name = "normals_mesh.png";
