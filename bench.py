@@ -218,6 +218,8 @@ def main():
     iters = sum(s.iterations for s in pstats)
     segs_rank = sum(s.segments for s in pstats); paths_rank = sum(s.paths for s in pstats)
 
+    ctx.set_profiling(False)   # the e2e leg below runs the production path (forked shade streams, no per-stage events)
+
     # ---- end to end through the C ABI with host buffers: scene upload (H2D) + render + reduce + image D2H, every step
     def e2e_step(i):
         t_a = time.perf_counter()
