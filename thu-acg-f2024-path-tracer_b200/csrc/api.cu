@@ -20,6 +20,12 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
         if (e_ != cudaSuccess) return fail(PT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
     } while (0)
 
+// Tail of a render (nothing left to generate, the live count only shrinks): kTailBatch wavefront iterations are enqueued
+// back to back, each reading its ray count from the survivors counter of the one before, and the host reads all the
+// counters in one round trip.  Grids are sized by the live count at the start of the batch (an upper bound).
+constexpr int kTailBatch = 8;
+constexpr uint32_t kTailBatchMaxLive = 1u << 22;
+
 struct pt_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -29,10 +35,10 @@ struct pt_ctx {
     double* pool_f[2] = {nullptr, nullptr};
     uint4* pool_ids[2] = {nullptr, nullptr};
     HitRec* hits = nullptr;
-    uint32_t* d_count = nullptr;            // [16]: [0] survivors counter, [4 .. 4+N_CLS) shade-class queue lengths
+    uint32_t* d_count = nullptr;            // kTailBatch slots of [16]: [0] survivors counter, [4 .. 4+N_CLS) shade-class queue lengths
     uint32_t* q_items = nullptr;            // N_CLS queues of `pool` path slots each
     unsigned long long* d_nonfinite = nullptr;
-    uint32_t* h_count = nullptr;            // pinned
+    uint32_t* h_count = nullptr;            // pinned, same shape as d_count
     void* h_stage = nullptr; size_t stage_bytes = 0;  // pinned staging buffer for scene uploads
     std::vector<std::pair<void*, size_t>> free_blocks;  // device blocks of destroyed scenes, reused by the next upload
     // cudaMalloc/cudaFree cost milliseconds each and synchronise the device; returns the block and its true size
@@ -81,9 +87,9 @@ int pt_ctx_create(int device, pt_ctx** out) {
     auto* c = new pt_ctx(); c->device = device;
     CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
-    CU(cudaMalloc(&c->d_count, 16 * sizeof(uint32_t)));
+    CU(cudaMalloc(&c->d_count, kTailBatch * 16 * sizeof(uint32_t)));
     CU(cudaMalloc(&c->d_nonfinite, 4 * sizeof(unsigned long long)));  // [0] non-finite samples, [1..3] traversal work counters
-    CU(cudaMallocHost(&c->h_count, 2 * sizeof(uint32_t)));
+    CU(cudaMallocHost(&c->h_count, kTailBatch * 16 * sizeof(uint32_t)));
     CU(cudaEventCreate(&c->ev0)); CU(cudaEventCreate(&c->ev1));
     for (auto& e : c->evs) CU(cudaEventCreate(&e));
     CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
@@ -692,7 +698,68 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
     uint64_t generated = 0; uint32_t live = 0, live_spawning = 0; int cur = 0;
     const bool nee = (p->flags & PT_RENDER_NEE) != 0;
     if (nee && rcst.env_importance) return fail(PT_ERR_UNSUPPORTED, "PT_RENDER_NEE and PT_RENDER_ENV_IMPORTANCE cannot be combined yet");
+    unsigned long long* const wk = ctx->profiling ? ctx->d_nonfinite + 1 : nullptr;
+    // World::intersect_all for the n (or min(n, *n_dev)) paths of `in`; one compile-time flavour per scene / mode
+    auto launch_trace = [&](const PathBuf& in, uint32_t n, const Queues& q, const uint32_t* n_dev) {
+        const unsigned tg = (n + kTraceBlock - 1) / kTraceBlock;
+        if (scene->has_volumes) {  // media: the trace kernel variant that draws keyed free-flight uniforms
+            if (scene->wide) { if (wk) k_trace<6, true, true, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, p->seed, n_dev); else k_trace<6, true, false, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, p->seed, n_dev); }
+            else { if (wk) k_trace<6, false, true, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, p->seed, n_dev); else k_trace<6, false, false, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, p->seed, n_dev); }
+        } else if (wk) {
+            if (scene->wide) k_trace<6, true, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, 0, n_dev);
+            else k_trace<6, false, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, 0, n_dev);
+        } else if (!scene->wide) k_trace<6, false><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, nullptr, 0, n_dev);  // 80 regs (72: -2 % .. +1.5 %)
+        else switch ((p->flags >> 4) & 7u) {  // experiment knob: resident blocks per SM the compiler must allow (register cap)
+            case 4: k_trace<4, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, nullptr, 0, n_dev); break;  // 120 regs
+            case 5: k_trace<5, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, nullptr, 0, n_dev); break;  // 96 regs
+            case 6: k_trace<6, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, nullptr, 0, n_dev); break;  // 80 regs
+            case 7: k_trace<8, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, nullptr, 0, n_dev); break;  // 64 regs, spills
+            default: k_trace<7, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, nullptr, 0, n_dev);        // 72 regs, 28 warps/SM (measured best: +2 % over 80)
+        }
+        S.kernel_launches++;
+    };
+    // one specialised kernel per shade class present in the scene; each walks its queue grid-stride (n: upper bound of the
+    // paths in all queues together).  fork: the class kernels run on side streams and join `st` again.
+    auto launch_shades = [&](const PathBuf& in, const PathBuf& outb, uint32_t n, const Queues& q, uint32_t* out_count, bool fork) -> int {
+        const unsigned sg = std::min<unsigned>((n + kBlock - 1) / kBlock, 148u * 16u);
+        if (fork) CU(cudaEventRecord(ctx->ev_fork, st));
+#define PT_SHADE(CLS)                                                                                                                    \
+        if (scene->class_mask & (1u << CLS)) {                                                                                           \
+            cudaStream_t ss = fork ? ctx->shade_stream[CLS] : st;                                                                        \
+            if (fork) CU(cudaStreamWaitEvent(ss, ctx->ev_fork, 0));                                                                      \
+            if (nee) k_shade_nee<CLS><<<sg, kBlock, 0, ss>>>(in, q, ctx->hits, outb, out_count, d_accum, ctx->d_nonfinite, scene->d, dcam, rcst);    \
+            else if (rcst.env_importance) k_shade<CLS, 3><<<sg, kBlock, 0, ss>>>(in, q, ctx->hits, outb, out_count, d_accum, ctx->d_nonfinite, scene->d, dcam, rcst);  \
+            else if (scene->general_lights) k_shade<CLS, 2><<<sg, kBlock, 0, ss>>>(in, q, ctx->hits, outb, out_count, d_accum, ctx->d_nonfinite, scene->d, dcam, rcst); \
+            else k_shade<CLS, 0><<<sg, kBlock, 0, ss>>>(in, q, ctx->hits, outb, out_count, d_accum, ctx->d_nonfinite, scene->d, dcam, rcst); \
+            if (fork) { CU(cudaEventRecord(ctx->ev_join[CLS], ss)); CU(cudaStreamWaitEvent(st, ctx->ev_join[CLS], 0)); }                 \
+            S.kernel_launches++;                                                                                                         \
+        }
+        PT_SHADE(CLS_MISS) PT_SHADE(CLS_LIGHT) PT_SHADE(CLS_DIFFUSE) PT_SHADE(CLS_METAL) PT_SHADE(CLS_GLASS) PT_SHADE(CLS_PRINCIPLED) PT_SHADE(CLS_OTHER)
+#undef PT_SHADE
+        return PT_OK;
+    };
+    // flag 0x4000: opt out of the batched tail (A/B measurements)
+    const bool tail_batching = !nee && !ctx->profiling && !(p->flags & 0x4000u);
     while (dcam.c.max_depth > 0 && (live > 0 || generated < total)) {
+        if (tail_batching && generated == total && live <= kTailBatchMaxLive) {
+            // ---- batched tail: kTailBatch iterations per host round trip (see kTailBatch)
+            const uint32_t n0 = live;
+            CU(cudaMemsetAsync(ctx->d_count, 0, kTailBatch * 16 * sizeof(uint32_t), st));
+            for (int k = 0; k < kTailBatch; k++) {
+                uint32_t* slot = ctx->d_count + 16 * k;
+                const Queues q{ctx->q_items, slot + 4, ctx->pool};
+                launch_trace(path_buf(ctx, cur), n0, q, k ? slot - 16 : nullptr);
+                if ((rc = launch_shades(path_buf(ctx, cur), path_buf(ctx, cur ^ 1), n0, q, slot, false))) return rc;
+                cur ^= 1;
+            }
+            CU(cudaMemcpyAsync(ctx->h_count, ctx->d_count, kTailBatch * 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            uint32_t nk = n0;
+            for (int k = 0; k < kTailBatch && nk > 0; k++) { S.segments += nk; S.iterations++; nk = ctx->h_count[16 * k]; }
+            live = ctx->h_count[16 * (kTailBatch - 1)];
+            if (live > pool) return fail(PT_ERR_CUDA, "internal error: the shade stage produced more paths than the pool holds");
+            continue;
+        }
         PathBuf in = path_buf(ctx, cur), outb = path_buf(ctx, cur ^ 1);
         uint32_t n_new = (uint32_t)std::min<uint64_t>(pool - live, total - generated);
         // NEE: a path may spawn a shadow path, so at most pool / 2 spawning (non-shadow) paths enter an iteration
@@ -706,45 +773,14 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
         CU(cudaMemsetAsync(ctx->d_count, 0, 16 * sizeof(uint32_t), st));
         const Queues q{ctx->q_items, ctx->d_count + 4, ctx->pool};
         if (ctx->profiling) CU(cudaEventRecord(ctx->evs[1], st));
-            const unsigned tg = (n + kTraceBlock - 1) / kTraceBlock;
-            if (scene->has_volumes) {  // media: the trace kernel variant that draws keyed free-flight uniforms
-                unsigned long long* wk = ctx->profiling ? ctx->d_nonfinite + 1 : nullptr;
-                if (scene->wide) { if (wk) k_trace<6, true, true, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, p->seed); else k_trace<6, true, false, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, p->seed); }
-                else { if (wk) k_trace<6, false, true, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, p->seed); else k_trace<6, false, false, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, p->seed); }
-            } else
-            if (ctx->profiling) {
-                if (scene->wide) k_trace<6, true, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, ctx->d_nonfinite + 1);
-                else k_trace<6, false, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, ctx->d_nonfinite + 1);
-            } else if (!scene->wide) k_trace<6, false><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d);  // 80 regs (72: -2 % .. +1.5 %)
-            else switch ((p->flags >> 4) & 7u) {  // experiment knob: resident blocks per SM the compiler must allow (register cap)
-                case 4: k_trace<4, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d); break;  // 120 regs
-                case 5: k_trace<5, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d); break;  // 96 regs
-                case 6: k_trace<6, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d); break;  // 80 regs
-                case 7: k_trace<8, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d); break;  // 64 regs, spills
-                default: k_trace<7, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d);        // 72 regs, 28 warps/SM (measured best: +2 % over 80)
-            }
+        launch_trace(in, n, q, nullptr);
         if (ctx->profiling) CU(cudaEventRecord(ctx->evs[2], st));
-        // one specialised kernel per shade class present in the scene; each walks its queue grid-stride
-        const unsigned sg = std::min<unsigned>((n + kBlock - 1) / kBlock, 148u * 16u);
         // fork: the class kernels run on side streams (unless per-stage events are wanted, or the caller opted out with flag
         // 0x2000).  Measured (repeated runs): scene 6 FHD 168.3 -> 164.1 ms per 128 spp, scene 3 128.0 -> 124.8 ms (+2.5 % each).
-        const bool fork = !ctx->profiling && !(p->flags & 0x2000u);
-        if (fork) CU(cudaEventRecord(ctx->ev_fork, st));
-#define PT_SHADE(CLS)                                                                                                                    \
-        if (scene->class_mask & (1u << CLS)) {                                                                                           \
-            cudaStream_t ss = fork ? ctx->shade_stream[CLS] : st;                                                                        \
-            if (fork) CU(cudaStreamWaitEvent(ss, ctx->ev_fork, 0));                                                                      \
-            if (nee) k_shade_nee<CLS><<<sg, kBlock, 0, ss>>>(in, q, ctx->hits, outb, ctx->d_count, d_accum, ctx->d_nonfinite, scene->d, dcam, rcst);    \
-            else if (rcst.env_importance) k_shade<CLS, 3><<<sg, kBlock, 0, ss>>>(in, q, ctx->hits, outb, ctx->d_count, d_accum, ctx->d_nonfinite, scene->d, dcam, rcst);  \
-            else if (scene->general_lights) k_shade<CLS, 2><<<sg, kBlock, 0, ss>>>(in, q, ctx->hits, outb, ctx->d_count, d_accum, ctx->d_nonfinite, scene->d, dcam, rcst); \
-            else k_shade<CLS, 0><<<sg, kBlock, 0, ss>>>(in, q, ctx->hits, outb, ctx->d_count, d_accum, ctx->d_nonfinite, scene->d, dcam, rcst); \
-            if (fork) { CU(cudaEventRecord(ctx->ev_join[CLS], ss)); CU(cudaStreamWaitEvent(st, ctx->ev_join[CLS], 0)); }                 \
-            S.kernel_launches++;                                                                                                         \
-        }
-        PT_SHADE(CLS_MISS) PT_SHADE(CLS_LIGHT) PT_SHADE(CLS_DIFFUSE) PT_SHADE(CLS_METAL) PT_SHADE(CLS_GLASS) PT_SHADE(CLS_PRINCIPLED) PT_SHADE(CLS_OTHER)
-#undef PT_SHADE
+        // Small iterations are latency-bound: the cross-stream events would cost more than the overlap returns.
+        const bool fork = !ctx->profiling && !(p->flags & 0x2000u) && n >= (1u << 16);
+        if ((rc = launch_shades(in, outb, n, q, ctx->d_count, fork))) return rc;
         if (ctx->profiling) CU(cudaEventRecord(ctx->evs[3], st));
-        S.kernel_launches += 1;
         CU(cudaMemcpyAsync(ctx->h_count, ctx->d_count, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         if (ctx->profiling) {

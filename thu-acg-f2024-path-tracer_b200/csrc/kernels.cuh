@@ -164,7 +164,11 @@ struct PathVol {
 };
 template <int MIN_BLOCKS, bool WIDE, bool COUNT = false, bool VOL = false>
 __global__ void __launch_bounds__(kTraceBlock, MIN_BLOCKS * kBlock / kTraceBlock) k_trace(PathBuf in, uint32_t n, HitRec* __restrict__ hits, Queues q, DScene S,
-                                                              unsigned long long* __restrict__ work = nullptr, uint64_t seed = 0) {
+                                                              unsigned long long* __restrict__ work = nullptr, uint64_t seed = 0,
+                                                              const uint32_t* __restrict__ n_dev = nullptr) {
+    // batched tail iterations (api.cu): the host only knows an upper bound of the live count, the survivors counter of the
+    // previous iteration (still in device memory) is the real one
+    if (n_dev) n = min(n, *n_dev);
     const uint32_t i = blockIdx.x * kTraceBlock + threadIdx.x;
     uint32_t cls = N_CLS;
     uint32_t w0 = 0, w1 = 0, w2 = 0;
