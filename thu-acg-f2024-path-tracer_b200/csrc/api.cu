@@ -690,6 +690,8 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
         if (scene->env_image != cam->env_image) return fail(PT_ERR_INVALID, "PT_RENDER_ENV_IMPORTANCE: call pt_scene_build_env_sampler for the camera's env_image first");
         rcst.env_importance = 1; rcst.env = scene->env;
     }
+    // experiment knob: flag 0x8000 overrides the octant mask of the survivor grouping with flag bits 16-18
+    rcst.sort_mask = (p->flags & 0x8000u) ? ((p->flags >> 16) & 7u) : 7u;
     cudaStream_t st = ctx->stream;
     CU(cudaMemsetAsync(ctx->d_nonfinite, 0, 4 * sizeof(unsigned long long), st));
     pt_stats S{}; S.width = dcam.c.width; S.height = dcam.c.height;

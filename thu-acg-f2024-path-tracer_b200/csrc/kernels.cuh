@@ -37,6 +37,7 @@ struct DEnvDist { const double* marginal; const double* cond; uint32_t rows, col
 struct RenderConst {
     uint64_t seed; uint32_t sample_begin, sample_stride, nan_policy, env_importance;
     DEnvDist env;
+    uint32_t sort_mask = 0;  // survivors of a shade block are grouped by (direction octant & sort_mask): bit 0 = y, 1 = x, 2 = z
 };
 
 // ---------------------------------------------------------------- camera.rs:133-168
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(kBlock, PT_SHADE_MIN_BLOCKS) k_shade(PathBuf i
     constexpr int K = ClassKind<CLS>::value;
     const uint32_t count = q.count[CLS];
     const uint32_t* __restrict__ items = q.items + (size_t)CLS * q.stride;
-    __shared__ uint32_t warp_count[kBlock / 32];
+    __shared__ uint32_t bin_count[8][kBlock / 32];  // survivors per (octant bin, warp), then their exclusive prefix
     __shared__ uint32_t block_base;
     for (uint32_t base = blockIdx.x * kBlock; base < count; base += gridDim.x * kBlock) {
         const uint32_t j = base + threadIdx.x;
@@ -284,23 +285,29 @@ __global__ void __launch_bounds__(kBlock, PT_SHADE_MIN_BLOCKS) k_shade(PathBuf i
             }
         }
         if (CLS == CLS_MISS) continue;  // a miss ends the path: nothing to compact
-        // ---- compaction: ballot within the warp, prefix across warps, one atomic per block
+        // ---- compaction: survivors grouped by direction octant within the block (warps of the next trace launch then hold
+        //      rays that walk the BVH in the same order and tend to cost the same), one atomic per block
         const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, alive);
-        if (lane == 0) warp_count[warp] = __popc(ballot);
+        const uint32_t key = alive ? (((next.d.y < 0.0) | ((next.d.x < 0.0) << 1) | ((next.d.z < 0.0) << 2)) & rc.sort_mask) : 8u;
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+        if (threadIdx.x < 8 * (kBlock / 32)) (&bin_count[0][0])[threadIdx.x] = 0;
+        __syncthreads();
+        if (alive && lane == (uint32_t)(__ffs(peers) - 1)) bin_count[key][warp] = __popc(peers);
         __syncthreads();
         if (threadIdx.x == 0) {
             uint32_t total = 0;
 #pragma unroll
-            for (int w = 0; w < kBlock / 32; w++) { uint32_t c = warp_count[w]; warp_count[w] = total; total += c; }
+            for (int b = 0; b < 8; b++)
+#pragma unroll
+                for (int w = 0; w < kBlock / 32; w++) { uint32_t c = bin_count[b][w]; bin_count[b][w] = total; total += c; }
             block_base = total ? atomicAdd(out_count, total) : 0;
         }
         __syncthreads();
         if (alive) {
-            uint32_t dst = block_base + warp_count[warp] + __popc(ballot & ((1u << lane) - 1u));
+            uint32_t dst = block_base + bin_count[key][warp] + __popc(peers & ((1u << lane) - 1u));
             store_path(out, dst, next, thr, ids);
         }
-        __syncthreads();  // warp_count / block_base are reused by the next grid-stride iteration
+        __syncthreads();  // bin_count / block_base are reused by the next grid-stride iteration
     }
 }
 
