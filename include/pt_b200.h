@@ -199,6 +199,10 @@ typedef struct {
 /* flags bits 4-6: k_trace register-cap variant for 4-wide scenes (0 = default 72 regs; 4: 120, 5: 96, 6: 80, 7: 64) — tuning knob */
 /* flags bit 13 (0x2000): run the per-class shade kernels of an iteration one after the other on the render stream instead
  * of forking them onto side streams (tuning / debugging knob; forking is the default and measured 2.5 % faster) */
+/* flags bit 14 (0x4000): one host round trip per wavefront iteration even in the tail of a render (default: once nothing
+ * is left to generate, 8 iterations are enqueued per round trip) — tuning / debugging knob, same image either way */
+/* flags bit 15 (0x8000): take the octant mask of the survivor grouping from bits 16-18 (bit 16 = y, 17 = x, 18 = z sign of
+ * the next ray direction; default 7, 0 = plain compaction) — tuning knob, same image either way */
 /* PT_RENDER_ENV_IMPORTANCE (NOT reference behaviour): when the camera's environment is a map, the
  * direction mixture of camera.rs:199-215 gains a third sampler that draws from the map's luminance (built by
  * pt_scene_build_env_sampler): p_bsdf = 0.5, p_env = 0.5 without lights, p_light = p_env = 0.25 with lights; the

@@ -377,6 +377,19 @@ def test_virtual_rank_split_equals_single_rank(pt, pairs):
     assert np.allclose(full, small_pool, rtol=2e-5, atol=2e-6)
 
 
+@pytest.mark.parametrize("scene_id,width,spp", [(3, 96, 8), (6, 128, 6)])
+def test_scheduling_knobs_do_not_change_the_image(pt, pairs, scene_id, width, spp):
+    """The batched tail (8 iterations per host round trip), the forked shade streams and the octant grouping of survivors
+    only reorder work: same paths, same segments, same iteration count, same image (up to fp32 atomic-add order)."""
+    p = pairs(scene_id, width)
+    base, st0 = p.dev.render(spp=spp, seed=9, nan_policy=1)
+    for flags in (0x4000, 0x2000, 0x8000, 0x4000 | 0x2000 | 0x8000 | (5 << 16)):
+        img, st = p.dev.render(spp=spp, seed=9, nan_policy=1, flags=flags)
+        assert (st.paths, st.segments, st.iterations, st.nonfinite) == (st0.paths, st0.segments, st0.iterations, st0.nonfinite), hex(flags)
+        assert np.allclose(img, base, rtol=2e-5, atol=2e-6), hex(flags)
+    assert st0.iterations > 8 and st0.segments > st0.paths
+
+
 def test_progressive_checkpoint_resume_and_noise_floor(pt, ctx, tmp_path):
     """batches + checkpoint/resume give the image of one pt_render call; the A/B half estimate of the noise
     predicts the relRMSE actually measured against a converged render."""
