@@ -278,6 +278,15 @@ int  pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* c
  * mean radiance (W*H*3 fp32, row-major, top row first) to host memory. */
 int  pt_render(pt_ctx* ctx, const pt_scene* scene, const pt_camera* cam,
                const pt_render_params* params, float* h_mean_rgb, pt_stats* stats);
+/* Camera::render on several GPUs from ONE process — what a single-process host like the reference's binary calls
+ * (camera.rs:79; the reference parallelises over pixels with rayon inside that call, camera.rs:102).  One host thread
+ * per entry of `devices` creates its own context, uploads `desc`, and renders the samples g, g + n, g + 2n, ... of the
+ * call (spp split, independent counter-based streams); the partial sums are added on the host in device
+ * order and divided by sample_count.  Same image as pt_render on one device up to fp32 summation order.  The same
+ * device may be listed more than once.  stats: counters summed, times = the slowest device.  bench.py and the tests'
+ * multi-GPU path use one process per GPU + NCCL instead (pt_render_accumulate). */
+int  pt_render_multi(int n_devices, const int* devices, const pt_scene_desc* desc, const pt_camera* cam,
+                     const pt_render_params* params, float* h_mean_rgb, pt_stats* stats);
 /* sqrt-gamma, clamp(0,0.999)*256 as u8 (camera.rs:109-114,128-130). Device in, host out. */
 int  pt_tonemap_rgb8(pt_ctx* ctx, const float* d_accum, double scale, uint32_t n_pixels,
                      uint8_t* h_rgb8);

@@ -47,6 +47,8 @@ def test_no_device_fails_loudly(pt):
         pytest.skip("a CUDA device is present")
     with pytest.raises(pt.PtError, match="no CUDA device"):
         pt.Context(0)
+    with pytest.raises(pt.PtError, match="device 0: no CUDA device"):     # the single-process multi-GPU entry: same refusal,
+        pt.render_multi(pt.Scene.build(3, 32, 1, 1), [0, 0], spp=2)        # carried over from the worker thread
 
 
 def test_product_never_touches_oracle():

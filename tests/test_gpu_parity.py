@@ -390,6 +390,23 @@ def test_scheduling_knobs_do_not_change_the_image(pt, pairs, scene_id, width, sp
     assert st0.iterations > 8 and st0.segments > st0.paths
 
 
+def test_render_multi_equals_single_device(pt, pairs):
+    """pt_render_multi (one process, one host thread per listed device, spp split, host reduce) gives pt_render's image.
+    On a one-GPU box the shares run as three contexts on device 0; with more GPUs they spread over real devices."""
+    p = pairs(6, 128)
+    n_dev = pt.device_lib().pt_device_count()
+    devices = [g % n_dev for g in range(3)]
+    for kw in (dict(), dict(flags=pt.PT_RENDER_NEE), dict(sample_begin=5, sample_stride=2)):
+        single, st1 = p.dev.render(spp=7, seed=4, nan_policy=1, **kw)
+        multi, stm = pt.render_multi(p.scene, devices, spp=7, seed=4, nan_policy=1, **kw)
+        assert (stm.paths, stm.segments, stm.nonfinite) == (st1.paths, st1.segments, st1.nonfinite), kw
+        assert np.allclose(multi, single, rtol=2e-5, atol=2e-6), kw
+    two, st2 = pt.render_multi(p.scene, [0] * 5, spp=2, seed=4, nan_policy=1)      # more devices than samples: two shares
+    assert np.allclose(two, p.dev.render(spp=2, seed=4, nan_policy=1)[0], rtol=2e-5, atol=2e-6) and st2.paths == 2 * 128 * 72
+    with pytest.raises(pt.PtError, match="device 99"):
+        pt.render_multi(p.scene, [0, 99], spp=2)
+
+
 def test_progressive_checkpoint_resume_and_noise_floor(pt, ctx, tmp_path):
     """batches + checkpoint/resume give the image of one pt_render call; the A/B half estimate of the noise
     predicts the relRMSE actually measured against a converged render."""

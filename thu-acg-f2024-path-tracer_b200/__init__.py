@@ -70,7 +70,8 @@ assert BSDF_RESULT_DTYPE.itemsize == 64 and BSDF_SAMPLE_DTYPE.itemsize == 32
 ABI_SYMBOLS = ["pt_ctx_create", "pt_ctx_destroy", "pt_ctx_set_stream", "pt_ctx_set_profiling", "pt_last_error", "pt_device_count",
                "pt_scene_create", "pt_scene_destroy", "pt_scene_device_bytes", "pt_camera_image_height", "pt_render_accumulate",
                "pt_render", "pt_tonemap_rgb8", "pt_trace_closest", "pt_trace_any", "pt_bsdf_eval_pdf", "pt_bsdf_sample",
-               "pt_camera_rays", "pt_lights_sample_pdf", "pt_scene_build_env_sampler", "pt_env_sample_pdf", "pt_sah_sweep"]
+               "pt_camera_rays", "pt_lights_sample_pdf", "pt_scene_build_env_sampler", "pt_env_sample_pdf", "pt_sah_sweep",
+               "pt_render_multi"]
 
 
 class PtError(RuntimeError):
@@ -128,6 +129,7 @@ def device_lib():
         lib.pt_scene_build_env_sampler.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
         lib.pt_env_sample_pdf.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.pt_sah_sweep.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.pt_render_multi.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.POINTER(CameraABI), C.c_void_p, C.c_void_p, C.c_void_p]
         _dev = lib
     return _dev
 
@@ -536,6 +538,22 @@ class DeviceScene:
         p = self.params(spp, **kw)
         self.ctx._check(self.ctx.lib.pt_render_accumulate(self.ctx.ptr, self.ptr, C.byref(cam), C.byref(p), C.c_void_p(d_accum_ptr), C.byref(st)))
         return st
+
+
+def render_multi(scene, devices, camera=None, spp=None, seed=1, sample_begin=0, sample_stride=1, nan_policy=PT_NAN_REFERENCE, pool_paths=0, flags=0):
+    """pt_render_multi: Camera::render on several GPUs of this one process (one host thread per listed device)."""
+    lib = device_lib()
+    cam = camera if camera is not None else scene.camera
+    spp = spp if spp is not None else cam.samples_per_pixel
+    h = lib.pt_camera_image_height(C.byref(cam))
+    out = np.zeros((h, cam.image_width, 3), dtype=np.float32)
+    st = Stats()
+    p = RenderParams(seed, sample_begin, spp, sample_stride, nan_policy, pool_paths, flags)
+    devs = (C.c_int * len(devices))(*devices)
+    rc = lib.pt_render_multi(len(devices), devs, scene.desc, C.byref(cam), C.byref(p), _ptr(out), C.byref(st))
+    if rc != 0:
+        raise PtError(f"pt_b200 error {rc}: {lib.pt_last_error().decode()}")
+    return out, st
 
 
 def camera_rays(ctx, camera, seed, rows, cols, samples):

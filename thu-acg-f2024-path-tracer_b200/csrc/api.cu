@@ -6,6 +6,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "kernels.cuh"
@@ -825,6 +826,85 @@ int pt_render(pt_ctx* ctx, const pt_scene* scene, const pt_camera* cam, const pt
     }
     cudaFree(d_accum);
     return rc;
+}
+
+}  // extern "C"
+
+// One device's share of pt_render_multi: own context, own copy of the scene, samples share, share + n_shares, ... of the call.
+static int render_share(int device, const pt_scene_desc* desc, const pt_camera* cam, const pt_render_params* p, uint32_t share,
+                        uint32_t n_shares, float* h_sum, size_t n, pt_stats* st) {
+    pt_ctx* ctx = nullptr; pt_scene* scene = nullptr; float* d_accum = nullptr;
+    int rc = pt_ctx_create(device, &ctx);
+    if (rc == PT_OK) rc = pt_scene_create(ctx, desc, &scene);
+    if (rc == PT_OK && (p->flags & PT_RENDER_ENV_IMPORTANCE) && cam->env_is_map) rc = pt_scene_build_env_sampler(scene, cam->env_image, 0, 0);
+    if (rc == PT_OK) {
+        cudaError_t e = cudaMalloc(&d_accum, n * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_accum, 0, n * sizeof(float), ctx->stream);
+        if (e != cudaSuccess) rc = fail(PT_ERR_CUDA, cudaGetErrorString(e));
+    }
+    if (rc == PT_OK) {
+        pt_render_params q = *p;
+        const uint32_t stride = p->sample_stride ? p->sample_stride : 1u;
+        q.sample_begin = p->sample_begin + share * stride;
+        q.sample_stride = stride * n_shares;
+        q.sample_count = (p->sample_count - share + n_shares - 1) / n_shares;
+        rc = pt_render_accumulate(ctx, scene, cam, &q, d_accum, st);
+    }
+    if (rc == PT_OK) {
+        cudaError_t e = cudaMemcpyAsync(h_sum, d_accum, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fail(PT_ERR_CUDA, cudaGetErrorString(e));
+    }
+    if (d_accum) cudaFree(d_accum);
+    if (scene) pt_scene_destroy(scene);
+    if (ctx) pt_ctx_destroy(ctx);
+    return rc;
+}
+
+extern "C" {
+
+int pt_render_multi(int n_devices, const int* devices, const pt_scene_desc* desc, const pt_camera* cam, const pt_render_params* p,
+                    float* h_mean, pt_stats* stats) {
+    if (n_devices < 1 || !devices || !desc || !cam || !p || !h_mean) return fail(PT_ERR_INVALID, "pt_render_multi: bad argument");
+    if (p->sample_count == 0) return fail(PT_ERR_INVALID, "pt_render_multi: sample_count is zero");
+    const size_t n = (size_t)cam->image_width * pt_camera_image_height(cam) * 3;
+    const uint32_t G = std::min<uint32_t>((uint32_t)n_devices, p->sample_count);  // a share is at least one sample per pixel
+    std::vector<std::vector<float>> sums(G);
+    std::vector<int> rcs(G, PT_OK);
+    std::vector<std::string> errs(G);
+    std::vector<pt_stats> sts(G);
+    auto work = [&](uint32_t g) {
+        try {
+            sums[g].resize(n);
+            rcs[g] = render_share(devices[g], desc, cam, p, g, G, sums[g].data(), n, &sts[g]);
+            if (rcs[g] != PT_OK) errs[g] = g_err;  // the message is thread-local: carry it to the caller's thread
+        } catch (const std::exception& e) { rcs[g] = PT_ERR_CUDA; errs[g] = e.what(); }
+    };
+    std::vector<std::thread> threads;
+    for (uint32_t g = 1; g < G; g++) threads.emplace_back(work, g);
+    work(0);
+    for (auto& t : threads) t.join();
+    for (uint32_t g = 0; g < G; g++)
+        if (rcs[g] != PT_OK) return fail(rcs[g], "pt_render_multi: device " + std::to_string(devices[g]) + ": " + errs[g]);
+    // the reduce(sum) of SURVEY 8(e), on the host and in device order (deterministic given the partial sums)
+    const double inv = 1.0 / (double)p->sample_count;
+    for (size_t i = 0; i < n; i++) {
+        double acc = 0.0;
+        for (uint32_t g = 0; g < G; g++) acc += (double)sums[g][i];
+        h_mean[i] = (float)(acc * inv);
+    }
+    if (stats) {
+        pt_stats S = sts[0];
+        for (uint32_t g = 1; g < G; g++) {
+            const pt_stats& t = sts[g];
+            S.paths += t.paths; S.segments += t.segments; S.nonfinite += t.nonfinite; S.kernel_launches += t.kernel_launches;
+            S.node_pairs += t.node_pairs; S.ref_boxes += t.ref_boxes; S.prim_tests += t.prim_tests;
+            S.iterations = std::max(S.iterations, t.iterations); S.device_ms = std::max(S.device_ms, t.device_ms);
+            S.trace_ms = std::max(S.trace_ms, t.trace_ms); S.shade_ms = std::max(S.shade_ms, t.shade_ms); S.raygen_ms = std::max(S.raygen_ms, t.raygen_ms);
+        }
+        *stats = S;
+    }
+    return PT_OK;
 }
 
 int pt_tonemap_rgb8(pt_ctx* ctx, const float* d_accum, double scale, uint32_t n_pixels, uint8_t* h_rgb8) {

@@ -176,6 +176,7 @@ struct RenderOptions {  // knobs the reference does not have (it is unseeded / s
     uint64_t seed = 1; int device = 0; uint32_t nan_policy = PT_NAN_REFERENCE; bool verbose = true;
     bool env_importance = false;  // PT_RENDER_ENV_IMPORTANCE: sample the environment map by luminance (not reference behaviour)
     bool nee = false;             // PT_RENDER_NEE: next-event estimation with MIS (not reference behaviour)
+    int gpus = 1;                 // > 1: pt_render_multi on devices device .. device + gpus - 1 (spp split, one process)
 };
 struct Camera {
     double aspect_ratio = 1.0; uint32_t image_width = 0, samples_per_pixel = 0, max_depth = 0;

@@ -392,39 +392,55 @@ int Camera::render(const World& world, const std::string& filename, const Render
     pt_camera cam = to_abi(*flat);
     return render_flat(flat->desc, cam, filename, opt, stats_out);
 }
+// camera.rs:109-123: tonemap the mean radiance and save the PNG
+static void save_image(const std::vector<float>& mean, uint32_t W, uint32_t H, const std::string& filename) {
+    std::vector<uint8_t> rgb(mean.size());
+    for (size_t i = 0; i < mean.size(); i++) {  // camera.rs:109-114,128-130
+        double g = std::sqrt(std::fmax((double)mean[i], 0.0));
+        double v = (g < 0.0 ? 0.0 : (g > 0.999 ? 0.999 : g)) * 256.0;
+        rgb[i] = std::isnan(v) ? 0 : (uint8_t)v;
+    }
+    if (!write_png_rgb8(filename, rgb.data(), W, H)) fprintf(stderr, "Failed to save image %s\n", filename.c_str());  // camera.rs:118-123
+}
+static void report(const RenderOptions& opt, uint32_t W, uint32_t H, uint32_t spp, const pt_stats& st) {
+    if (opt.verbose)
+        fprintf(stderr, "[pt_b200] %ux%u spp=%u on %d GPU(s): %.3f s device, %.1f Mrays/s, %.3g samples/s, %llu segments, %llu non-finite\n", W, H, spp,
+                std::max(opt.gpus, 1), st.device_ms * 1e-3, st.segments / (st.device_ms * 1e3), st.paths / (st.device_ms * 1e-3),
+                (unsigned long long)st.segments, (unsigned long long)st.nonfinite);
+}
 int render_flat(const pt_scene_desc& desc, const pt_camera& cam, const std::string& filename, const RenderOptions& opt, pt_stats* stats_out) {
+    const uint32_t samples_per_pixel = cam.samples_per_pixel;
+    uint32_t H = pt_camera_image_height(&cam), W = cam.image_width;
+    std::vector<float> mean((size_t)W * H * 3);
+    pt_render_params p{}; p.seed = opt.seed; p.sample_begin = 0; p.sample_count = samples_per_pixel; p.sample_stride = 1; p.nan_policy = opt.nan_policy;
+    if (opt.nee) p.flags |= PT_RENDER_NEE;
+    if (opt.gpus > 1) {  // one process, several GPUs: spp split inside the library
+        if (opt.env_importance && cam.env_is_map) p.flags |= PT_RENDER_ENV_IMPORTANCE;
+        std::vector<int> devices(opt.gpus);
+        for (int g = 0; g < opt.gpus; g++) devices[g] = opt.device + g;
+        pt_stats st{};
+        if (opt.verbose) printf("rendering production\n");  // camera.rs:101
+        int rc = pt_render_multi(opt.gpus, devices.data(), &desc, &cam, &p, mean.data(), &st);
+        if (rc) fprintf(stderr, "pt_render_multi: %s\n", pt_last_error());
+        else { save_image(mean, W, H, filename); report(opt, W, H, samples_per_pixel, st); }
+        if (stats_out) *stats_out = st;
+        return rc;
+    }
     pt_ctx* ctx = nullptr; pt_scene* scene = nullptr;
     int rc = pt_ctx_create(opt.device, &ctx);
     if (rc) { fprintf(stderr, "pt_ctx_create: %s\n", pt_last_error()); return rc; }
     rc = pt_scene_create(ctx, &desc, &scene);
     if (rc) { fprintf(stderr, "pt_scene_create: %s\n", pt_last_error()); pt_ctx_destroy(ctx); return rc; }
-    const uint32_t samples_per_pixel = cam.samples_per_pixel;
-    uint32_t H = pt_camera_image_height(&cam), W = cam.image_width;
-    std::vector<float> mean((size_t)W * H * 3);
-    pt_render_params p{}; p.seed = opt.seed; p.sample_begin = 0; p.sample_count = samples_per_pixel; p.sample_stride = 1; p.nan_policy = opt.nan_policy;
     if (opt.env_importance && cam.env_is_map) {
         rc = pt_scene_build_env_sampler(scene, cam.env_image, 0, 0);
         if (rc) { fprintf(stderr, "pt_scene_build_env_sampler: %s\n", pt_last_error()); pt_scene_destroy(scene); pt_ctx_destroy(ctx); return rc; }
         p.flags |= PT_RENDER_ENV_IMPORTANCE;
     }
-    if (opt.nee) p.flags |= PT_RENDER_NEE;
     pt_stats st{};
     if (opt.verbose) printf("rendering production\n");  // camera.rs:101
     rc = pt_render(ctx, scene, &cam, &p, mean.data(), &st);
     if (rc) fprintf(stderr, "pt_render: %s\n", pt_last_error());
-    else {
-        std::vector<uint8_t> rgb(mean.size());
-        for (size_t i = 0; i < mean.size(); i++) {  // camera.rs:109-114,128-130
-            double g = std::sqrt(std::fmax((double)mean[i], 0.0));
-            double v = (g < 0.0 ? 0.0 : (g > 0.999 ? 0.999 : g)) * 256.0;
-            rgb[i] = std::isnan(v) ? 0 : (uint8_t)v;
-        }
-        if (!write_png_rgb8(filename, rgb.data(), W, H)) fprintf(stderr, "Failed to save image %s\n", filename.c_str());  // camera.rs:118-123
-        if (opt.verbose)
-            fprintf(stderr, "[pt_b200] %ux%u spp=%u: %.3f s device, %.1f Mrays/s, %.3g samples/s, %llu segments, %llu non-finite\n", W, H,
-                    samples_per_pixel, st.device_ms * 1e-3, st.segments / (st.device_ms * 1e3), st.paths / (st.device_ms * 1e-3),
-                    (unsigned long long)st.segments, (unsigned long long)st.nonfinite);
-    }
+    else { save_image(mean, W, H, filename); report(opt, W, H, samples_per_pixel, st); }
     if (stats_out) *stats_out = st;
     pt_scene_destroy(scene); pt_ctx_destroy(ctx);
     return rc;
