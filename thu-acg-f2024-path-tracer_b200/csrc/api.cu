@@ -38,6 +38,8 @@ struct pt_ctx {
     HitRec* hits = nullptr;
     uint32_t* d_count = nullptr;            // kTailBatch slots of [16]: [0] survivors counter, [4 .. 4+N_CLS) shade-class queue lengths
     uint32_t* q_items = nullptr;            // N_CLS queues of `pool` path slots each
+    uint4* bq_items = nullptr;              // two-pass traversal: kDeferMax queues of `pool` deferred mesh visits each
+    uint2* ties = nullptr;                  //   and the tie ranks of the provisional hit of every path
     unsigned long long* d_nonfinite = nullptr;
     uint32_t* h_count = nullptr;            // pinned, same shape as d_count
     void* h_stage = nullptr; size_t stage_bytes = 0;  // pinned staging buffer for scene uploads
@@ -69,6 +71,7 @@ struct pt_scene {
     std::vector<DImage> images;
     bool general_lights = false;            // World.lights holds something other than quads and spheres (shade kernel variant)
     bool has_volumes = false;               // constant-density media present (trace kernel variant with keyed uniforms)
+    bool defer_meshes = false;              // two-pass traversal (k_trace<DEFER> + k_trace_blas): wide scenes that hold meshes
     DEnvDist env{};                         // pt_scene_build_env_sampler: importance sampler of image `env_image`
     uint32_t env_image = 0xFFFFFFFFu;
     void* env_block = nullptr;
@@ -104,6 +107,7 @@ int pt_ctx_create(int device, pt_ctx** out) {
 static void free_pool(pt_ctx* c) {
     for (int i = 0; i < 2; i++) { cudaFree(c->pool_f[i]); cudaFree(c->pool_ids[i]); c->pool_f[i] = nullptr; c->pool_ids[i] = nullptr; }
     cudaFree(c->hits); c->hits = nullptr; cudaFree(c->q_items); c->q_items = nullptr; c->pool = 0;
+    cudaFree(c->bq_items); c->bq_items = nullptr; cudaFree(c->ties); c->ties = nullptr;
 }
 void pt_ctx_destroy(pt_ctx* c) {
     if (!c) return;
@@ -485,6 +489,7 @@ int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
     for (uint32_t i = 0; i < d->n_volumes; i++)
         volumes[i] = DVolume{d->volumes[i].boundary.kind, d->volumes[i].boundary.index, d->volumes[i].material, 0, -1.0 / d->volumes[i].density, 0.0};
     s->has_volumes = d->n_volumes > 0;
+    s->defer_meshes = s->wide && d->n_meshes > 0 && !s->has_volumes;
     // ---- textures, images, materials
     std::vector<DTexture> textures(d->n_textures);
     for (uint32_t i = 0; i < d->n_textures; i++) {
@@ -660,6 +665,8 @@ static int ensure_pool(pt_ctx* c, uint32_t paths) {
     }
     CU(cudaMalloc(&c->hits, (size_t)paths * sizeof(HitRec)));
     CU(cudaMalloc(&c->q_items, (size_t)paths * N_CLS * sizeof(uint32_t)));
+    CU(cudaMalloc(&c->bq_items, (size_t)paths * kDeferMax * sizeof(uint4)));
+    CU(cudaMalloc(&c->ties, (size_t)paths * sizeof(uint2)));
     c->pool = paths;
     return PT_OK;
 }
@@ -705,6 +712,19 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
     // World::intersect_all for the n (or min(n, *n_dev)) paths of `in`; one compile-time flavour per scene / mode
     auto launch_trace = [&](const PathBuf& in, uint32_t n, const Queues& q, const uint32_t* n_dev) {
         const unsigned tg = (n + kTraceBlock - 1) / kTraceBlock;
+        // two-pass traversal; not for small iterations (three more launches each); flag 0x100000 opts out (A/B measurements)
+        if (scene->defer_meshes && n >= (1u << 16) && !(p->flags & 0x100000u)) {
+            const BlasQueues bq{ctx->bq_items, q.count + 8, ctx->pool};  // counters in the free tail of the iteration's slot
+            if (wk) k_trace<7, true, true, false, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, 0, n_dev, bq, ctx->ties);
+            else k_trace<7, true, false, false, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, nullptr, 0, n_dev, bq, ctx->ties);
+            const unsigned bg = std::min<unsigned>(tg, 148u * 56u);
+            for (uint32_t r = 0; r < (uint32_t)kDeferMax; r++) {
+                if (wk) k_trace_blas<true><<<bg, kTraceBlock, 0, st>>>(in, r, bq, ctx->hits, ctx->ties, q, scene->d, wk);
+                else k_trace_blas<false><<<bg, kTraceBlock, 0, st>>>(in, r, bq, ctx->hits, ctx->ties, q, scene->d, nullptr);
+            }
+            S.kernel_launches += 1 + kDeferMax;
+            return;
+        }
         if (scene->has_volumes) {  // media: the trace kernel variant that draws keyed free-flight uniforms
             if (scene->wide) { if (wk) k_trace<6, true, true, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, p->seed, n_dev); else k_trace<6, true, false, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, p->seed, n_dev); }
             else { if (wk) k_trace<6, false, true, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, p->seed, n_dev); else k_trace<6, false, false, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, p->seed, n_dev); }

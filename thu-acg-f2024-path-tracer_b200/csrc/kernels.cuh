@@ -163,34 +163,112 @@ struct PathVol {
     uint64_t seed; const uint4* __restrict__ ids; uint32_t i;
     PT_D double operator()(uint32_t v) const { const uint4 id = ids[i]; return keyed_uniform(seed, id.x, id.y, id.z >> 16, v); }
 };
-template <int MIN_BLOCKS, bool WIDE, bool COUNT = false, bool VOL = false>
+// Two-pass traversal for scenes with mesh BLASes (DEFER): a warp of k_trace mixes rays that leave the top-level BVH after a
+// node or two with rays that walk a mesh for ten times as long, so the short ones idle (8.9 of 32 lanes active on scene 6).
+// With DEFER, k_trace walks the top level only — simple primitives are tested, every mesh whose box the ray enters is
+// queued (up to kDeferMax per ray; a further one is walked inline) — and k_trace_blas<round> then walks the r-th queued
+// mesh of each such ray, compacted so that its warps hold only rays inside a BLAS.  Hit record and tie ranks travel through
+// `hits` / `ties`; a ray joins its shade-class queue after its last round.  Same closest hit, same tie rules (ranks).
+constexpr int kDeferMax = 3;
+struct BlasQueues { uint4* items; uint32_t* count; uint32_t stride; };  // items[round * stride + k] = {path, ref slot | last << 31, entry t, -}
+struct DeferList {
+    static constexpr bool kEnabled = true;
+    uint32_t* n; uint32_t* slot; float* t;
+    PT_D bool operator()(uint32_t s, float tt) const {
+        if (*n >= (uint32_t)kDeferMax) return false;
+        slot[*n] = s; t[*n] = tt; (*n)++;
+        return true;
+    }
+};
+
+template <int MIN_BLOCKS, bool WIDE, bool COUNT = false, bool VOL = false, bool DEFER = false>
 __global__ void __launch_bounds__(kTraceBlock, MIN_BLOCKS * kBlock / kTraceBlock) k_trace(PathBuf in, uint32_t n, HitRec* __restrict__ hits, Queues q, DScene S,
                                                               unsigned long long* __restrict__ work = nullptr, uint64_t seed = 0,
-                                                              const uint32_t* __restrict__ n_dev = nullptr) {
+                                                              const uint32_t* __restrict__ n_dev = nullptr, BlasQueues bq = BlasQueues{nullptr, nullptr, 0},
+                                                              uint2* __restrict__ ties = nullptr) {
     // batched tail iterations (api.cu): the host only knows an upper bound of the live count, the survivors counter of the
     // previous iteration (still in device memory) is the real one
     if (n_dev) n = min(n, *n_dev);
     const uint32_t i = blockIdx.x * kTraceBlock + threadIdx.x;
     uint32_t cls = N_CLS;
     uint32_t w0 = 0, w1 = 0, w2 = 0;
+    uint32_t nd = 0, dslot[kDeferMax]; float dt[kDeferMax];
     if (i < n) {
         Closest c;
         // Interval::new(eps, INFINITY), camera.rs:171,179
         if constexpr (VOL) trace_closest<false, COUNT, WIDE>(S, [&]() { return load_ray(in, i); }, 1e-3, 0.0, c, PathVol{seed, in.ids, i});
+        else if constexpr (DEFER) trace_closest<false, COUNT, WIDE>(S, [&]() { return load_ray(in, i); }, 1e-3, 0.0, c, NoVol(), DeferList{&nd, dslot, dt});
         else trace_closest<false, COUNT, WIDE>(S, [&]() { return load_ray(in, i); }, 1e-3, 0.0, c);
         if (COUNT) { w0 = c.n_pairs + 2 * c.n_wide; w1 = c.n_refs; w2 = c.n_prims; }  // in 64-byte units
         HitRec h; h.t = c.t; h.ref = c.ref; h.inst_light = (c.inst & 0x7FFFFFFFu) | (c.is_light ? 0x80000000u : 0u);
         hits[i] = h;
-        cls = c.ref == kNone ? (uint32_t)CLS_MISS : class_of_kind(S.materials[hit_material(S, c.ref)].kind);
+        if (DEFER && nd) ties[i] = make_uint2(c.tie_outer, c.tie_inner);
+        else cls = c.ref == kNone ? (uint32_t)CLS_MISS : class_of_kind(S.materials[hit_material(S, c.ref)].kind);
     }
     __syncwarp();
     queue_append(q, cls, i);
+    if (DEFER) {
+        const uint32_t lane = threadIdx.x & 31;
+#pragma unroll
+        for (int r = 0; r < kDeferMax; r++) {
+            const bool has = nd > (uint32_t)r;
+            const uint32_t b = __ballot_sync(0xFFFFFFFFu, has);
+            if (!b) break;
+            const int leader = __ffs(b) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(bq.count + r, __popc(b));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (has) bq.items[(size_t)r * bq.stride + base + __popc(b & ((1u << lane) - 1u))] =
+                         make_uint4(i, dslot[r] | (nd == (uint32_t)r + 1 ? 0x80000000u : 0u), __float_as_uint(dt[r]), 0u);
+        }
+    }
     if (COUNT) {
 #ifdef PT_DIAG_WARP  // diagnostic build: ref_boxes := sum of per-ray cost, prim_tests := sum of the warp's maximum cost per lane
         w1 = 3 * w0 + w1 + 4 * w2 + 1; w2 = __reduce_max_sync(0xFFFFFFFFu, w1);
 #endif
         w0 = __reduce_add_sync(0xFFFFFFFFu, w0); w1 = __reduce_add_sync(0xFFFFFFFFu, w1); w2 = __reduce_add_sync(0xFFFFFFFFu, w2);
         if ((threadIdx.x & 31) == 0) { atomicAdd(work, (unsigned long long)w0); atomicAdd(work + 1, (unsigned long long)w1); atomicAdd(work + 2, (unsigned long long)w2); }
+    }
+}
+
+// Round `round` of the two-pass traversal: the round-th queued mesh of every ray that queued at least round + 1 of them.
+// Warp-granular grid-stride loop over the compacted queue; one ray per lane.
+template <bool COUNT>
+__global__ void __launch_bounds__(kTraceBlock, 7 * kBlock / kTraceBlock) k_trace_blas(PathBuf in, uint32_t round, BlasQueues bq, HitRec* __restrict__ hits,
+                                                              uint2* __restrict__ ties, Queues q, DScene S, unsigned long long* __restrict__ work) {
+    const uint32_t count = bq.count[round];
+    const uint4* __restrict__ items = bq.items + (size_t)round * bq.stride;
+    uint32_t w0 = 0, w1 = 0, w2 = 0;
+    for (uint32_t j = blockIdx.x * kTraceBlock + threadIdx.x; j - (threadIdx.x & 31) < count; j += gridDim.x * kTraceBlock) {
+        uint32_t cls = N_CLS, i = 0;
+        if (j < count) {
+            const uint4 e = items[j];
+            i = e.x;
+            const HitRec h0 = hits[i];
+            const uint2 tie = ties[i];
+            Closest c; c.t = h0.t; c.ref = h0.ref; c.inst = h0.inst_light & 0x7FFFFFFFu; c.tie_outer = tie.x; c.tie_inner = tie.y;
+            c.is_light = (h0.inst_light >> 31) != 0;
+            if (__uint_as_float(e.z) <= __double2float_ru(c.t)) {  // the mesh may since have fallen behind the closest hit
+                const DNode rf = S.refs[e.y & 0x7FFFFFFFu];  // a = kind | index of the queued mesh or instance, b = its outer tie rank
+                const uint32_t kind = ref_kind(rf.a), index = ref_index(rf.a);
+                RayD r = load_ray(in, i);
+                uint32_t mesh = index, inst = kInstNone;
+                if (kind == PT_OBJ_INSTANCE) { const DInstance& ins = S.instances[index]; r = instance_local_ray(ins, r); mesh = ins.child_index; inst = index; }
+                c.n_pairs = 0; c.n_wide = 0; c.n_refs = 0; c.n_prims = 0;
+                trace_blas<COUNT>(S, S.meshes[mesh].root_entry, r, 1e-3, c, inst, rf.b);
+                if (COUNT) { w0 += c.n_pairs + 2 * c.n_wide; w1 += c.n_refs; w2 += c.n_prims; }
+                HitRec h; h.t = c.t; h.ref = c.ref; h.inst_light = (c.inst & 0x7FFFFFFFu) | (c.is_light ? 0x80000000u : 0u);
+                hits[i] = h;
+                if (!(e.y >> 31)) ties[i] = make_uint2(c.tie_outer, c.tie_inner);
+            }
+            if (e.y >> 31) cls = c.ref == kNone ? (uint32_t)CLS_MISS : class_of_kind(S.materials[hit_material(S, c.ref)].kind);
+        }
+        __syncwarp();
+        queue_append(q, cls, i);
+    }
+    if (COUNT) {
+        w0 = __reduce_add_sync(0xFFFFFFFFu, w0); w1 = __reduce_add_sync(0xFFFFFFFFu, w1); w2 = __reduce_add_sync(0xFFFFFFFFu, w2);
+        if ((threadIdx.x & 31) == 0 && (w0 | w1 | w2)) { atomicAdd(work, (unsigned long long)w0); atomicAdd(work + 1, (unsigned long long)w1); atomicAdd(work + 2, (unsigned long long)w2); }
     }
 }
 
