@@ -383,7 +383,7 @@ def test_scheduling_knobs_do_not_change_the_image(pt, pairs, scene_id, width, sp
     only reorder work: same paths, same segments, same iteration count, same image (up to fp32 atomic-add order)."""
     p = pairs(scene_id, width)
     base, st0 = p.dev.render(spp=spp, seed=9, nan_policy=1)
-    for flags in (0x4000, 0x2000, 0x8000, 0x100000, 0x4000 | 0x2000 | 0x8000 | (5 << 16) | 0x100000):
+    for flags in (0x4000, 0x2000, 0x8000, 0x100000, 0x200000, 0x4000 | 0x2000 | 0x8000 | (5 << 16) | 0x100000):
         img, st = p.dev.render(spp=spp, seed=9, nan_policy=1, flags=flags)
         assert (st.paths, st.segments, st.iterations, st.nonfinite) == (st0.paths, st0.segments, st0.iterations, st0.nonfinite), hex(flags)
         assert np.allclose(img, base, rtol=2e-5, atol=2e-6), hex(flags)

@@ -25,6 +25,7 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 // back to back, each reading its ray count from the survivors counter of the one before, and the host reads all the
 // counters in one round trip.  Grids are sized by the live count at the start of the batch (an upper bound).
 constexpr int kTailBatch = 8;
+constexpr int kSlot = 32;  // uint32 counters per wavefront iteration (see pt_ctx::d_count)
 constexpr uint32_t kTailBatchMaxLive = 1u << 22;
 
 struct pt_ctx {
@@ -36,7 +37,7 @@ struct pt_ctx {
     double* pool_f[2] = {nullptr, nullptr};
     uint4* pool_ids[2] = {nullptr, nullptr};
     HitRec* hits = nullptr;
-    uint32_t* d_count = nullptr;            // kTailBatch slots of [16]: [0] survivors counter, [4 .. 4+N_CLS) shade-class queue lengths
+    uint32_t* d_count = nullptr;            // kTailBatch slots of [kSlot]: [0] survivors counter, [4 .. 4+N_CLS) shade-class queue lengths, [12 .. 15) mesh-visit queue lengths, [16 .. 19) their fetch cursors
     uint32_t* q_items = nullptr;            // N_CLS queues of `pool` path slots each
     uint4* bq_items = nullptr;              // two-pass traversal: kDeferMax queues of `pool` deferred mesh visits each
     uint2* ties = nullptr;                  //   and the tie ranks of the provisional hit of every path
@@ -91,9 +92,9 @@ int pt_ctx_create(int device, pt_ctx** out) {
     auto* c = new pt_ctx(); c->device = device;
     CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
-    CU(cudaMalloc(&c->d_count, kTailBatch * 16 * sizeof(uint32_t)));
+    CU(cudaMalloc(&c->d_count, kTailBatch * kSlot * sizeof(uint32_t)));
     CU(cudaMalloc(&c->d_nonfinite, 4 * sizeof(unsigned long long)));  // [0] non-finite samples, [1..3] traversal work counters
-    CU(cudaMallocHost(&c->h_count, kTailBatch * 16 * sizeof(uint32_t)));
+    CU(cudaMallocHost(&c->h_count, kTailBatch * kSlot * sizeof(uint32_t)));
     CU(cudaEventCreate(&c->ev0)); CU(cudaEventCreate(&c->ev1));
     for (auto& e : c->evs) CU(cudaEventCreate(&e));
     CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
@@ -718,8 +719,13 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
             if (wk) k_trace<7, true, true, false, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, 0, n_dev, bq, ctx->ties);
             else k_trace<7, true, false, false, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, nullptr, 0, n_dev, bq, ctx->ties);
             const unsigned bg = std::min<unsigned>(tg, 148u * 56u);
+            const bool refill = !(p->flags & 0x200000u);  // flag 0x200000: plain grid-stride rounds instead of persistent lanes with refill
+            const unsigned pg = std::min<unsigned>(tg, 148u * 28u);  // persistent: one resident warp per slot
             for (uint32_t r = 0; r < (uint32_t)kDeferMax; r++) {
-                if (wk) k_trace_blas<true><<<bg, kTraceBlock, 0, st>>>(in, r, bq, ctx->hits, ctx->ties, q, scene->d, wk);
+                if (refill) {
+                    if (wk) k_trace_blas_refill<true><<<pg, kTraceBlock, 0, st>>>(in, r, bq, ctx->hits, ctx->ties, q, scene->d, wk);
+                    else k_trace_blas_refill<false><<<pg, kTraceBlock, 0, st>>>(in, r, bq, ctx->hits, ctx->ties, q, scene->d, nullptr);
+                } else if (wk) k_trace_blas<true><<<bg, kTraceBlock, 0, st>>>(in, r, bq, ctx->hits, ctx->ties, q, scene->d, wk);
                 else k_trace_blas<false><<<bg, kTraceBlock, 0, st>>>(in, r, bq, ctx->hits, ctx->ties, q, scene->d, nullptr);
             }
             S.kernel_launches += 1 + kDeferMax;
@@ -767,19 +773,19 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
         if (tail_batching && generated == total && live <= kTailBatchMaxLive) {
             // ---- batched tail: kTailBatch iterations per host round trip (see kTailBatch)
             const uint32_t n0 = live;
-            CU(cudaMemsetAsync(ctx->d_count, 0, kTailBatch * 16 * sizeof(uint32_t), st));
+            CU(cudaMemsetAsync(ctx->d_count, 0, kTailBatch * kSlot * sizeof(uint32_t), st));
             for (int k = 0; k < kTailBatch; k++) {
-                uint32_t* slot = ctx->d_count + 16 * k;
+                uint32_t* slot = ctx->d_count + kSlot * k;
                 const Queues q{ctx->q_items, slot + 4, ctx->pool};
-                launch_trace(path_buf(ctx, cur), n0, q, k ? slot - 16 : nullptr);
+                launch_trace(path_buf(ctx, cur), n0, q, k ? slot - kSlot : nullptr);
                 if ((rc = launch_shades(path_buf(ctx, cur), path_buf(ctx, cur ^ 1), n0, q, slot, false))) return rc;
                 cur ^= 1;
             }
-            CU(cudaMemcpyAsync(ctx->h_count, ctx->d_count, kTailBatch * 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(ctx->h_count, ctx->d_count, kTailBatch * kSlot * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
             uint32_t nk = n0;
-            for (int k = 0; k < kTailBatch && nk > 0; k++) { S.segments += nk; S.iterations++; nk = ctx->h_count[16 * k]; }
-            live = ctx->h_count[16 * (kTailBatch - 1)];
+            for (int k = 0; k < kTailBatch && nk > 0; k++) { S.segments += nk; S.iterations++; nk = ctx->h_count[kSlot * k]; }
+            live = ctx->h_count[kSlot * (kTailBatch - 1)];
             if (live > pool) return fail(PT_ERR_CUDA, "internal error: the shade stage produced more paths than the pool holds");
             continue;
         }
@@ -793,7 +799,7 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
             S.kernel_launches++;
         }
         const uint32_t n = live + n_new;
-        CU(cudaMemsetAsync(ctx->d_count, 0, 16 * sizeof(uint32_t), st));
+        CU(cudaMemsetAsync(ctx->d_count, 0, kSlot * sizeof(uint32_t), st));
         const Queues q{ctx->q_items, ctx->d_count + 4, ctx->pool};
         if (ctx->profiling) CU(cudaEventRecord(ctx->evs[1], st));
         launch_trace(in, n, q, nullptr);

@@ -354,75 +354,82 @@ PT_D bool trace_closest(const DScene& S, Reload reload, double t_min, double t_m
 }
 
 // Closest hit inside ONE mesh BLAS (4-wide nodes, triangle leaves) for a ray already in the mesh's space: the second pass of
-// the two-pass traversal (k_trace_blas).  `c` comes in holding the best hit so far.  Same node step, leaf loop, culling and
+// the two-pass traversal (k_trace_blas*).  `c` comes in holding the best hit so far.  Same node step, leaf loop, culling and
 // tie ranks as trace_closest, without the top-level cases (instances, simple primitives, media, sentinel).
+// blas_round = one while-while round: wide nodes until a leaf surfaces, then that leaf; the traversal state between rounds is
+// the stack alone, so a caller may stop after any round (the persistent kernel does, to hand idle lanes a new ray).
+// Returns true when the stack has run dry (traversal finished).
 template <bool COUNT>
-PT_D void trace_blas(const DScene& S, uint32_t root_entry, const RayD& r, double t_min, Closest& c, uint32_t cur_inst, uint32_t cur_tie) {
-    uint2 stack[kStack];
-    int sp = 0;
-    const BoxRay br = make_boxray(r);
-    const float tmin_f = __double2float_rd(t_min);
-    float tmax_f = __double2float_ru(c.t);
-    uint32_t cur = root_entry;
-    while (true) {
-        uint32_t pending = kNone;
-        while (true) {  // phase 1: wide nodes
-            if (cur == kNone) {
-                while (sp > 0) {
-                    --sp;
-                    const uint2 top = stack[sp];
-                    if (!(__uint_as_float(top.y) <= tmax_f)) continue;
-                    if ((top.x & kTagMask) == 0) cur = top.x; else pending = top.x;
-                    break;
-                }
-                if (cur == kNone) break;
+PT_D bool blas_round(const DScene& S, const RayD& r, const BoxRay& br, float tmin_f, float& tmax_f, uint2* stack, int& sp, Closest& c,
+                     uint32_t cur_inst, uint32_t cur_tie) {
+    uint32_t pending = kNone, cur = kNone;
+    while (true) {  // phase 1: wide nodes
+        if (cur == kNone) {
+            while (sp > 0) {
+                --sp;
+                const uint2 top = stack[sp];
+                if (!(__uint_as_float(top.y) <= tmax_f)) continue;
+                if ((top.x & kTagMask) == 0) cur = top.x; else pending = top.x;
+                break;
             }
-            const DWide& w = S.wide[cur & ~kWideBit];
-            const float4 lx = *reinterpret_cast<const float4*>(w.lo[0]), ly = *reinterpret_cast<const float4*>(w.lo[1]),
-                         lz = *reinterpret_cast<const float4*>(w.lo[2]), hx = *reinterpret_cast<const float4*>(w.hi[0]),
-                         hy = *reinterpret_cast<const float4*>(w.hi[1]), hz = *reinterpret_cast<const float4*>(w.hi[2]);
-            const uint4 ch = *reinterpret_cast<const uint4*>(w.child);
-            if (COUNT) c.n_wide++;
-            const float kInf = __int_as_float(0x7f800000);
-            const bool sx = br.ix < 0.f, sy = br.iy < 0.f, sz = br.iz < 0.f;
-#define PT_SLAB4(I)                                                                                                          \
-            float t##I;                                                                                                      \
-            {                                                                                                                \
-                const float x0 = __fmaf_rn(sx ? hx.I : lx.I, br.ix, br.nx), x1 = __fmaf_rn(sx ? lx.I : hx.I, br.ix, br.fx); \
-                const float y0 = __fmaf_rn(sy ? hy.I : ly.I, br.iy, br.ny), y1 = __fmaf_rn(sy ? ly.I : hy.I, br.iy, br.fy); \
-                const float z0 = __fmaf_rn(sz ? hz.I : lz.I, br.iz, br.nz), z1 = __fmaf_rn(sz ? lz.I : hz.I, br.iz, br.fz); \
-                const float tn = fmaxf(fmaxf(x0, y0), fmaxf(z0, tmin_f)), tf = fminf(fminf(x1, y1), fminf(z1, tmax_f));     \
-                t##I = tn <= tf ? tn : kInf;                                                                                 \
-            }
-            PT_SLAB4(x) PT_SLAB4(y) PT_SLAB4(z) PT_SLAB4(w)
+            if (cur == kNone) break;
+        }
+        const DWide& w = S.wide[cur & ~kWideBit];
+        const float4 lx = *reinterpret_cast<const float4*>(w.lo[0]), ly = *reinterpret_cast<const float4*>(w.lo[1]),
+                     lz = *reinterpret_cast<const float4*>(w.lo[2]), hx = *reinterpret_cast<const float4*>(w.hi[0]),
+                     hy = *reinterpret_cast<const float4*>(w.hi[1]), hz = *reinterpret_cast<const float4*>(w.hi[2]);
+        const uint4 ch = *reinterpret_cast<const uint4*>(w.child);
+        if (COUNT) c.n_wide++;
+        const float kInf = __int_as_float(0x7f800000);
+        const bool sx = br.ix < 0.f, sy = br.iy < 0.f, sz = br.iz < 0.f;
+#define PT_SLAB4(I)                                                                                                      \
+        float t##I;                                                                                                      \
+        {                                                                                                                \
+            const float x0 = __fmaf_rn(sx ? hx.I : lx.I, br.ix, br.nx), x1 = __fmaf_rn(sx ? lx.I : hx.I, br.ix, br.fx); \
+            const float y0 = __fmaf_rn(sy ? hy.I : ly.I, br.iy, br.ny), y1 = __fmaf_rn(sy ? ly.I : hy.I, br.iy, br.fy); \
+            const float z0 = __fmaf_rn(sz ? hz.I : lz.I, br.iz, br.nz), z1 = __fmaf_rn(sz ? lz.I : hz.I, br.iz, br.fz); \
+            const float tn = fmaxf(fmaxf(x0, y0), fmaxf(z0, tmin_f)), tf = fminf(fminf(x1, y1), fminf(z1, tmax_f));     \
+            t##I = tn <= tf ? tn : kInf;                                                                                 \
+        }
+        PT_SLAB4(x) PT_SLAB4(y) PT_SLAB4(z) PT_SLAB4(w)
 #undef PT_SLAB4
-            uint32_t e0 = ch.x, e1 = ch.y, e2 = ch.z, e3 = ch.w;
-            float t0 = tx, t1 = ty, t2 = tz, t3 = tw;
+        uint32_t e0 = ch.x, e1 = ch.y, e2 = ch.z, e3 = ch.w;
+        float t0 = tx, t1 = ty, t2 = tz, t3 = tw;
 #define PT_CSWAP(A, B) { const bool s_ = t##B < t##A; const float tt = s_ ? t##A : t##B; t##A = s_ ? t##B : t##A; t##B = tt; \
                          const uint32_t ee = s_ ? e##A : e##B; e##A = s_ ? e##B : e##A; e##B = ee; }
-            PT_CSWAP(0, 1) PT_CSWAP(2, 3) PT_CSWAP(0, 2) PT_CSWAP(1, 3) PT_CSWAP(1, 2)
+        PT_CSWAP(0, 1) PT_CSWAP(2, 3) PT_CSWAP(0, 2) PT_CSWAP(1, 3) PT_CSWAP(1, 2)
 #undef PT_CSWAP
-            cur = kNone;
-            if (t3 < kInf && sp < kStack) { stack[sp] = make_uint2(e3, __float_as_uint(t3)); sp++; }
-            if (t2 < kInf && sp < kStack) { stack[sp] = make_uint2(e2, __float_as_uint(t2)); sp++; }
-            if (t1 < kInf && sp < kStack) { stack[sp] = make_uint2(e1, __float_as_uint(t1)); sp++; }
-            if (t0 < kInf) {
-                if ((e0 & kTagMask) == 0) cur = e0;
-                else if (sp < kStack) { stack[sp] = make_uint2(e0, __float_as_uint(t0)); sp++; }
-            }
-        }
-        if (pending == kNone) break;
-        const DNode& n = S.nodes[pending & ~kTagMask];  // phase 2: one triangle leaf
-        const uint32_t first = n.a, count = n.b;
-        for (uint32_t k = 0; k < count; k++) {
-            const DNode rb = S.refs[first + k];
-            if (COUNT) c.n_refs++;
-            if (!(slab(rb, br, tmin_f, tmax_f) <= tmax_f)) continue;
-            if (COUNT) c.n_prims++;
-            double t, u, v;
-            if (tri_t(S.tris[ref_index(rb.a)], r, t_min, t, u, v) && t <= c.t) { consider(c, t, rb.a, cur_inst, cur_tie, rb.b); tmax_f = __double2float_ru(c.t); }
+        cur = kNone;
+        if (t3 < kInf && sp < kStack) { stack[sp] = make_uint2(e3, __float_as_uint(t3)); sp++; }
+        if (t2 < kInf && sp < kStack) { stack[sp] = make_uint2(e2, __float_as_uint(t2)); sp++; }
+        if (t1 < kInf && sp < kStack) { stack[sp] = make_uint2(e1, __float_as_uint(t1)); sp++; }
+        if (t0 < kInf) {
+            if ((e0 & kTagMask) == 0) cur = e0;
+            else if (sp < kStack) { stack[sp] = make_uint2(e0, __float_as_uint(t0)); sp++; }
         }
     }
+    if (pending == kNone) return true;
+    const DNode& n = S.nodes[pending & ~kTagMask];  // phase 2: one triangle leaf
+    const uint32_t first = n.a, count = n.b;
+    for (uint32_t k = 0; k < count; k++) {
+        const DNode rb = S.refs[first + k];
+        if (COUNT) c.n_refs++;
+        if (!(slab(rb, br, tmin_f, tmax_f) <= tmax_f)) continue;
+        if (COUNT) c.n_prims++;
+        double t, u, v;
+        if (tri_t(S.tris[ref_index(rb.a)], r, 1e-3, t, u, v) && t <= c.t) { consider(c, t, rb.a, cur_inst, cur_tie, rb.b); tmax_f = __double2float_ru(c.t); }
+    }
+    return false;
+}
+template <bool COUNT>
+PT_D void trace_blas(const DScene& S, uint32_t root_entry, const RayD& r, Closest& c, uint32_t cur_inst, uint32_t cur_tie) {
+    uint2 stack[kStack];
+    int sp = 1;
+    stack[0] = make_uint2(root_entry, 0u);  // entry distance 0: never culled
+    const BoxRay br = make_boxray(r);
+    const float tmin_f = __double2float_rd(1e-3);  // Interval::new(eps, INFINITY), camera.rs:171,179
+    float tmax_f = __double2float_ru(c.t);
+    while (!blas_round<COUNT>(S, r, br, tmin_f, tmax_f, stack, sp, c, cur_inst, cur_tie)) {}
     c.is_light = c.ref != kNone && !(c.tie_outer >> 31);
 }
 

@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(kTraceBlock, 7 * kBlock / kTraceBlock) k_trace
                 uint32_t mesh = index, inst = kInstNone;
                 if (kind == PT_OBJ_INSTANCE) { const DInstance& ins = S.instances[index]; r = instance_local_ray(ins, r); mesh = ins.child_index; inst = index; }
                 c.n_pairs = 0; c.n_wide = 0; c.n_refs = 0; c.n_prims = 0;
-                trace_blas<COUNT>(S, S.meshes[mesh].root_entry, r, 1e-3, c, inst, rf.b);
+                trace_blas<COUNT>(S, S.meshes[mesh].root_entry, r, c, inst, rf.b);
                 if (COUNT) { w0 += c.n_pairs + 2 * c.n_wide; w1 += c.n_refs; w2 += c.n_prims; }
                 HitRec h; h.t = c.t; h.ref = c.ref; h.inst_light = (c.inst & 0x7FFFFFFFu) | (c.is_light ? 0x80000000u : 0u);
                 hits[i] = h;
@@ -269,6 +269,88 @@ __global__ void __launch_bounds__(kTraceBlock, 7 * kBlock / kTraceBlock) k_trace
     if (COUNT) {
         w0 = __reduce_add_sync(0xFFFFFFFFu, w0); w1 = __reduce_add_sync(0xFFFFFFFFu, w1); w2 = __reduce_add_sync(0xFFFFFFFFu, w2);
         if ((threadIdx.x & 31) == 0 && (w0 | w1 | w2)) { atomicAdd(work, (unsigned long long)w0); atomicAdd(work + 1, (unsigned long long)w1); atomicAdd(work + 2, (unsigned long long)w2); }
+    }
+}
+
+// The same round as a persistent kernel with lane refill: rays inside a mesh differ widely in length (most leave after the
+// root node, a few walk thirty), so k_trace_blas runs at 5-6 of 32 lanes.  Here a warp keeps pulling entries from the queue
+// (one atomicAdd per fetch on the round's cursor): every kBlasBurst while-while rounds the lanes meet, finished rays join
+// their shade queue, and once kBlasRefillMin lanes are idle they fetch new rays.  With only two kinds of work in the loop
+// (node step, triangle leaf) a fresh ray next to an old one costs little, unlike in the fused kernel.
+constexpr int kBlasBurst = 2;
+constexpr int kBlasRefillMin = 8;
+template <bool COUNT>
+__global__ void __launch_bounds__(kTraceBlock, 7 * kBlock / kTraceBlock) k_trace_blas_refill(PathBuf in, uint32_t round, BlasQueues bq, HitRec* __restrict__ hits,
+                                                              uint2* __restrict__ ties, Queues q, DScene S, unsigned long long* __restrict__ work) {
+    const uint32_t count = bq.count[round];
+    uint32_t* __restrict__ cursor = bq.count + 4 + round;
+    const uint4* __restrict__ items = bq.items + (size_t)round * bq.stride;
+    const uint32_t lane = threadIdx.x & 31;
+    const float tmin_f = __double2float_rd(1e-3);
+    uint2 stack[kStack];
+    int sp = 0;
+    RayD r = make_ray(mk(0, 0, 0), mk(0, 0, 1), 0.0);
+    BoxRay br = make_boxray(r);
+    Closest c; c.t = 0.0; c.ref = kNone; c.inst = kInstNone; c.tie_outer = 0; c.tie_inner = 0; c.is_light = false; c.n_pairs = 0; c.n_wide = 0; c.n_refs = 0; c.n_prims = 0;
+    uint32_t i = 0, cur_inst = kInstNone, cur_tie = 0, done_cls = N_CLS, done_i = 0;
+    float tmax_f = 0.f;
+    bool active = false, last = false, drained = false;
+    uint32_t w0 = 0, w1 = 0, w2 = 0;
+    while (true) {
+        // ---- all 32 lanes meet here: finished rays join their shade-class queue, idle lanes fetch
+        if (__any_sync(0xFFFFFFFFu, done_cls != N_CLS)) { queue_append(q, done_cls, done_i); done_cls = N_CLS; }
+        const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !active);
+        if (!drained && __popc(idle) >= kBlasRefillMin) {
+            const int leader = __ffs(idle) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(cursor, __popc(idle));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            drained = base + __popc(idle) >= count;
+            const uint32_t j = base + __popc(idle & ((1u << lane) - 1u));
+            if (!active && j < count) {
+                const uint4 e = items[j];
+                i = e.x; last = (e.y >> 31) != 0;
+                const HitRec h0 = hits[i];
+                const uint2 tie = ties[i];
+                c.t = h0.t; c.ref = h0.ref; c.inst = h0.inst_light & 0x7FFFFFFFu; c.tie_outer = tie.x; c.tie_inner = tie.y;
+                if (__uint_as_float(e.z) <= __double2float_ru(c.t)) {  // else the mesh has since fallen behind the closest hit
+                    const DNode rf = S.refs[e.y & 0x7FFFFFFFu];  // a = kind | index of the queued mesh or instance, b = its outer tie rank
+                    const uint32_t kind = ref_kind(rf.a), index = ref_index(rf.a);
+                    r = load_ray(in, i);
+                    uint32_t mesh = index;
+                    cur_inst = kInstNone;
+                    if (kind == PT_OBJ_INSTANCE) { const DInstance& ins = S.instances[index]; r = instance_local_ray(ins, r); mesh = ins.child_index; cur_inst = index; }
+                    cur_tie = rf.b;
+                    br = make_boxray(r);
+                    tmax_f = __double2float_ru(c.t);
+                    stack[0] = make_uint2(S.meshes[mesh].root_entry, 0u); sp = 1;
+                    c.n_wide = 0; c.n_refs = 0; c.n_prims = 0;
+                    active = true;
+                } else if (last) { done_cls = c.ref == kNone ? (uint32_t)CLS_MISS : class_of_kind(S.materials[hit_material(S, c.ref)].kind); done_i = i; }
+            }
+        }
+        if (!__any_sync(0xFFFFFFFFu, active)) {
+            if (!drained) continue;
+            if (__any_sync(0xFFFFFFFFu, done_cls != N_CLS)) queue_append(q, done_cls, done_i);
+            break;
+        }
+        // ---- a burst of while-while rounds
+#pragma unroll 1
+        for (int s = 0; s < kBlasBurst; s++) {
+            if (active && blas_round<COUNT>(S, r, br, tmin_f, tmax_f, stack, sp, c, cur_inst, cur_tie)) {
+                active = false;
+                const bool is_light = c.ref != kNone && !(c.tie_outer >> 31);
+                HitRec h; h.t = c.t; h.ref = c.ref; h.inst_light = (c.inst & 0x7FFFFFFFu) | (is_light ? 0x80000000u : 0u);
+                hits[i] = h;
+                if (!last) ties[i] = make_uint2(c.tie_outer, c.tie_inner);
+                else { done_cls = c.ref == kNone ? (uint32_t)CLS_MISS : class_of_kind(S.materials[hit_material(S, c.ref)].kind); done_i = i; }
+                if (COUNT) { w0 += 2 * c.n_wide; w1 += c.n_refs; w2 += c.n_prims; }
+            }
+        }
+    }
+    if (COUNT) {
+        w0 = __reduce_add_sync(0xFFFFFFFFu, w0); w1 = __reduce_add_sync(0xFFFFFFFFu, w1); w2 = __reduce_add_sync(0xFFFFFFFFu, w2);
+        if (lane == 0 && (w0 | w1 | w2)) { atomicAdd(work, (unsigned long long)w0); atomicAdd(work + 1, (unsigned long long)w1); atomicAdd(work + 2, (unsigned long long)w2); }
     }
 }
 
