@@ -213,10 +213,13 @@ def main():
 
     # ---- per-stage CUDA-event times for the roofline of the dominant kernel (separate pass: the per-stage events
     #      are recorded on the launching stream around every launch; their overhead is kept out of `value`)
-    ms_p, (segs_p, paths_p, _, _), pstats = timed(args.steps, 100, True)
+    ms_p, (segs_p, paths_p, _, _), pstats = timed(args.steps, 100, 1)
     trace_ms, shade_ms, gen_ms = (sum(getattr(s, k) for s in pstats) for k in ("trace_ms", "shade_ms", "raygen_ms"))
     iters = sum(s.iterations for s in pstats)
     segs_rank = sum(s.segments for s in pstats); paths_rank = sum(s.paths for s in pstats)
+    # traversal work counters: one more step with the counting kernel variants (slower, so kept out of the stage times)
+    _, _, cstats = timed(1, 100, 2)
+    csegs = sum(s.segments for s in cstats)
 
     ctx.set_profiling(False)   # the e2e leg below runs the production path (forked shade streams, no per-stage events)
 
@@ -272,7 +275,7 @@ def main():
         b_seg = b_trace + b_shade + b_gen
         # the same kernel judged by what the DEVICE requests (live counters of the profiling pass): ordered traversal with
         # culling touches far fewer nodes than the reference's un-narrowed recursion that the oracle counters describe
-        d_pairs, d_refs, d_prims = (sum(getattr(s, k) for s in pstats) / max(segs_rank, 1) for k in ("node_pairs", "ref_boxes", "prim_tests"))
+        d_pairs, d_refs, d_prims = (sum(getattr(s, k) for s in cstats) / max(csegs, 1) for k in ("node_pairs", "ref_boxes", "prim_tests"))
         prim_bytes = (n_sph * B_SPHERE + n_quad * B_QUAD + n_tri * B_TRI) / max(n_sph + n_quad + n_tri, 1e-9)
         b_trace_dev = B_RAY + B_HIT + d_pairs * 2 * B_NODE + d_refs * B_REF + d_prims * prim_bytes
         ach_dev = segs_rank * b_trace_dev / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else 0.0
@@ -293,6 +296,8 @@ def main():
                          "traffic": (K_TRACE_DRAM_BYTES_PER_RAY * segs_rank / max(iters, 1)) if dom == "k_trace" and args.scene == SCENE else None,
                          "traffic_note": "DRAM bytes per launch = ncu dram read+write per ray (profiles/r1_h_k_trace_ncu.md) x rays per launch; far below the algorithmic bytes because the scene is L2-resident",
                          "peak_source": peak_src,
+                         "kernel_note": "k_trace = the traversal stage of one wavefront iteration: k_trace (top level) + the k_trace_blas_refill mesh rounds on "
+                                        "scenes with meshes; a 'launch' below is one iteration's stage, timed with CUDA events around it",
                          "bytes_per_segment": dom_b, "bytes_per_launch": dom_b * segs_rank / max(iters, 1),
                          "avg_launch_ms": dom_ms / max(iters, 1), "launches": iters,
                          "stage_ms_per_step": {"k_generate": gen_ms / args.steps, "k_trace": trace_ms / args.steps, "k_shade": shade_ms / args.steps},

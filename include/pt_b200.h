@@ -253,7 +253,9 @@ int  pt_ctx_create(int device, pt_ctx** out);
 void pt_ctx_destroy(pt_ctx* ctx);
 /* Use an external stream (e.g. torch's current stream handle); NULL = the ctx's own. */
 int  pt_ctx_set_stream(pt_ctx* ctx, void* cuda_stream);
-int  pt_ctx_set_profiling(pt_ctx* ctx, int per_stage_timing);
+/* 0: off.  1: per-stage CUDA events around every launch (pt_stats.trace_ms / shade_ms / raygen_ms; the shade kernels then run
+ * unforked and the tail unbatched).  2: additionally the traversal work counters in pt_stats; slower kernel variants. */
+int  pt_ctx_set_profiling(pt_ctx* ctx, int level);
 const char* pt_last_error(void);
 int  pt_device_count(void);
 

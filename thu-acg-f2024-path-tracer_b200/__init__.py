@@ -445,8 +445,9 @@ class Context:
         default stream, which the C ABI spells cudaStreamLegacy (0x1) because NULL there means "the ctx's own"."""
         self._check(self.lib.pt_ctx_set_stream(self.ptr, C.c_void_p(cuda_stream if cuda_stream else 1)))
 
-    def set_profiling(self, on):
-        self._check(self.lib.pt_ctx_set_profiling(self.ptr, int(on)))
+    def set_profiling(self, level):
+        """0 off, 1 per-stage event times, 2 also the traversal work counters (slower kernel variants)."""
+        self._check(self.lib.pt_ctx_set_profiling(self.ptr, int(level)))
 
     def upload(self, scene):
         return DeviceScene(self, scene)

@@ -31,7 +31,7 @@ constexpr uint32_t kTailBatchMaxLive = 1u << 22;
 struct pt_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    bool profiling = false;
+    int profiling = 0;                      // 1: per-stage CUDA events; 2: also the traversal work counters (COUNT kernel variants)
     // path pool (ping-pong SoA) + hit records, grown on demand
     uint32_t pool = 0;
     double* pool_f[2] = {nullptr, nullptr};
@@ -125,7 +125,7 @@ void pt_ctx_destroy(pt_ctx* c) {
     delete c;
 }
 int pt_ctx_set_stream(pt_ctx* c, void* s) { if (!c) return fail(PT_ERR_INVALID, "null ctx"); c->stream = s ? (cudaStream_t)s : c->own_stream; return PT_OK; }
-int pt_ctx_set_profiling(pt_ctx* c, int on) { if (!c) return fail(PT_ERR_INVALID, "null ctx"); c->profiling = on != 0; return PT_OK; }
+int pt_ctx_set_profiling(pt_ctx* c, int on) { if (!c) return fail(PT_ERR_INVALID, "null ctx"); c->profiling = on < 0 ? 0 : (on > 2 ? 2 : on); return PT_OK; }
 
 }  // extern "C"
 
@@ -709,7 +709,7 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
     uint64_t generated = 0; uint32_t live = 0, live_spawning = 0; int cur = 0;
     const bool nee = (p->flags & PT_RENDER_NEE) != 0;
     if (nee && rcst.env_importance) return fail(PT_ERR_UNSUPPORTED, "PT_RENDER_NEE and PT_RENDER_ENV_IMPORTANCE cannot be combined yet");
-    unsigned long long* const wk = ctx->profiling ? ctx->d_nonfinite + 1 : nullptr;
+    unsigned long long* const wk = ctx->profiling >= 2 ? ctx->d_nonfinite + 1 : nullptr;
     // World::intersect_all for the n (or min(n, *n_dev)) paths of `in`; one compile-time flavour per scene / mode
     auto launch_trace = [&](const PathBuf& in, uint32_t n, const Queues& q, const uint32_t* n_dev) {
         const unsigned tg = (n + kTraceBlock - 1) / kTraceBlock;

@@ -277,8 +277,14 @@ __global__ void __launch_bounds__(kTraceBlock, 7 * kBlock / kTraceBlock) k_trace
 // (one atomicAdd per fetch on the round's cursor): every kBlasBurst while-while rounds the lanes meet, finished rays join
 // their shade queue, and once kBlasRefillMin lanes are idle they fetch new rays.  With only two kinds of work in the loop
 // (node step, triangle leaf) a fresh ray next to an old one costs little, unlike in the fused kernel.
-constexpr int kBlasBurst = 2;
-constexpr int kBlasRefillMin = 8;
+#ifndef PT_BLAS_BURST
+#define PT_BLAS_BURST 2
+#endif
+#ifndef PT_BLAS_REFILL_MIN
+#define PT_BLAS_REFILL_MIN 8
+#endif
+constexpr int kBlasBurst = PT_BLAS_BURST;
+constexpr int kBlasRefillMin = PT_BLAS_REFILL_MIN;
 template <bool COUNT>
 __global__ void __launch_bounds__(kTraceBlock, 7 * kBlock / kTraceBlock) k_trace_blas_refill(PathBuf in, uint32_t round, BlasQueues bq, HitRec* __restrict__ hits,
                                                               uint2* __restrict__ ties, Queues q, DScene S, unsigned long long* __restrict__ work) {
