@@ -720,7 +720,7 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
             else k_trace<7, true, false, false, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, nullptr, 0, n_dev, bq, ctx->ties);
             const unsigned bg = std::min<unsigned>(tg, 148u * 56u);
             const bool refill = !(p->flags & 0x200000u);  // flag 0x200000: plain grid-stride rounds instead of persistent lanes with refill
-            const unsigned pg = std::min<unsigned>(tg, 148u * 28u);  // persistent: one resident warp per slot
+            const unsigned pg = std::min<unsigned>(tg, 148u * 4u * (unsigned)kBlasMinBlocks);  // persistent: one resident warp per slot
             for (uint32_t r = 0; r < (uint32_t)kDeferMax; r++) {
                 if (refill) {
                     if (wk) k_trace_blas_refill<true><<<pg, kTraceBlock, 0, st>>>(in, r, bq, ctx->hits, ctx->ties, q, scene->d, wk);

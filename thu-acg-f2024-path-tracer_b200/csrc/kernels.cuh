@@ -283,10 +283,14 @@ __global__ void __launch_bounds__(kTraceBlock, 7 * kBlock / kTraceBlock) k_trace
 #ifndef PT_BLAS_REFILL_MIN
 #define PT_BLAS_REFILL_MIN 8
 #endif
+#ifndef PT_BLAS_MIN_BLOCKS
+#define PT_BLAS_MIN_BLOCKS 7  // resident 128-thread-equivalents per SM the refill kernel must allow (7 -> 72 registers, 28 warps)
+#endif
+constexpr int kBlasMinBlocks = PT_BLAS_MIN_BLOCKS;
 constexpr int kBlasBurst = PT_BLAS_BURST;
 constexpr int kBlasRefillMin = PT_BLAS_REFILL_MIN;
 template <bool COUNT>
-__global__ void __launch_bounds__(kTraceBlock, 7 * kBlock / kTraceBlock) k_trace_blas_refill(PathBuf in, uint32_t round, BlasQueues bq, HitRec* __restrict__ hits,
+__global__ void __launch_bounds__(kTraceBlock, kBlasMinBlocks * kBlock / kTraceBlock) k_trace_blas_refill(PathBuf in, uint32_t round, BlasQueues bq, HitRec* __restrict__ hits,
                                                               uint2* __restrict__ ties, Queues q, DScene S, unsigned long long* __restrict__ work) {
     const uint32_t count = bq.count[round];
     uint32_t* __restrict__ cursor = bq.count + 4 + round;
