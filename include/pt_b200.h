@@ -201,6 +201,9 @@ typedef struct {
  * of forking them onto side streams (tuning / debugging knob; forking is the default and measured 2.5 % faster) */
 /* flags bit 14 (0x4000): one host round trip per wavefront iteration even in the tail of a render (default: once nothing
  * is left to generate, 8 iterations are enqueued per round trip) — tuning / debugging knob, same image either way */
+/* flags bit 20 (0x100000): keep the fused traversal kernel on scenes with meshes (default there: k_trace queues mesh visits and
+ * k_trace_blas_refill walks them); bit 21 (0x200000): walk them with plain grid-stride rounds instead of persistent lanes
+ * with refill — tuning / A-B knobs, same image either way */
 /* flags bit 15 (0x8000): take the octant mask of the survivor grouping from bits 16-18 (bit 16 = y, 17 = x, 18 = z sign of
  * the next ray direction; default 7, 0 = plain compaction) — tuning knob, same image either way */
 /* PT_RENDER_ENV_IMPORTANCE (NOT reference behaviour): when the camera's environment is a map, the
