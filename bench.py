@@ -31,10 +31,12 @@ SCENE_NAMES = {3: "scene3_cornell_box", 1: "scene1_bouncing_balls", 5: "scene5_p
 # device structs (csrc/device_scene.cuh, csrc/kernels.cuh): bytes one segment moves through HBM per stage
 B_RAY, B_HIT, B_STATE = 56, 16, 96   # ray (o,d,time f64), HitRec, full path state (ray + throughput f64x3 + ids uint4)
 B_NODE, B_REF, B_SPHERE, B_QUAD, B_TRI = 32, 32, 64, 128, 80
-# dram__bytes_read.sum + dram__bytes_write.sum per ray of k_trace from the ncu --set full capture of this workload
-# (profiles/r1_h_k_trace_ncu.md: 64.1 MB + 17.8 MB for one launch of 26 999 x 32 rays; the earlier r1_b capture of a
-# 2.5 M-ray launch gave 72.5 B/ray): the ray stream, hit records and stack spills come from HBM, the 4.6 MB scene from L2.
-K_TRACE_DRAM_BYTES_PER_RAY = (64.13e6 + 17.79e6) / (26999 * 32)  # profiles/r1_h_k_trace_ncu.md (a bounce-ray launch of 864 k rays)
+# dram__bytes_read.sum + dram__bytes_write.sum per ray of the traversal stage from the ncu --set full capture of this workload
+# (profiles/r1_l_k_trace_ncu.md, first bounce iteration of 79 364 x 32 rays: k_trace<DEFER> 152.2 + 66.6 MB, mesh round 0
+# 120.2 + 8.1 MB; rounds 1-2 are two orders of magnitude smaller).  The fused kernel moved 95 B per ray
+# (profiles/r1_h_k_trace_ncu.md); the two-pass traversal re-reads the ray and the hit record of every queued mesh visit.
+# The ray stream, hit records, queues and stack spills come from HBM, the 5 MB scene from L2.
+K_TRACE_DRAM_BYTES_PER_RAY = (152.23e6 + 66.61e6 + 120.23e6 + 8.12e6) / (79364 * 32)
 
 
 def peaks():
@@ -294,7 +296,7 @@ def main():
                     "what": "pt_scene_create (scene H2D) + pt_render_accumulate + reduce + D2H of the fp32 image, every step"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
                          "traffic": (K_TRACE_DRAM_BYTES_PER_RAY * segs_rank / max(iters, 1)) if dom == "k_trace" and args.scene == SCENE else None,
-                         "traffic_note": "DRAM bytes per launch = ncu dram read+write per ray (profiles/r1_h_k_trace_ncu.md) x rays per launch; far below the algorithmic bytes because the scene is L2-resident",
+                         "traffic_note": "DRAM bytes per launch = ncu dram read+write per ray of k_trace<DEFER> + mesh round 0 (profiles/r1_l_k_trace_ncu.md, 137 B) x rays per launch; far below the algorithmic bytes because the scene is L2-resident",
                          "peak_source": peak_src,
                          "kernel_note": "k_trace = the traversal stage of one wavefront iteration: k_trace (top level) + the k_trace_blas_refill mesh rounds on "
                                         "scenes with meshes; a 'launch' below is one iteration's stage, timed with CUDA events around it",
