@@ -51,6 +51,15 @@ def test_no_device_fails_loudly(pt):
         pt.render_multi(pt.Scene.build(3, 32, 1, 1), [0, 0], spp=2)        # carried over from the worker thread
 
 
+def test_render_multi_rejects_bad_arguments(pt):
+    """pt_render_multi validates before it touches a device (so this runs on the CPU box too)."""
+    scene = pt.Scene.build(3, 32, 1, 1)
+    with pytest.raises(pt.PtError, match="bad argument"):
+        pt.render_multi(scene, [], spp=2)
+    with pytest.raises(pt.PtError, match="sample_count is zero"):
+        pt.render_multi(scene, [0], spp=0)
+
+
 def test_product_never_touches_oracle():
     pkg = os.path.join(ROOT, "thu-acg-f2024-path-tracer_b200")
     for dp, _, fs in os.walk(pkg):
