@@ -568,3 +568,55 @@ def test_scene6_fhd_4000spp_matches_reference_demo(pt, ctx):
     assert st.paths == 1920 * 1080 * 4000 and st.segments > st.paths and np.isfinite(img).all()
     assert err < 0.03  # measured 0.0132: the floor is the demo's 8-bit quantisation and its own 4000-spp noise
     dev.close()
+
+
+def _holey_sheets_world(pt, n_sheets=5, g=9, seed=11):
+    """n_sheets wavy triangle sheets with holes, stacked along z: odd ones behind a rotated Instance, even ones directly in
+    World.objects.  Every camera ray enters all their boxes, so it queues three mesh visits and walks the others inline."""
+    rng = np.random.default_rng(seed)
+    xs = np.linspace(-1.0, 1.0, g + 1)
+    w = pt.World()
+    keep_alive = []
+    for s in range(n_sheets):
+        X, Y = np.meshgrid(xs, xs, indexing="ij")
+        Z = 0.12 * np.sin(3.0 * X + s) * np.cos(2.0 * Y - s) + rng.normal(scale=0.01, size=X.shape)
+        z0 = -2.0 + s
+        direct = s % 2 == 0
+        pos = np.stack([X, Y, Z + (z0 if direct else 0.0)], axis=-1).reshape(-1, 3).astype(np.float32)
+        vid = np.arange((g + 1) * (g + 1)).reshape(g + 1, g + 1)
+        tris = np.concatenate([np.stack([vid[:-1, :-1], vid[1:, :-1], vid[1:, 1:]], axis=-1).reshape(-1, 3),
+                               np.stack([vid[:-1, :-1], vid[1:, 1:], vid[:-1, 1:]], axis=-1).reshape(-1, 3)])
+        tris = tris[rng.uniform(size=len(tris)) > 0.4].astype(np.uint32)            # holes: deeper sheets stay visible
+        assert len(tris) >= 64                                                       # large enough for the 4-wide flavour
+        mat = pt.DiffuseBRDF(tuple(0.25 + 0.7 * rng.uniform(size=3))) if s != 2 else pt.MetalBRDF((0.9, 0.8, 0.6), 0.2)
+        mesh = pt.TriangleMesh.from_arrays(1.6, pos, tris, mat)
+        obj = mesh if direct else pt.Instance(mesh, (0.1, 0.2, 1.0), 0.3 * s, (0.05 * s, -0.03 * s, z0))
+        keep_alive += [mat, mesh, obj]
+        w.add_object(obj)
+    w.add_object(pt.Sphere.new_still(0.5, (0.3, 0.2, -3.2), pt.DiffuseBRDF((0.8, 0.3, 0.3))))
+    w.build_bvh()
+    cam = pt.make_camera(96, 1.0, 4, 12, vfov=34.0, look_from=(0.2, 0.1, 7.0), look_at=(0, 0, 0), env_color=(0.7, 0.8, 1.0))
+    return w, cam, keep_alive
+
+
+def test_two_pass_traversal_beyond_the_reference_scenes(pt, orc, ctx):
+    """The two-pass traversal (k_trace<DEFER> + k_trace_blas_refill) where no reference scene takes it: meshes that sit in
+    World.objects directly, and rays that enter more mesh boxes than the three visit queues hold (the rest is walked inline).
+    Sample for sample against the oracle, and against the fused kernel (flag 0x100000) and the grid-stride rounds (0x200000)."""
+    w, cam, keep = _holey_sheets_world(pt)
+    scene = pt.Scene.from_world(w, cam)
+    assert H.desc_header(scene)["n_meshes"] == 5 and H.desc_header(scene)["n_instances"] == 2
+    dev, ora = ctx.upload(scene), orc.OracleScene(scene.desc, pt)
+    spp = 12                                                                          # 96 x 96 x 12 = 110 592 paths: above the 64 Ki floor of the two-pass path
+    img, st = dev.render(spp=spp, seed=5, nan_policy=1)
+    ref, ost = ora.render(cam, spp, seed=5, nan_policy=1)
+    assert st.paths == ost.paths == 96 * 96 * spp
+    assert abs(int(st.segments) - int(ost.segments)) <= max(64, ost.segments // 2000)
+    d = np.abs(img - ref).reshape(-1, 3).max(axis=1)
+    assert (d > 1e-4 * np.maximum(ref.reshape(-1, 3).max(axis=1), 1.0)).mean() < 0.02
+    assert H.rel_rmse(img, ref) < 0.05
+    for flags in (0x100000, 0x200000):
+        other, st2 = dev.render(spp=spp, seed=5, nan_policy=1, flags=flags)
+        assert (st2.paths, st2.segments) == (st.paths, st.segments), hex(flags)
+        assert np.allclose(other, img, rtol=2e-5, atol=2e-6), hex(flags)
+    dev.close(); ora.close()
