@@ -246,6 +246,10 @@ typedef struct {
     /* traversal work summed over all segments (profiling mode only, else 0): 64-byte node pairs fetched,
      * 32-byte reference boxes fetched, f64 primitive tests */
     uint64_t node_pairs, ref_boxes, prim_tests;
+    uint32_t two_pass_iterations; /* wavefront iterations whose traversal stage took the two-pass path (top-level pass +
+                                   * mesh rounds) instead of the fused kernel: tests assert on it so that an ID comparison
+                                   * can never silently run on the other flavour */
+    uint32_t _pad;
 } pt_stats;
 
 typedef struct pt_ctx pt_ctx;
@@ -313,6 +317,14 @@ typedef struct {
 /* World::intersect_all(ray, [t_min, inf)) for a batch of host rays. */
 int  pt_trace_closest(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_ray* rays,
                       double t_min, pt_hit* hits);
+/* The same query through the RENDER's traversal stage: the batch is loaded into the wavefront path pool and traced by
+ * exactly the kernels, grids and queues pt_render_accumulate launches for an iteration of that many live paths (two-pass
+ * traversal on scenes with meshes from 65 536 rays up, the fused kernel below that or with flags bit 20), in chunks of
+ * 4 Mi rays.  `flags`: the traversal knobs of pt_render_params.flags (bits 4-6, 20, 21).  Same result as pt_trace_closest
+ * (`work` = 0); stats->two_pass_iterations tells which flavour ran.  This is the entry the ID-exactness tests use, so the
+ * benchmarked traversal is the tested one. */
+int  pt_trace_closest_wavefront(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_ray* rays,
+                                double t_min, uint32_t flags, pt_hit* hits, pt_stats* stats);
 /* World::shadow_ray-style any-hit against World.objects on [t_min, t_max] (world.rs:31-36). */
 int  pt_trace_any(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_ray* rays,
                   double t_min, const double* t_max, uint8_t* occluded);

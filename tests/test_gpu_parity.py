@@ -71,6 +71,61 @@ def test_closest_hit_matches_oracle(pt, orc, ctx, pairs, scene_id):
     assert_hits_equal(pt, p.dev.trace_closest(bounce[:20000], 0.0), p.ora.trace_closest(bounce[:20000], 0.0), f"scene {scene_id} t_min=0")
 
 
+# ---------------------------------------------------------------- the render's own traversal stage, ID for ID
+TWO_PASS_MIN = 1 << 16   # launch_trace (csrc/api.cu) takes the two-pass path from this many live rays up
+
+
+@pytest.mark.parametrize("scene_id,width", [(6, 400), (70, 300)])
+def test_render_traversal_stage_matches_oracle(pt, orc, ctx, pairs, scene_id, width):
+    """pt_trace_closest_wavefront pushes a host batch through launch_trace — the kernels, grids and queues that
+    pt_render_accumulate launches per wavefront iteration (k_trace<DEFER> + the mesh rounds on these scenes) — and the result
+    must equal the oracle's World::intersect_all ID for ID (t within 4 ulp; we get 0): camera rays, >= 150 k bounce rays,
+    t_min = 1e-3 and 0, persistent-lane rounds and plain grid-stride rounds (flag 0x200000), and the fused kernel (0x100000)."""
+    p = pairs(scene_id, width)
+    cam = p.scene.camera
+    h, w = p.scene.image_height(), cam.image_width
+    rows, cols = np.divmod(np.arange(w * h, dtype=np.uint32), w)
+    rays = orc.camera_rays(cam, 7, rows, cols, np.zeros_like(rows), pt)
+    assert len(rays) >= TWO_PASS_MIN
+    want = p.ora.trace_closest(rays)
+    got, st = p.dev.trace_closest_wavefront(rays)
+    assert st.two_pass_iterations == 1 and st.segments == len(rays)        # the production flavour ran, not the fused kernel
+    assert_hits_equal(pt, got, want, f"scene {scene_id} camera rays, two-pass")
+    bounce = p.ora.dump_path_rays(cam, 11, 1, 4, 1, 400000)                 # incoherent rays from bounces >= 1
+    assert len(bounce) >= 150000
+    want = p.ora.trace_closest(bounce)
+    frac_mesh = (want["prim_kind"][want["hit"] == 1] == 2).mean()
+    assert frac_mesh > 0.05                                                  # a good share of them ends on a mesh triangle
+    for flags, two_pass in ((0, 1), (0x200000, 1), (0x100000, 0)):
+        got, st = p.dev.trace_closest_wavefront(bounce, flags=flags)
+        assert st.two_pass_iterations == two_pass, hex(flags)
+        assert_hits_equal(pt, got, want, f"scene {scene_id} bounce rays, flags {flags:#x}")
+    want0 = p.ora.trace_closest(bounce, 0.0)                                 # light-pdf style rays use t_min = 0 (quad.rs:90)
+    got0, st = p.dev.trace_closest_wavefront(bounce, 0.0)
+    assert st.two_pass_iterations == 1
+    assert_hits_equal(pt, got0, want0, f"scene {scene_id} t_min=0, two-pass")
+    assert scene_id != 6 or not np.array_equal(want0["t"], want["t"])      # on scene 6 a few of these rays do hit inside [0, 1e-3)
+    small, st = p.dev.trace_closest_wavefront(bounce[:TWO_PASS_MIN - 1])     # one ray under the floor: the fused kernel
+    assert st.two_pass_iterations == 0
+    assert_hits_equal(pt, small, want[:TWO_PASS_MIN - 1], f"scene {scene_id} below the two-pass floor")
+
+
+def test_render_traversal_stage_other_flavours(pt, orc, ctx, pairs):
+    """The same entry on scenes without meshes (binary-pair and 4-wide fused flavours) and with media."""
+    for scene_id in (3, 1):
+        p = pairs(scene_id)
+        bounce = p.ora.dump_path_rays(p.scene.camera, 11, 2, 2, 1, 100000)
+        got, st = p.dev.trace_closest_wavefront(bounce)
+        assert st.two_pass_iterations == 0
+        assert_hits_equal(pt, got, p.ora.trace_closest(bounce), f"scene {scene_id} wavefront stage")
+    scene = fog_world(pt, 64)
+    dev, ora = ctx.upload(scene), orc.OracleScene(scene.desc, pt)
+    bounce = ora.dump_path_rays(scene.camera, 5, 1, 2, 1, 60000)
+    got, st = dev.trace_closest_wavefront(bounce)
+    assert_hits_equal(pt, got, ora.trace_closest(bounce), "fog world wavefront stage")
+    dev.close(); ora.close()
+
+
 @pytest.mark.parametrize("scene_id", [3, 6, 1])
 def test_any_hit_matches_oracle(pt, pairs, scene_id):
     p = pairs(scene_id)
@@ -346,7 +401,7 @@ def test_volumes_match_oracle(pt, orc, ctx):
 
 
 # ---------------------------------------------------------------- renders
-@pytest.mark.parametrize("scene_id,width,spp", [(3, 96, 8), (1, 128, 8), (7, 96, 8), (6, 128, 6), (5, 128, 8), (4, 128, 8)])
+@pytest.mark.parametrize("scene_id,width,spp", [(3, 96, 8), (1, 128, 8), (7, 96, 8), (6, 128, 6), (5, 128, 8), (4, 128, 8), (6, 256, 4), (70, 192, 4)])
 @pytest.mark.parametrize("policy", [0, 1])
 def test_render_matches_oracle_sample_for_sample(pt, pairs, scene_id, width, spp, policy):
     """Same Philox streams => the device follows the same paths as the oracle.  A path diverges only where a
@@ -355,6 +410,8 @@ def test_render_matches_oracle_sample_for_sample(pt, pairs, scene_id, width, spp
     img, st = p.dev.render(spp=spp, seed=21, nan_policy=policy)
     ref, ost = p.ora.render(p.scene.camera, spp, seed=21, nan_policy=policy)
     assert st.paths == ost.paths == img.shape[0] * img.shape[1] * spp
+    # the two mesh scenes at >= 65 536 paths in flight go through the two-pass traversal, like every benchmarked iteration
+    assert (st.two_pass_iterations > 0) == (scene_id in (6, 70) and st.paths >= TWO_PASS_MIN)
     assert abs(int(st.segments) - int(ost.segments)) <= max(64, ost.segments // 2000)
     fin = np.isfinite(ref).all(axis=2) & np.isfinite(img).all(axis=2)
     assert np.array_equal(np.isfinite(ref).all(axis=2), np.isfinite(img).all(axis=2)) or policy == 0
@@ -377,7 +434,7 @@ def test_virtual_rank_split_equals_single_rank(pt, pairs):
     assert np.allclose(full, small_pool, rtol=2e-5, atol=2e-6)
 
 
-@pytest.mark.parametrize("scene_id,width,spp", [(3, 96, 8), (6, 128, 6)])
+@pytest.mark.parametrize("scene_id,width,spp", [(3, 96, 8), (6, 160, 8)])
 def test_scheduling_knobs_do_not_change_the_image(pt, pairs, scene_id, width, spp):
     """The batched tail (8 iterations per host round trip), the forked shade streams and the octant grouping of survivors
     only reorder work: same paths, same segments, same iteration count, same image (up to fp32 atomic-add order)."""
@@ -387,13 +444,16 @@ def test_scheduling_knobs_do_not_change_the_image(pt, pairs, scene_id, width, sp
         img, st = p.dev.render(spp=spp, seed=9, nan_policy=1, flags=flags)
         assert (st.paths, st.segments, st.iterations, st.nonfinite) == (st0.paths, st0.segments, st0.iterations, st0.nonfinite), hex(flags)
         assert np.allclose(img, base, rtol=2e-5, atol=2e-6), hex(flags)
+        # flags 0x100000 / 0x200000 only mean something when the two-pass path is taken (scene 6: 115 200 paths in flight)
+        assert st.two_pass_iterations == (0 if flags & 0x100000 else st0.two_pass_iterations), hex(flags)
     assert st0.iterations > 8 and st0.segments > st0.paths
+    assert (st0.two_pass_iterations > 0) == (scene_id == 6)
 
 
 def test_render_multi_equals_single_device(pt, pairs):
     """pt_render_multi (one process, one host thread per listed device, spp split, host reduce) gives pt_render's image.
     On a one-GPU box the shares run as three contexts on device 0; with more GPUs they spread over real devices."""
-    p = pairs(6, 128)
+    p = pairs(6, 160)                                                           # 160 x 90 x 7 spp: the shares run the two-pass traversal too
     n_dev = pt.device_lib().pt_device_count()
     devices = [g % n_dev for g in range(3)]
     for kw in (dict(), dict(flags=pt.PT_RENDER_NEE), dict(sample_begin=5, sample_stride=2)):
@@ -402,7 +462,7 @@ def test_render_multi_equals_single_device(pt, pairs):
         assert (stm.paths, stm.segments, stm.nonfinite) == (st1.paths, st1.segments, st1.nonfinite), kw
         assert np.allclose(multi, single, rtol=2e-5, atol=2e-6), kw
     two, st2 = pt.render_multi(p.scene, [0] * 5, spp=2, seed=4, nan_policy=1)      # more devices than samples: two shares
-    assert np.allclose(two, p.dev.render(spp=2, seed=4, nan_policy=1)[0], rtol=2e-5, atol=2e-6) and st2.paths == 2 * 128 * 72
+    assert np.allclose(two, p.dev.render(spp=2, seed=4, nan_policy=1)[0], rtol=2e-5, atol=2e-6) and st2.paths == 2 * 160 * 90
     with pytest.raises(pt.PtError, match="device 99"):
         pt.render_multi(p.scene, [0, 99], spp=2)
 
@@ -482,6 +542,60 @@ def test_edge_sizes_and_error_codes(pt, orc, ctx):
     rc, _ = create(lambda b: None)                                                           # the untouched copy is fine
     assert rc == 0
     dev.close(); ora.close()
+
+
+def test_malformed_descriptions_are_rejected_before_use(pt, ctx):
+    """Every index the uploader follows is range-checked first (no host or device out-of-bounds read through the C ABI):
+    a cuboid whose six quads run past the quad table, a mesh whose triangle range does, a mesh BVH leaf that holds
+    something other than the mesh's own triangles, and a bare triangle inside a top-level leaf."""
+    import ctypes as C
+    PTR = {"cuboids": 120, "meshes": 128, "leaf_refs": 152}
+
+    def create(scene, table, dtype, count, mutate):
+        arr = H.desc_array(scene, table, dtype, count)
+        mutate(arr)
+        buf = C.create_string_buffer(C.string_at(scene.desc, 200), 200)
+        C.memmove(C.addressof(buf) + PTR[table], (C.c_uint64 * 1)(arr.ctypes.data), 8)
+        out = C.c_void_p()
+        rc = ctx.lib.pt_scene_create(ctx.ptr, C.cast(buf, C.c_void_p), C.byref(out))
+        msg = ctx.lib.pt_last_error().decode()
+        if rc == 0:
+            ctx.lib.pt_scene_destroy(out)
+        return rc, msg
+
+    CUBOID_DT = np.dtype([("first_quad", "<u4"), ("material", "<u4"), ("a", "<f8", 3), ("b", "<f8", 3)])
+    s3 = pt.Scene.build(3, width=32, spp=1, seed=1)
+    hd = H.desc_header(s3)
+    assert hd["n_cuboids"] == 2
+    rc, msg = create(s3, "cuboids", CUBOID_DT, 2, lambda a: a["first_quad"].__setitem__(1, hd["n_quads"] - 3))
+    assert rc == pt.PT_ERR_INVALID and "cuboid" in msg
+    rc, msg = create(s3, "cuboids", CUBOID_DT, 2, lambda a: None)
+    assert rc == 0
+    s6 = pt.Scene.build(6, width=32, spp=1, seed=1)
+    hd = H.desc_header(s6)
+    rc, msg = create(s6, "meshes", H.MESH_DT, hd["n_meshes"], lambda a: a["first"].__setitem__(0, hd["n_triangles"] - 1))
+    assert rc == pt.PT_ERR_INVALID and "mesh" in msg
+    nodes = H.desc_array(s6, "nodes", H.NODE_DT, hd["n_nodes"])
+    meshes = H.desc_array(s6, "meshes", H.MESH_DT, hd["n_meshes"])
+
+    def first_leaf_ref(root):
+        i = root
+        while nodes[i]["left"] != 0xFFFFFFFF:
+            i = int(nodes[i]["left"])
+        return int(nodes[i]["first"])
+    k = first_leaf_ref(int(meshes[1]["root"]))
+
+    def put(a, i, kind, index):
+        a["kind"][i] = kind; a["index"][i] = index
+    rc, msg = create(s6, "leaf_refs", H.REF_DT, hd["n_leaf_refs"], lambda a: put(a, k, pt.PRIM_SPHERE, 0))
+    assert rc == pt.PT_ERR_INVALID and "mesh BVH leaf" in msg                                  # not a triangle
+    rc, msg = create(s6, "leaf_refs", H.REF_DT, hd["n_leaf_refs"], lambda a: put(a, k, pt.PRIM_TRIANGLE, int(meshes[0]["first"])))
+    assert rc == pt.PT_ERR_INVALID and "mesh BVH leaf" in msg                                  # another mesh's triangle
+    k_top = first_leaf_ref(H.desc_roots(s6)[0])
+    rc, msg = create(s6, "leaf_refs", H.REF_DT, hd["n_leaf_refs"], lambda a: put(a, k_top, pt.PRIM_TRIANGLE, 0))
+    assert rc == pt.PT_ERR_INVALID and "top-level" in msg
+    rc, msg = create(s6, "leaf_refs", H.REF_DT, hd["n_leaf_refs"], lambda a: None)
+    assert rc == 0
 
 
 def test_device_sah_sweep_builds_the_same_trees(pt, ctx):
@@ -610,7 +724,7 @@ def test_two_pass_traversal_beyond_the_reference_scenes(pt, orc, ctx):
     spp = 12                                                                          # 96 x 96 x 12 = 110 592 paths: above the 64 Ki floor of the two-pass path
     img, st = dev.render(spp=spp, seed=5, nan_policy=1)
     ref, ost = ora.render(cam, spp, seed=5, nan_policy=1)
-    assert st.paths == ost.paths == 96 * 96 * spp
+    assert st.paths == ost.paths == 96 * 96 * spp and st.two_pass_iterations > 0
     assert abs(int(st.segments) - int(ost.segments)) <= max(64, ost.segments // 2000)
     d = np.abs(img - ref).reshape(-1, 3).max(axis=1)
     assert (d > 1e-4 * np.maximum(ref.reshape(-1, 3).max(axis=1), 1.0)).mean() < 0.02

@@ -49,7 +49,8 @@ class Stats(C.Structure):  # pt_stats
     _fields_ = [("paths", C.c_uint64), ("segments", C.c_uint64), ("nonfinite", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("iterations", C.c_uint32), ("width", C.c_uint32), ("height", C.c_uint32), ("device_ms", C.c_float),
                 ("trace_ms", C.c_float), ("shade_ms", C.c_float), ("raygen_ms", C.c_float),
-                ("node_pairs", C.c_uint64), ("ref_boxes", C.c_uint64), ("prim_tests", C.c_uint64)]
+                ("node_pairs", C.c_uint64), ("ref_boxes", C.c_uint64), ("prim_tests", C.c_uint64),
+                ("two_pass_iterations", C.c_uint32), ("_pad", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -71,7 +72,7 @@ ABI_SYMBOLS = ["pt_ctx_create", "pt_ctx_destroy", "pt_ctx_set_stream", "pt_ctx_s
                "pt_scene_create", "pt_scene_destroy", "pt_scene_device_bytes", "pt_camera_image_height", "pt_render_accumulate",
                "pt_render", "pt_tonemap_rgb8", "pt_trace_closest", "pt_trace_any", "pt_bsdf_eval_pdf", "pt_bsdf_sample",
                "pt_camera_rays", "pt_lights_sample_pdf", "pt_scene_build_env_sampler", "pt_env_sample_pdf", "pt_sah_sweep",
-               "pt_render_multi"]
+               "pt_render_multi", "pt_trace_closest_wavefront"]
 
 
 class PtError(RuntimeError):
@@ -122,6 +123,7 @@ def device_lib():
         lib.pt_tonemap_rgb8.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_uint32, C.c_void_p]
         lib.pt_trace_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_double, C.c_void_p]
         lib.pt_trace_any.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+        lib.pt_trace_closest_wavefront.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_double, C.c_uint32, C.c_void_p, C.POINTER(Stats)]
         lib.pt_bsdf_eval_pdf.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_size_t, C.c_void_p, C.c_void_p]
         lib.pt_bsdf_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.pt_camera_rays.argtypes = [C.c_void_p, C.POINTER(CameraABI), C.c_uint64, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -476,6 +478,14 @@ class DeviceScene:
         hits = np.zeros(rays.shape[0], dtype=HIT_DTYPE)
         self.ctx._check(self.ctx.lib.pt_trace_closest(self.ctx.ptr, self.ptr, rays.shape[0], _ptr(rays), t_min, _ptr(hits)))
         return hits
+
+    def trace_closest_wavefront(self, rays, t_min=1e-3, flags=0):
+        """World::intersect_all through the render's own traversal stage (pt_trace_closest_wavefront); returns (hits, stats)."""
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        hits = np.zeros(rays.shape[0], dtype=HIT_DTYPE)
+        st = Stats()
+        self.ctx._check(self.ctx.lib.pt_trace_closest_wavefront(self.ctx.ptr, self.ptr, rays.shape[0], _ptr(rays), t_min, flags, _ptr(hits), C.byref(st)))
+        return hits, st
 
     def trace_any(self, rays, t_max, t_min=1e-3):
         rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)

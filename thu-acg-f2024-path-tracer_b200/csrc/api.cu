@@ -40,7 +40,8 @@ struct pt_ctx {
     uint32_t* d_count = nullptr;            // kTailBatch slots of [kSlot]: [0] survivors counter, [4 .. 4+N_CLS) shade-class queue lengths, [12 .. 15) mesh-visit queue lengths, [16 .. 19) their fetch cursors
     uint32_t* q_items = nullptr;            // N_CLS queues of `pool` path slots each
     uint4* bq_items = nullptr;              // two-pass traversal: kDeferMax queues of `pool` deferred mesh visits each
-    uint2* ties = nullptr;                  //   and the tie ranks of the provisional hit of every path
+    uint2* ties = nullptr;                  //   and the tie ranks of the provisional hit of every path (both allocated on first use)
+    void* scratch = nullptr; size_t scratch_bytes = 0;  // pt_render / pt_tonemap_rgb8 output staging, grown on demand (no cudaMalloc per call)
     unsigned long long* d_nonfinite = nullptr;
     uint32_t* h_count = nullptr;            // pinned, same shape as d_count
     void* h_stage = nullptr; size_t stage_bytes = 0;  // pinned staging buffer for scene uploads
@@ -76,20 +77,22 @@ struct pt_scene {
     DEnvDist env{};                         // pt_scene_build_env_sampler: importance sampler of image `env_image`
     uint32_t env_image = 0xFFFFFFFFu;
     void* env_block = nullptr;
+    // every exit path (pt_scene_destroy and the error returns of pt_scene_create) hands the device blocks back to the context
+    ~pt_scene() {
+        if (!ctx) return;
+        for (auto& b : allocs) ctx->free_blocks.push_back(b);
+        while (ctx->free_blocks.size() > 8) { cudaFree(ctx->free_blocks.front().first); ctx->free_blocks.erase(ctx->free_blocks.begin()); }
+        if (env_block) cudaFree(env_block);
+    }
 };
 
 extern "C" {
 
 const char* pt_last_error(void) { return g_err.c_str(); }
+void pt_ctx_destroy(pt_ctx* c);
 int pt_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
 
-int pt_ctx_create(int device, pt_ctx** out) {
-    if (!out) return fail(PT_ERR_INVALID, "pt_ctx_create: null out");
-    int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return fail(PT_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
-    if (device < 0 || device >= n) return fail(PT_ERR_INVALID, "pt_ctx_create: bad device index");
-    CU(cudaSetDevice(device));
-    auto* c = new pt_ctx(); c->device = device;
+static int ctx_init(pt_ctx* c) {
     CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CU(cudaMalloc(&c->d_count, kTailBatch * kSlot * sizeof(uint32_t)));
@@ -102,6 +105,17 @@ int pt_ctx_create(int device, pt_ctx** out) {
         CU(cudaStreamCreateWithFlags(&c->shade_stream[k], cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming));
     }
+    return PT_OK;
+}
+int pt_ctx_create(int device, pt_ctx** out) {
+    if (!out) return fail(PT_ERR_INVALID, "pt_ctx_create: null out");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return fail(PT_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
+    if (device < 0 || device >= n) return fail(PT_ERR_INVALID, "pt_ctx_create: bad device index");
+    CU(cudaSetDevice(device));
+    auto* c = new pt_ctx(); c->device = device;
+    const int rc = ctx_init(c);
+    if (rc) { const std::string msg = g_err; pt_ctx_destroy(c); return fail(rc, msg); }  // nothing created so far may leak
     *out = c;
     return PT_OK;
 }
@@ -114,14 +128,17 @@ void pt_ctx_destroy(pt_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     free_pool(c);
-    cudaFree(c->d_count); cudaFree(c->d_nonfinite); cudaFreeHost(c->h_count);
+    cudaFree(c->d_count); cudaFree(c->d_nonfinite); cudaFree(c->scratch);
+    if (c->h_count) cudaFreeHost(c->h_count);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     for (auto& b : c->free_blocks) cudaFree(b.first);
-    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
-    for (auto& e : c->evs) cudaEventDestroy(e);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    for (auto& e : c->evs) if (e) cudaEventDestroy(e);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (int k = 0; k < N_CLS; k++) { if (c->shade_stream[k]) cudaStreamDestroy(c->shade_stream[k]); if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]); }
-    cudaStreamDestroy(c->own_stream);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    cudaGetLastError();  // a half-built context may have handed CUDA a null handle above
     delete c;
 }
 int pt_ctx_set_stream(pt_ctx* c, void* s) { if (!c) return fail(PT_ERR_INVALID, "null ctx"); c->stream = s ? (cudaStream_t)s : c->own_stream; return PT_OK; }
@@ -175,6 +192,10 @@ struct Converter {
     uint32_t tie_counter = 0;
     uint32_t max_depth = 0;
     std::string err;
+    // which tree is being converted: -1 = a top-level list (objects / lights: anything but bare triangles), else the mesh whose
+    // BLAS it is (leaves may hold only that mesh's own triangles: blas_round indexes S.tris without looking at the kind)
+    int64_t leaf_mesh = -1;
+    uint32_t max_deferred_in_leaf = 0;  // most mesh / instance / volume references in one top-level leaf (each takes a stack slot)
 
     static bool tie_is_sphere(const pt_scene_desc* d, pt_ref r) {
         if (r.kind == PT_PRIM_SPHERE) return true;
@@ -248,7 +269,20 @@ struct Converter {
         for (int k = 0; k < 3; k++) { n.lo[k] = round_down(lo[k] - pad); n.hi[k] = round_up(hi[k] + pad); }
     }
     // leaf refs of host node `hn` -> device refs (appended), with exact-tie ranks in DFS order
-    void make_leaf(DNode& out, const pt_ref* items, uint32_t n, uint32_t top_bit, bool box_inf, const double* lo, const double* hi) {
+    bool make_leaf(DNode& out, const pt_ref* items, uint32_t n, uint32_t top_bit, bool box_inf, const double* lo, const double* hi) {
+        uint32_t deferred = 0;
+        for (uint32_t p = 0; p < n; p++) {
+            if (leaf_mesh >= 0) {
+                const pt_mesh& m = d->meshes[leaf_mesh];
+                if (items[p].kind != PT_PRIM_TRIANGLE || items[p].index < m.first_triangle || items[p].index - m.first_triangle >= m.n_triangles) {
+                    err = "a mesh BVH leaf may hold only the mesh's own triangles"; return false;
+                }
+            } else {
+                if (items[p].kind == PT_PRIM_TRIANGLE) { err = "a bare triangle cannot be a top-level object"; return false; }
+                deferred += items[p].kind >= PT_OBJ_MESH;
+            }
+        }
+        max_deferred_in_leaf = std::max(max_deferred_in_leaf, deferred);
         out.a = (uint32_t)refs.size(); out.b = n;
         if (box_inf) { for (int k = 0; k < 3; k++) { out.lo[k] = -INFINITY; out.hi[k] = INFINITY; } } else set_box(out, lo, hi);
         uint32_t base = tie_counter; tie_counter += 2 * n + 2;
@@ -261,6 +295,7 @@ struct Converter {
             rn.a = ref_pack(items[p].kind, items[p].index); rn.b = rank | top_bit;
             refs.push_back(rn);
         }
+        return true;
     }
     // writes host node hn into nodes[slot]; children become a fresh adjacent pair
     bool fill(uint32_t slot, uint32_t hn, uint32_t top_bit, uint32_t depth) {
@@ -270,7 +305,8 @@ struct Converter {
         const pt_bvh_node& h = d->nodes[hn];
         if (h.left == PT_NONE) {
             if ((uint64_t)h.first_ref + h.n_refs > d->n_leaf_refs) { err = "leaf refs out of range"; return false; }
-            DNode n{}; make_leaf(n, d->leaf_refs + h.first_ref, h.n_refs, top_bit, false, h.bmin, h.bmax);
+            DNode n{};
+            if (!make_leaf(n, d->leaf_refs + h.first_ref, h.n_refs, top_bit, false, h.bmin, h.bmax)) return false;
             nodes[slot] = n;
             return true;
         }
@@ -345,6 +381,22 @@ static int check_desc(const pt_scene_desc* d) {
         }
     };
     if (d->n_volumes && !d->volumes) return fail(PT_ERR_INVALID, "scene description has a null array with a non-zero count");
+    // everything the uploader dereferences through an index is range-checked here, before any of it is touched
+    for (uint32_t i = 0; i < d->n_spheres; i++) if (d->spheres[i].material >= d->n_materials) return fail(PT_ERR_INVALID, "bad sphere material");
+    for (uint32_t i = 0; i < d->n_quads; i++) if (d->quads[i].material >= d->n_materials) return fail(PT_ERR_INVALID, "bad quad material");
+    for (uint32_t i = 0; i < d->n_cuboids; i++)
+        if ((uint64_t)d->cuboids[i].first_quad + 6 > d->n_quads) return fail(PT_ERR_INVALID, "bad cuboid: first_quad + 6 exceeds n_quads");
+    for (uint32_t i = 0; i < d->n_meshes; i++) {
+        const pt_mesh& m = d->meshes[i];
+        if ((uint64_t)m.first_triangle + m.n_triangles > d->n_triangles || m.material >= d->n_materials) return fail(PT_ERR_INVALID, "bad mesh: triangle range or material");
+        if ((m.has_normals && !d->tri_normals) || (m.has_uvs && !d->tri_uvs)) return fail(PT_ERR_INVALID, "mesh flags without arrays");
+        if (m.bvh_root != PT_NONE && m.bvh_root >= d->n_nodes) return fail(PT_ERR_INVALID, "bad mesh: bvh_root out of range");
+    }
+    for (uint32_t i = 0; i < d->n_nodes; i++) {
+        const pt_bvh_node& nd = d->nodes[i];
+        if (nd.left == PT_NONE ? (uint64_t)nd.first_ref + nd.n_refs > d->n_leaf_refs : (nd.left >= d->n_nodes || nd.right >= d->n_nodes))
+            return fail(PT_ERR_INVALID, "bad bvh node " + std::to_string(i));
+    }
     for (uint32_t i = 0; i < d->n_volumes; i++) {
         const pt_volume& v = d->volumes[i];
         if ((v.boundary.kind != PT_PRIM_SPHERE && v.boundary.kind != PT_OBJ_CUBOID) || !ref_ok(v.boundary, false))
@@ -402,7 +454,7 @@ int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
     C.nodes.resize(2);
     auto top_list = [&](uint32_t slot, uint32_t root, const pt_ref* items, uint32_t n, uint32_t top_bit) -> bool {
         if (n == 0) { C.dummy(slot); return true; }
-        if (root == PT_NONE) { DNode leaf{}; C.make_leaf(leaf, items, n, top_bit, true, nullptr, nullptr); C.nodes[slot] = leaf; return true; }  // list.rs:57-66
+        if (root == PT_NONE) { DNode leaf{}; if (!C.make_leaf(leaf, items, n, top_bit, true, nullptr, nullptr)) return false; C.nodes[slot] = leaf; return true; }  // list.rs:57-66
         return C.fill(slot, root, top_bit, 1);
     };
     // lights first so that their ranks are lower; objects additionally carry bit 31 (object beats light, world.rs:55-59)
@@ -419,9 +471,8 @@ int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
     uint32_t blas_depth = 0;
     for (uint32_t mi = 0; mi < d->n_meshes; mi++) {
         const pt_mesh& m = d->meshes[mi];
-        if ((uint64_t)m.first_triangle + m.n_triangles > d->n_triangles || m.material >= d->n_materials) return fail(PT_ERR_INVALID, "bad mesh");
-        if ((m.has_normals && !d->tri_normals) || (m.has_uvs && !d->tri_uvs)) return fail(PT_ERR_INVALID, "mesh flags without arrays");
         for (uint32_t k = 0; k < m.n_triangles; k++) tri_mesh[m.first_triangle + k] = mi;
+        C.leaf_mesh = mi;
         uint32_t pair = (uint32_t)C.nodes.size();
         C.nodes.resize(C.nodes.size() + 2);
         C.dummy(pair + 1);
@@ -429,7 +480,9 @@ int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
         if (m.bvh_root == PT_NONE) {
             std::vector<pt_ref> items(m.n_triangles);
             for (uint32_t k = 0; k < m.n_triangles; k++) items[k] = pt_ref{PT_PRIM_TRIANGLE, m.first_triangle + k};
-            DNode leaf{}; C.make_leaf(leaf, items.data(), m.n_triangles, 0u, true, nullptr, nullptr); C.nodes[pair] = leaf;
+            DNode leaf{};
+            if (!C.make_leaf(leaf, items.data(), m.n_triangles, 0u, true, nullptr, nullptr)) return fail(PT_ERR_INVALID, C.err);
+            C.nodes[pair] = leaf;
         } else if (!C.fill(pair, m.bvh_root, 0u, 1)) return fail(PT_ERR_INVALID, C.err);
         // large BVHs are collapsed to 4-wide nodes; small ones keep the binary pairs (cheaper when most rays leave at once)
         uint32_t root_entry = pair, depth_slots = C.max_depth;
@@ -439,23 +492,21 @@ int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
     }
     uint32_t world_root = 0, tlas_slots = tlas_depth;
     if (use_wide) { C.wide_depth = 0; world_root = 0x20000000u | C.make_wide({0u, 1u}, 1); tlas_slots = 3 * C.wide_depth; }
-    // stack bound: one pending sibling per binary level / three per wide level + deferred mesh/instance refs of a TLAS leaf + sentinel
-    uint32_t top_leaf = std::max(d->objects_bvh_root == PT_NONE ? d->n_objects : 0u, d->lights_bvh_root == PT_NONE ? d->n_lights : 0u);
-    s->max_stack = tlas_slots + blas_depth + 2 + std::max(top_leaf, 8u);
+    // stack bound: one pending sibling per binary level / three per wide level + the mesh / instance / volume references one
+    // top-level leaf can defer (counted while converting: a failed SAH split leaves a leaf of any size, bvh.rs:37-42) + sentinel
+    s->max_stack = tlas_slots + blas_depth + 2 + std::max(C.max_deferred_in_leaf, 8u);
     if (s->max_stack > (uint32_t)kStack) return fail(PT_ERR_UNSUPPORTED, "BVH too deep for the device traversal stack (" + std::to_string(s->max_stack) + " > " + std::to_string(kStack) + ")");
 
     // ---- primitives
     std::vector<DSphere> spheres(d->n_spheres);
     for (uint32_t i = 0; i < d->n_spheres; i++) {
         const pt_sphere& p = d->spheres[i];
-        if (p.material >= d->n_materials) return fail(PT_ERR_INVALID, "bad sphere material");
         DSphere o{}; o.p1[0] = p.position1.x; o.p1[1] = p.position1.y; o.p1[2] = p.position1.z; o.p2[0] = p.position2.x; o.p2[1] = p.position2.y; o.p2[2] = p.position2.z;
         o.radius = p.radius; o.material = p.material; spheres[i] = o;
     }
     std::vector<DQuad> quads(d->n_quads); std::vector<uint32_t> quad_mat(d->n_quads);
     for (uint32_t i = 0; i < d->n_quads; i++) {
         const pt_quad& p = d->quads[i];
-        if (p.material >= d->n_materials) return fail(PT_ERR_INVALID, "bad quad material");
         DQuad o{}; const pt_vec3* src[5] = {&p.q, &p.u, &p.v, &p.w, &p.normal}; double* dst[5] = {o.q, o.u, o.v, o.w, o.n};
         for (int k = 0; k < 5; k++) { dst[k][0] = src[k]->x; dst[k][1] = src[k]->y; dst[k][2] = src[k]->z; }
         o.d = p.d; quads[i] = o; quad_mat[i] = p.material;
@@ -474,10 +525,7 @@ int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
     if (any_n) { tri_normals.resize(9ull * d->n_triangles); memcpy(tri_normals.data(), d->tri_normals, tri_normals.size() * 8); }
     if (any_uv) { tri_uvs.assign(d->tri_uvs, d->tri_uvs + 6ull * d->n_triangles); }
     std::vector<DCuboid> cuboids(d->n_cuboids);
-    for (uint32_t i = 0; i < d->n_cuboids; i++) {
-        if ((uint64_t)d->cuboids[i].first_quad + 6 > d->n_quads) return fail(PT_ERR_INVALID, "bad cuboid");
-        cuboids[i] = DCuboid{d->cuboids[i].first_quad, d->cuboids[i].material};
-    }
+    for (uint32_t i = 0; i < d->n_cuboids; i++) cuboids[i] = DCuboid{d->cuboids[i].first_quad, d->cuboids[i].material};  // ranges: check_desc
     std::vector<DInstance> instances(d->n_instances);
     for (uint32_t i = 0; i < d->n_instances; i++) {
         const pt_instance& p = d->instances[i];
@@ -565,9 +613,6 @@ void pt_scene_destroy(pt_scene* s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);  // no kernel may still read the tables
-    for (auto& b : s->allocs) s->ctx->free_blocks.push_back(b);
-    while (s->ctx->free_blocks.size() > 8) { cudaFree(s->ctx->free_blocks.front().first); s->ctx->free_blocks.erase(s->ctx->free_blocks.begin()); }
-    if (s->env_block) cudaFree(s->env_block);
     delete s;
 }
 uint64_t pt_scene_device_bytes(const pt_scene* s) { return s ? s->bytes : 0; }
@@ -666,9 +711,33 @@ static int ensure_pool(pt_ctx* c, uint32_t paths) {
     }
     CU(cudaMalloc(&c->hits, (size_t)paths * sizeof(HitRec)));
     CU(cudaMalloc(&c->q_items, (size_t)paths * N_CLS * sizeof(uint32_t)));
-    CU(cudaMalloc(&c->bq_items, (size_t)paths * kDeferMax * sizeof(uint4)));
-    CU(cudaMalloc(&c->ties, (size_t)paths * sizeof(uint2)));
     c->pool = paths;
+    return PT_OK;
+}
+// mesh-visit queues and tie ranks of the two-pass traversal: 56 B per path, only for scenes that take that path
+static int ensure_two_pass(pt_ctx* c) {
+    if (c->bq_items) return PT_OK;
+    CU(cudaMalloc(&c->bq_items, (size_t)c->pool * kDeferMax * sizeof(uint4)));
+    CU(cudaMalloc(&c->ties, (size_t)c->pool * sizeof(uint2)));
+    return PT_OK;
+}
+// Path pool of `want` paths (plus the two-pass buffers when the scene needs them); on cudaErrorMemoryAllocation the pool is
+// halved and the allocation retried (a smaller pool only means more wavefront iterations), down to 64 Ki paths.
+static int ensure_render_buffers(pt_ctx* c, uint32_t want, bool two_pass, uint32_t* got) {
+    for (uint32_t pool = want;; pool = std::max((pool / 2 + kBlock - 1) / kBlock * kBlock, 1u << 16)) {
+        int rc = ensure_pool(c, pool);
+        if (rc == PT_OK && two_pass) rc = ensure_two_pass(c);
+        if (rc == PT_OK) { *got = std::min(pool, c->pool); return PT_OK; }
+        const bool oom = cudaGetLastError() == cudaErrorMemoryAllocation || g_err.find("out of memory") != std::string::npos;
+        free_pool(c);
+        if (!oom || pool <= (1u << 16)) return rc;
+    }
+}
+static int ensure_scratch(pt_ctx* c, size_t bytes) {
+    if (c->scratch_bytes >= bytes) return PT_OK;
+    cudaFree(c->scratch); c->scratch = nullptr; c->scratch_bytes = 0;
+    CU(cudaMalloc(&c->scratch, bytes));
+    c->scratch_bytes = bytes;
     return PT_OK;
 }
 static PathBuf path_buf(pt_ctx* c, int which) {
@@ -676,6 +745,55 @@ static PathBuf path_buf(pt_ctx* c, int which) {
     for (int k = 0; k < 10; k++) b.f[k] = c->pool_f[which] + (size_t)k * c->pool;
     b.ids = c->pool_ids[which];
     return b;
+}
+
+// World::intersect_all for the n (or min(n, *n_dev)) paths of `in` — THE traversal stage of a wavefront iteration, shared by
+// the render loop and by pt_trace_closest_wavefront (so ray batches can be ID-compared on exactly what the render runs).
+// One compile-time flavour per scene / mode.
+struct TraceStage {
+    pt_ctx* ctx; const pt_scene* scene; uint32_t flags; uint64_t seed; double t_min; unsigned long long* wk; pt_stats* S;
+};
+static void launch_trace(const TraceStage& T, const PathBuf& in, uint32_t n, const Queues& q, const uint32_t* n_dev) {
+    pt_ctx* ctx = T.ctx; const pt_scene* scene = T.scene; pt_stats& S = *T.S;
+    unsigned long long* const wk = T.wk;
+    cudaStream_t st = ctx->stream;
+    const unsigned tg = (n + kTraceBlock - 1) / kTraceBlock;
+    // two-pass traversal; not for small iterations (three more launches each); flag 0x100000 opts out (A/B measurements)
+    if (scene->defer_meshes && n >= (1u << 16) && !(T.flags & 0x100000u)) {
+        const BlasQueues bq{ctx->bq_items, q.count + 8, ctx->pool};  // counters in the free tail of the iteration's slot
+        if (wk) k_trace<7, true, true, false, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, 0, n_dev, bq, ctx->ties, T.t_min);
+        else k_trace<7, true, false, false, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, nullptr, 0, n_dev, bq, ctx->ties, T.t_min);
+        const unsigned bg = std::min<unsigned>(tg, 148u * 56u);
+        const bool refill = !(T.flags & 0x200000u);  // flag 0x200000: plain grid-stride rounds instead of persistent lanes with refill
+        const unsigned pg = std::min<unsigned>(tg, 148u * 4u * (unsigned)kBlasMinBlocks);  // persistent: one resident warp per slot
+        for (uint32_t r = 0; r < (uint32_t)kDeferMax; r++) {
+            if (refill) {
+                if (wk) k_trace_blas_refill<true><<<pg, kTraceBlock, 0, st>>>(in, r, bq, ctx->hits, ctx->ties, q, scene->d, wk, T.t_min);
+                else k_trace_blas_refill<false><<<pg, kTraceBlock, 0, st>>>(in, r, bq, ctx->hits, ctx->ties, q, scene->d, nullptr, T.t_min);
+            } else if (wk) k_trace_blas<true><<<bg, kTraceBlock, 0, st>>>(in, r, bq, ctx->hits, ctx->ties, q, scene->d, wk, T.t_min);
+            else k_trace_blas<false><<<bg, kTraceBlock, 0, st>>>(in, r, bq, ctx->hits, ctx->ties, q, scene->d, nullptr, T.t_min);
+        }
+        S.kernel_launches += 1 + kDeferMax;
+        S.two_pass_iterations++;
+        return;
+    }
+    const BlasQueues nobq{nullptr, nullptr, 0};
+#define PT_TRACE(...) k_trace<__VA_ARGS__><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, T.seed, n_dev, nobq, nullptr, T.t_min)
+    if (scene->has_volumes) {  // media: the trace kernel variant that draws keyed free-flight uniforms
+        if (scene->wide) { if (wk) PT_TRACE(6, true, true, true); else PT_TRACE(6, true, false, true); }
+        else { if (wk) PT_TRACE(6, false, true, true); else PT_TRACE(6, false, false, true); }
+    } else if (wk) {
+        if (scene->wide) PT_TRACE(6, true, true); else PT_TRACE(6, false, true);
+    } else if (!scene->wide) PT_TRACE(6, false);  // 80 regs (72: -2 % .. +1.5 %)
+    else switch ((T.flags >> 4) & 7u) {  // experiment knob: resident blocks per SM the compiler must allow (register cap)
+        case 4: PT_TRACE(4, true); break;  // 120 regs
+        case 5: PT_TRACE(5, true); break;  // 96 regs
+        case 6: PT_TRACE(6, true); break;  // 80 regs
+        case 7: PT_TRACE(8, true); break;  // 64 regs, spills
+        default: PT_TRACE(7, true);        // 72 regs, 28 warps/SM (measured best: +2 % over 80)
+    }
+#undef PT_TRACE
+    S.kernel_launches++;
 }
 
 int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* cam, const pt_render_params* p, float* d_accum, pt_stats* stats) {
@@ -687,13 +805,13 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
     if (rc) return rc;
     const uint32_t n_pixels = dcam.c.width * dcam.c.height;
     const uint64_t total = (uint64_t)n_pixels * p->sample_count;
-    // default 32 Mi paths in flight (7.9 GB of state): each wavefront iteration costs one host round trip (~0.2 ms with its
+    // default 32 Mi paths in flight (8.0 GB of state, 9.8 GB with the two-pass traversal's queues): each wavefront iteration costs one host round trip (~0.2 ms with its
     // small-launch tail), so large iterations amortise it (scene 6 FHD: 4 Mi 2681, 8 Mi 2827, 16 Mi 2913 Mrays/s at the
     // time; with the final kernels 16 Mi 3113, 32 Mi 3170, 64 Mi 3204); never more than the render needs
     uint32_t pool = p->pool_paths ? p->pool_paths : (32u << 20);
     if ((uint64_t)pool > total) pool = (uint32_t)std::max<uint64_t>(total, 1);
     pool = (pool + kBlock - 1) / kBlock * kBlock;
-    if ((rc = ensure_pool(ctx, pool))) return rc;
+    if ((rc = ensure_render_buffers(ctx, pool, scene->defer_meshes, &pool))) return rc;
     RenderConst rcst{p->seed, p->sample_begin, p->sample_stride ? p->sample_stride : 1u, p->nan_policy, 0, DEnvDist{nullptr, nullptr, 0, 0}};
     if ((p->flags & PT_RENDER_ENV_IMPORTANCE) && cam->env_is_map) {  // a constant-colour environment needs no importance sampling
         if (scene->env_image != cam->env_image) return fail(PT_ERR_INVALID, "PT_RENDER_ENV_IMPORTANCE: call pt_scene_build_env_sampler for the camera's env_image first");
@@ -710,43 +828,8 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
     const bool nee = (p->flags & PT_RENDER_NEE) != 0;
     if (nee && rcst.env_importance) return fail(PT_ERR_UNSUPPORTED, "PT_RENDER_NEE and PT_RENDER_ENV_IMPORTANCE cannot be combined yet");
     unsigned long long* const wk = ctx->profiling >= 2 ? ctx->d_nonfinite + 1 : nullptr;
-    // World::intersect_all for the n (or min(n, *n_dev)) paths of `in`; one compile-time flavour per scene / mode
-    auto launch_trace = [&](const PathBuf& in, uint32_t n, const Queues& q, const uint32_t* n_dev) {
-        const unsigned tg = (n + kTraceBlock - 1) / kTraceBlock;
-        // two-pass traversal; not for small iterations (three more launches each); flag 0x100000 opts out (A/B measurements)
-        if (scene->defer_meshes && n >= (1u << 16) && !(p->flags & 0x100000u)) {
-            const BlasQueues bq{ctx->bq_items, q.count + 8, ctx->pool};  // counters in the free tail of the iteration's slot
-            if (wk) k_trace<7, true, true, false, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, 0, n_dev, bq, ctx->ties);
-            else k_trace<7, true, false, false, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, nullptr, 0, n_dev, bq, ctx->ties);
-            const unsigned bg = std::min<unsigned>(tg, 148u * 56u);
-            const bool refill = !(p->flags & 0x200000u);  // flag 0x200000: plain grid-stride rounds instead of persistent lanes with refill
-            const unsigned pg = std::min<unsigned>(tg, 148u * 4u * (unsigned)kBlasMinBlocks);  // persistent: one resident warp per slot
-            for (uint32_t r = 0; r < (uint32_t)kDeferMax; r++) {
-                if (refill) {
-                    if (wk) k_trace_blas_refill<true><<<pg, kTraceBlock, 0, st>>>(in, r, bq, ctx->hits, ctx->ties, q, scene->d, wk);
-                    else k_trace_blas_refill<false><<<pg, kTraceBlock, 0, st>>>(in, r, bq, ctx->hits, ctx->ties, q, scene->d, nullptr);
-                } else if (wk) k_trace_blas<true><<<bg, kTraceBlock, 0, st>>>(in, r, bq, ctx->hits, ctx->ties, q, scene->d, wk);
-                else k_trace_blas<false><<<bg, kTraceBlock, 0, st>>>(in, r, bq, ctx->hits, ctx->ties, q, scene->d, nullptr);
-            }
-            S.kernel_launches += 1 + kDeferMax;
-            return;
-        }
-        if (scene->has_volumes) {  // media: the trace kernel variant that draws keyed free-flight uniforms
-            if (scene->wide) { if (wk) k_trace<6, true, true, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, p->seed, n_dev); else k_trace<6, true, false, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, p->seed, n_dev); }
-            else { if (wk) k_trace<6, false, true, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, p->seed, n_dev); else k_trace<6, false, false, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, p->seed, n_dev); }
-        } else if (wk) {
-            if (scene->wide) k_trace<6, true, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, 0, n_dev);
-            else k_trace<6, false, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, 0, n_dev);
-        } else if (!scene->wide) k_trace<6, false><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, nullptr, 0, n_dev);  // 80 regs (72: -2 % .. +1.5 %)
-        else switch ((p->flags >> 4) & 7u) {  // experiment knob: resident blocks per SM the compiler must allow (register cap)
-            case 4: k_trace<4, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, nullptr, 0, n_dev); break;  // 120 regs
-            case 5: k_trace<5, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, nullptr, 0, n_dev); break;  // 96 regs
-            case 6: k_trace<6, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, nullptr, 0, n_dev); break;  // 80 regs
-            case 7: k_trace<8, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, nullptr, 0, n_dev); break;  // 64 regs, spills
-            default: k_trace<7, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, nullptr, 0, n_dev);        // 72 regs, 28 warps/SM (measured best: +2 % over 80)
-        }
-        S.kernel_launches++;
-    };
+    const TraceStage tstage{ctx, scene, p->flags, p->seed, 1e-3, wk, &S};  // Interval::new(eps, INFINITY), camera.rs:171,179
+    auto launch_trace = [&](const PathBuf& in, uint32_t n, const Queues& q, const uint32_t* n_dev) { ::launch_trace(tstage, in, n, q, n_dev); };
     // one specialised kernel per shade class present in the scene; each walks its queue grid-stride (n: upper bound of the
     // paths in all queues together).  fork: the class kernels run on side streams and join `st` again.
     auto launch_shades = [&](const PathBuf& in, const PathBuf& outb, uint32_t n, const Queues& q, uint32_t* out_count, bool fork) -> int {
@@ -839,8 +922,9 @@ int pt_render(pt_ctx* ctx, const pt_scene* scene, const pt_camera* cam, const pt
     if (p->sample_count == 0) return fail(PT_ERR_INVALID, "pt_render: sample_count is zero");
     CU(cudaSetDevice(ctx->device));
     const size_t n = (size_t)cam->image_width * pt_camera_image_height(cam) * 3;
-    float* d_accum = nullptr;
-    CU(cudaMalloc(&d_accum, n * sizeof(float)));
+    int rcs = ensure_scratch(ctx, n * sizeof(float));  // context-owned, reused by every call
+    if (rcs) return rcs;
+    float* d_accum = (float*)ctx->scratch;
     cudaError_t e = cudaMemsetAsync(d_accum, 0, n * sizeof(float), ctx->stream);
     int rc = e == cudaSuccess ? pt_render_accumulate(ctx, scene, cam, p, d_accum, stats) : fail(PT_ERR_CUDA, cudaGetErrorString(e));
     if (rc == PT_OK) {
@@ -850,7 +934,6 @@ int pt_render(pt_ctx* ctx, const pt_scene* scene, const pt_camera* cam, const pt
         if (e != cudaSuccess) rc = fail(PT_ERR_CUDA, cudaGetErrorString(e));
         if (stats) stats->kernel_launches++;
     }
-    cudaFree(d_accum);
     return rc;
 }
 
@@ -936,12 +1019,14 @@ int pt_render_multi(int n_devices, const int* devices, const pt_scene_desc* desc
 int pt_tonemap_rgb8(pt_ctx* ctx, const float* d_accum, double scale, uint32_t n_pixels, uint8_t* h_rgb8) {
     if (!ctx || !d_accum || !h_rgb8) return fail(PT_ERR_INVALID, "pt_tonemap_rgb8: null argument");
     CU(cudaSetDevice(ctx->device));
-    uint8_t* d_out = nullptr; const uint32_t n = n_pixels * 3;
-    CU(cudaMalloc(&d_out, n));
+    const uint32_t n = n_pixels * 3;
+    if (d_accum == (const float*)ctx->scratch) return fail(PT_ERR_INVALID, "pt_tonemap_rgb8: d_accum must be a caller-owned buffer");
+    int rcs = ensure_scratch(ctx, n);
+    if (rcs) return rcs;
+    uint8_t* d_out = (uint8_t*)ctx->scratch;
     k_tonemap<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_accum, scale, n, d_out);
     cudaError_t e = cudaMemcpyAsync(h_rgb8, d_out, n, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_out);
     if (e != cudaSuccess) return fail(PT_ERR_CUDA, cudaGetErrorString(e));
     return PT_OK;
 }
@@ -971,6 +1056,44 @@ int pt_trace_closest(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_ray*
     if (scene->wide) k_trace_batch<true><<<grid_for(n), 128, 0, ctx->stream>>>((const pt_ray*)in.p, n, t_min, (pt_hit*)out.p, scene->d);
     else k_trace_batch<false><<<grid_for(n), 128, 0, ctx->stream>>>((const pt_ray*)in.p, n, t_min, (pt_hit*)out.p, scene->d);
     return out.to_host(hits, n * sizeof(pt_hit), ctx->stream);
+}
+int pt_trace_closest_wavefront(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_ray* rays, double t_min, uint32_t flags, pt_hit* hits, pt_stats* stats) {
+    if (!ctx || !scene || (n && (!rays || !hits))) return fail(PT_ERR_INVALID, "pt_trace_closest_wavefront: null argument");
+    if (scene->ctx != ctx) return fail(PT_ERR_INVALID, "scene belongs to another context");
+    pt_stats S{};
+    if (stats) *stats = S;
+    if (n == 0) return PT_OK;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    uint32_t chunk = (uint32_t)std::min<size_t>(n, 4u << 20);  // like a wavefront iteration of that many live paths
+    chunk = (chunk + kBlock - 1) / kBlock * kBlock;
+    int rc = ensure_render_buffers(ctx, chunk, scene->defer_meshes, &chunk);
+    if (rc) return rc;
+    DevBuf in, out;
+    if ((rc = in.alloc((size_t)chunk * sizeof(pt_ray))) || (rc = out.alloc((size_t)chunk * sizeof(pt_hit)))) return rc;
+    unsigned long long* const wk = ctx->profiling >= 2 ? ctx->d_nonfinite + 1 : nullptr;
+    if (wk) CU(cudaMemsetAsync(ctx->d_nonfinite, 0, 4 * sizeof(unsigned long long), st));
+    const TraceStage T{ctx, scene, flags, 0, t_min, wk, &S};  // seed 0: media uniforms keyed like pt_trace_closest's
+    const PathBuf pool = path_buf(ctx, 0);
+    for (size_t first = 0; first < n; first += chunk) {
+        const uint32_t m = (uint32_t)std::min<size_t>(chunk, n - first);
+        CU(cudaMemcpyAsync(in.p, rays + first, (size_t)m * sizeof(pt_ray), cudaMemcpyHostToDevice, st));
+        k_rays_to_pool<<<(m + 127) / 128, 128, 0, st>>>((const pt_ray*)in.p, m, (uint32_t)first, pool);
+        CU(cudaMemsetAsync(ctx->d_count, 0, kSlot * sizeof(uint32_t), st));
+        const Queues q{ctx->q_items, ctx->d_count + 4, ctx->pool};
+        launch_trace(T, pool, m, q, nullptr);
+        k_hits_to_abi<<<(m + 127) / 128, 128, 0, st>>>((const pt_ray*)in.p, m, ctx->hits, (pt_hit*)out.p, scene->d);
+        if ((rc = out.to_host(hits + first, (size_t)m * sizeof(pt_hit), st))) return rc;
+        S.segments += m; S.iterations++; S.kernel_launches += 2;
+    }
+    if (wk) {
+        unsigned long long nf[4] = {0, 0, 0, 0};
+        CU(cudaMemcpyAsync(nf, ctx->d_nonfinite, sizeof(nf), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        S.node_pairs = nf[1]; S.ref_boxes = nf[2]; S.prim_tests = nf[3];
+    }
+    if (stats) *stats = S;
+    return PT_OK;
 }
 int pt_trace_any(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_ray* rays, double t_min, const double* t_max, uint8_t* occluded) {
     if (!ctx || !scene || (n && (!rays || !t_max || !occluded))) return fail(PT_ERR_INVALID, "pt_trace_any: null argument");

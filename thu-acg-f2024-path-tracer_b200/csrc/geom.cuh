@@ -360,7 +360,7 @@ PT_D bool trace_closest(const DScene& S, Reload reload, double t_min, double t_m
 // the stack alone, so a caller may stop after any round (the persistent kernel does, to hand idle lanes a new ray).
 // Returns true when the stack has run dry (traversal finished).
 template <bool COUNT>
-PT_D bool blas_round(const DScene& S, const RayD& r, const BoxRay& br, float tmin_f, float& tmax_f, uint2* stack, int& sp, Closest& c,
+PT_D bool blas_round(const DScene& S, const RayD& r, const BoxRay& br, double t_min, float tmin_f, float& tmax_f, uint2* stack, int& sp, Closest& c,
                      uint32_t cur_inst, uint32_t cur_tie) {
     uint32_t pending = kNone, cur = kNone;
     while (true) {  // phase 1: wide nodes
@@ -417,19 +417,19 @@ PT_D bool blas_round(const DScene& S, const RayD& r, const BoxRay& br, float tmi
         if (!(slab(rb, br, tmin_f, tmax_f) <= tmax_f)) continue;
         if (COUNT) c.n_prims++;
         double t, u, v;
-        if (tri_t(S.tris[ref_index(rb.a)], r, 1e-3, t, u, v) && t <= c.t) { consider(c, t, rb.a, cur_inst, cur_tie, rb.b); tmax_f = __double2float_ru(c.t); }
+        if (tri_t(S.tris[ref_index(rb.a)], r, t_min, t, u, v) && t <= c.t) { consider(c, t, rb.a, cur_inst, cur_tie, rb.b); tmax_f = __double2float_ru(c.t); }
     }
     return false;
 }
 template <bool COUNT>
-PT_D void trace_blas(const DScene& S, uint32_t root_entry, const RayD& r, Closest& c, uint32_t cur_inst, uint32_t cur_tie) {
+PT_D void trace_blas(const DScene& S, uint32_t root_entry, const RayD& r, double t_min, Closest& c, uint32_t cur_inst, uint32_t cur_tie) {
     uint2 stack[kStack];
     int sp = 1;
     stack[0] = make_uint2(root_entry, 0u);  // entry distance 0: never culled
     const BoxRay br = make_boxray(r);
-    const float tmin_f = __double2float_rd(1e-3);  // Interval::new(eps, INFINITY), camera.rs:171,179
+    const float tmin_f = __double2float_rd(t_min);  // the render passes Interval::new(eps, INFINITY), camera.rs:171,179
     float tmax_f = __double2float_ru(c.t);
-    while (!blas_round<COUNT>(S, r, br, tmin_f, tmax_f, stack, sp, c, cur_inst, cur_tie)) {}
+    while (!blas_round<COUNT>(S, r, br, t_min, tmin_f, tmax_f, stack, sp, c, cur_inst, cur_tie)) {}
     c.is_light = c.ref != kNone && !(c.tie_outer >> 31);
 }
 

@@ -185,7 +185,7 @@ template <int MIN_BLOCKS, bool WIDE, bool COUNT = false, bool VOL = false, bool 
 __global__ void __launch_bounds__(kTraceBlock, MIN_BLOCKS * kBlock / kTraceBlock) k_trace(PathBuf in, uint32_t n, HitRec* __restrict__ hits, Queues q, DScene S,
                                                               unsigned long long* __restrict__ work = nullptr, uint64_t seed = 0,
                                                               const uint32_t* __restrict__ n_dev = nullptr, BlasQueues bq = BlasQueues{nullptr, nullptr, 0},
-                                                              uint2* __restrict__ ties = nullptr) {
+                                                              uint2* __restrict__ ties = nullptr, double t_min = 1e-3) {
     // batched tail iterations (api.cu): the host only knows an upper bound of the live count, the survivors counter of the
     // previous iteration (still in device memory) is the real one
     if (n_dev) n = min(n, *n_dev);
@@ -195,10 +195,10 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_BLOCKS * kBlock / kTraceBlock
     uint32_t nd = 0, dslot[kDeferMax]; float dt[kDeferMax];
     if (i < n) {
         Closest c;
-        // Interval::new(eps, INFINITY), camera.rs:171,179
-        if constexpr (VOL) trace_closest<false, COUNT, WIDE>(S, [&]() { return load_ray(in, i); }, 1e-3, 0.0, c, PathVol{seed, in.ids, i});
-        else if constexpr (DEFER) trace_closest<false, COUNT, WIDE>(S, [&]() { return load_ray(in, i); }, 1e-3, 0.0, c, NoVol(), DeferList{&nd, dslot, dt});
-        else trace_closest<false, COUNT, WIDE>(S, [&]() { return load_ray(in, i); }, 1e-3, 0.0, c);
+        // t_min: the render passes eps = 1e-3 (Interval::new(eps, INFINITY), camera.rs:171,179); ray batches pass their own
+        if constexpr (VOL) trace_closest<false, COUNT, WIDE>(S, [&]() { return load_ray(in, i); }, t_min, 0.0, c, PathVol{seed, in.ids, i});
+        else if constexpr (DEFER) trace_closest<false, COUNT, WIDE>(S, [&]() { return load_ray(in, i); }, t_min, 0.0, c, NoVol(), DeferList{&nd, dslot, dt});
+        else trace_closest<false, COUNT, WIDE>(S, [&]() { return load_ray(in, i); }, t_min, 0.0, c);
         if (COUNT) { w0 = c.n_pairs + 2 * c.n_wide; w1 = c.n_refs; w2 = c.n_prims; }  // in 64-byte units
         HitRec h; h.t = c.t; h.ref = c.ref; h.inst_light = (c.inst & 0x7FFFFFFFu) | (c.is_light ? 0x80000000u : 0u);
         hits[i] = h;
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_BLOCKS * kBlock / kTraceBlock
 // Warp-granular grid-stride loop over the compacted queue; one ray per lane.
 template <bool COUNT>
 __global__ void __launch_bounds__(kTraceBlock, 7 * kBlock / kTraceBlock) k_trace_blas(PathBuf in, uint32_t round, BlasQueues bq, HitRec* __restrict__ hits,
-                                                              uint2* __restrict__ ties, Queues q, DScene S, unsigned long long* __restrict__ work) {
+                                                              uint2* __restrict__ ties, Queues q, DScene S, unsigned long long* __restrict__ work, double t_min) {
     const uint32_t count = bq.count[round];
     const uint4* __restrict__ items = bq.items + (size_t)round * bq.stride;
     uint32_t w0 = 0, w1 = 0, w2 = 0;
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(kTraceBlock, 7 * kBlock / kTraceBlock) k_trace
                 uint32_t mesh = index, inst = kInstNone;
                 if (kind == PT_OBJ_INSTANCE) { const DInstance& ins = S.instances[index]; r = instance_local_ray(ins, r); mesh = ins.child_index; inst = index; }
                 c.n_pairs = 0; c.n_wide = 0; c.n_refs = 0; c.n_prims = 0;
-                trace_blas<COUNT>(S, S.meshes[mesh].root_entry, r, c, inst, rf.b);
+                trace_blas<COUNT>(S, S.meshes[mesh].root_entry, r, t_min, c, inst, rf.b);
                 if (COUNT) { w0 += c.n_pairs + 2 * c.n_wide; w1 += c.n_refs; w2 += c.n_prims; }
                 HitRec h; h.t = c.t; h.ref = c.ref; h.inst_light = (c.inst & 0x7FFFFFFFu) | (c.is_light ? 0x80000000u : 0u);
                 hits[i] = h;
@@ -291,12 +291,12 @@ constexpr int kBlasBurst = PT_BLAS_BURST;
 constexpr int kBlasRefillMin = PT_BLAS_REFILL_MIN;
 template <bool COUNT>
 __global__ void __launch_bounds__(kTraceBlock, kBlasMinBlocks * kBlock / kTraceBlock) k_trace_blas_refill(PathBuf in, uint32_t round, BlasQueues bq, HitRec* __restrict__ hits,
-                                                              uint2* __restrict__ ties, Queues q, DScene S, unsigned long long* __restrict__ work) {
+                                                              uint2* __restrict__ ties, Queues q, DScene S, unsigned long long* __restrict__ work, double t_min) {
     const uint32_t count = bq.count[round];
     uint32_t* __restrict__ cursor = bq.count + 4 + round;
     const uint4* __restrict__ items = bq.items + (size_t)round * bq.stride;
     const uint32_t lane = threadIdx.x & 31;
-    const float tmin_f = __double2float_rd(1e-3);
+    const float tmin_f = __double2float_rd(t_min);
     uint2 stack[kStack];
     int sp = 0;
     RayD r = make_ray(mk(0, 0, 0), mk(0, 0, 1), 0.0);
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(kTraceBlock, kBlasMinBlocks * kBlock / kTraceB
         // ---- a burst of while-while rounds
 #pragma unroll 1
         for (int s = 0; s < kBlasBurst; s++) {
-            if (active && blas_round<COUNT>(S, r, br, tmin_f, tmax_f, stack, sp, c, cur_inst, cur_tie)) {
+            if (active && blas_round<COUNT>(S, r, br, t_min, tmin_f, tmax_f, stack, sp, c, cur_inst, cur_tie)) {
                 active = false;
                 const bool is_light = c.ref != kNone && !(c.tie_outer >> 31);
                 HitRec h; h.t = c.t; h.ref = c.ref; h.inst_light = (c.inst & 0x7FFFFFFFu) | (is_light ? 0x80000000u : 0u);
@@ -629,6 +629,32 @@ __global__ void k_trace_any_batch(const pt_ray* __restrict__ rays, size_t n, dou
     RayD r; r.o = from_abi(rays[i].origin); r.d = from_abi(rays[i].direction); r.time = rays[i].time;
     Closest c;
     out[i] = trace_closest<true, false, WIDE>(S, [&]() { return r; }, t_min, t_max[i], c, BatchVol{(uint32_t)i}) ? 1 : 0;
+}
+// pt_trace_closest_wavefront: a host ray batch goes through the RENDER's traversal stage (launch_trace in api.cu: the same
+// kernels, grids and queues as a wavefront iteration).  These two kernels are only the adapters around it: rays into the
+// SoA path pool (pixel = ray index keys the media uniforms exactly as BatchVol does with seed 0), hit records back out
+// through the shade stage's own reconstruct_hit.
+__global__ void k_rays_to_pool(const pt_ray* __restrict__ rays, uint32_t n, uint32_t first, PathBuf out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    RayD r; r.o = from_abi(rays[i].origin); r.d = from_abi(rays[i].direction); r.time = rays[i].time;
+    store_path(out, i, r, mk(1, 1, 1), make_uint4(first + i, 0u, 0u, 0u));
+}
+__global__ void k_hits_to_abi(const pt_ray* __restrict__ rays, uint32_t n, const HitRec* __restrict__ hits, pt_hit* __restrict__ out, DScene S) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    RayD r; r.o = from_abi(rays[i].origin); r.d = from_abi(rays[i].direction); r.time = rays[i].time;
+    const HitRec hr = hits[i];
+    pt_hit o; memset(&o, 0, sizeof(o)); o.instance = PT_NONE;
+    if (hr.ref != kNone) {
+        const uint32_t inst = hr.inst_light & 0x7FFFFFFFu;
+        HitInfoD h;
+        reconstruct_hit(S, r, hr.ref, inst, hr.t, h);
+        o.hit = 1; o.t = hr.t; o.u = h.u; o.v = h.v; o.point = to_abi(h.point); o.geometric_normal = to_abi(h.gn); o.shading_normal = to_abi(h.sn);
+        o.prim_kind = ref_kind(hr.ref); o.prim_index = ref_index(hr.ref); o.instance = inst == kInstNone ? PT_NONE : inst;
+        o.material = h.material; o.front_face = h.front_face; o.is_light = hr.inst_light >> 31;
+    }
+    out[i] = o;
 }
 PT_D HitInfoD info_from_query(const pt_bsdf_query& q, uint32_t material) {
     HitInfoD h; h.point = from_abi(q.point); h.gn = from_abi(q.geometric_normal); h.sn = from_abi(q.shading_normal);
