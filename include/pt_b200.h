@@ -361,6 +361,10 @@ int  pt_sah_sweep(pt_ctx* ctx, uint32_t n, const double* boxes6, const double* p
 /* The environment sampler of pt_scene_build_env_sampler: direction from 2 uniforms per query and its solid-angle pdf. */
 int  pt_env_sample_pdf(pt_ctx* ctx, const pt_scene* scene, size_t n, const double* uniforms2, pt_vec3* dir, double* pdf);
 
+/* Diagnostics (profiling level 2 only): eight 64-bin histograms of per-ray / per-mesh-visit traversal work gathered by the
+ * counting kernel variants since the last reset (layout: csrc/kernels.cuh, g_hist).  out512 may be NULL. */
+int  pt_debug_histograms(pt_ctx* ctx, uint64_t* out512, int reset);
+
 #ifdef __cplusplus
 }
 #endif

@@ -445,7 +445,8 @@ def test_scheduling_knobs_do_not_change_the_image(pt, pairs, scene_id, width, sp
         assert (st.paths, st.segments, st.iterations, st.nonfinite) == (st0.paths, st0.segments, st0.iterations, st0.nonfinite), hex(flags)
         assert np.allclose(img, base, rtol=2e-5, atol=2e-6), hex(flags)
         # flags 0x100000 / 0x200000 only mean something when the two-pass path is taken (scene 6: 115 200 paths in flight)
-        assert st.two_pass_iterations == (0 if flags & 0x100000 else st0.two_pass_iterations), hex(flags)
+        # (the batched tail sizes its launches by the live count at the start of a batch, so the exact number may differ)
+        assert (st.two_pass_iterations > 0) == (st0.two_pass_iterations > 0 and not flags & 0x100000), hex(flags)
     assert st0.iterations > 8 and st0.segments > st0.paths
     assert (st0.two_pass_iterations > 0) == (scene_id == 6)
 

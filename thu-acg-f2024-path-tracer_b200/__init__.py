@@ -72,7 +72,7 @@ ABI_SYMBOLS = ["pt_ctx_create", "pt_ctx_destroy", "pt_ctx_set_stream", "pt_ctx_s
                "pt_scene_create", "pt_scene_destroy", "pt_scene_device_bytes", "pt_camera_image_height", "pt_render_accumulate",
                "pt_render", "pt_tonemap_rgb8", "pt_trace_closest", "pt_trace_any", "pt_bsdf_eval_pdf", "pt_bsdf_sample",
                "pt_camera_rays", "pt_lights_sample_pdf", "pt_scene_build_env_sampler", "pt_env_sample_pdf", "pt_sah_sweep",
-               "pt_render_multi", "pt_trace_closest_wavefront"]
+               "pt_render_multi", "pt_trace_closest_wavefront", "pt_debug_histograms"]
 
 
 class PtError(RuntimeError):
@@ -453,6 +453,13 @@ class Context:
 
     def upload(self, scene):
         return DeviceScene(self, scene)
+
+    def histograms(self, reset=True):
+        """pt_debug_histograms: [8, 64] counters of the profiling-level-2 kernel variants since the last reset."""
+        out = np.zeros((8, 64), dtype=np.uint64)
+        self.lib.pt_debug_histograms.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        self._check(self.lib.pt_debug_histograms(self.ptr, _ptr(out), int(reset)))
+        return out
 
     def close(self):
         if self.ptr:

@@ -9,7 +9,7 @@
 #include <thread>
 #include <vector>
 
-#include "kernels.cuh"
+#include "launch.h"
 
 using namespace ptd;
 
@@ -761,38 +761,21 @@ static void launch_trace(const TraceStage& T, const PathBuf& in, uint32_t n, con
     // two-pass traversal; not for small iterations (three more launches each); flag 0x100000 opts out (A/B measurements)
     if (scene->defer_meshes && n >= (1u << 16) && !(T.flags & 0x100000u)) {
         const BlasQueues bq{ctx->bq_items, q.count + 8, ctx->pool};  // counters in the free tail of the iteration's slot
-        if (wk) k_trace<7, true, true, false, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, 0, n_dev, bq, ctx->ties, T.t_min);
-        else k_trace<7, true, false, false, true><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, nullptr, 0, n_dev, bq, ctx->ties, T.t_min);
-        const unsigned bg = std::min<unsigned>(tg, 148u * 56u);
+        run_k_trace(TraceFlavour{7, true, wk != nullptr, false, true}, tg, st, in, n, ctx->hits, q, scene->d, wk, 0, n_dev, bq, ctx->ties, T.t_min);
         const bool refill = !(T.flags & 0x200000u);  // flag 0x200000: plain grid-stride rounds instead of persistent lanes with refill
-        const unsigned pg = std::min<unsigned>(tg, 148u * 4u * (unsigned)kBlasMinBlocks);  // persistent: one resident warp per slot
-        for (uint32_t r = 0; r < (uint32_t)kDeferMax; r++) {
-            if (refill) {
-                if (wk) k_trace_blas_refill<true><<<pg, kTraceBlock, 0, st>>>(in, r, bq, ctx->hits, ctx->ties, q, scene->d, wk, T.t_min);
-                else k_trace_blas_refill<false><<<pg, kTraceBlock, 0, st>>>(in, r, bq, ctx->hits, ctx->ties, q, scene->d, nullptr, T.t_min);
-            } else if (wk) k_trace_blas<true><<<bg, kTraceBlock, 0, st>>>(in, r, bq, ctx->hits, ctx->ties, q, scene->d, wk, T.t_min);
-            else k_trace_blas<false><<<bg, kTraceBlock, 0, st>>>(in, r, bq, ctx->hits, ctx->ties, q, scene->d, nullptr, T.t_min);
-        }
+        const unsigned grid = refill ? std::min<unsigned>(tg, 148u * 4u * (unsigned)kBlasMinBlocks)  // persistent: one resident warp per slot
+                                     : std::min<unsigned>(tg, 148u * 56u);
+        for (uint32_t r = 0; r < (uint32_t)kDeferMax; r++)
+            run_k_trace_blas(refill, wk != nullptr, grid, st, in, r, bq, ctx->hits, ctx->ties, q, scene->d, wk, T.t_min);
         S.kernel_launches += 1 + kDeferMax;
         S.two_pass_iterations++;
         return;
     }
-    const BlasQueues nobq{nullptr, nullptr, 0};
-#define PT_TRACE(...) k_trace<__VA_ARGS__><<<tg, kTraceBlock, 0, st>>>(in, n, ctx->hits, q, scene->d, wk, T.seed, n_dev, nobq, nullptr, T.t_min)
-    if (scene->has_volumes) {  // media: the trace kernel variant that draws keyed free-flight uniforms
-        if (scene->wide) { if (wk) PT_TRACE(6, true, true, true); else PT_TRACE(6, true, false, true); }
-        else { if (wk) PT_TRACE(6, false, true, true); else PT_TRACE(6, false, false, true); }
-    } else if (wk) {
-        if (scene->wide) PT_TRACE(6, true, true); else PT_TRACE(6, false, true);
-    } else if (!scene->wide) PT_TRACE(6, false);  // 80 regs (72: -2 % .. +1.5 %)
-    else switch ((T.flags >> 4) & 7u) {  // experiment knob: resident blocks per SM the compiler must allow (register cap)
-        case 4: PT_TRACE(4, true); break;  // 120 regs
-        case 5: PT_TRACE(5, true); break;  // 96 regs
-        case 6: PT_TRACE(6, true); break;  // 80 regs
-        case 7: PT_TRACE(8, true); break;  // 64 regs, spills
-        default: PT_TRACE(7, true);        // 72 regs, 28 warps/SM (measured best: +2 % over 80)
-    }
-#undef PT_TRACE
+    // fused kernel; for 4-wide scenes flags bits 4-6 pick the register cap (experiment knob): 4: 120, 5: 96, 6: 80, 7: 64 registers
+    const uint32_t knob = (T.flags >> 4) & 7u;
+    const int min_blocks = !scene->wide || scene->has_volumes || wk ? 6 : knob == 7 ? 8 : knob >= 4 ? (int)knob : 7;
+    run_k_trace(TraceFlavour{min_blocks, scene->wide, wk != nullptr, scene->has_volumes, false}, tg, st, in, n, ctx->hits, q, scene->d, wk, T.seed,
+                n_dev, BlasQueues{nullptr, nullptr, 0}, nullptr, T.t_min);
     S.kernel_launches++;
 }
 
@@ -835,19 +818,18 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
     auto launch_shades = [&](const PathBuf& in, const PathBuf& outb, uint32_t n, const Queues& q, uint32_t* out_count, bool fork) -> int {
         const unsigned sg = std::min<unsigned>((n + kBlock - 1) / kBlock, 148u * 16u);
         if (fork) CU(cudaEventRecord(ctx->ev_fork, st));
-#define PT_SHADE(CLS)                                                                                                                    \
-        if (scene->class_mask & (1u << CLS)) {                                                                                           \
-            cudaStream_t ss = fork ? ctx->shade_stream[CLS] : st;                                                                        \
-            if (fork) CU(cudaStreamWaitEvent(ss, ctx->ev_fork, 0));                                                                      \
-            if (nee) k_shade_nee<CLS><<<sg, kBlock, 0, ss>>>(in, q, ctx->hits, outb, out_count, d_accum, ctx->d_nonfinite, scene->d, dcam, rcst);    \
-            else if (rcst.env_importance) k_shade<CLS, 3><<<sg, kBlock, 0, ss>>>(in, q, ctx->hits, outb, out_count, d_accum, ctx->d_nonfinite, scene->d, dcam, rcst);  \
-            else if (scene->general_lights) k_shade<CLS, 2><<<sg, kBlock, 0, ss>>>(in, q, ctx->hits, outb, out_count, d_accum, ctx->d_nonfinite, scene->d, dcam, rcst); \
-            else k_shade<CLS, 0><<<sg, kBlock, 0, ss>>>(in, q, ctx->hits, outb, out_count, d_accum, ctx->d_nonfinite, scene->d, dcam, rcst); \
-            if (fork) { CU(cudaEventRecord(ctx->ev_join[CLS], ss)); CU(cudaStreamWaitEvent(st, ctx->ev_join[CLS], 0)); }                 \
-            S.kernel_launches++;                                                                                                         \
+        const ShadeArgs sa{in, q, ctx->hits, outb, out_count, d_accum, ctx->d_nonfinite, scene->d, dcam, rcst};
+        for (int cls = 0; cls < N_CLS; cls++) {
+            if (!(scene->class_mask & (1u << cls))) continue;
+            cudaStream_t ss = fork ? ctx->shade_stream[cls] : st;
+            if (fork) CU(cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
+            if (nee) run_k_shade_nee(cls, sg, ss, sa);
+            else if (rcst.env_importance) run_k_shade_var(cls, 3, sg, ss, sa);
+            else if (scene->general_lights) run_k_shade_var(cls, 2, sg, ss, sa);
+            else run_k_shade_ref(cls, sg, ss, sa);
+            if (fork) { CU(cudaEventRecord(ctx->ev_join[cls], ss)); CU(cudaStreamWaitEvent(st, ctx->ev_join[cls], 0)); }
+            S.kernel_launches++;
         }
-        PT_SHADE(CLS_MISS) PT_SHADE(CLS_LIGHT) PT_SHADE(CLS_DIFFUSE) PT_SHADE(CLS_METAL) PT_SHADE(CLS_GLASS) PT_SHADE(CLS_PRINCIPLED) PT_SHADE(CLS_OTHER)
-#undef PT_SHADE
         return PT_OK;
     };
     // flag 0x4000: opt out of the batched tail (A/B measurements)
@@ -878,7 +860,7 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
         if (nee) n_new = std::min<uint32_t>(n_new, pool / 2 > live_spawning ? pool / 2 - live_spawning : 0u);
         if (ctx->profiling) CU(cudaEventRecord(ctx->evs[0], st));
         if (n_new) {
-            k_generate<<<(n_new + kBlock - 1) / kBlock, kBlock, 0, st>>>(in, live, n_new, generated, n_pixels, dcam, rcst);
+            run_k_generate(st, in, live, n_new, generated, n_pixels, dcam, rcst);
             S.kernel_launches++;
         }
         const uint32_t n = live + n_new;
@@ -928,7 +910,7 @@ int pt_render(pt_ctx* ctx, const pt_scene* scene, const pt_camera* cam, const pt
     cudaError_t e = cudaMemsetAsync(d_accum, 0, n * sizeof(float), ctx->stream);
     int rc = e == cudaSuccess ? pt_render_accumulate(ctx, scene, cam, p, d_accum, stats) : fail(PT_ERR_CUDA, cudaGetErrorString(e));
     if (rc == PT_OK) {
-        k_scale<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_accum, 1.0f / (float)p->sample_count, (uint32_t)n, d_accum);
+        run_k_scale(ctx->stream, d_accum, 1.0f / (float)p->sample_count, (uint32_t)n, d_accum);
         e = cudaMemcpyAsync(h_mean, d_accum, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) rc = fail(PT_ERR_CUDA, cudaGetErrorString(e));
@@ -1024,7 +1006,7 @@ int pt_tonemap_rgb8(pt_ctx* ctx, const float* d_accum, double scale, uint32_t n_
     int rcs = ensure_scratch(ctx, n);
     if (rcs) return rcs;
     uint8_t* d_out = (uint8_t*)ctx->scratch;
-    k_tonemap<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_accum, scale, n, d_out);
+    run_k_tonemap(ctx->stream, d_accum, scale, n, d_out);
     cudaError_t e = cudaMemcpyAsync(h_rgb8, d_out, n, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) return fail(PT_ERR_CUDA, cudaGetErrorString(e));
@@ -1042,7 +1024,6 @@ struct DevBuf {
     int from_host(const void* h, size_t bytes, cudaStream_t st) { int rc = alloc(bytes); if (rc) return rc; if (bytes) CU(cudaMemcpyAsync(p, h, bytes, cudaMemcpyHostToDevice, st)); return PT_OK; }
     int to_host(void* h, size_t bytes, cudaStream_t st) { if (bytes) CU(cudaMemcpyAsync(h, p, bytes, cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st)); CU(cudaGetLastError()); return PT_OK; }
 };
-unsigned grid_for(size_t n) { return (unsigned)((n + 127) / 128); }
 }  // namespace
 
 extern "C" {
@@ -1053,8 +1034,7 @@ int pt_trace_closest(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_ray*
     CU(cudaSetDevice(ctx->device));
     DevBuf in, out; int rc;
     if ((rc = in.from_host(rays, n * sizeof(pt_ray), ctx->stream)) || (rc = out.alloc(n * sizeof(pt_hit)))) return rc;
-    if (scene->wide) k_trace_batch<true><<<grid_for(n), 128, 0, ctx->stream>>>((const pt_ray*)in.p, n, t_min, (pt_hit*)out.p, scene->d);
-    else k_trace_batch<false><<<grid_for(n), 128, 0, ctx->stream>>>((const pt_ray*)in.p, n, t_min, (pt_hit*)out.p, scene->d);
+    run_k_trace_batch(scene->wide, ctx->stream, (const pt_ray*)in.p, n, t_min, (pt_hit*)out.p, scene->d);
     return out.to_host(hits, n * sizeof(pt_hit), ctx->stream);
 }
 int pt_trace_closest_wavefront(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_ray* rays, double t_min, uint32_t flags, pt_hit* hits, pt_stats* stats) {
@@ -1078,11 +1058,11 @@ int pt_trace_closest_wavefront(pt_ctx* ctx, const pt_scene* scene, size_t n, con
     for (size_t first = 0; first < n; first += chunk) {
         const uint32_t m = (uint32_t)std::min<size_t>(chunk, n - first);
         CU(cudaMemcpyAsync(in.p, rays + first, (size_t)m * sizeof(pt_ray), cudaMemcpyHostToDevice, st));
-        k_rays_to_pool<<<(m + 127) / 128, 128, 0, st>>>((const pt_ray*)in.p, m, (uint32_t)first, pool);
+        run_k_rays_to_pool(st, (const pt_ray*)in.p, m, (uint32_t)first, pool);
         CU(cudaMemsetAsync(ctx->d_count, 0, kSlot * sizeof(uint32_t), st));
         const Queues q{ctx->q_items, ctx->d_count + 4, ctx->pool};
         launch_trace(T, pool, m, q, nullptr);
-        k_hits_to_abi<<<(m + 127) / 128, 128, 0, st>>>((const pt_ray*)in.p, m, ctx->hits, (pt_hit*)out.p, scene->d);
+        run_k_hits_to_abi(st, (const pt_ray*)in.p, m, ctx->hits, (pt_hit*)out.p, scene->d);
         if ((rc = out.to_host(hits + first, (size_t)m * sizeof(pt_hit), st))) return rc;
         S.segments += m; S.iterations++; S.kernel_launches += 2;
     }
@@ -1095,14 +1075,20 @@ int pt_trace_closest_wavefront(pt_ctx* ctx, const pt_scene* scene, size_t n, con
     if (stats) *stats = S;
     return PT_OK;
 }
+int pt_debug_histograms(pt_ctx* ctx, uint64_t* out512, int reset) {
+    if (!ctx) return fail(PT_ERR_INVALID, "pt_debug_histograms: null ctx");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(debug_histograms((unsigned long long*)out512, reset != 0));
+    return PT_OK;
+}
 int pt_trace_any(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_ray* rays, double t_min, const double* t_max, uint8_t* occluded) {
     if (!ctx || !scene || (n && (!rays || !t_max || !occluded))) return fail(PT_ERR_INVALID, "pt_trace_any: null argument");
     if (n == 0) return PT_OK;
     CU(cudaSetDevice(ctx->device));
     DevBuf in, tm, out; int rc;
     if ((rc = in.from_host(rays, n * sizeof(pt_ray), ctx->stream)) || (rc = tm.from_host(t_max, n * 8, ctx->stream)) || (rc = out.alloc(n))) return rc;
-    if (scene->wide) k_trace_any_batch<true><<<grid_for(n), 128, 0, ctx->stream>>>((const pt_ray*)in.p, n, t_min, (const double*)tm.p, (uint8_t*)out.p, scene->d);
-    else k_trace_any_batch<false><<<grid_for(n), 128, 0, ctx->stream>>>((const pt_ray*)in.p, n, t_min, (const double*)tm.p, (uint8_t*)out.p, scene->d);
+    run_k_trace_any_batch(scene->wide, ctx->stream, (const pt_ray*)in.p, n, t_min, (const double*)tm.p, (uint8_t*)out.p, scene->d);
     return out.to_host(occluded, n, ctx->stream);
 }
 int pt_bsdf_eval_pdf(pt_ctx* ctx, const pt_scene* scene, uint32_t material, size_t n, const pt_bsdf_query* q, pt_bsdf_result* o) {
@@ -1112,7 +1098,7 @@ int pt_bsdf_eval_pdf(pt_ctx* ctx, const pt_scene* scene, uint32_t material, size
     CU(cudaSetDevice(ctx->device));
     DevBuf in, out; int rc;
     if ((rc = in.from_host(q, n * sizeof(pt_bsdf_query), ctx->stream)) || (rc = out.alloc(n * sizeof(pt_bsdf_result)))) return rc;
-    k_bsdf_eval<<<grid_for(n), 128, 0, ctx->stream>>>(material, n, (const pt_bsdf_query*)in.p, (pt_bsdf_result*)out.p, scene->d);
+    run_k_bsdf_eval(ctx->stream, material, n, (const pt_bsdf_query*)in.p, (pt_bsdf_result*)out.p, scene->d);
     return out.to_host(o, n * sizeof(pt_bsdf_result), ctx->stream);
 }
 int pt_bsdf_sample(pt_ctx* ctx, const pt_scene* scene, uint32_t material, size_t n, const pt_bsdf_query* q, const double* uniforms8, pt_bsdf_sample_result* o) {
@@ -1122,7 +1108,7 @@ int pt_bsdf_sample(pt_ctx* ctx, const pt_scene* scene, uint32_t material, size_t
     CU(cudaSetDevice(ctx->device));
     DevBuf in, un, out; int rc;
     if ((rc = in.from_host(q, n * sizeof(pt_bsdf_query), ctx->stream)) || (rc = un.from_host(uniforms8, n * 64, ctx->stream)) || (rc = out.alloc(n * sizeof(pt_bsdf_sample_result)))) return rc;
-    k_bsdf_sample<<<grid_for(n), 128, 0, ctx->stream>>>(material, n, (const pt_bsdf_query*)in.p, (const double*)un.p, (pt_bsdf_sample_result*)out.p, scene->d);
+    run_k_bsdf_sample(ctx->stream, material, n, (const pt_bsdf_query*)in.p, (const double*)un.p, (pt_bsdf_sample_result*)out.p, scene->d);
     return out.to_host(o, n * sizeof(pt_bsdf_sample_result), ctx->stream);
 }
 int pt_camera_rays(pt_ctx* ctx, const pt_camera* cam, uint64_t seed, size_t n, const uint32_t* row, const uint32_t* col, const uint32_t* sample, pt_ray* o) {
@@ -1134,7 +1120,7 @@ int pt_camera_rays(pt_ctx* ctx, const pt_camera* cam, uint64_t seed, size_t n, c
     if (rc) return rc;
     DevBuf r, cc, s, out;
     if ((rc = r.from_host(row, n * 4, ctx->stream)) || (rc = cc.from_host(col, n * 4, ctx->stream)) || (rc = s.from_host(sample, n * 4, ctx->stream)) || (rc = out.alloc(n * sizeof(pt_ray)))) return rc;
-    k_camera_rays<<<grid_for(n), 128, 0, ctx->stream>>>(dcam, seed, n, (const uint32_t*)r.p, (const uint32_t*)cc.p, (const uint32_t*)s.p, (pt_ray*)out.p);
+    run_k_camera_rays(ctx->stream, dcam, seed, n, (const uint32_t*)r.p, (const uint32_t*)cc.p, (const uint32_t*)s.p, (pt_ray*)out.p);
     return out.to_host(o, n * sizeof(pt_ray), ctx->stream);
 }
 int pt_lights_sample_pdf(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_vec3* origin, const double* time, const double* uniforms4, pt_vec3* dir, uint32_t* valid, double* pdf) {
@@ -1144,7 +1130,7 @@ int pt_lights_sample_pdf(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_
     DevBuf o, t, u, dd, vv, pp; int rc;
     if ((rc = o.from_host(origin, n * 24, ctx->stream)) || (rc = t.from_host(time, n * 8, ctx->stream)) || (rc = u.from_host(uniforms4, n * 32, ctx->stream)) ||
         (rc = dd.alloc(n * 24)) || (rc = vv.alloc(n * 4)) || (rc = pp.alloc(n * 8))) return rc;
-    k_lights<<<grid_for(n), 128, 0, ctx->stream>>>(n, (const pt_vec3*)o.p, (const double*)t.p, (const double*)u.p, (pt_vec3*)dd.p, (uint32_t*)vv.p, (double*)pp.p, scene->d);
+    run_k_lights(ctx->stream, n, (const pt_vec3*)o.p, (const double*)t.p, (const double*)u.p, (pt_vec3*)dd.p, (uint32_t*)vv.p, (double*)pp.p, scene->d);
     if ((rc = dd.to_host(dir, n * 24, ctx->stream)) || (rc = vv.to_host(valid, n * 4, ctx->stream)) || (rc = pp.to_host(pdf, n * 8, ctx->stream))) return rc;
     return PT_OK;
 }
@@ -1156,7 +1142,7 @@ int pt_sah_sweep(pt_ctx* ctx, uint32_t n, const double* boxes6, const double* pa
     DevBuf b, c; int rc;
     if ((rc = b.from_host(boxes6, (size_t)n * sizeof(SahBox), ctx->stream)) || (rc = c.alloc((size_t)n * 3 * sizeof(double)))) return rc;
     SahBox parent; memcpy(&parent, parent6, sizeof(parent));
-    k_sah_sweep<<<(3u * n + kSahTile - 1) / kSahTile, kSahTile, 0, ctx->stream>>>(n, (const SahBox*)b.p, parent, (double*)c.p);
+    run_k_sah_sweep(ctx->stream, n, (const SahBox*)b.p, parent, (double*)c.p);
     return c.to_host(cost3n, (size_t)n * 3 * sizeof(double), ctx->stream);
 }
 int pt_env_sample_pdf(pt_ctx* ctx, const pt_scene* scene, size_t n, const double* uniforms2, pt_vec3* dir, double* pdf) {
@@ -1166,7 +1152,7 @@ int pt_env_sample_pdf(pt_ctx* ctx, const pt_scene* scene, size_t n, const double
     CU(cudaSetDevice(ctx->device));
     DevBuf u, dd, pp; int rc;
     if ((rc = u.from_host(uniforms2, n * 16, ctx->stream)) || (rc = dd.alloc(n * 24)) || (rc = pp.alloc(n * 8))) return rc;
-    k_env<<<grid_for(n), 128, 0, ctx->stream>>>(n, (const double*)u.p, (pt_vec3*)dd.p, (double*)pp.p, scene->env);
+    run_k_env(ctx->stream, n, (const double*)u.p, (pt_vec3*)dd.p, (double*)pp.p, scene->env);
     if ((rc = dd.to_host(dir, n * 24, ctx->stream)) || (rc = pp.to_host(pdf, n * 8, ctx->stream))) return rc;
     return PT_OK;
 }

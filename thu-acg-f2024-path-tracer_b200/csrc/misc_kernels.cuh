@@ -1,0 +1,136 @@
+// Ray generation, tonemap and the parity / test entry kernels — compiled by misc.cu only.
+#pragma once
+#include "wavefront.cuh"
+
+namespace ptd {
+
+// g = global index of the path within this render call: sample-major so that consecutive threads take
+// neighbouring pixels of the same sample (coherent primary rays).
+__global__ void __launch_bounds__(kBlock) k_generate(PathBuf out, uint32_t slot0, uint32_t n_new, uint64_t g0, uint32_t n_pixels,
+                                                      DCameraEx cam, RenderConst rc) {
+    uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n_new) return;
+    uint64_t g = g0 + i;
+    uint32_t s_local = (uint32_t)(g / n_pixels), pix = (uint32_t)(g % n_pixels);
+    if ((cam.c.width & 7u) == 0 && (cam.c.height & 3u) == 0) {  // a warp covers an 8x4 pixel tile: tighter ray bundles than a 32x1 strip
+        const uint32_t tile = pix >> 5, within = pix & 31u, tiles_x = cam.c.width >> 3;
+        pix = ((tile / tiles_x) * 4u + (within >> 3)) * cam.c.width + (tile % tiles_x) * 8u + (within & 7u);
+    }
+    uint32_t sample = rc.sample_begin + s_local * rc.sample_stride;
+    Rng rng; rng.init(rc.seed, pix, sample, 0);
+    RayD r = generate_ray(cam, pix / cam.c.width, pix % cam.c.width, rng);
+    store_path(out, slot0 + i, r, mk(1, 1, 1), make_uint4(pix, sample, rng.used, 0));
+}
+
+// sqrt-gamma + 8-bit quantisation of camera.rs:109-114,128-130 on `scale * accum`
+__global__ void k_tonemap(const float* __restrict__ accum, double scale, uint32_t n_values, uint8_t* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_values) return;
+    double x = (double)accum[i] * scale;
+    double g = sqrt(fmax(x, 0.0));
+    double v = clampd(g, 0.0, 0.999) * 256.0;
+    out[i] = (v != v) ? 0 : (uint8_t)v;
+}
+__global__ void k_scale(const float* __restrict__ accum, float scale, uint32_t n_values, float* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_values) out[i] = accum[i] * scale;
+}
+
+PT_D HitInfoD info_from_query(const pt_bsdf_query& q, uint32_t material) {
+    HitInfoD h; h.point = from_abi(q.point); h.gn = from_abi(q.geometric_normal); h.sn = from_abi(q.shading_normal);
+    h.t = 0; h.u = q.u; h.v = q.v; h.front_face = q.front_face != 0; h.material = material;
+    return h;
+}
+__global__ void k_bsdf_eval(uint32_t material, size_t n, const pt_bsdf_query* __restrict__ q, pt_bsdf_result* __restrict__ out, DScene S) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    HitInfoD h = info_from_query(q[i], material);
+    d3 f; double pdf;
+    bsdf_eval_pdf(S, material, from_abi(q[i].view_dir), from_abi(q[i].light_dir), h, f, pdf);
+    pt_bsdf_result r; r.eval = to_abi(f); r.pdf = pdf; r.emitted = to_abi(bsdf_emitted(S, material, h.u, h.v, h.point)); r._pad = 0;
+    out[i] = r;
+}
+__global__ void k_bsdf_sample(uint32_t material, size_t n, const pt_bsdf_query* __restrict__ q, const double* __restrict__ uniforms8,
+                              pt_bsdf_sample_result* __restrict__ out, DScene S) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    HitInfoD h = info_from_query(q[i], material);
+    Rng rng; rng.init_array(uniforms8 + 8 * i, 8);
+    d3 dir = mk(0, 0, 0);
+    bool ok = bsdf_sample(S, material, -from_abi(q[i].view_dir), h, rng, dir);
+    pt_bsdf_sample_result r; r.dir = ok ? to_abi(dir) : to_abi(mk(0, 0, 0)); r.valid = ok; r.n_uniforms = rng.used;
+    out[i] = r;
+}
+__global__ void k_camera_rays(DCameraEx cam, uint64_t seed, size_t n, const uint32_t* __restrict__ row, const uint32_t* __restrict__ col,
+                              const uint32_t* __restrict__ sample, pt_ray* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Rng rng; rng.init(seed, row[i] * cam.c.width + col[i], sample[i], 0);
+    RayD r = generate_ray(cam, row[i], col[i], rng);
+    pt_ray o; o.origin = to_abi(r.o); o.direction = to_abi(r.d); o.time = r.time;
+    out[i] = o;
+}
+__global__ void k_lights(size_t n, const pt_vec3* __restrict__ origin, const double* __restrict__ time, const double* __restrict__ uniforms4,
+                         pt_vec3* __restrict__ dir, uint32_t* __restrict__ valid, double* __restrict__ pdf, DScene S) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Rng rng; rng.init_array(uniforms4 + 4 * i, 4);
+    d3 d = mk(0, 0, 0);
+    bool ok = lights_sample(S, from_abi(origin[i]), time[i], rng, d);
+    valid[i] = ok; dir[i] = to_abi(ok ? d : mk(0, 0, 0));
+    pdf[i] = ok ? lights_pdf(S, from_abi(origin[i]), d, time[i]) : 0.0;
+}
+
+// ---- exact SAH sweep of bvh.rs:54-120 for one node (the step before the path).  Thread (axis, k) folds all
+// n items in list order into a left / right box exactly as BVH::evaluate_sah does (AABB::union pads 1e-3 on EVERY union,
+// aabb.rs:16-25, so the fold order is part of the result) and prices the split at item k's centroid.  O(n^2) work like the
+// reference, but 3n folds run at once; items are staged through shared memory, every thread reads the same item (broadcast).
+PT_D void sah_merge(SahBox& b, const SahBox& o) {  // AABB::union -> AABB::new(min, max) with its padding
+    for (int a = 0; a < 3; a++) {
+        const double mn = fmin(b.lo[a], o.lo[a]), mx = fmax(b.hi[a], o.hi[a]);
+        b.lo[a] = fmin(mn, mx) - 1e-3; b.hi[a] = fmax(mn, mx) + 1e-3;
+    }
+}
+PT_D double sah_half_area(const SahBox& b) {
+    const double ex = b.hi[0] - b.lo[0], ey = b.hi[1] - b.lo[1], ez = b.hi[2] - b.lo[2];
+    return ex * ey + ex * ez + ey * ez;
+}
+__global__ void __launch_bounds__(kSahTile) k_sah_sweep(uint32_t n, const SahBox* __restrict__ boxes, SahBox parent, double* __restrict__ cost) {
+    __shared__ SahBox tile[kSahTile];
+    const uint32_t t = blockIdx.x * kSahTile + threadIdx.x;
+    const bool active = t < 3u * n;
+    const uint32_t axis = active ? t / n : 0u, k = active ? t % n : 0u;
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    const double split = 0.5 * (boxes[k].lo[axis] + boxes[k].hi[axis]);  // AABB::centroid
+    SahBox lb, rb;
+    for (int a = 0; a < 3; a++) { lb.lo[a] = rb.lo[a] = inf; lb.hi[a] = rb.hi[a] = -inf; }
+    uint32_t lc = 0, rc = 0;
+    for (uint32_t base = 0; base < n; base += kSahTile) {
+        const uint32_t m = min((uint32_t)kSahTile, n - base);
+        __syncthreads();
+        if (threadIdx.x < m) tile[threadIdx.x] = boxes[base + threadIdx.x];
+        __syncthreads();
+        for (uint32_t i = 0; i < m; i++) {
+            const SahBox& o = tile[i];
+            if (0.5 * (o.lo[axis] + o.hi[axis]) < split) { sah_merge(lb, o); lc++; } else { sah_merge(rb, o); rc++; }
+        }
+    }
+    if (!active) return;
+    double c = inf;
+    if (lc != 0 && rc != 0) {
+        const double v = sah_half_area(lb) * (double)lc + sah_half_area(rb) * (double)rc;
+        const double parent_cost = sah_half_area(parent) * (double)n;
+        if (v > 0.0 && v < parent_cost) c = v;
+    }
+    cost[t] = c;
+}
+
+__global__ void k_env(size_t n, const double* __restrict__ uniforms2, pt_vec3* __restrict__ dir, double* __restrict__ pdf, DEnvDist E) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const d3 d = env_sample(E, uniforms2[2 * i], uniforms2[2 * i + 1]);
+    dir[i] = to_abi(d);
+    pdf[i] = env_pdf(E, d);
+}
+
+}  // namespace ptd

@@ -1,0 +1,226 @@
+// Shade-stage kernels (the loop body of Camera::trace after intersect_all, camera.rs:180-225) — templates instantiated by shade_*.cu.
+#pragma once
+#include "wavefront.cuh"
+
+namespace ptd {
+
+PT_D void add_radiance(float* __restrict__ accum, uint32_t pix, d3 v, uint32_t nan_policy, unsigned long long* nonfinite, bool& dead) {
+    if (!finite3(v)) {
+        atomicAdd(nonfinite, 1ull);
+        if (nan_policy == PT_NAN_DROP) { dead = true; return; }  // drop the contribution and end the path
+    }
+    if (v.x != 0.0) atomicAdd(accum + 3ull * pix, (float)v.x);
+    if (v.y != 0.0) atomicAdd(accum + 3ull * pix + 1, (float)v.y);
+    if (v.z != 0.0) atomicAdd(accum + 3ull * pix + 2, (float)v.z);
+}
+
+template <int CLS> struct ClassKind { static constexpr int value = -1; };
+template <> struct ClassKind<CLS_LIGHT> { static constexpr int value = PT_MAT_LIGHT; };
+template <> struct ClassKind<CLS_DIFFUSE> { static constexpr int value = PT_MAT_DIFFUSE; };
+template <> struct ClassKind<CLS_METAL> { static constexpr int value = PT_MAT_METAL; };
+template <> struct ClassKind<CLS_GLASS> { static constexpr int value = PT_MAT_GLASS; };
+template <> struct ClassKind<CLS_PRINCIPLED> { static constexpr int value = PT_MAT_PRINCIPLED; };
+
+// One loop iteration of Camera::trace after intersect_all (camera.rs:180-225) for the paths of ONE shade class.
+// Grid-stride over the class queue; survivors are written compacted into `out` (ballot + block prefix + one atomic).
+// VAR bit 0: environment importance sampling joins the mixture; bit 1: World.lights holds more than quads and spheres
+// (cuboid / mesh / instance lights).  The reference's shipped scenes need neither, and their kernels carry none of that code.
+template <int CLS, int VAR = 0>
+__global__ void __launch_bounds__(kBlock, PT_SHADE_MIN_BLOCKS) k_shade(PathBuf in, Queues q, const HitRec* __restrict__ hits, PathBuf out,
+                                                    uint32_t* __restrict__ out_count, float* __restrict__ accum,
+                                                    unsigned long long* __restrict__ nonfinite, DScene S, DCameraEx cam, RenderConst rc) {
+    constexpr int K = ClassKind<CLS>::value;
+    const uint32_t count = q.count[CLS];
+    const uint32_t* __restrict__ items = q.items + (size_t)CLS * q.stride;
+    __shared__ uint32_t bin_count[8][kBlock / 32];  // survivors per (octant bin, warp), then their exclusive prefix
+    __shared__ uint32_t block_base;
+    for (uint32_t base = blockIdx.x * kBlock; base < count; base += gridDim.x * kBlock) {
+        const uint32_t j = base + threadIdx.x;
+        bool alive = false;
+        RayD next; d3 thr = mk(0, 0, 0); uint4 ids = make_uint4(0, 0, 0, 0);
+        if (j < count) {
+            const uint32_t i = items[j];
+            RayD ray = load_ray(in, i);
+            thr = mk(in.f[7][i], in.f[8][i], in.f[9][i]);
+            ids = in.ids[i];
+            const uint32_t pix = ids.x, bounces = ids.z >> 16;
+            bool dead = false;
+            if (CLS == CLS_MISS) {  // camera.rs:180-183
+                add_radiance(accum, pix, thr * sample_environment(S, cam.c, ray.d), rc.nan_policy, nonfinite, dead);
+            } else {
+                const HitRec hr = hits[i];
+                Rng rng; rng.init(rc.seed, pix, ids.y, ids.z & 0xFFFFu);
+                HitInfoD h;
+                reconstruct_hit<false>(S, ray, hr.ref, hr.inst_light & 0x7FFFFFFFu, hr.t, h);
+                const DMaterial& m = S.materials[h.material];
+                // camera.rs:186-187: `radiance += throughput * emitted` runs for every hit; for non-emitters it only
+                // matters when the throughput is already inf/NaN (inf * 0 = NaN poisons the pixel, Q32).
+                if (CLS == CLS_LIGHT || !finite3(thr)) {
+                    d3 em = CLS == CLS_LIGHT ? texture_value(S, m.base_color_tex, h.u, h.v, h.point) : mk(0, 0, 0);
+                    add_radiance(accum, pix, thr * em, rc.nan_policy, nonfinite, dead);
+                }
+                bool go = !dead;
+                if (go && bounces > 5) {  // Russian roulette, camera.rs:190-196
+                    double p = clampd(luminance(thr), 0.01, 1.0);
+                    if (rng.next() > p) go = false;
+                    else thr = thr / p;
+                }
+                if (go) {
+                    // camera.rs:199-200: p_light = 0.5 iff lights exist.  With PT_RENDER_ENV_IMPORTANCE (ours) the environment map
+                    // joins the mixture as a third sampler: p_bsdf = 0.5, the other half is split between lights and environment.
+                    constexpr bool env_is = (VAR & 1) != 0, GEN = (VAR & 2) != 0;
+                    const double p_env = env_is ? (S.n_lights == 0 ? 0.5 : 0.25) : 0.0;
+                    const double p_light = S.n_lights == 0 ? 0.0 : 0.5 - p_env, p_bsdf = env_is ? 0.5 : 1.0 - p_light;
+                    const double rsel = rng.next();
+                    d3 dir;
+                    bool ok;
+                    if (rsel < p_light) ok = lights_sample<GEN>(S, h.point, ray.time, rng, dir);
+                    else if (env_is && rsel < p_light + p_env) { const double u1 = rng.next(), u2 = rng.next(); dir = env_sample(rc.env, u1, u2); ok = true; }
+                    else ok = bsdf_sample<K>(S, h.material, ray.d, h, rng, dir);
+                    if (ok) {  // camera.rs:212-225
+                        d3 f; double bsdf_pdf;
+                        bsdf_eval_pdf<K>(S, h.material, -ray.d, dir, h, f, bsdf_pdf);
+                        double light_pdf = lights_pdf<GEN>(S, h.point, dir, ray.time);
+                        double pdf = p_bsdf * bsdf_pdf + p_light * light_pdf;
+                        if (env_is) pdf = pdf + p_env * env_pdf(rc.env, dir);
+                        d3 attenuation = f / pdf;
+                        double e = 1e-3 * signum(dot(dir, h.gn));
+                        next = make_ray(h.point + e * h.gn, dir, ray.time);
+                        thr = thr * attenuation;
+                        alive = bounces + 1 < cam.c.max_depth;  // `for bounces in 0..max_depth`, camera.rs:177
+                        if (rc.nan_policy == PT_NAN_DROP && !finite3(thr)) { atomicAdd(nonfinite, 1ull); alive = false; }
+                        ids.z = (rng.used & 0xFFFFu) | ((bounces + 1) << 16);
+                    }
+                }
+            }
+        }
+        if (CLS == CLS_MISS) continue;  // a miss ends the path: nothing to compact
+        // ---- compaction: survivors grouped by direction octant within the block (warps of the next trace launch then hold
+        //      rays that walk the BVH in the same order and tend to cost the same), one atomic per block
+        const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const uint32_t key = alive ? (((next.d.y < 0.0) | ((next.d.x < 0.0) << 1) | ((next.d.z < 0.0) << 2)) & rc.sort_mask) : 8u;
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+        if (threadIdx.x < 8 * (kBlock / 32)) (&bin_count[0][0])[threadIdx.x] = 0;
+        __syncthreads();
+        if (alive && lane == (uint32_t)(__ffs(peers) - 1)) bin_count[key][warp] = __popc(peers);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t total = 0;
+#pragma unroll
+            for (int b = 0; b < 8; b++)
+#pragma unroll
+                for (int w = 0; w < kBlock / 32; w++) { uint32_t c = bin_count[b][w]; bin_count[b][w] = total; total += c; }
+            block_base = total ? atomicAdd(out_count, total) : 0;
+        }
+        __syncthreads();
+        if (alive) {
+            uint32_t dst = block_base + bin_count[key][warp] + __popc(peers & ((1u << lane) - 1u));
+            store_path(out, dst, next, thr, ids);
+        }
+        __syncthreads();  // bin_count / block_base are reused by the next grid-stride iteration
+    }
+}
+
+// ---- PT_RENDER_NEE (ours): next-event estimation with MIS instead of the reference's one-sample mixture.
+// At every non-emissive hit: (1) a light direction from World.lights.sample spawns a SHADOW PATH — an ordinary pool entry
+// marked kShadowMark that carries W = throughput * f / (pdf_light + pdf_bsdf) (balance heuristic folded in); it is traced
+// by k_trace like any ray and only ever adds W * emitted if its closest hit is an emitter; (2) the path continues by BSDF
+// sampling alone and remembers w = pdf_bsdf / (pdf_bsdf + pdf_light(dir)) (as fp32 in ids.w) to weight the emission it may
+// run into next.  Environment hits keep weight 1 (the environment is not a NEE light).  Two outputs per input at most:
+// out_count[0] counts all outputs, out_count[1] the non-shadow ones (the host keeps those <= pool / 2).
+constexpr uint32_t kShadowMark = 0xFFFFFFFFu;
+#ifndef PT_NEE_MIN_BLOCKS
+#define PT_NEE_MIN_BLOCKS 4  // 128 registers; 3 blocks (168 registers, far fewer spills) measured 2-10 % slower
+#endif
+template <int CLS>
+__global__ void __launch_bounds__(kBlock, PT_NEE_MIN_BLOCKS) k_shade_nee(PathBuf in, Queues q, const HitRec* __restrict__ hits, PathBuf out,
+                                                        uint32_t* __restrict__ out_count, float* __restrict__ accum,
+                                                        unsigned long long* __restrict__ nonfinite, DScene S, DCameraEx cam, RenderConst rc) {
+    constexpr int K = ClassKind<CLS>::value;
+    const uint32_t count = q.count[CLS];
+    const uint32_t* __restrict__ items = q.items + (size_t)CLS * q.stride;
+    __shared__ uint32_t warp_count[kBlock / 32], warp_alive[kBlock / 32];
+    __shared__ uint32_t block_base;
+    for (uint32_t base = blockIdx.x * kBlock; base < count; base += gridDim.x * kBlock) {
+        const uint32_t j = base + threadIdx.x;
+        bool alive = false, shadow = false;
+        RayD next, sray; d3 thr = mk(0, 0, 0), sthr = mk(0, 0, 0); uint4 ids = make_uint4(0, 0, 0, 0);
+        if (j < count) {
+            const uint32_t i = items[j];
+            RayD ray = load_ray(in, i);
+            thr = mk(in.f[7][i], in.f[8][i], in.f[9][i]);
+            ids = in.ids[i];
+            const uint32_t pix = ids.x, bounces = ids.z >> 16;
+            const bool is_shadow = ids.w == kShadowMark;
+            bool dead = false;
+            if (CLS == CLS_MISS) {
+                if (!is_shadow) add_radiance(accum, pix, thr * sample_environment(S, cam.c, ray.d), rc.nan_policy, nonfinite, dead);
+            } else {
+                const HitRec hr = hits[i];
+                HitInfoD h;
+                reconstruct_hit<false>(S, ray, hr.ref, hr.inst_light & 0x7FFFFFFFu, hr.t, h);
+                const DMaterial& m = S.materials[h.material];
+                if (CLS == CLS_LIGHT) {  // emitters end the path (DiffuseLight::sample -> None); MIS weight of the strategy that got here
+                    const double w = (is_shadow || bounces == 0) ? 1.0 : (double)__uint_as_float(ids.w);
+                    add_radiance(accum, pix, thr * texture_value(S, m.base_color_tex, h.u, h.v, h.point) * w, rc.nan_policy, nonfinite, dead);
+                } else if (!is_shadow) {
+                    Rng rng; rng.init(rc.seed, pix, ids.y, ids.z & 0xFFFFu);
+                    if (!finite3(thr)) add_radiance(accum, pix, thr * 0.0, rc.nan_policy, nonfinite, dead);  // poisons like camera.rs:186-187 (Q32)
+                    bool go = !dead;
+                    if (go && bounces > 5) {  // Russian roulette, camera.rs:190-196
+                        double p = clampd(luminance(thr), 0.01, 1.0);
+                        if (rng.next() > p) go = false;
+                        else thr = thr / p;
+                    }
+                    if (go) {
+                        const bool deeper = bounces + 1 < cam.c.max_depth;
+                        d3 dir;
+                        if (S.n_lights != 0 && lights_sample<true>(S, h.point, ray.time, rng, dir)) {
+                            const double pl = lights_pdf<true>(S, h.point, dir, ray.time);
+                            d3 fl; double pb;
+                            bsdf_eval_pdf<K>(S, h.material, -ray.d, dir, h, fl, pb);
+                            const d3 W = thr * (fl / (pl + pb));
+                            if (deeper && pl > 0.0 && (W.x != 0.0 || W.y != 0.0 || W.z != 0.0)) {
+                                shadow = true; sthr = W;
+                                sray = make_ray(h.point + (1e-3 * signum(dot(dir, h.gn))) * h.gn, dir, ray.time);
+                            }
+                        }
+                        if (bsdf_sample<K>(S, h.material, ray.d, h, rng, dir)) {
+                            d3 f; double pb;
+                            bsdf_eval_pdf<K>(S, h.material, -ray.d, dir, h, f, pb);
+                            const double pl = S.n_lights != 0 ? lights_pdf<true>(S, h.point, dir, ray.time) : 0.0;
+                            const float w = pl > 0.0 ? (float)(pb / (pb + pl)) : 1.0f;
+                            next = make_ray(h.point + (1e-3 * signum(dot(dir, h.gn))) * h.gn, dir, ray.time);
+                            thr = thr * (f / pb);
+                            alive = deeper;
+                            if (rc.nan_policy == PT_NAN_DROP && !finite3(thr)) { atomicAdd(nonfinite, 1ull); alive = false; }
+                            ids.w = __float_as_uint(w);
+                        }
+                        ids.z = (rng.used & 0xFFFFu) | ((bounces + 1) << 16);
+                    }
+                }
+            }
+        }
+        if (CLS == CLS_MISS || CLS == CLS_LIGHT) continue;  // nothing survives a miss or an emitter
+        // ---- compaction of up to two outputs per lane
+        const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const uint32_t b_alive = __ballot_sync(0xFFFFFFFFu, alive), b_shadow = __ballot_sync(0xFFFFFFFFu, shadow);
+        if (lane == 0) { warp_count[warp] = __popc(b_alive) + __popc(b_shadow); warp_alive[warp] = __popc(b_alive); }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t total = 0, total_alive = 0;
+#pragma unroll
+            for (int w = 0; w < kBlock / 32; w++) { uint32_t c = warp_count[w]; warp_count[w] = total; total += c; total_alive += warp_alive[w]; }
+            block_base = total ? atomicAdd(out_count, total) : 0;
+            if (total_alive) atomicAdd(out_count + 1, total_alive);
+        }
+        __syncthreads();
+        const uint32_t below = (1u << lane) - 1u;
+        const uint32_t wbase = block_base + warp_count[warp];
+        if (alive) store_path(out, wbase + __popc(b_alive & below), next, thr, ids);
+        if (shadow) store_path(out, wbase + __popc(b_alive) + __popc(b_shadow & below), sray, sthr, make_uint4(ids.x, ids.y, ids.z, kShadowMark));
+        __syncthreads();
+    }
+}
+
+}  // namespace ptd

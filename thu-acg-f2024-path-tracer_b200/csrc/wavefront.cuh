@@ -1,0 +1,161 @@
+// Wavefront integrator kernels for sm_100a (device side of Camera::trace, src/camera.rs:170-228).
+//
+// Pipeline per iteration over a pool of in-flight paths held as SoA arrays in HBM:
+//   k_generate  — camera rays for freshly started paths (camera.rs:153-168), appended after the survivors
+//   k_trace     — World::intersect_all for every live path (world.rs:47-62) -> 16-byte hit records
+//   k_shade     — miss/environment, emission, Russian roulette, light/BSDF mixture sampling, next ray
+//                 (camera.rs:178-225); survivors are written COMPACTED into the other SoA buffer through a
+//                 warp-ballot + block-prefix + one atomicAdd per block, so every later kernel reads dense,
+//                 coalesced arrays and warps stay full.
+// Radiance contributions go straight to the fp32 accumulators with red.global.add.f32.
+#pragma once
+#include "bsdf.cuh"
+
+namespace ptd {
+
+constexpr int kBlock = 128;
+#ifndef PT_TRACE_BLOCK
+#define PT_TRACE_BLOCK 32
+#endif
+// k_trace has no block-level cooperation, so its block size only decides how soon the slots of finished warps are reused:
+// one warp per block measured 2-3 % faster than 128 threads on the mesh scenes (scene 6 FHD trace 38.1 -> 37.0 ms).
+// MIN_BLOCKS in its launch bounds is stated for 128-thread blocks and scaled.
+constexpr int kTraceBlock = PT_TRACE_BLOCK;
+#ifndef PT_SHADE_MIN_BLOCKS
+#define PT_SHADE_MIN_BLOCKS 4  // resident blocks per SM the shade kernels must allow (register cap 128)
+#endif
+
+struct PathBuf {
+    double* f[10];  // ox oy oz dx dy dz time thr_r thr_g thr_b
+    uint4* ids;     // pixel, sample, rng_used | bounce << 16, spare
+};
+// Importance sampler of a lat-long environment map (PT_RENDER_ENV_IMPORTANCE; not reference behaviour):
+// a piecewise-constant density over rows x cols cells of the (u, theta/pi) unit square, built on the host in f64 by
+// pt_scene_build_env_sampler.  marginal[rows + 1] is the CDF over rows (row 0 = theta 0 = +y), cond[r * (cols + 1) ...]
+// the CDF over the columns of row r; both start at 0 and end at 1.
+struct DEnvDist { const double* marginal; const double* cond; uint32_t rows, cols; };
+struct RenderConst {
+    uint64_t seed; uint32_t sample_begin, sample_stride, nan_policy, env_importance;
+    DEnvDist env;
+    uint32_t sort_mask = 0;  // survivors of a shade block are grouped by (direction octant & sort_mask): bit 0 = y, 1 = x, 2 = z
+};
+
+// ---------------------------------------------------------------- camera.rs:133-168
+PT_D void random_offsets(Rng& rng, double& x, double& y) {
+    double radius = sqrt(rng.next());
+    double angle = rng.next() * 2.0 * kPi;
+    x = radius * cos(angle); y = radius * sin(angle);
+}
+struct DCameraEx { DCamera c; d3 dof_right, dof_up; };  // dof_* = right/up * lens radius (camera.rs:159-161), host-derived
+PT_D RayD generate_ray(const DCameraEx& cam, uint32_t row, uint32_t col, Rng& rng) {
+    double bx, by; random_offsets(rng, bx, by);
+    bx = bx * cam.c.blur_strength; by = by * cam.c.blur_strength;
+    d3 sample_location = cam.c.pixel00 + (cam.c.pixel_dv * ((double)row + bx)) + (cam.c.pixel_du * ((double)col + by));
+    double px, py; random_offsets(rng, px, py);
+    d3 origin = cam.c.center + (cam.dof_right * px) + (cam.dof_up * py);
+    d3 direction = sample_location - origin;
+    double time = rng.next();
+    return make_ray(origin, direction, time);
+}
+PT_D d3 sample_environment(const DScene& S, const DCamera& cam, d3 dir) {  // camera.rs:140-151
+    if (!cam.env_is_map) return cam.env_color;
+    double theta = acos(dir.y);
+    double phi = atan2(dir.z, dir.x);
+    double u = (phi + kPi) / (2.0 * kPi);
+    double v = 1.0 - theta / kPi;
+    return image_value(S, cam.env_image, u, v);
+}
+// largest i in [0, n) with cdf[i] <= u  (cdf[0] = 0, cdf[n] = 1)
+PT_D uint32_t cdf_find(const double* __restrict__ cdf, uint32_t n, double u) {
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (cdf[mid] <= u) lo = mid; else hi = mid; }
+    return lo;
+}
+// direction ~ the cell density; inverse of sample_environment's mapping (theta = acos(d.y), phi = atan2(d.z, d.x))
+PT_D d3 env_sample(const DEnvDist& E, double u1, double u2) {
+    const uint32_t r = cdf_find(E.marginal, E.rows, u1);
+    const double m0 = E.marginal[r], m1 = E.marginal[r + 1];
+    const double* __restrict__ row = E.cond + (size_t)r * (E.cols + 1);
+    const uint32_t c = cdf_find(row, E.cols, u2);
+    const double c0 = row[c], c1 = row[c + 1];
+    const double fr = m1 > m0 ? (u1 - m0) / (m1 - m0) : 0.5, fc = c1 > c0 ? (u2 - c0) / (c1 - c0) : 0.5;
+    const double theta = (((double)r + fr) / (double)E.rows) * kPi;
+    const double phi = (((double)c + fc) / (double)E.cols) * (2.0 * kPi) - kPi;
+    const double st = sin(theta);
+    return mk(st * cos(phi), cos(theta), st * sin(phi));
+}
+PT_D double env_pdf(const DEnvDist& E, d3 dir) {  // solid-angle density of env_sample
+    const double theta = acos(dir.y), phi = atan2(dir.z, dir.x);
+    const double st = sin(theta);
+    if (!(st > 0.0)) return 0.0;
+    const double fu = (phi + kPi) / (2.0 * kPi) * (double)E.cols, fv = theta / kPi * (double)E.rows;
+    uint32_t c = fu > 0.0 ? (uint32_t)fu : 0u, r = fv > 0.0 ? (uint32_t)fv : 0u;
+    if (c >= E.cols) c = E.cols - 1;
+    if (r >= E.rows) r = E.rows - 1;
+    const double* __restrict__ row = E.cond + (size_t)r * (E.cols + 1);
+    const double cell = (E.marginal[r + 1] - E.marginal[r]) * (row[c + 1] - row[c]);
+    return cell * (double)E.rows * (double)E.cols / (2.0 * kPi * kPi * st);
+}
+
+PT_D void store_path(const PathBuf& b, uint32_t i, const RayD& r, d3 thr, uint4 ids) {
+    b.f[0][i] = r.o.x; b.f[1][i] = r.o.y; b.f[2][i] = r.o.z; b.f[3][i] = r.d.x; b.f[4][i] = r.d.y; b.f[5][i] = r.d.z; b.f[6][i] = r.time;
+    b.f[7][i] = thr.x; b.f[8][i] = thr.y; b.f[9][i] = thr.z; b.ids[i] = ids;
+}
+PT_D RayD load_ray(const PathBuf& b, uint32_t i) {
+    RayD r;
+    r.o = mk(b.f[0][i], b.f[1][i], b.f[2][i]); r.d = mk(b.f[3][i], b.f[4][i], b.f[5][i]); r.time = b.f[6][i];
+    return r;
+}
+
+// Shade classes: one queue and one specialised shade kernel per class, so warps shade one material kind.
+enum { CLS_MISS = 0, CLS_LIGHT, CLS_DIFFUSE, CLS_METAL, CLS_GLASS, CLS_PRINCIPLED, CLS_OTHER, N_CLS };
+PT_D uint32_t hit_material(const DScene& S, uint32_t ref) {
+    const uint32_t kind = ref_kind(ref), index = ref_index(ref);
+    if (kind == PT_PRIM_SPHERE) return S.spheres[index].material;
+    if (kind == PT_PRIM_QUAD) return S.quad_material[index];
+    if (kind == PT_OBJ_VOLUME) return S.volumes[index].material;
+    return S.meshes[S.tri_mesh[index]].material;
+}
+PT_D uint32_t class_of_kind(uint32_t k) {
+    return k == PT_MAT_LIGHT ? CLS_LIGHT : k == PT_MAT_DIFFUSE ? CLS_DIFFUSE : k == PT_MAT_METAL ? CLS_METAL : k == PT_MAT_GLASS ? CLS_GLASS
+           : k == PT_MAT_PRINCIPLED ? CLS_PRINCIPLED : CLS_OTHER;
+}
+struct Queues { uint32_t* items; uint32_t* count; uint32_t stride; };  // items[cls * stride + k] = path slot
+
+// Appends a traced path to the queue of its shade class (warp-aggregated: lanes of the same class share one atomicAdd).
+// Must be called by all 32 lanes; lanes with nothing to append pass cls = N_CLS.
+PT_D void queue_append(const Queues& q, uint32_t cls, uint32_t i) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, cls);
+    if (cls != N_CLS) {
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if ((int)lane == leader) base = atomicAdd(q.count + cls, __popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        q.items[(size_t)cls * q.stride + base + __popc(peers & ((1u << lane) - 1u))] = i;
+    }
+}
+
+// ---------------------------------------------------------------- parity / test entry kernels
+PT_D pt_vec3 to_abi(d3 v) { pt_vec3 r; r.x = v.x; r.y = v.y; r.z = v.z; return r; }
+PT_D d3 from_abi(pt_vec3 v) { return mk(v.x, v.y, v.z); }
+
+// two-pass traversal (trace_kernels.cuh): at most kDeferMax mesh visits are queued per ray and walked by later rounds
+constexpr int kDeferMax = 3;
+struct BlasQueues { uint4* items; uint32_t* count; uint32_t stride; };  // items[round * stride + k] = {path, ref slot | last << 31, entry t, -}
+#ifndef PT_BLAS_BURST
+#define PT_BLAS_BURST 2
+#endif
+#ifndef PT_BLAS_REFILL_MIN
+#define PT_BLAS_REFILL_MIN 8
+#endif
+#ifndef PT_BLAS_MIN_BLOCKS
+#define PT_BLAS_MIN_BLOCKS 7  // resident 128-thread-equivalents per SM the refill kernel must allow (7 -> 72 registers, 28 warps)
+#endif
+constexpr int kBlasMinBlocks = PT_BLAS_MIN_BLOCKS;
+constexpr int kBlasBurst = PT_BLAS_BURST;
+constexpr int kBlasRefillMin = PT_BLAS_REFILL_MIN;
+struct SahBox { double lo[3], hi[3]; };  // pt_sah_sweep (misc_kernels.cuh)
+constexpr int kSahTile = 128;
+
+}  // namespace ptd
