@@ -201,9 +201,12 @@ typedef struct {
  * of forking them onto side streams (tuning / debugging knob; forking is the default and measured 2.5 % faster) */
 /* flags bit 14 (0x4000): one host round trip per wavefront iteration even in the tail of a render (default: once nothing
  * is left to generate, 8 iterations are enqueued per round trip) — tuning / debugging knob, same image either way */
-/* flags bit 20 (0x100000): keep the fused traversal kernel on scenes with meshes (default there: k_trace queues mesh visits and
- * k_trace_blas_refill walks them); bit 21 (0x200000): walk them with plain grid-stride rounds instead of persistent lanes
- * with refill — tuning / A-B knobs, same image either way */
+/* Traversal flavours (tuning / A-B knobs and test pins; same image either way).  Default: scenes whose World holds at most 32
+ * objects + lights run the flat top level (k_top: reference list instead of a BVH, camera rays generated in the same kernel)
+ * with mesh visits queued for k_mesh_enter + k_mesh_walk rounds; other scenes run the BVH kernel k_trace, which on scenes with
+ * meshes queues mesh visits for k_trace_blas_refill.  flags bit 22 (0x400000): no flat top level (BVH kernels instead);
+ * bit 20 (0x100000): no multi-pass traversal at all (one fused BVH kernel); bit 21 (0x200000): with the BVH kernels, walk the
+ * queued meshes with plain grid-stride rounds instead of persistent lanes with refill. */
 /* flags bit 15 (0x8000): take the octant mask of the survivor grouping from bits 16-18 (bit 16 = y, 17 = x, 18 = z sign of
  * the next ray direction; default 7, 0 = plain compaction) — tuning knob, same image either way */
 /* PT_RENDER_ENV_IMPORTANCE (NOT reference behaviour): when the camera's environment is a map, the
@@ -325,6 +328,13 @@ int  pt_trace_closest(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_ray
  * benchmarked traversal is the tested one. */
 int  pt_trace_closest_wavefront(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_ray* rays,
                                 double t_min, uint32_t flags, pt_hit* hits, pt_stats* stats);
+/* The first wavefront iteration of a render, as a query: sample `sample` of every pixel — the camera ray
+ * (Camera::generate_ray, camera.rs:153-168, from the library's counter-based RNG with `seed`) and its closest hit on
+ * [1e-3, inf) — produced by the render's own start-of-path traversal stage (on scenes with a small World the top-level kernel
+ * generates the ray in registers and traces it in the same launch; this entry is how that fused kernel is ID-compared).
+ * rays / hits: W*H entries, row-major by pixel.  `flags` as in pt_trace_closest_wavefront. */
+int  pt_trace_camera_wavefront(pt_ctx* ctx, const pt_scene* scene, const pt_camera* cam, uint64_t seed, uint32_t sample,
+                               uint32_t flags, pt_ray* rays, pt_hit* hits, pt_stats* stats);
 /* World::shadow_ray-style any-hit against World.objects on [t_min, t_max] (world.rs:31-36). */
 int  pt_trace_any(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_ray* rays,
                   double t_min, const double* t_max, uint8_t* occluded);

@@ -78,7 +78,7 @@ TWO_PASS_MIN = 1 << 16   # launch_trace (csrc/api.cu) takes the two-pass path fr
 @pytest.mark.parametrize("scene_id,width", [(6, 400), (70, 300)])
 def test_render_traversal_stage_matches_oracle(pt, orc, ctx, pairs, scene_id, width):
     """pt_trace_closest_wavefront pushes a host batch through launch_trace — the kernels, grids and queues that
-    pt_render_accumulate launches per wavefront iteration (k_trace<DEFER> + the mesh rounds on these scenes) — and the result
+    pt_render_accumulate launches per wavefront iteration (k_top + k_mesh_enter / k_mesh_walk on these scenes) — and the result
     must equal the oracle's World::intersect_all ID for ID (t within 4 ulp; we get 0): camera rays, >= 150 k bounce rays,
     t_min = 1e-3 and 0, persistent-lane rounds and plain grid-stride rounds (flag 0x200000), and the fused kernel (0x100000)."""
     p = pairs(scene_id, width)
@@ -96,7 +96,9 @@ def test_render_traversal_stage_matches_oracle(pt, orc, ctx, pairs, scene_id, wi
     want = p.ora.trace_closest(bounce)
     frac_mesh = (want["prim_kind"][want["hit"] == 1] == 2).mean()
     assert frac_mesh > 0.05                                                  # a good share of them ends on a mesh triangle
-    for flags, two_pass in ((0, 1), (0x200000, 1), (0x100000, 0)):
+    # 0: flat top level + k_mesh_enter / k_mesh_walk rounds (what the benchmark runs); 0x400000: BVH kernels, k_trace<DEFER> +
+    # k_trace_blas_refill; + 0x200000: grid-stride mesh rounds; 0x100000: one fused BVH kernel
+    for flags, two_pass in ((0, 1), (0x400000, 1), (0x400000 | 0x200000, 1), (0x100000, 0)):
         got, st = p.dev.trace_closest_wavefront(bounce, flags=flags)
         assert st.two_pass_iterations == two_pass, hex(flags)
         assert_hits_equal(pt, got, want, f"scene {scene_id} bounce rays, flags {flags:#x}")
@@ -108,6 +110,27 @@ def test_render_traversal_stage_matches_oracle(pt, orc, ctx, pairs, scene_id, wi
     small, st = p.dev.trace_closest_wavefront(bounce[:TWO_PASS_MIN - 1])     # one ray under the floor: the fused kernel
     assert st.two_pass_iterations == 0
     assert_hits_equal(pt, small, want[:TWO_PASS_MIN - 1], f"scene {scene_id} below the two-pass floor")
+
+
+@pytest.mark.parametrize("scene_id,width", [(6, 400), (70, 300), (3, 128), (5, 160), (1, 160)])
+def test_start_of_path_stage_matches_oracle(pt, orc, ctx, pairs, scene_id, width):
+    """pt_trace_camera_wavefront = the first iteration of a render: on flat scenes k_top<PRIMARY> generates the camera ray in
+    registers and traces it in the same launch (there is no k_generate).  Rays equal the oracle's generate_ray for the same
+    (seed, pixel, sample); hits equal the oracle's World::intersect_all of those very rays, ID for ID."""
+    p = pairs(scene_id, width)
+    cam = p.scene.camera
+    h, w = p.scene.image_height(), cam.image_width
+    rows, cols = np.divmod(np.arange(w * h, dtype=np.uint32), w)
+    for sample in (0, 3):
+        rays, hits, st = p.dev.trace_camera_wavefront(seed=7, sample=sample)
+        want_rays = orc.camera_rays(cam, 7, rows, cols, np.full_like(rows, sample), pt)
+        assert np.abs(rays["origin"] - want_rays["origin"]).max() < 1e-12 and np.abs(rays["direction"] - want_rays["direction"]).max() < 1e-12
+        assert np.array_equal(rays["time"], want_rays["time"])
+        assert (st.two_pass_iterations > 0) == (scene_id in (6, 70))
+        assert_hits_equal(pt, hits, p.ora.trace_closest(rays), f"scene {scene_id} start of path, sample {sample}")
+    rays2, hits2, st = p.dev.trace_camera_wavefront(seed=7, sample=3, flags=0x400000)      # k_generate + the BVH kernels
+    assert np.array_equal(rays2, rays) and st.two_pass_iterations == (1 if scene_id in (6, 70) else 0)
+    assert_hits_equal(pt, hits2, hits, f"scene {scene_id} start of path, BVH kernels")
 
 
 def test_render_traversal_stage_other_flavours(pt, orc, ctx, pairs):
@@ -440,7 +463,7 @@ def test_scheduling_knobs_do_not_change_the_image(pt, pairs, scene_id, width, sp
     only reorder work: same paths, same segments, same iteration count, same image (up to fp32 atomic-add order)."""
     p = pairs(scene_id, width)
     base, st0 = p.dev.render(spp=spp, seed=9, nan_policy=1)
-    for flags in (0x4000, 0x2000, 0x8000, 0x100000, 0x200000, 0x4000 | 0x2000 | 0x8000 | (5 << 16) | 0x100000):
+    for flags in (0x4000, 0x2000, 0x8000, 0x100000, 0x400000, 0x400000 | 0x200000, 0x4000 | 0x2000 | 0x8000 | (5 << 16) | 0x100000):
         img, st = p.dev.render(spp=spp, seed=9, nan_policy=1, flags=flags)
         assert (st.paths, st.segments, st.iterations, st.nonfinite) == (st0.paths, st0.segments, st0.iterations, st0.nonfinite), hex(flags)
         assert np.allclose(img, base, rtol=2e-5, atol=2e-6), hex(flags)
@@ -715,9 +738,10 @@ def _holey_sheets_world(pt, n_sheets=5, g=9, seed=11):
 
 
 def test_two_pass_traversal_beyond_the_reference_scenes(pt, orc, ctx):
-    """The two-pass traversal (k_trace<DEFER> + k_trace_blas_refill) where no reference scene takes it: meshes that sit in
-    World.objects directly, and rays that enter more mesh boxes than the three visit queues hold (the rest is walked inline).
-    Sample for sample against the oracle, and against the fused kernel (flag 0x100000) and the grid-stride rounds (0x200000)."""
+    """The multi-pass traversals where no reference scene takes them: meshes that sit in World.objects directly, five mesh
+    visits per ray (five k_mesh_enter / k_mesh_walk rounds; with the BVH kernels, flag 0x400000, more than the three visit
+    queues of k_trace<DEFER> hold, so the rest is walked inline).  Sample for sample against the oracle, and against the fused
+    kernel (flag 0x100000) and the grid-stride rounds (0x200000)."""
     w, cam, keep = _holey_sheets_world(pt)
     scene = pt.Scene.from_world(w, cam)
     assert H.desc_header(scene)["n_meshes"] == 5 and H.desc_header(scene)["n_instances"] == 2
@@ -730,8 +754,9 @@ def test_two_pass_traversal_beyond_the_reference_scenes(pt, orc, ctx):
     d = np.abs(img - ref).reshape(-1, 3).max(axis=1)
     assert (d > 1e-4 * np.maximum(ref.reshape(-1, 3).max(axis=1), 1.0)).mean() < 0.02
     assert H.rel_rmse(img, ref) < 0.05
-    for flags in (0x100000, 0x200000):
+    for flags in (0x100000, 0x400000, 0x400000 | 0x200000):
         other, st2 = dev.render(spp=spp, seed=5, nan_policy=1, flags=flags)
         assert (st2.paths, st2.segments) == (st.paths, st.segments), hex(flags)
+        assert (st2.two_pass_iterations > 0) == (flags != 0x100000)
         assert np.allclose(other, img, rtol=2e-5, atol=2e-6), hex(flags)
     dev.close(); ora.close()

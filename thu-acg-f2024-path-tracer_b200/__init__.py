@@ -72,7 +72,7 @@ ABI_SYMBOLS = ["pt_ctx_create", "pt_ctx_destroy", "pt_ctx_set_stream", "pt_ctx_s
                "pt_scene_create", "pt_scene_destroy", "pt_scene_device_bytes", "pt_camera_image_height", "pt_render_accumulate",
                "pt_render", "pt_tonemap_rgb8", "pt_trace_closest", "pt_trace_any", "pt_bsdf_eval_pdf", "pt_bsdf_sample",
                "pt_camera_rays", "pt_lights_sample_pdf", "pt_scene_build_env_sampler", "pt_env_sample_pdf", "pt_sah_sweep",
-               "pt_render_multi", "pt_trace_closest_wavefront", "pt_debug_histograms"]
+               "pt_render_multi", "pt_trace_closest_wavefront", "pt_trace_camera_wavefront", "pt_debug_histograms"]
 
 
 class PtError(RuntimeError):
@@ -493,6 +493,16 @@ class DeviceScene:
         st = Stats()
         self.ctx._check(self.ctx.lib.pt_trace_closest_wavefront(self.ctx.ptr, self.ptr, rays.shape[0], _ptr(rays), t_min, flags, _ptr(hits), C.byref(st)))
         return hits, st
+
+    def trace_camera_wavefront(self, camera=None, seed=1, sample=0, flags=0):
+        """pt_trace_camera_wavefront: (camera rays, their closest hits, stats) of one sample per pixel through the render's
+        own start-of-path traversal stage."""
+        cam = camera if camera is not None else self.host_scene.camera
+        n = self.ctx.lib.pt_camera_image_height(C.byref(cam)) * cam.image_width
+        rays, hits, st = np.zeros(n, dtype=RAY_DTYPE), np.zeros(n, dtype=HIT_DTYPE), Stats()
+        self.ctx.lib.pt_trace_camera_wavefront.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(CameraABI), C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(Stats)]
+        self.ctx._check(self.ctx.lib.pt_trace_camera_wavefront(self.ctx.ptr, self.ptr, C.byref(cam), seed, sample, flags, _ptr(rays), _ptr(hits), C.byref(st)))
+        return rays, hits, st
 
     def trace_any(self, rays, t_max, t_min=1e-3):
         rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)

@@ -25,7 +25,7 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 // back to back, each reading its ray count from the survivors counter of the one before, and the host reads all the
 // counters in one round trip.  Grids are sized by the live count at the start of the batch (an upper bound).
 constexpr int kTailBatch = 8;
-constexpr int kSlot = 32;  // uint32 counters per wavefront iteration (see pt_ctx::d_count)
+constexpr int kSlot = 64;  // uint32 counters per wavefront iteration (see pt_ctx::d_count)
 constexpr uint32_t kTailBatchMaxLive = 1u << 22;
 
 struct pt_ctx {
@@ -34,13 +34,16 @@ struct pt_ctx {
     int profiling = 0;                      // 1: per-stage CUDA events; 2: also the traversal work counters (COUNT kernel variants)
     // path pool (ping-pong SoA) + hit records, grown on demand
     uint32_t pool = 0;
-    double* pool_f[2] = {nullptr, nullptr};
-    uint4* pool_ids[2] = {nullptr, nullptr};
+    RayRec* pool_ray[2] = {nullptr, nullptr};
+    StateRec* pool_state[2] = {nullptr, nullptr};
     HitRec* hits = nullptr;
-    uint32_t* d_count = nullptr;            // kTailBatch slots of [kSlot]: [0] survivors counter, [4 .. 4+N_CLS) shade-class queue lengths, [12 .. 15) mesh-visit queue lengths, [16 .. 19) their fetch cursors
+    uint32_t* d_count = nullptr;            // kTailBatch slots of [kSlot]: [0] survivors counter, [4 .. 4+N_CLS) shade-class queue lengths; flat scenes: [12 .. 20) mesh-visit
+                                            // queue lengths per round, [20 .. 28) walk records per round, [28 .. 36) their fetch cursors; k_trace<DEFER>: [12 .. 15) queue lengths, [16 .. 19) cursors
     uint32_t* q_items = nullptr;            // N_CLS queues of `pool` path slots each
     uint4* bq_items = nullptr;              // two-pass traversal: kDeferMax queues of `pool` deferred mesh visits each
     uint2* ties = nullptr;                  //   and the tie ranks of the provisional hit of every path (both allocated on first use)
+    uint2* mq_items = nullptr; uint32_t mq_rounds = 0;  // flat scenes with meshes: mq_rounds queues of `pool` mesh visits each (k_top -> k_mesh_enter)
+    uint4* walk = nullptr;                  //   and `pool` 128-byte walk records (k_mesh_enter -> k_mesh_walk)
     void* scratch = nullptr; size_t scratch_bytes = 0;  // pt_render / pt_tonemap_rgb8 output staging, grown on demand (no cudaMalloc per call)
     unsigned long long* d_nonfinite = nullptr;
     uint32_t* h_count = nullptr;            // pinned, same shape as d_count
@@ -74,6 +77,9 @@ struct pt_scene {
     bool general_lights = false;            // World.lights holds something other than quads and spheres (shade kernel variant)
     bool has_volumes = false;               // constant-density media present (trace kernel variant with keyed uniforms)
     bool defer_meshes = false;              // two-pass traversal (k_trace<DEFER> + k_trace_blas): wide scenes that hold meshes
+    bool flat = false;                      // flat top level (k_top): at most kTopMax objects + lights, no media, meshes walkable by k_mesh_walk
+    TopList top{};                          //   its reference list
+    uint32_t mesh_rounds = 0;               //   mesh references in it = rounds of k_mesh_enter + k_mesh_walk per iteration
     DEnvDist env{};                         // pt_scene_build_env_sampler: importance sampler of image `env_image`
     uint32_t env_image = 0xFFFFFFFFu;
     void* env_block = nullptr;
@@ -120,9 +126,10 @@ int pt_ctx_create(int device, pt_ctx** out) {
     return PT_OK;
 }
 static void free_pool(pt_ctx* c) {
-    for (int i = 0; i < 2; i++) { cudaFree(c->pool_f[i]); cudaFree(c->pool_ids[i]); c->pool_f[i] = nullptr; c->pool_ids[i] = nullptr; }
+    for (int i = 0; i < 2; i++) { cudaFree(c->pool_ray[i]); cudaFree(c->pool_state[i]); c->pool_ray[i] = nullptr; c->pool_state[i] = nullptr; }
     cudaFree(c->hits); c->hits = nullptr; cudaFree(c->q_items); c->q_items = nullptr; c->pool = 0;
     cudaFree(c->bq_items); c->bq_items = nullptr; cudaFree(c->ties); c->ties = nullptr;
+    cudaFree(c->mq_items); c->mq_items = nullptr; c->mq_rounds = 0; cudaFree(c->walk); c->walk = nullptr;
 }
 void pt_ctx_destroy(pt_ctx* c) {
     if (!c) return;
@@ -318,6 +325,59 @@ struct Converter {
     }
     void dummy(uint32_t slot) { DNode n{}; for (int k = 0; k < 3; k++) { n.lo[k] = INFINITY; n.hi[k] = -INFINITY; } n.a = 0; n.b = 0; nodes[slot] = n; }
 
+    // ---- mesh-walk layout (device_scene.cuh: DWide2): 4-wide nodes whose children are nodes or single triangles
+    std::vector<DWide2> wide2;
+    std::vector<uint32_t> tri_rank;
+    uint32_t wide2_depth = 0;
+    struct Item { bool tri; uint32_t id; };  // tri: index into refs (a triangle reference); else a binary node slot
+    const DNode& item_box(const Item& it) const { return it.tri ? refs[it.id] : nodes[it.id]; }
+    uint32_t make_wide2(std::vector<Item> items, uint32_t depth) {
+        wide2_depth = std::max(wide2_depth, depth);
+        // open the largest openable item until four are held: an internal node into its two children, a leaf into its
+        // triangles (when they fit)
+        while (items.size() < 4) {
+            int best = -1; float best_area = -1.f;
+            for (size_t i = 0; i < items.size(); i++) {
+                if (items[i].tri) continue;
+                const DNode& n = nodes[items[i].id];
+                const size_t grow = n.b == kNone ? 2 : n.b;
+                if (items.size() - 1 + grow > 4 || (n.b != kNone && n.b == 0)) continue;
+                if (half_area(n) > best_area) { best = (int)i; best_area = half_area(n); }
+            }
+            if (best < 0) break;
+            const DNode n = nodes[items[best].id];
+            std::vector<Item> repl;
+            if (n.b == kNone) repl = {Item{false, n.a}, Item{false, n.a + 1}};
+            else for (uint32_t k = 0; k < n.b; k++) repl.push_back(Item{true, n.a + k});
+            items.erase(items.begin() + best);
+            items.insert(items.begin() + best, repl.begin(), repl.end());
+        }
+        const uint32_t wi = (uint32_t)wide2.size();
+        wide2.emplace_back();
+        DWide2 w{};
+        for (int i = 0; i < 4; i++) { for (int k = 0; k < 3; k++) { w.lo[k][i] = INFINITY; w.hi[k][i] = -INFINITY; } w.child[i] = kNone; w.pad[i] = 0; }
+        // more than four items can only be the triangles of one oversized leaf (a failed SAH split, bvh.rs:37-42, or an
+        // un-built mesh): group them into four runs, each run becomes a child node
+        std::vector<std::vector<Item>> slots;
+        if (items.size() <= 4) for (auto& it : items) slots.push_back({it});
+        else for (size_t g = 0; g < 4; g++) slots.emplace_back(items.begin() + items.size() * g / 4, items.begin() + items.size() * (g + 1) / 4);
+        for (size_t i = 0; i < slots.size(); i++) {
+            const auto& sl = slots[i];
+            float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+            for (const Item& it : sl) { const DNode& b = item_box(it); for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], b.lo[k]); hi[k] = std::max(hi[k], b.hi[k]); } }
+            for (int k = 0; k < 3; k++) { w.lo[k][i] = lo[k]; w.hi[k][i] = hi[k]; }
+            if (sl.size() == 1 && sl[0].tri) w.child[i] = kTriBit | ref_index(refs[sl[0].id].a);
+            else if (sl.size() == 1) {
+                const DNode& n = nodes[sl[0].id];
+                if (n.b == kNone) w.child[i] = make_wide2({Item{false, n.a}, Item{false, n.a + 1}}, depth + 1);
+                else if (n.b == 0) { w.child[i] = kNone; for (int k = 0; k < 3; k++) { w.lo[k][i] = INFINITY; w.hi[k][i] = -INFINITY; } }
+                else { std::vector<Item> tr; for (uint32_t k = 0; k < n.b; k++) tr.push_back(Item{true, n.a + k}); w.child[i] = make_wide2(tr, depth + 1); }
+            } else w.child[i] = make_wide2(sl, depth + 1);
+        }
+        wide2[wi] = w;
+        return wi;
+    }
+
     // ---- collapse of the binary tree into 4-wide nodes (device_scene.cuh: DWide)
     std::vector<DWide> wide;
     uint32_t wide_depth = 0;
@@ -461,6 +521,7 @@ int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
     if (!top_list(1, d->lights_bvh_root, d->lights, d->n_lights, 0u)) return fail(PT_ERR_INVALID, C.err);
     if (!top_list(0, d->objects_bvh_root, d->objects, d->n_objects, 0x80000000u)) return fail(PT_ERR_INVALID, C.err);
     const uint32_t tlas_depth = C.max_depth;
+    const uint32_t n_top = (uint32_t)C.refs.size();  // refs[0 .. n_top) are the top-level references: lights, then objects, in leaf order
     if (C.tie_counter >= 0x7FFFFFFFu) return fail(PT_ERR_UNSUPPORTED, "too many top-level objects");
     // one traversal flavour per scene (compile-time in the kernels): 4-wide nodes as soon as any BVH is large
     bool use_wide = d->n_objects + d->n_lights >= kWideMinItems;
@@ -488,7 +549,8 @@ int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
         uint32_t root_entry = pair, depth_slots = C.max_depth;
         if (use_wide) { C.wide_depth = 0; root_entry = 0x20000000u | C.make_wide({pair}, 1); depth_slots = 3 * C.wide_depth; }
         blas_depth = std::max(blas_depth, depth_slots);
-        meshes[mi] = DMesh{root_entry, m.first_triangle, m.n_triangles, m.material, m.has_normals, m.has_uvs, m.bvh_root == PT_NONE, 0};
+        const uint32_t root2 = m.n_triangles ? C.make_wide2({Converter::Item{false, pair}}, 1) : 0u;
+        meshes[mi] = DMesh{root_entry, m.first_triangle, m.n_triangles, m.material, m.has_normals, m.has_uvs, m.bvh_root == PT_NONE, root2};
     }
     uint32_t world_root = 0, tlas_slots = tlas_depth;
     if (use_wide) { C.wide_depth = 0; world_root = 0x20000000u | C.make_wide({0u, 1u}, 1); tlas_slots = 3 * C.wide_depth; }
@@ -586,6 +648,39 @@ int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
         s->class_mask |= 1u << (m.kind == PT_MAT_LIGHT ? CLS_LIGHT : m.kind == PT_MAT_DIFFUSE ? CLS_DIFFUSE : m.kind == PT_MAT_METAL ? CLS_METAL
                                 : m.kind == PT_MAT_GLASS ? CLS_GLASS : m.kind == PT_MAT_PRINCIPLED ? CLS_PRINCIPLED : CLS_OTHER);
     }
+    // ---- flat top level (wavefront.cuh: TopList): what k_top walks instead of a BVH when World is small
+    {
+        auto cls_of_mat = [&](uint32_t m) -> uint8_t {
+            const uint32_t k = d->materials[m].kind;
+            return (uint8_t)(k == PT_MAT_LIGHT ? CLS_LIGHT : k == PT_MAT_DIFFUSE ? CLS_DIFFUSE : k == PT_MAT_METAL ? CLS_METAL : k == PT_MAT_GLASS ? CLS_GLASS
+                             : k == PT_MAT_PRINCIPLED ? CLS_PRINCIPLED : CLS_OTHER);
+        };
+        auto mat_of = [&](uint32_t kind, uint32_t index) -> uint32_t {
+            switch (kind) {
+                case PT_PRIM_SPHERE: return d->spheres[index].material;
+                case PT_PRIM_QUAD: return d->quads[index].material;
+                case PT_OBJ_CUBOID: return d->quads[d->cuboids[index].first_quad].material;
+                case PT_OBJ_MESH: return d->meshes[index].material;
+                default: return 0;
+            }
+        };
+        TopList T{};
+        bool ok = !s->has_volumes && n_top >= 1 && n_top <= (uint32_t)kTopMax && 3 * C.wide2_depth + 4 <= (uint32_t)kStack2;
+        for (uint32_t k = 0; ok && k < n_top; k++) {
+            uint32_t kind = ref_kind(C.refs[k].a), index = ref_index(C.refs[k].a);
+            if (kind == PT_OBJ_INSTANCE) { const pt_ref c = d->instances[index].child; kind = c.kind; index = c.index; }
+            if (kind == PT_OBJ_VOLUME || kind == PT_PRIM_TRIANGLE) { ok = false; break; }
+            if (kind == PT_OBJ_MESH) { T.mesh_bits |= 1u << k; if (d->meshes[index].n_triangles == 0) T.mesh_bits &= ~(1u << k); }
+            T.cls[k] = cls_of_mat(mat_of(kind, index));
+        }
+        T.n = n_top;
+        s->mesh_rounds = (uint32_t)__builtin_popcount(T.mesh_bits);
+        s->flat = ok && s->mesh_rounds <= (uint32_t)kMeshRounds;
+        s->top = T;
+    }
+    std::vector<uint32_t> tri_rank(d->n_triangles, 0u);
+    for (const DNode& rn : C.refs) if (ref_kind(rn.a) == PT_PRIM_TRIANGLE) tri_rank[ref_index(rn.a)] = rn.b;
+
     std::vector<DRef> lights(d->n_lights);
     bool mesh_light = false;  // Triangle::sample needs the original vertices (mesh.rs:126), which the traversal layout does not keep
     for (uint32_t i = 0; i < d->n_lights; i++) {
@@ -601,7 +696,7 @@ int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
     U.up(C.wide, &D.wide); U.up(C.nodes, &D.nodes); U.up(C.refs, &D.refs); U.up(spheres, &D.spheres); U.up(quads, &D.quads); U.up(quad_mat, &D.quad_material);
     U.up(tris, &D.tris); U.up(tri_normals, &D.tri_normals); U.up(tri_uvs, &D.tri_uvs); U.up(tri_mesh, &D.tri_mesh); U.up(cuboids, &D.cuboids);
     U.up(meshes, &D.meshes); U.up(instances, &D.instances); U.up(textures, &D.textures); U.up(images, &D.images); U.up(materials, &D.materials);
-    U.up(lights, &D.lights); U.up(tri_verts, &D.tri_verts); U.up(volumes, &D.volumes);
+    U.up(lights, &D.lights); U.up(tri_verts, &D.tri_verts); U.up(volumes, &D.volumes); U.up(C.wide2, &D.wide2); U.up(tri_rank, &D.tri_rank);
     if ((rc = U.commit())) return rc;
     D.image_data = d_img; D.n_lights = d->n_lights; D.root_entry = world_root;
     s->n_materials = d->n_materials; s->n_images = d->n_images; s->images = images;
@@ -706,27 +801,35 @@ static int ensure_pool(pt_ctx* c, uint32_t paths) {
     if (c->pool >= paths) return PT_OK;
     free_pool(c);
     for (int i = 0; i < 2; i++) {
-        CU(cudaMalloc(&c->pool_f[i], (size_t)paths * 10 * sizeof(double)));
-        CU(cudaMalloc(&c->pool_ids[i], (size_t)paths * sizeof(uint4)));
+        CU(cudaMalloc(&c->pool_ray[i], (size_t)paths * sizeof(RayRec)));
+        CU(cudaMalloc(&c->pool_state[i], (size_t)paths * sizeof(StateRec)));
     }
     CU(cudaMalloc(&c->hits, (size_t)paths * sizeof(HitRec)));
     CU(cudaMalloc(&c->q_items, (size_t)paths * N_CLS * sizeof(uint32_t)));
     c->pool = paths;
     return PT_OK;
 }
-// mesh-visit queues and tie ranks of the two-pass traversal: 56 B per path, only for scenes that take that path
-static int ensure_two_pass(pt_ctx* c) {
-    if (c->bq_items) return PT_OK;
-    CU(cudaMalloc(&c->bq_items, (size_t)c->pool * kDeferMax * sizeof(uint4)));
-    CU(cudaMalloc(&c->ties, (size_t)c->pool * sizeof(uint2)));
+// Buffers of the multi-pass traversals, only for scenes that take them: tie ranks of the provisional hits (8 B per path), then
+// either the visit queues of k_top (8 B per path and round) + the walk records (128 B per path), or the queues of k_trace<DEFER>.
+static int ensure_two_pass(pt_ctx* c, const pt_scene* scene) {
+    if (!c->ties) CU(cudaMalloc(&c->ties, (size_t)c->pool * sizeof(uint2)));
+    if (scene->flat && scene->mesh_rounds) {
+        if (c->mq_rounds < scene->mesh_rounds) {
+            cudaFree(c->mq_items); c->mq_items = nullptr; c->mq_rounds = 0;
+            CU(cudaMalloc(&c->mq_items, (size_t)c->pool * scene->mesh_rounds * sizeof(uint2)));
+            c->mq_rounds = scene->mesh_rounds;
+        }
+        if (!c->walk) CU(cudaMalloc(&c->walk, (size_t)c->pool * kWalkRecU4 * sizeof(uint4)));
+    }
+    if (scene->defer_meshes && !c->bq_items) CU(cudaMalloc(&c->bq_items, (size_t)c->pool * kDeferMax * sizeof(uint4)));
     return PT_OK;
 }
 // Path pool of `want` paths (plus the two-pass buffers when the scene needs them); on cudaErrorMemoryAllocation the pool is
 // halved and the allocation retried (a smaller pool only means more wavefront iterations), down to 64 Ki paths.
-static int ensure_render_buffers(pt_ctx* c, uint32_t want, bool two_pass, uint32_t* got) {
+static int ensure_render_buffers(pt_ctx* c, uint32_t want, const pt_scene* scene, uint32_t* got) {
     for (uint32_t pool = want;; pool = std::max((pool / 2 + kBlock - 1) / kBlock * kBlock, 1u << 16)) {
         int rc = ensure_pool(c, pool);
-        if (rc == PT_OK && two_pass) rc = ensure_two_pass(c);
+        if (rc == PT_OK && (scene->defer_meshes || (scene->flat && scene->mesh_rounds))) rc = ensure_two_pass(c, scene);
         if (rc == PT_OK) { *got = std::min(pool, c->pool); return PT_OK; }
         const bool oom = cudaGetLastError() == cudaErrorMemoryAllocation || g_err.find("out of memory") != std::string::npos;
         free_pool(c);
@@ -741,10 +844,7 @@ static int ensure_scratch(pt_ctx* c, size_t bytes) {
     return PT_OK;
 }
 static PathBuf path_buf(pt_ctx* c, int which) {
-    PathBuf b;
-    for (int k = 0; k < 10; k++) b.f[k] = c->pool_f[which] + (size_t)k * c->pool;
-    b.ids = c->pool_ids[which];
-    return b;
+    return PathBuf{c->pool_ray[which], c->pool_state[which]};
 }
 
 // World::intersect_all for the n (or min(n, *n_dev)) paths of `in` — THE traversal stage of a wavefront iteration, shared by
@@ -753,10 +853,32 @@ static PathBuf path_buf(pt_ctx* c, int which) {
 struct TraceStage {
     pt_ctx* ctx; const pt_scene* scene; uint32_t flags; uint64_t seed; double t_min; unsigned long long* wk; pt_stats* S;
 };
-static void launch_trace(const TraceStage& T, const PathBuf& in, uint32_t n, const Queues& q, const uint32_t* n_dev) {
+// `in` holds n_old live paths in slots [0, n_old); n_new more are STARTED in slots [n_old, n_old + n_new) — camera rays
+// (camera.rs:153-168) generated by the top-level kernel itself on flat scenes, by k_generate otherwise.
+static void launch_trace(const TraceStage& T, const PathBuf& in, uint32_t n_old, uint32_t n_new, const GenArgs* gen, const Queues& q, const uint32_t* n_dev) {
     pt_ctx* ctx = T.ctx; const pt_scene* scene = T.scene; pt_stats& S = *T.S;
     unsigned long long* const wk = T.wk;
     cudaStream_t st = ctx->stream;
+    const uint32_t n = n_old + n_new;
+    // flat top level (k_top) + mesh rounds: every scene with a small World; with meshes not for small iterations (two more
+    // launches per round); flags 0x100000 / 0x400000 opt out (A/B measurements, and the tests that pin this path to the BVH kernels)
+    if (scene->flat && !(T.flags & 0x500000u) && (scene->mesh_rounds == 0 || n >= (1u << 16))) {
+        uint32_t* slot = q.count - 4;
+        const MeshQueues mq{ctx->mq_items, slot + 12, ctx->pool, ctx->walk, slot + 20};
+        static const GenArgs no_gen{};
+        if (n_old) { run_k_top(false, wk != nullptr, st, in, 0, n_old, ctx->hits, q, scene->d, scene->top, mq, ctx->ties, T.t_min, no_gen, n_dev, wk); S.kernel_launches++; }
+        if (n_new) { run_k_top(true, wk != nullptr, st, in, n_old, n_new, ctx->hits, q, scene->d, scene->top, mq, ctx->ties, T.t_min, *gen, nullptr, wk); S.kernel_launches++; }
+        const unsigned eg = std::min<unsigned>((n + kBlock - 1) / kBlock, 148u * 16u);
+        const unsigned wg = std::min<unsigned>((n + kTraceBlock - 1) / kTraceBlock, mesh_walk_resident_warps());
+        for (uint32_t r = 0; r < scene->mesh_rounds; r++) {
+            run_k_mesh_enter(wk != nullptr, eg, st, in, r, mq, ctx->hits, ctx->ties, q, scene->d, scene->top, T.t_min, wk);
+            run_k_mesh_walk(wk != nullptr, wg, st, r, mq, ctx->hits, ctx->ties, q, scene->d, T.t_min, wk);
+            S.kernel_launches += 2;
+        }
+        if (scene->mesh_rounds) S.two_pass_iterations++;
+        return;
+    }
+    if (n_new) { run_k_generate(st, in, n_old, n_new, gen->g0, gen->n_pixels, gen->cam, gen->rc); S.kernel_launches++; }
     const unsigned tg = (n + kTraceBlock - 1) / kTraceBlock;
     // two-pass traversal; not for small iterations (three more launches each); flag 0x100000 opts out (A/B measurements)
     if (scene->defer_meshes && n >= (1u << 16) && !(T.flags & 0x100000u)) {
@@ -794,7 +916,7 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
     uint32_t pool = p->pool_paths ? p->pool_paths : (32u << 20);
     if ((uint64_t)pool > total) pool = (uint32_t)std::max<uint64_t>(total, 1);
     pool = (pool + kBlock - 1) / kBlock * kBlock;
-    if ((rc = ensure_render_buffers(ctx, pool, scene->defer_meshes, &pool))) return rc;
+    if ((rc = ensure_render_buffers(ctx, pool, scene, &pool))) return rc;
     RenderConst rcst{p->seed, p->sample_begin, p->sample_stride ? p->sample_stride : 1u, p->nan_policy, 0, DEnvDist{nullptr, nullptr, 0, 0}};
     if ((p->flags & PT_RENDER_ENV_IMPORTANCE) && cam->env_is_map) {  // a constant-colour environment needs no importance sampling
         if (scene->env_image != cam->env_image) return fail(PT_ERR_INVALID, "PT_RENDER_ENV_IMPORTANCE: call pt_scene_build_env_sampler for the camera's env_image first");
@@ -812,7 +934,6 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
     if (nee && rcst.env_importance) return fail(PT_ERR_UNSUPPORTED, "PT_RENDER_NEE and PT_RENDER_ENV_IMPORTANCE cannot be combined yet");
     unsigned long long* const wk = ctx->profiling >= 2 ? ctx->d_nonfinite + 1 : nullptr;
     const TraceStage tstage{ctx, scene, p->flags, p->seed, 1e-3, wk, &S};  // Interval::new(eps, INFINITY), camera.rs:171,179
-    auto launch_trace = [&](const PathBuf& in, uint32_t n, const Queues& q, const uint32_t* n_dev) { ::launch_trace(tstage, in, n, q, n_dev); };
     // one specialised kernel per shade class present in the scene; each walks its queue grid-stride (n: upper bound of the
     // paths in all queues together).  fork: the class kernels run on side streams and join `st` again.
     auto launch_shades = [&](const PathBuf& in, const PathBuf& outb, uint32_t n, const Queues& q, uint32_t* out_count, bool fork) -> int {
@@ -842,7 +963,7 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
             for (int k = 0; k < kTailBatch; k++) {
                 uint32_t* slot = ctx->d_count + kSlot * k;
                 const Queues q{ctx->q_items, slot + 4, ctx->pool};
-                launch_trace(path_buf(ctx, cur), n0, q, k ? slot - kSlot : nullptr);
+                launch_trace(tstage, path_buf(ctx, cur), n0, 0, nullptr, q, k ? slot - kSlot : nullptr);
                 if ((rc = launch_shades(path_buf(ctx, cur), path_buf(ctx, cur ^ 1), n0, q, slot, false))) return rc;
                 cur ^= 1;
             }
@@ -858,16 +979,12 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
         uint32_t n_new = (uint32_t)std::min<uint64_t>(pool - live, total - generated);
         // NEE: a path may spawn a shadow path, so at most pool / 2 spawning (non-shadow) paths enter an iteration
         if (nee) n_new = std::min<uint32_t>(n_new, pool / 2 > live_spawning ? pool / 2 - live_spawning : 0u);
-        if (ctx->profiling) CU(cudaEventRecord(ctx->evs[0], st));
-        if (n_new) {
-            run_k_generate(st, in, live, n_new, generated, n_pixels, dcam, rcst);
-            S.kernel_launches++;
-        }
         const uint32_t n = live + n_new;
         CU(cudaMemsetAsync(ctx->d_count, 0, kSlot * sizeof(uint32_t), st));
         const Queues q{ctx->q_items, ctx->d_count + 4, ctx->pool};
         if (ctx->profiling) CU(cudaEventRecord(ctx->evs[1], st));
-        launch_trace(in, n, q, nullptr);
+        const GenArgs gen{generated, n_pixels, dcam, rcst};  // the n_new camera rays of this iteration are generated inside the traversal stage
+        launch_trace(tstage, in, live, n_new, &gen, q, nullptr);
         if (ctx->profiling) CU(cudaEventRecord(ctx->evs[2], st));
         // fork: the class kernels run on side streams (unless per-stage events are wanted, or the caller opted out with flag
         // 0x2000).  Measured (repeated runs): scene 6 FHD 168.3 -> 164.1 ms per 128 spp, scene 3 128.0 -> 124.8 ms (+2.5 % each).
@@ -879,7 +996,7 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
         CU(cudaStreamSynchronize(st));
         if (ctx->profiling) {
             float a = 0, b = 0, c2 = 0;
-            cudaEventElapsedTime(&a, ctx->evs[0], ctx->evs[1]); cudaEventElapsedTime(&b, ctx->evs[1], ctx->evs[2]); cudaEventElapsedTime(&c2, ctx->evs[2], ctx->evs[3]);
+            cudaEventElapsedTime(&b, ctx->evs[1], ctx->evs[2]); cudaEventElapsedTime(&c2, ctx->evs[2], ctx->evs[3]);  // ray generation is part of the traversal stage
             ms_gen += a; ms_trace += b; ms_shade += c2;
         }
         generated += n_new; S.segments += n; S.iterations++;
@@ -1047,7 +1164,7 @@ int pt_trace_closest_wavefront(pt_ctx* ctx, const pt_scene* scene, size_t n, con
     cudaStream_t st = ctx->stream;
     uint32_t chunk = (uint32_t)std::min<size_t>(n, 4u << 20);  // like a wavefront iteration of that many live paths
     chunk = (chunk + kBlock - 1) / kBlock * kBlock;
-    int rc = ensure_render_buffers(ctx, chunk, scene->defer_meshes, &chunk);
+    int rc = ensure_render_buffers(ctx, chunk, scene, &chunk);
     if (rc) return rc;
     DevBuf in, out;
     if ((rc = in.alloc((size_t)chunk * sizeof(pt_ray))) || (rc = out.alloc((size_t)chunk * sizeof(pt_hit)))) return rc;
@@ -1061,7 +1178,7 @@ int pt_trace_closest_wavefront(pt_ctx* ctx, const pt_scene* scene, size_t n, con
         run_k_rays_to_pool(st, (const pt_ray*)in.p, m, (uint32_t)first, pool);
         CU(cudaMemsetAsync(ctx->d_count, 0, kSlot * sizeof(uint32_t), st));
         const Queues q{ctx->q_items, ctx->d_count + 4, ctx->pool};
-        launch_trace(T, pool, m, q, nullptr);
+        launch_trace(T, pool, m, 0, nullptr, q, nullptr);
         run_k_hits_to_abi(st, (const pt_ray*)in.p, m, ctx->hits, (pt_hit*)out.p, scene->d);
         if ((rc = out.to_host(hits + first, (size_t)m * sizeof(pt_hit), st))) return rc;
         S.segments += m; S.iterations++; S.kernel_launches += 2;
@@ -1072,6 +1189,34 @@ int pt_trace_closest_wavefront(pt_ctx* ctx, const pt_scene* scene, size_t n, con
         CU(cudaStreamSynchronize(st));
         S.node_pairs = nf[1]; S.ref_boxes = nf[2]; S.prim_tests = nf[3];
     }
+    if (stats) *stats = S;
+    return PT_OK;
+}
+int pt_trace_camera_wavefront(pt_ctx* ctx, const pt_scene* scene, const pt_camera* cam, uint64_t seed, uint32_t sample, uint32_t flags, pt_ray* rays, pt_hit* hits, pt_stats* stats) {
+    if (!ctx || !scene || !cam || !rays || !hits) return fail(PT_ERR_INVALID, "pt_trace_camera_wavefront: null argument");
+    if (scene->ctx != ctx) return fail(PT_ERR_INVALID, "scene belongs to another context");
+    CU(cudaSetDevice(ctx->device));
+    DCameraEx dcam;
+    int rc = make_camera(scene, cam, &dcam);
+    if (rc) return rc;
+    const uint32_t n = dcam.c.width * dcam.c.height;
+    uint32_t pool = (n + kBlock - 1) / kBlock * kBlock;
+    if ((rc = ensure_render_buffers(ctx, pool, scene, &pool))) return rc;
+    if (pool < n) return fail(PT_ERR_UNSUPPORTED, "pt_trace_camera_wavefront: the image does not fit the path pool");
+    cudaStream_t st = ctx->stream;
+    pt_stats S{}; S.width = dcam.c.width; S.height = dcam.c.height;
+    DevBuf d_rays, d_hits;
+    if ((rc = d_rays.alloc((size_t)n * sizeof(pt_ray))) || (rc = d_hits.alloc((size_t)n * sizeof(pt_hit)))) return rc;
+    const RenderConst rcst{seed, sample, 1u, PT_NAN_REFERENCE, 0, DEnvDist{nullptr, nullptr, 0, 0}};
+    const GenArgs gen{0, n, dcam, rcst};
+    const TraceStage T{ctx, scene, flags, seed, 1e-3, nullptr, &S};  // Interval::new(eps, INFINITY), camera.rs:171,179
+    const PathBuf in = path_buf(ctx, 0);
+    CU(cudaMemsetAsync(ctx->d_count, 0, kSlot * sizeof(uint32_t), st));
+    const Queues q{ctx->q_items, ctx->d_count + 4, ctx->pool};
+    launch_trace(T, in, 0, n, &gen, q, nullptr);
+    run_k_pool_to_abi(st, in, n, ctx->hits, (pt_ray*)d_rays.p, (pt_hit*)d_hits.p, scene->d);
+    if ((rc = d_rays.to_host(rays, (size_t)n * sizeof(pt_ray), st)) || (rc = d_hits.to_host(hits, (size_t)n * sizeof(pt_hit), st))) return rc;
+    S.paths = n; S.segments = n; S.iterations = 1; S.kernel_launches++;
     if (stats) *stats = S;
     return PT_OK;
 }

@@ -11,10 +11,19 @@ void run_k_trace(const TraceFlavour& f, unsigned grid, cudaStream_t st, PathBuf 
                  unsigned long long* work, uint64_t seed, const uint32_t* n_dev, BlasQueues bq, uint2* ties, double t_min);
 void run_k_trace_blas(bool refill, bool count, unsigned grid, cudaStream_t st, PathBuf in, uint32_t round, BlasQueues bq, HitRec* hits, uint2* ties,
                       Queues q, const DScene& S, unsigned long long* work, double t_min);
+// flat top level + mesh rounds (trace_kernels.cuh)
+void run_k_top(bool primary, bool count, cudaStream_t st, PathBuf pool, uint32_t slot0, uint32_t n, HitRec* hits, Queues q, const DScene& S, const TopList& top,
+               MeshQueues mq, uint2* ties, double t_min, const GenArgs& gen, const uint32_t* n_dev, unsigned long long* work);
+void run_k_mesh_enter(bool count, unsigned grid, cudaStream_t st, PathBuf pool, uint32_t round, MeshQueues mq, const HitRec* hits, const uint2* ties, Queues q,
+                      const DScene& S, const TopList& top, double t_min, unsigned long long* work);
+void run_k_mesh_walk(bool count, unsigned grid, cudaStream_t st, uint32_t round, MeshQueues mq, HitRec* hits, uint2* ties, Queues q, const DScene& S, double t_min,
+                     unsigned long long* work);
+unsigned mesh_walk_resident_warps();  // persistent grid of k_mesh_walk: one warp per resident slot
 void run_k_trace_batch(bool wide, cudaStream_t st, const pt_ray* rays, size_t n, double t_min, pt_hit* out, const DScene& S);
 void run_k_trace_any_batch(bool wide, cudaStream_t st, const pt_ray* rays, size_t n, double t_min, const double* t_max, uint8_t* out, const DScene& S);
 void run_k_rays_to_pool(cudaStream_t st, const pt_ray* rays, uint32_t n, uint32_t first, PathBuf out);
 void run_k_hits_to_abi(cudaStream_t st, const pt_ray* rays, uint32_t n, const HitRec* hits, pt_hit* out, const DScene& S);
+void run_k_pool_to_abi(cudaStream_t st, PathBuf pool, uint32_t n, const HitRec* hits, pt_ray* out_rays, pt_hit* out_hits, const DScene& S);
 cudaError_t debug_histograms(unsigned long long* out512, bool reset);
 
 // ---- shade_*.cu: one loop iteration of Camera::trace after intersect_all (camera.rs:180-225) per shade class

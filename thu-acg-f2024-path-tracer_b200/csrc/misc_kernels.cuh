@@ -10,12 +10,8 @@ __global__ void __launch_bounds__(kBlock) k_generate(PathBuf out, uint32_t slot0
                                                       DCameraEx cam, RenderConst rc) {
     uint32_t i = blockIdx.x * kBlock + threadIdx.x;
     if (i >= n_new) return;
-    uint64_t g = g0 + i;
-    uint32_t s_local = (uint32_t)(g / n_pixels), pix = (uint32_t)(g % n_pixels);
-    if ((cam.c.width & 7u) == 0 && (cam.c.height & 3u) == 0) {  // a warp covers an 8x4 pixel tile: tighter ray bundles than a 32x1 strip
-        const uint32_t tile = pix >> 5, within = pix & 31u, tiles_x = cam.c.width >> 3;
-        pix = ((tile / tiles_x) * 4u + (within >> 3)) * cam.c.width + (tile % tiles_x) * 8u + (within & 7u);
-    }
+    uint32_t s_local, pix;
+    path_pixel(g0 + i, n_pixels, cam.c, pix, s_local);
     uint32_t sample = rc.sample_begin + s_local * rc.sample_stride;
     Rng rng; rng.init(rc.seed, pix, sample, 0);
     RayD r = generate_ray(cam, pix / cam.c.width, pix % cam.c.width, rng);

@@ -40,9 +40,8 @@ __global__ void __launch_bounds__(kBlock, PT_SHADE_MIN_BLOCKS) k_shade(PathBuf i
         RayD next; d3 thr = mk(0, 0, 0); uint4 ids = make_uint4(0, 0, 0, 0);
         if (j < count) {
             const uint32_t i = items[j];
-            RayD ray = load_ray(in, i);
-            thr = mk(in.f[7][i], in.f[8][i], in.f[9][i]);
-            ids = in.ids[i];
+            RayD ray = load_ray(in, i, &ids.x, &ids.y);
+            thr = load_state(in, i, ids.z, ids.w);
             const uint32_t pix = ids.x, bounces = ids.z >> 16;
             bool dead = false;
             if (CLS == CLS_MISS) {  // camera.rs:180-183
@@ -147,9 +146,8 @@ __global__ void __launch_bounds__(kBlock, PT_NEE_MIN_BLOCKS) k_shade_nee(PathBuf
         RayD next, sray; d3 thr = mk(0, 0, 0), sthr = mk(0, 0, 0); uint4 ids = make_uint4(0, 0, 0, 0);
         if (j < count) {
             const uint32_t i = items[j];
-            RayD ray = load_ray(in, i);
-            thr = mk(in.f[7][i], in.f[8][i], in.f[9][i]);
-            ids = in.ids[i];
+            RayD ray = load_ray(in, i, &ids.x, &ids.y);
+            thr = load_state(in, i, ids.z, ids.w);
             const uint32_t pix = ids.x, bounces = ids.z >> 16;
             const bool is_shadow = ids.w == kShadowMark;
             bool dead = false;

@@ -32,6 +32,25 @@ void run_k_trace_blas(bool refill, bool count, unsigned grid, cudaStream_t st, P
     } else if (count) k_trace_blas<true><<<grid, kTraceBlock, 0, st>>>(in, round, bq, hits, ties, q, S, work, t_min);
     else k_trace_blas<false><<<grid, kTraceBlock, 0, st>>>(in, round, bq, hits, ties, q, S, work, t_min);
 }
+void run_k_top(bool primary, bool count, cudaStream_t st, PathBuf pool, uint32_t slot0, uint32_t n, HitRec* hits, Queues q, const DScene& S, const TopList& top,
+               MeshQueues mq, uint2* ties, double t_min, const GenArgs& gen, const uint32_t* n_dev, unsigned long long* work) {
+    const unsigned grid = (n + kBlock - 1) / kBlock;
+#define PT_GO(P, C) k_top<P, C><<<grid, kBlock, 0, st>>>(pool, slot0, n, hits, q, S, top, mq, ties, t_min, gen, n_dev, work)
+    if (primary) { if (count) PT_GO(true, true); else PT_GO(true, false); }
+    else { if (count) PT_GO(false, true); else PT_GO(false, false); }
+#undef PT_GO
+}
+void run_k_mesh_enter(bool count, unsigned grid, cudaStream_t st, PathBuf pool, uint32_t round, MeshQueues mq, const HitRec* hits, const uint2* ties, Queues q,
+                      const DScene& S, const TopList& top, double t_min, unsigned long long* work) {
+    if (count) k_mesh_enter<true><<<grid, kBlock, 0, st>>>(pool, round, mq, hits, ties, q, S, top, t_min, work);
+    else k_mesh_enter<false><<<grid, kBlock, 0, st>>>(pool, round, mq, hits, ties, q, S, top, t_min, work);
+}
+void run_k_mesh_walk(bool count, unsigned grid, cudaStream_t st, uint32_t round, MeshQueues mq, HitRec* hits, uint2* ties, Queues q, const DScene& S, double t_min,
+                     unsigned long long* work) {
+    if (count) k_mesh_walk<true><<<grid, kTraceBlock, 0, st>>>(round, mq, hits, ties, q, S, t_min, work);
+    else k_mesh_walk<false><<<grid, kTraceBlock, 0, st>>>(round, mq, hits, ties, q, S, t_min, work);
+}
+unsigned mesh_walk_resident_warps() { return 148u * 4u * (unsigned)kWalkMinBlocks; }
 static unsigned grid128(size_t n) { return (unsigned)((n + 127) / 128); }
 void run_k_trace_batch(bool wide, cudaStream_t st, const pt_ray* rays, size_t n, double t_min, pt_hit* out, const DScene& S) {
     if (wide) k_trace_batch<true><<<grid128(n), 128, 0, st>>>(rays, n, t_min, out, S);
@@ -46,6 +65,9 @@ void run_k_rays_to_pool(cudaStream_t st, const pt_ray* rays, uint32_t n, uint32_
 }
 void run_k_hits_to_abi(cudaStream_t st, const pt_ray* rays, uint32_t n, const HitRec* hits, pt_hit* out, const DScene& S) {
     k_hits_to_abi<<<grid128(n), 128, 0, st>>>(rays, n, hits, out, S);
+}
+void run_k_pool_to_abi(cudaStream_t st, PathBuf pool, uint32_t n, const HitRec* hits, pt_ray* out_rays, pt_hit* out_hits, const DScene& S) {
+    k_pool_to_abi<<<grid128(n), 128, 0, st>>>(pool, n, hits, out_rays, out_hits, S);
 }
 cudaError_t debug_histograms(unsigned long long* out512, bool reset) {
     cudaError_t e = cudaSuccess;

@@ -17,8 +17,10 @@ PT_D void hist_add(int h, uint32_t v) { atomicAdd(&g_hist[h * 64 + min(v, 63u)],
 // VOL: the scene holds constant-density media; their free-flight uniforms are keyed by (seed, pixel, sample, bounce).
 struct PathVol {
     static constexpr bool kEnabled = true;
-    uint64_t seed; const uint4* __restrict__ ids; uint32_t i;
-    PT_D double operator()(uint32_t v) const { const uint4 id = ids[i]; return keyed_uniform(seed, id.x, id.y, id.z >> 16, v); }
+    uint64_t seed; PathBuf in; uint32_t i;
+    PT_D double operator()(uint32_t v) const {
+        return keyed_uniform(seed, in.ray[i].pixel, in.ray[i].sample, in.state[i].rng_bounce >> 16, v);
+    }
 };
 // Two-pass traversal for scenes with mesh BLASes (DEFER): a warp of k_trace mixes rays that leave the top-level BVH after a
 // node or two with rays that walk a mesh for ten times as long, so the short ones idle (8.9 of 32 lanes active on scene 6).
@@ -51,7 +53,7 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_BLOCKS * kBlock / kTraceBlock
     if (i < n) {
         Closest c;
         // t_min: the render passes eps = 1e-3 (Interval::new(eps, INFINITY), camera.rs:171,179); ray batches pass their own
-        if constexpr (VOL) trace_closest<false, COUNT, WIDE>(S, [&]() { return load_ray(in, i); }, t_min, 0.0, c, PathVol{seed, in.ids, i});
+        if constexpr (VOL) trace_closest<false, COUNT, WIDE>(S, [&]() { return load_ray(in, i); }, t_min, 0.0, c, PathVol{seed, in, i});
         else if constexpr (DEFER) trace_closest<false, COUNT, WIDE>(S, [&]() { return load_ray(in, i); }, t_min, 0.0, c, NoVol(), DeferList{&nd, dslot, dt});
         else trace_closest<false, COUNT, WIDE>(S, [&]() { return load_ray(in, i); }, t_min, 0.0, c);
         if (COUNT) {
@@ -222,6 +224,354 @@ __global__ void __launch_bounds__(kTraceBlock, kBlasMinBlocks * kBlock / kTraceB
     }
 }
 
+// ================================================================== flat top level + mesh rounds (the production traversal of
+// every scene whose World is small: all of the reference's scenes but the 480-sphere one)
+//
+//   k_top         one ray per lane over the top-level reference LIST (wavefront.cuh: TopList).  PRIMARY: the ray is a camera ray
+//                 generated in registers (camera.rs:153-168) and its path record is written here, once — there is no separate
+//                 ray-generation kernel and no re-read.  Simple primitives are tested in f64 on the spot; a mesh whose world
+//                 box the ray enters is only noted in a bit mask and queued for the rounds below.
+//   k_mesh_enter  round r, one queued visit per lane, fully convergent: the ray goes into the mesh's space (instance.rs:36-38),
+//                 the mesh's root node is tested, and only rays that enter a child get a 128-byte walk record.  (Measured
+//                 before the split: 37 % of the visits ended at the root node, yet paid the gathers and the f64 transform
+//                 inside the divergent walk kernel.)
+//   k_mesh_walk   persistent warps with lane refill from the walk records.  A lane holds at most one node to open (`cur`) and
+//                 one triangle to test (`pend`); the warp votes on which of the two kinds of work runs next, so a 4-wide box
+//                 step or an f64 Moeller-Trumbore test is issued for many lanes at once instead of each lane switching kinds
+//                 on its own.
+// Same closest hit as World::intersect_all: minimum t, exact ties by the precomputed ranks, so neither
+// the visit order nor the split into passes can change a result.
+struct __align__(16) WalkRec {
+    double o[3], d[3];                       // ray in the mesh's space
+    double t;                                // closest hit so far (provisional hit of the top-level pass and earlier rounds)
+    uint32_t path, flags;                    // flags: last visit of this ray << 31 | shade class of the mesh << 12 | of the provisional hit << 8
+    uint32_t ref, inst_light, tie_o, tie_i;  // provisional hit
+    uint32_t cur_inst, cur_tie, n_init, pad;
+    uint2 init[4];                           // children of the root node the ray enters, nearest first: (child, entry distance)
+};
+static_assert(sizeof(WalkRec) == 16 * kWalkRecU4, "walk record size");
+
+// 4-wide box step: entry distances of the four children, ascending, +inf = not entered
+PT_D void wide2_step(const DWide2& w, const BoxRay& br, float tmin_f, float tmax_f, uint32_t e[4], float t[4]) {
+    const float4 lx = *reinterpret_cast<const float4*>(w.lo[0]), ly = *reinterpret_cast<const float4*>(w.lo[1]),
+                 lz = *reinterpret_cast<const float4*>(w.lo[2]), hx = *reinterpret_cast<const float4*>(w.hi[0]),
+                 hy = *reinterpret_cast<const float4*>(w.hi[1]), hz = *reinterpret_cast<const float4*>(w.hi[2]);
+    const uint4 ch = *reinterpret_cast<const uint4*>(w.child);
+    const float kInf = __int_as_float(0x7f800000);
+    const bool sx = br.ix < 0.f, sy = br.iy < 0.f, sz = br.iz < 0.f;
+#define PT_SLAB4(I, K)                                                                                                   \
+    {                                                                                                                    \
+        const float x0 = __fmaf_rn(sx ? hx.I : lx.I, br.ix, br.nx), x1 = __fmaf_rn(sx ? lx.I : hx.I, br.ix, br.fx);     \
+        const float y0 = __fmaf_rn(sy ? hy.I : ly.I, br.iy, br.ny), y1 = __fmaf_rn(sy ? ly.I : hy.I, br.iy, br.fy);     \
+        const float z0 = __fmaf_rn(sz ? hz.I : lz.I, br.iz, br.nz), z1 = __fmaf_rn(sz ? lz.I : hz.I, br.iz, br.fz);     \
+        const float tn = fmaxf(fmaxf(x0, y0), fmaxf(z0, tmin_f)), tf = fminf(fminf(x1, y1), fminf(z1, tmax_f));         \
+        t[K] = tn <= tf ? tn : kInf; /* NaN planes (0*inf) drop out of fmaxf/fminf: conservative */                      \
+    }
+    PT_SLAB4(x, 0) PT_SLAB4(y, 1) PT_SLAB4(z, 2) PT_SLAB4(w, 3)
+#undef PT_SLAB4
+    e[0] = ch.x; e[1] = ch.y; e[2] = ch.z; e[3] = ch.w;
+#define PT_CSWAP(A, B) { const bool s_ = t[B] < t[A]; const float tt = s_ ? t[A] : t[B]; t[A] = s_ ? t[B] : t[A]; t[B] = tt; \
+                         const uint32_t ee = s_ ? e[A] : e[B]; e[A] = s_ ? e[B] : e[A]; e[B] = ee; }
+    PT_CSWAP(0, 1) PT_CSWAP(2, 3) PT_CSWAP(0, 2) PT_CSWAP(1, 3) PT_CSWAP(1, 2)
+#undef PT_CSWAP
+}
+
+#ifndef PT_TOP_MIN_BLOCKS
+#define PT_TOP_MIN_BLOCKS 5
+#endif
+template <bool PRIMARY, bool COUNT>
+__global__ void __launch_bounds__(kBlock, PT_TOP_MIN_BLOCKS) k_top(PathBuf pool, uint32_t slot0, uint32_t n, HitRec* __restrict__ hits, Queues q, DScene S,
+                                                                    TopList top, MeshQueues mq, uint2* __restrict__ ties, double t_min, GenArgs gen,
+                                                                    const uint32_t* __restrict__ n_dev, unsigned long long* __restrict__ work) {
+    if (!PRIMARY && n_dev) n = min(n, *n_dev);  // batched tail iterations: the survivors counter of the iteration before
+    const uint32_t j = blockIdx.x * kBlock + threadIdx.x;
+    const uint32_t i = slot0 + j;
+    uint32_t cls = N_CLS, mesh_mask = 0, prov_cls = CLS_MISS;
+    uint32_t w1 = 0, w2 = 0;
+    if (j < n) {
+        RayD r;
+        if (PRIMARY) {
+            uint32_t s_local, pix;
+            path_pixel(gen.g0 + j, gen.n_pixels, gen.cam.c, pix, s_local);
+            const uint32_t sample = gen.rc.sample_begin + s_local * gen.rc.sample_stride;
+            Rng rng; rng.init(gen.rc.seed, pix, sample, 0);
+            r = generate_ray(gen.cam, pix / gen.cam.c.width, pix % gen.cam.c.width, rng);
+            store_path(pool, i, r, mk(1, 1, 1), make_uint4(pix, sample, rng.used, 0));
+        } else r = load_ray(pool, i);
+        const BoxRay br = make_boxray(r);
+        const float tmin_f = __double2float_rd(t_min);
+        float tmax_f = __int_as_float(0x7f800000);
+        Closest c;
+        c.t = __longlong_as_double(0x7ff0000000000000ll); c.ref = kNone; c.inst = kInstNone; c.tie_outer = 0; c.tie_inner = 0; c.is_light = false;
+        uint32_t kbest = 0;
+#pragma unroll 1
+        for (uint32_t k = 0; k < top.n; k++) {  // warp-uniform trip count, reference and primitive kind
+            const DNode rb = S.refs[k];
+            if (COUNT) w1++;
+            if (!(slab(rb, br, tmin_f, tmax_f) <= tmax_f)) continue;
+            if ((top.mesh_bits >> k) & 1u) { mesh_mask |= 1u << k; continue; }
+            if (COUNT) w2++;
+            const uint32_t kind = ref_kind(rb.a), index = ref_index(rb.a);
+            if (kind <= PT_OBJ_CUBOID) test_simple(S, kind, index, r, t_min, c, kInstNone, rb.b, 0);
+            else {  // instance of a simple primitive or cuboid (instance.rs:34-54)
+                const DInstance& in = S.instances[index];
+                test_simple(S, in.child_kind, in.child_index, instance_local_ray(in, r), t_min, c, index, rb.b, 0);
+            }
+            if (c.ref != kNone && c.tie_outer == rb.b) { kbest = k; tmax_f = __double2float_ru(c.t); }  // outer ranks are unique per reference
+        }
+        c.is_light = c.ref != kNone && !(c.tie_outer >> 31);  // objects carry bit 31 in their outer rank (object beats light, Q31)
+        HitRec h; h.t = c.t; h.ref = c.ref; h.inst_light = (c.inst & 0x7FFFFFFFu) | (c.is_light ? 0x80000000u : 0u);
+        hits[i] = h;
+        prov_cls = c.ref == kNone ? (uint32_t)CLS_MISS : (uint32_t)top.cls[kbest];
+        if (mesh_mask) ties[i] = make_uint2(c.tie_outer, c.tie_inner); else cls = prov_cls;
+        if (COUNT) { hist_add(1, w1); hist_add(2, w2); hist_add(3, __popc(mesh_mask)); }
+    }
+    __syncwarp();
+    queue_append(q, cls, i);
+    if (top.mesh_bits) {  // queue the r-th entered mesh of every ray for round r (warp-aggregated appends)
+        const uint32_t lane = threadIdx.x & 31, nm = __popc(mesh_mask);
+#pragma unroll 1
+        for (uint32_t r = 0; r < (uint32_t)kMeshRounds; r++) {
+            const bool has = nm > r;
+            const uint32_t b = __ballot_sync(0xFFFFFFFFu, has);
+            if (!b) break;
+            const int leader = __ffs(b) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(mq.count + r, __popc(b));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (has) mq.items[(size_t)r * mq.stride + base + __popc(b & ((1u << lane) - 1u))] =
+                         make_uint2(i, __fns(mesh_mask, 0, r + 1) | (prov_cls << 8) | (nm == r + 1 ? 0x80000000u : 0u));
+        }
+    }
+    if (COUNT) {
+        w1 = __reduce_add_sync(0xFFFFFFFFu, w1); w2 = __reduce_add_sync(0xFFFFFFFFu, w2);
+        if ((threadIdx.x & 31) == 0) { atomicAdd(work + 1, (unsigned long long)w1); atomicAdd(work + 2, (unsigned long long)w2); }
+    }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock, 4) k_mesh_enter(PathBuf pool, uint32_t round, MeshQueues mq, const HitRec* __restrict__ hits, const uint2* __restrict__ ties,
+                                                           Queues q, DScene S, TopList top, double t_min, unsigned long long* __restrict__ work) {
+    const uint32_t count = mq.count[round];
+    const uint2* __restrict__ items = mq.items + (size_t)round * mq.stride;
+    const float tmin_f = __double2float_rd(t_min);
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t w0 = 0;
+    for (uint32_t base = blockIdx.x * kBlock; base < count; base += gridDim.x * kBlock) {
+        const uint32_t j = base + threadIdx.x;
+        bool walk = false;
+        uint32_t cls = N_CLS, i = 0;
+        WalkRec rec;
+        if (j < count) {
+            const uint2 e = items[j];
+            i = e.x;
+            const uint32_t k = e.y & 0xFFu, prov_cls = (e.y >> 8) & 0xFu;
+            const bool last = (e.y >> 31) != 0;
+            const DNode rb = S.refs[k];
+            const HitRec h0 = hits[i];
+            RayD r = load_ray(pool, i);
+            BoxRay br = make_boxray(r);
+            const float tmax_f = __double2float_ru(h0.t);
+            if (slab(rb, br, tmin_f, tmax_f) <= tmax_f) {  // else the mesh has fallen behind the closest hit since it was queued
+                uint32_t mesh = ref_index(rb.a), inst = kInstNone;
+                if (ref_kind(rb.a) == PT_OBJ_INSTANCE) {
+                    const DInstance& ins = S.instances[mesh];
+                    r = instance_local_ray(ins, r); br = make_boxray(r); inst = mesh; mesh = ins.child_index;
+                }
+                uint32_t ce[4]; float ct[4];
+                wide2_step(S.wide2[S.meshes[mesh].root2], br, tmin_f, tmax_f, ce, ct);
+                if (COUNT) w0 += 2;
+                const float kInf = __int_as_float(0x7f800000);
+                if (ct[0] < kInf) {
+                    walk = true;
+                    const uint2 tie = ties[i];
+                    rec.o[0] = r.o.x; rec.o[1] = r.o.y; rec.o[2] = r.o.z; rec.d[0] = r.d.x; rec.d[1] = r.d.y; rec.d[2] = r.d.z;
+                    rec.t = h0.t; rec.path = i;
+                    rec.flags = (last ? 0x80000000u : 0u) | ((uint32_t)top.cls[k] << 12) | (prov_cls << 8);
+                    rec.ref = h0.ref; rec.inst_light = h0.inst_light; rec.tie_o = tie.x; rec.tie_i = tie.y;
+                    rec.cur_inst = inst; rec.cur_tie = rb.b; rec.pad = 0;
+                    uint32_t ni = 0;
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; c4++) { rec.init[c4] = make_uint2(ce[c4], __float_as_uint(ct[c4])); ni += ct[c4] < kInf; }
+                    rec.n_init = ni;
+                }
+            }
+            if (!walk && last) cls = prov_cls;  // nothing to walk: the provisional hit stands
+            if (COUNT && !walk) hist_add(7, 0);
+        }
+        __syncwarp();
+        queue_append(q, cls, i);
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, walk);
+        if (b) {
+            const int leader = __ffs(b) - 1;
+            uint32_t wbase = 0;
+            if ((int)lane == leader) wbase = atomicAdd(mq.walk_count + round, __popc(b));
+            wbase = __shfl_sync(0xFFFFFFFFu, wbase, leader);
+            if (walk) {
+                uint4* dst = mq.walk + (size_t)(wbase + __popc(b & ((1u << lane) - 1u))) * kWalkRecU4;
+                const uint4* src = reinterpret_cast<const uint4*>(&rec);
+#pragma unroll
+                for (int k4 = 0; k4 < kWalkRecU4; k4++) dst[k4] = src[k4];
+            }
+        }
+    }
+    if (COUNT) { w0 = __reduce_add_sync(0xFFFFFFFFu, w0); if (lane == 0 && w0) atomicAdd(work, (unsigned long long)w0); }
+}
+
+#ifndef PT_WALK_MIN_BLOCKS
+#define PT_WALK_MIN_BLOCKS 7   // resident 128-thread-equivalents per SM (7 -> 72 registers, 28 warps)
+#endif
+#ifndef PT_WALK_BURST
+#define PT_WALK_BURST 4        // work steps between two meeting points of the warp (flush finished rays, refill idle lanes)
+#endif
+#ifndef PT_WALK_REFILL_MIN
+#define PT_WALK_REFILL_MIN 8   // idle lanes that trigger a fetch
+#endif
+#ifndef PT_WALK_TRI_MIN
+#define PT_WALK_TRI_MIN 10     // lanes holding a triangle that trigger a triangle step while other lanes still have nodes to open
+#endif
+constexpr int kWalkMinBlocks = PT_WALK_MIN_BLOCKS;
+template <bool COUNT>
+__global__ void __launch_bounds__(kTraceBlock, kWalkMinBlocks * kBlock / kTraceBlock) k_mesh_walk(uint32_t round, MeshQueues mq, HitRec* __restrict__ hits, uint2* __restrict__ ties,
+                                                                                                     Queues q, DScene S, double t_min, unsigned long long* __restrict__ work) {
+    const uint32_t count = mq.walk_count[round];
+    uint32_t* __restrict__ cursor = mq.walk_count + kMeshRounds + round;
+    const uint32_t lane = threadIdx.x & 31;
+    const float tmin_f = __double2float_rd(t_min);
+    uint2 stack[kStack2];
+    int sp = 0;
+    RayD r = make_ray(mk(0, 0, 0), mk(0, 0, 1), 0.0);
+    BoxRay br = make_boxray(r);
+    Closest c; c.t = 0.0; c.ref = kNone; c.inst = kInstNone; c.tie_outer = 0; c.tie_inner = 0; c.is_light = false;
+    uint32_t i = 0, flags = 0, cur_inst = kInstNone, cur_tie = 0, done_cls = N_CLS, done_i = 0;
+    uint32_t cur = kNone, pend = kNone;  // node to open / triangle to test
+    float tmax_f = 0.f, pend_t = 0.f;
+    bool active = false, drained = false, improved = false;
+    uint32_t w0 = 0, w2 = 0, n_nodes = 0, n_tris = 0;
+    while (true) {
+        // ---- all 32 lanes meet here: finished rays join their shade-class queue, idle lanes fetch walk records
+        if (__any_sync(0xFFFFFFFFu, done_cls != N_CLS)) { queue_append(q, done_cls, done_i); done_cls = N_CLS; }
+        const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !active);
+        if (!drained && __popc(idle) >= PT_WALK_REFILL_MIN) {
+            const int leader = __ffs(idle) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(cursor, __popc(idle));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            drained = base + __popc(idle) >= count;
+            const uint32_t j = base + __popc(idle & ((1u << lane) - 1u));
+            if (!active && j < count) {
+                const uint4* src = mq.walk + (size_t)j * kWalkRecU4;
+                const uint4 a0 = src[0], a1 = src[1], a2 = src[2], a3 = src[3], a4 = src[4], a5 = src[5], a6 = src[6], a7 = src[7];
+                r.o = mk(__hiloint2double((int)a0.y, (int)a0.x), __hiloint2double((int)a0.w, (int)a0.z), __hiloint2double((int)a1.y, (int)a1.x));
+                r.d = mk(__hiloint2double((int)a1.w, (int)a1.z), __hiloint2double((int)a2.y, (int)a2.x), __hiloint2double((int)a2.w, (int)a2.z));
+                c.t = __hiloint2double((int)a3.y, (int)a3.x); i = a3.z; flags = a3.w;
+                c.ref = a4.x; c.inst = a4.y & 0x7FFFFFFFu; c.tie_outer = a4.z; c.tie_inner = a4.w;
+                cur_inst = a5.x; cur_tie = a5.y;
+                br = make_boxray(r);
+                tmax_f = __double2float_ru(c.t);
+                // the root node was opened by k_mesh_enter: its entered children, far ones first so that the nearest is popped first
+                const uint32_t ni = a5.z;
+                sp = 0;
+                if (ni > 3) { stack[sp] = make_uint2(a7.z, a7.w); sp++; }
+                if (ni > 2) { stack[sp] = make_uint2(a7.x, a7.y); sp++; }
+                if (ni > 1) { stack[sp] = make_uint2(a6.z, a6.w); sp++; }
+                stack[sp] = make_uint2(a6.x, a6.y); sp++;
+                cur = kNone; pend = kNone; improved = false; active = true;
+                if (COUNT) { n_nodes = 1; n_tris = 0; }
+            }
+        }
+        if (!__any_sync(0xFFFFFFFFu, active)) {
+            if (!drained) continue;
+            if (__any_sync(0xFFFFFFFFu, done_cls != N_CLS)) queue_append(q, done_cls, done_i);
+            break;
+        }
+#pragma unroll 1
+        for (int s = 0; s < PT_WALK_BURST; s++) {
+            // ---- every active lane takes the nearest entries off its stack until it holds a node, or a second triangle turns up
+            if (active && cur == kNone) {
+                while (sp > 0) {
+                    const uint2 top = stack[sp - 1];
+                    if (!(__uint_as_float(top.y) <= tmax_f)) { sp--; continue; }  // beyond the closest hit
+                    if (top.x & kTriBit) { if (pend != kNone) break; pend = top.x; pend_t = __uint_as_float(top.y); sp--; continue; }
+                    cur = top.x; sp--;
+                    break;
+                }
+                if (cur == kNone && pend == kNone) {  // stack empty: this visit is finished
+                    active = false;
+                    const bool last = (flags >> 31) != 0;
+                    if (improved) {
+                        HitRec h; h.t = c.t; h.ref = c.ref; h.inst_light = (c.inst & 0x7FFFFFFFu) | ((c.tie_outer >> 31) ? 0u : 0x80000000u);
+                        hits[i] = h;
+                        if (!last) ties[i] = make_uint2(c.tie_outer, c.tie_inner);
+                    }
+                    if (last) { done_cls = improved ? ((flags >> 12) & 0xFu) : ((flags >> 8) & 0xFu); done_i = i; }
+                    if (COUNT) { hist_add(4, n_nodes); hist_add(6, n_tris); hist_add(7, 1); if (improved) hist_add(7, 2); }
+                }
+            }
+            const uint32_t nb = __ballot_sync(0xFFFFFFFFu, active && cur != kNone), tb = __ballot_sync(0xFFFFFFFFu, active && pend != kNone);
+            if (!(nb | tb)) break;
+            if (!nb || __popc(tb) >= PT_WALK_TRI_MIN) {
+                // ---- triangle step (mesh.rs:50-82 in f64) for every lane that holds one
+                if (active && pend != kNone) {
+                    const uint32_t tri = pend & ~kTriBit;
+                    pend = kNone;
+                    double t, u, v;
+                    if (COUNT && pend_t <= tmax_f) { w2++; n_tris++; }
+                    if (pend_t <= tmax_f && tri_t(S.tris[tri], r, t_min, t, u, v) && t <= c.t) {
+                        const uint32_t rank = S.tri_rank[tri];
+                        if (t < c.t || cur_tie > c.tie_outer || (cur_tie == c.tie_outer && rank > c.tie_inner)) {  // `consider`: ties by rank
+                            c.t = t; c.ref = ref_pack(PT_PRIM_TRIANGLE, tri); c.inst = cur_inst; c.tie_outer = cur_tie; c.tie_inner = rank;
+                            improved = true; tmax_f = __double2float_ru(t);
+                        }
+                    }
+                }
+            } else if (active && cur != kNone) {
+                // ---- box step: open one node, push the entered children far to near; the nearest stays in hand
+                uint32_t ce[4]; float ct[4];
+                wide2_step(S.wide2[cur], br, tmin_f, tmax_f, ce, ct);
+                if (COUNT) { w0 += 2; n_nodes++; }
+                const float kInf = __int_as_float(0x7f800000);
+                cur = kNone;
+                if (ct[3] < kInf && sp < kStack2) { stack[sp] = make_uint2(ce[3], __float_as_uint(ct[3])); sp++; }
+                if (ct[2] < kInf && sp < kStack2) { stack[sp] = make_uint2(ce[2], __float_as_uint(ct[2])); sp++; }
+                if (ct[1] < kInf && sp < kStack2) { stack[sp] = make_uint2(ce[1], __float_as_uint(ct[1])); sp++; }
+                if (ct[0] < kInf) {
+                    if (!(ce[0] & kTriBit)) cur = ce[0];
+                    else if (pend == kNone) { pend = ce[0]; pend_t = ct[0]; }
+                    else if (sp < kStack2) { stack[sp] = make_uint2(ce[0], __float_as_uint(ct[0])); sp++; }
+                }
+            }
+        }
+    }
+    if (COUNT) {
+        w0 = __reduce_add_sync(0xFFFFFFFFu, w0); w2 = __reduce_add_sync(0xFFFFFFFFu, w2);
+        if (lane == 0 && (w0 | w2)) { atomicAdd(work, (unsigned long long)w0); atomicAdd(work + 2, (unsigned long long)w2); }
+    }
+}
+
+// pt_trace_camera_wavefront: the camera rays k_top<PRIMARY> generated into the pool and their hit records, by pixel
+__global__ void k_pool_to_abi(PathBuf pool, uint32_t n, const HitRec* __restrict__ hits, pt_ray* __restrict__ out_rays, pt_hit* __restrict__ out_hits, DScene S) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t pixel, sample;
+    const RayD r = load_ray(pool, i, &pixel, &sample);
+    pt_ray ro; ro.origin.x = r.o.x; ro.origin.y = r.o.y; ro.origin.z = r.o.z; ro.direction.x = r.d.x; ro.direction.y = r.d.y; ro.direction.z = r.d.z; ro.time = r.time;
+    out_rays[pixel] = ro;
+    const HitRec hr = hits[i];
+    pt_hit o; memset(&o, 0, sizeof(o)); o.instance = PT_NONE;
+    if (hr.ref != kNone) {
+        const uint32_t inst = hr.inst_light & 0x7FFFFFFFu;
+        HitInfoD h;
+        reconstruct_hit(S, r, hr.ref, inst, hr.t, h);
+        o.hit = 1; o.t = hr.t; o.u = h.u; o.v = h.v;
+        o.point.x = h.point.x; o.point.y = h.point.y; o.point.z = h.point.z;
+        o.geometric_normal.x = h.gn.x; o.geometric_normal.y = h.gn.y; o.geometric_normal.z = h.gn.z;
+        o.shading_normal.x = h.sn.x; o.shading_normal.y = h.sn.y; o.shading_normal.z = h.sn.z;
+        o.prim_kind = ref_kind(hr.ref); o.prim_index = ref_index(hr.ref); o.instance = inst == kInstNone ? PT_NONE : inst;
+        o.material = h.material; o.front_face = h.front_face; o.is_light = hr.inst_light >> 31;
+    }
+    out_hits[pixel] = o;
+}
 // keyed uniforms of ray batches (pt_volume): seed 0, pixel = ray index, sample = bounce = 0
 struct BatchVol { static constexpr bool kEnabled = true; uint32_t i; PT_D double operator()(uint32_t v) const { return keyed_uniform(0, i, 0, 0, v); } };
 template <bool WIDE>

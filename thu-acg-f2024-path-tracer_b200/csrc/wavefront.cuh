@@ -25,10 +25,13 @@ constexpr int kTraceBlock = PT_TRACE_BLOCK;
 #define PT_SHADE_MIN_BLOCKS 4  // resident blocks per SM the shade kernels must allow (register cap 128)
 #endif
 
-struct PathBuf {
-    double* f[10];  // ox oy oz dx dy dz time thr_r thr_g thr_b
-    uint4* ids;     // pixel, sample, rng_used | bounce << 16, spare
-};
+// Path pool: two arrays of records per buffer (ping-pong A/B), moved with 128-bit loads and stores.  The trace stage reads
+// only the 64-byte ray record; the shade stage GATHERS both by path index through its class queue, and a gathered record
+// is made of whole 32-byte sectors (2 + 1), so no fetched byte is wasted (ten separate f64 arrays cost ten sectors for
+// 80 useful bytes).
+struct __align__(32) RayRec { double o[3], d[3], time; uint32_t pixel, sample; };    // 64 B
+struct __align__(32) StateRec { double thr[3]; uint32_t rng_bounce, spare; };        // 32 B: throughput, rng_used | bounce << 16, spare word
+struct PathBuf { RayRec* ray; StateRec* state; };
 // Importance sampler of a lat-long environment map (PT_RENDER_ENV_IMPORTANCE; not reference behaviour):
 // a piecewise-constant density over rows x cols cells of the (u, theta/pi) unit square, built on the host in f64 by
 // pt_scene_build_env_sampler.  marginal[rows + 1] is the CDF over rows (row 0 = theta 0 = +y), cond[r * (cols + 1) ...]
@@ -56,6 +59,15 @@ PT_D RayD generate_ray(const DCameraEx& cam, uint32_t row, uint32_t col, Rng& rn
     d3 direction = sample_location - origin;
     double time = rng.next();
     return make_ray(origin, direction, time);
+}
+// g = index of a path within one render call -> (pixel, local sample): sample-major, and within a sample a warp covers an
+// 8x4 pixel tile (tighter ray bundles than a 32x1 strip) when the image size allows
+PT_D void path_pixel(uint64_t g, uint32_t n_pixels, const DCamera& cam, uint32_t& pix, uint32_t& s_local) {
+    s_local = (uint32_t)(g / n_pixels); pix = (uint32_t)(g % n_pixels);
+    if ((cam.width & 7u) == 0 && (cam.height & 3u) == 0) {
+        const uint32_t tile = pix >> 5, within = pix & 31u, tiles_x = cam.width >> 3;
+        pix = ((tile / tiles_x) * 4u + (within >> 3)) * cam.width + (tile % tiles_x) * 8u + (within & 7u);
+    }
 }
 PT_D d3 sample_environment(const DScene& S, const DCamera& cam, d3 dir) {  // camera.rs:140-151
     if (!cam.env_is_map) return cam.env_color;
@@ -97,14 +109,31 @@ PT_D double env_pdf(const DEnvDist& E, d3 dir) {  // solid-angle density of env_
     return cell * (double)E.rows * (double)E.cols / (2.0 * kPi * kPi * st);
 }
 
+// ids = {pixel, sample, rng_used | bounce << 16, spare} as the shade kernels carry them
 PT_D void store_path(const PathBuf& b, uint32_t i, const RayD& r, d3 thr, uint4 ids) {
-    b.f[0][i] = r.o.x; b.f[1][i] = r.o.y; b.f[2][i] = r.o.z; b.f[3][i] = r.d.x; b.f[4][i] = r.d.y; b.f[5][i] = r.d.z; b.f[6][i] = r.time;
-    b.f[7][i] = thr.x; b.f[8][i] = thr.y; b.f[9][i] = thr.z; b.ids[i] = ids;
+    double2* p = reinterpret_cast<double2*>(b.ray + i);
+    p[0] = make_double2(r.o.x, r.o.y); p[1] = make_double2(r.o.z, r.d.x); p[2] = make_double2(r.d.y, r.d.z);
+    reinterpret_cast<uint4*>(p)[3] = make_uint4((uint32_t)__double2loint(r.time), (uint32_t)__double2hiint(r.time), ids.x, ids.y);
+    double2* s = reinterpret_cast<double2*>(b.state + i);
+    s[0] = make_double2(thr.x, thr.y);
+    reinterpret_cast<uint4*>(s)[1] = make_uint4((uint32_t)__double2loint(thr.z), (uint32_t)__double2hiint(thr.z), ids.z, ids.w);
 }
-PT_D RayD load_ray(const PathBuf& b, uint32_t i) {
+PT_D RayD load_ray(const PathBuf& b, uint32_t i, uint32_t* pixel = nullptr, uint32_t* sample = nullptr) {
+    const double2* p = reinterpret_cast<const double2*>(b.ray + i);
+    const double2 a = p[0], c = p[1], e = p[2];
+    const uint4 g = reinterpret_cast<const uint4*>(p)[3];
     RayD r;
-    r.o = mk(b.f[0][i], b.f[1][i], b.f[2][i]); r.d = mk(b.f[3][i], b.f[4][i], b.f[5][i]); r.time = b.f[6][i];
+    r.o = mk(a.x, a.y, c.x); r.d = mk(c.y, e.x, e.y); r.time = __hiloint2double((int)g.y, (int)g.x);
+    if (pixel) *pixel = g.z;
+    if (sample) *sample = g.w;
     return r;
+}
+PT_D d3 load_state(const PathBuf& b, uint32_t i, uint32_t& rng_bounce, uint32_t& spare) {
+    const double2* s = reinterpret_cast<const double2*>(b.state + i);
+    const double2 a = s[0];
+    const uint4 g = reinterpret_cast<const uint4*>(s)[1];
+    rng_bounce = g.z; spare = g.w;
+    return mk(a.x, a.y, __hiloint2double((int)g.y, (int)g.x));
 }
 
 // Shade classes: one queue and one specialised shade kernel per class, so warps shade one material kind.
@@ -139,6 +168,21 @@ PT_D void queue_append(const Queues& q, uint32_t cls, uint32_t i) {
 // ---------------------------------------------------------------- parity / test entry kernels
 PT_D pt_vec3 to_abi(d3 v) { pt_vec3 r; r.x = v.x; r.y = v.y; r.z = v.z; return r; }
 PT_D d3 from_abi(pt_vec3 v) { return mk(v.x, v.y, v.z); }
+
+// Flat top level (k_top): scenes whose World holds at most kTopMax objects + lights are traversed as a LIST — every lane
+// of a warp tests reference k at the same time, so the loop control, the reference loads and the primitive kind are
+// warp-uniform and only the box-hit predicate diverges.  refs[0 .. n) are the top-level references (lights, then objects);
+// cls[k] = shade class of what a hit on reference k shades with; mesh_bit k set = a mesh or an instance of one, which is
+// not walked here but queued for the mesh rounds (k_mesh_enter + k_mesh_walk), at most kMeshRounds per ray.
+constexpr int kTopMax = 32;
+constexpr int kMeshRounds = 8;
+struct TopList { uint32_t n, mesh_bits; uint8_t cls[kTopMax]; };
+// mesh-visit queues of one wavefront iteration: items[round * stride + j] = {path, top reference | provisional class << 8 |
+// last << 31}; walk records of the round that is being processed; counters: count[round], then the walk counter and cursor
+struct MeshQueues { uint2* items; uint32_t* count; uint32_t stride; uint4* walk; uint32_t* walk_count; };
+struct GenArgs { uint64_t g0; uint32_t n_pixels; DCameraEx cam; RenderConst rc; };  // k_top<PRIMARY>: paths g0 + j are generated in registers
+constexpr int kWalkRecU4 = 8;   // a walk record is 128 bytes (trace_kernels.cuh: WalkRec)
+constexpr int kStack2 = 32;     // traversal stack of the mesh walk (three pushes per level at most; checked on upload)
 
 // two-pass traversal (trace_kernels.cuh): at most kDeferMax mesh visits are queued per ray and walked by later rounds
 constexpr int kDeferMax = 3;
