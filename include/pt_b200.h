@@ -252,7 +252,8 @@ typedef struct {
     uint32_t two_pass_iterations; /* wavefront iterations whose traversal stage took the two-pass path (top-level pass +
                                    * mesh rounds) instead of the fused kernel: tests assert on it so that an ID comparison
                                    * can never silently run on the other flavour */
-    uint32_t _pad;
+    uint32_t queue_errors;        /* pt_trace_*_wavefront only: rays that did not join exactly one shade-class queue, or joined the
+                                   * queue of another class than their hit's material (an invariant of the traversal stage; 0) */
 } pt_stats;
 
 typedef struct pt_ctx pt_ctx;
@@ -374,6 +375,10 @@ int  pt_env_sample_pdf(pt_ctx* ctx, const pt_scene* scene, size_t n, const doubl
 /* Diagnostics (profiling level 2 only): eight 64-bin histograms of per-ray / per-mesh-visit traversal work gathered by the
  * counting kernel variants since the last reset (layout: csrc/kernels.cuh, g_hist).  out512 may be NULL. */
 int  pt_debug_histograms(pt_ctx* ctx, uint64_t* out512, int reset);
+/* Diagnostics (profiling level >= 1): CUDA-event time per kernel family of the traversal stage since the last reset, ms:
+ * [0] k_top on surviving paths, [1] k_top on new paths (camera rays generated in the kernel), [2] k_mesh_enter,
+ * [3] k_mesh_walk, [4] BVH trace kernels (k_trace, k_trace_blas*), [5] k_generate.  out16 may be NULL. */
+int  pt_debug_stage_ms(pt_ctx* ctx, double* out16, int reset);
 
 #ifdef __cplusplus
 }

@@ -50,7 +50,7 @@ class Stats(C.Structure):  # pt_stats
                 ("iterations", C.c_uint32), ("width", C.c_uint32), ("height", C.c_uint32), ("device_ms", C.c_float),
                 ("trace_ms", C.c_float), ("shade_ms", C.c_float), ("raygen_ms", C.c_float),
                 ("node_pairs", C.c_uint64), ("ref_boxes", C.c_uint64), ("prim_tests", C.c_uint64),
-                ("two_pass_iterations", C.c_uint32), ("_pad", C.c_uint32)]
+                ("two_pass_iterations", C.c_uint32), ("queue_errors", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -72,7 +72,7 @@ ABI_SYMBOLS = ["pt_ctx_create", "pt_ctx_destroy", "pt_ctx_set_stream", "pt_ctx_s
                "pt_scene_create", "pt_scene_destroy", "pt_scene_device_bytes", "pt_camera_image_height", "pt_render_accumulate",
                "pt_render", "pt_tonemap_rgb8", "pt_trace_closest", "pt_trace_any", "pt_bsdf_eval_pdf", "pt_bsdf_sample",
                "pt_camera_rays", "pt_lights_sample_pdf", "pt_scene_build_env_sampler", "pt_env_sample_pdf", "pt_sah_sweep",
-               "pt_render_multi", "pt_trace_closest_wavefront", "pt_trace_camera_wavefront", "pt_debug_histograms"]
+               "pt_render_multi", "pt_trace_closest_wavefront", "pt_trace_camera_wavefront", "pt_debug_histograms", "pt_debug_stage_ms"]
 
 
 class PtError(RuntimeError):
@@ -453,6 +453,14 @@ class Context:
 
     def upload(self, scene):
         return DeviceScene(self, scene)
+
+    def stage_ms(self, reset=True):
+        """pt_debug_stage_ms: per-kernel-family times of the traversal stage (profiling level >= 1) since the last reset."""
+        out = np.zeros(16, dtype=np.float64)
+        self.lib.pt_debug_stage_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        self._check(self.lib.pt_debug_stage_ms(self.ptr, _ptr(out), int(reset)))
+        names = ("top_old", "top_new", "mesh_enter", "mesh_walk", "bvh", "generate", "-", "-", "miss", "light", "diffuse", "metal", "glass", "principled", "other")
+        return {k: v for k, v in zip(names, out.tolist()) if k != "-"}
 
     def histograms(self, reset=True):
         """pt_debug_histograms: [8, 64] counters of the profiling-level-2 kernel variants since the last reset."""

@@ -44,6 +44,19 @@ struct pt_ctx {
     uint2* ties = nullptr;                  //   and the tie ranks of the provisional hit of every path (both allocated on first use)
     uint2* mq_items = nullptr; uint32_t mq_rounds = 0;  // flat scenes with meshes: mq_rounds queues of `pool` mesh visits each (k_top -> k_mesh_enter)
     uint4* walk = nullptr;                  //   and `pool` 128-byte walk records (k_mesh_enter -> k_mesh_walk)
+    // profiling level >= 1: event marks inside an iteration; the time since the previous mark goes to the mark's stage
+    // (pt_debug_stage_ms: 0 k_top on survivors, 1 k_top on new paths (+ ray generation), 2 k_mesh_enter, 3 k_mesh_walk,
+    //  4 BVH trace kernels, 5 k_generate, 6 shade kernels)
+    std::vector<cudaEvent_t> marks; std::vector<int> mark_tags; size_t n_marks = 0; double stage_ms[16] = {0};
+    void mark(int tag) {
+        if (!profiling) return;
+        if (n_marks == marks.size()) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return; marks.push_back(e); mark_tags.push_back(0); }
+        cudaEventRecord(marks[n_marks], stream); mark_tags[n_marks] = tag; n_marks++;
+    }
+    void collect_marks() {  // after the stream has been synchronised
+        for (size_t k = 1; k < n_marks; k++) { float ms = 0; if (cudaEventElapsedTime(&ms, marks[k - 1], marks[k]) == cudaSuccess && mark_tags[k] >= 0) stage_ms[mark_tags[k] & 15] += ms; }
+        n_marks = 0;
+    }
     void* scratch = nullptr; size_t scratch_bytes = 0;  // pt_render / pt_tonemap_rgb8 output staging, grown on demand (no cudaMalloc per call)
     unsigned long long* d_nonfinite = nullptr;
     uint32_t* h_count = nullptr;            // pinned, same shape as d_count
@@ -142,6 +155,7 @@ void pt_ctx_destroy(pt_ctx* c) {
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (auto& e : c->evs) if (e) cudaEventDestroy(e);
+    for (auto& e : c->marks) cudaEventDestroy(e);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (int k = 0; k < N_CLS; k++) { if (c->shade_stream[k]) cudaStreamDestroy(c->shade_stream[k]); if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]); }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -698,7 +712,7 @@ int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
     U.up(meshes, &D.meshes); U.up(instances, &D.instances); U.up(textures, &D.textures); U.up(images, &D.images); U.up(materials, &D.materials);
     U.up(lights, &D.lights); U.up(tri_verts, &D.tri_verts); U.up(volumes, &D.volumes); U.up(C.wide2, &D.wide2); U.up(tri_rank, &D.tri_rank);
     if ((rc = U.commit())) return rc;
-    D.image_data = d_img; D.n_lights = d->n_lights; D.root_entry = world_root;
+    D.image_data = d_img; D.n_lights = d->n_lights; D.root_entry = world_root; D.n_materials = d->n_materials; D.n_textures = d->n_textures;
     s->n_materials = d->n_materials; s->n_images = d->n_images; s->images = images;
     CU(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
     *out = s.release();
@@ -866,19 +880,23 @@ static void launch_trace(const TraceStage& T, const PathBuf& in, uint32_t n_old,
         uint32_t* slot = q.count - 4;
         const MeshQueues mq{ctx->mq_items, slot + 12, ctx->pool, ctx->walk, slot + 20};
         static const GenArgs no_gen{};
-        if (n_old) { run_k_top(false, wk != nullptr, st, in, 0, n_old, ctx->hits, q, scene->d, scene->top, mq, ctx->ties, T.t_min, no_gen, n_dev, wk); S.kernel_launches++; }
-        if (n_new) { run_k_top(true, wk != nullptr, st, in, n_old, n_new, ctx->hits, q, scene->d, scene->top, mq, ctx->ties, T.t_min, *gen, nullptr, wk); S.kernel_launches++; }
+        ctx->mark(-1);
+        if (n_old) { run_k_top(false, wk != nullptr, st, in, 0, n_old, ctx->hits, q, scene->d, scene->top, mq, ctx->ties, T.t_min, no_gen, n_dev, wk); S.kernel_launches++; ctx->mark(0); }
+        if (n_new) { run_k_top(true, wk != nullptr, st, in, n_old, n_new, ctx->hits, q, scene->d, scene->top, mq, ctx->ties, T.t_min, *gen, nullptr, wk); S.kernel_launches++; ctx->mark(1); }
         const unsigned eg = std::min<unsigned>((n + kBlock - 1) / kBlock, 148u * 16u);
         const unsigned wg = std::min<unsigned>((n + kTraceBlock - 1) / kTraceBlock, mesh_walk_resident_warps());
         for (uint32_t r = 0; r < scene->mesh_rounds; r++) {
             run_k_mesh_enter(wk != nullptr, eg, st, in, r, mq, ctx->hits, ctx->ties, q, scene->d, scene->top, T.t_min, wk);
+            ctx->mark(2);
             run_k_mesh_walk(wk != nullptr, wg, st, r, mq, ctx->hits, ctx->ties, q, scene->d, T.t_min, wk);
+            ctx->mark(3);
             S.kernel_launches += 2;
         }
         if (scene->mesh_rounds) S.two_pass_iterations++;
         return;
     }
-    if (n_new) { run_k_generate(st, in, n_old, n_new, gen->g0, gen->n_pixels, gen->cam, gen->rc); S.kernel_launches++; }
+    ctx->mark(-1);
+    if (n_new) { run_k_generate(st, in, n_old, n_new, gen->g0, gen->n_pixels, gen->cam, gen->rc); S.kernel_launches++; ctx->mark(5); }
     const unsigned tg = (n + kTraceBlock - 1) / kTraceBlock;
     // two-pass traversal; not for small iterations (three more launches each); flag 0x100000 opts out (A/B measurements)
     if (scene->defer_meshes && n >= (1u << 16) && !(T.flags & 0x100000u)) {
@@ -891,6 +909,7 @@ static void launch_trace(const TraceStage& T, const PathBuf& in, uint32_t n_old,
             run_k_trace_blas(refill, wk != nullptr, grid, st, in, r, bq, ctx->hits, ctx->ties, q, scene->d, wk, T.t_min);
         S.kernel_launches += 1 + kDeferMax;
         S.two_pass_iterations++;
+        ctx->mark(4);
         return;
     }
     // fused kernel; for 4-wide scenes flags bits 4-6 pick the register cap (experiment knob): 4: 120, 5: 96, 6: 80, 7: 64 registers
@@ -899,6 +918,7 @@ static void launch_trace(const TraceStage& T, const PathBuf& in, uint32_t n_old,
     run_k_trace(TraceFlavour{min_blocks, scene->wide, wk != nullptr, scene->has_volumes, false}, tg, st, in, n, ctx->hits, q, scene->d, wk, T.seed,
                 n_dev, BlasQueues{nullptr, nullptr, 0}, nullptr, T.t_min);
     S.kernel_launches++;
+    ctx->mark(4);
 }
 
 int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* cam, const pt_render_params* p, float* d_accum, pt_stats* stats) {
@@ -940,6 +960,7 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
         const unsigned sg = std::min<unsigned>((n + kBlock - 1) / kBlock, 148u * 16u);
         if (fork) CU(cudaEventRecord(ctx->ev_fork, st));
         const ShadeArgs sa{in, q, ctx->hits, outb, out_count, d_accum, ctx->d_nonfinite, scene->d, dcam, rcst};
+        ctx->mark(-1);
         for (int cls = 0; cls < N_CLS; cls++) {
             if (!(scene->class_mask & (1u << cls))) continue;
             cudaStream_t ss = fork ? ctx->shade_stream[cls] : st;
@@ -949,6 +970,7 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
             else if (scene->general_lights) run_k_shade_var(cls, 2, sg, ss, sa);
             else run_k_shade_ref(cls, sg, ss, sa);
             if (fork) { CU(cudaEventRecord(ctx->ev_join[cls], ss)); CU(cudaStreamWaitEvent(st, ctx->ev_join[cls], 0)); }
+            else ctx->mark(8 + cls);
             S.kernel_launches++;
         }
         return PT_OK;
@@ -995,6 +1017,7 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
         CU(cudaMemcpyAsync(ctx->h_count, ctx->d_count, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         if (ctx->profiling) {
+            ctx->collect_marks();
             float a = 0, b = 0, c2 = 0;
             cudaEventElapsedTime(&b, ctx->evs[1], ctx->evs[2]); cudaEventElapsedTime(&c2, ctx->evs[2], ctx->evs[3]);  // ray generation is part of the traversal stage
             ms_gen += a; ms_trace += b; ms_shade += c2;
@@ -1154,6 +1177,20 @@ int pt_trace_closest(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_ray*
     run_k_trace_batch(scene->wide, ctx->stream, (const pt_ray*)in.p, n, t_min, (pt_hit*)out.p, scene->d);
     return out.to_host(hits, n * sizeof(pt_hit), ctx->stream);
 }
+// parity entry points only: the shade-class queues the traversal stage filled are checked against the hit records
+static int check_queues(pt_ctx* ctx, const pt_scene* scene, const Queues& q, uint32_t n, pt_stats* S) {
+    DevBuf seen;
+    int rc = seen.alloc(((size_t)n + 1) * sizeof(uint32_t));
+    if (rc) return rc;
+    CU(cudaMemsetAsync(seen.p, 0, ((size_t)n + 1) * sizeof(uint32_t), ctx->stream));
+    uint32_t* errors = (uint32_t*)seen.p + n;
+    run_k_check_queues(ctx->stream, q, ctx->hits, n, (uint32_t*)seen.p, errors, scene->d);
+    uint32_t h_err = 0;
+    CU(cudaMemcpyAsync(&h_err, errors, sizeof(h_err), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    S->queue_errors += h_err;
+    return PT_OK;
+}
 int pt_trace_closest_wavefront(pt_ctx* ctx, const pt_scene* scene, size_t n, const pt_ray* rays, double t_min, uint32_t flags, pt_hit* hits, pt_stats* stats) {
     if (!ctx || !scene || (n && (!rays || !hits))) return fail(PT_ERR_INVALID, "pt_trace_closest_wavefront: null argument");
     if (scene->ctx != ctx) return fail(PT_ERR_INVALID, "scene belongs to another context");
@@ -1179,6 +1216,7 @@ int pt_trace_closest_wavefront(pt_ctx* ctx, const pt_scene* scene, size_t n, con
         CU(cudaMemsetAsync(ctx->d_count, 0, kSlot * sizeof(uint32_t), st));
         const Queues q{ctx->q_items, ctx->d_count + 4, ctx->pool};
         launch_trace(T, pool, m, 0, nullptr, q, nullptr);
+        if ((rc = check_queues(ctx, scene, q, m, &S))) return rc;
         run_k_hits_to_abi(st, (const pt_ray*)in.p, m, ctx->hits, (pt_hit*)out.p, scene->d);
         if ((rc = out.to_host(hits + first, (size_t)m * sizeof(pt_hit), st))) return rc;
         S.segments += m; S.iterations++; S.kernel_launches += 2;
@@ -1214,10 +1252,17 @@ int pt_trace_camera_wavefront(pt_ctx* ctx, const pt_scene* scene, const pt_camer
     CU(cudaMemsetAsync(ctx->d_count, 0, kSlot * sizeof(uint32_t), st));
     const Queues q{ctx->q_items, ctx->d_count + 4, ctx->pool};
     launch_trace(T, in, 0, n, &gen, q, nullptr);
+    if ((rc = check_queues(ctx, scene, q, n, &S))) return rc;
     run_k_pool_to_abi(st, in, n, ctx->hits, (pt_ray*)d_rays.p, (pt_hit*)d_hits.p, scene->d);
     if ((rc = d_rays.to_host(rays, (size_t)n * sizeof(pt_ray), st)) || (rc = d_hits.to_host(hits, (size_t)n * sizeof(pt_hit), st))) return rc;
     S.paths = n; S.segments = n; S.iterations = 1; S.kernel_launches++;
     if (stats) *stats = S;
+    return PT_OK;
+}
+int pt_debug_stage_ms(pt_ctx* ctx, double* out16, int reset) {
+    if (!ctx) return fail(PT_ERR_INVALID, "pt_debug_stage_ms: null ctx");
+    if (out16) memcpy(out16, ctx->stage_ms, sizeof(ctx->stage_ms));
+    if (reset) memset(ctx->stage_ms, 0, sizeof(ctx->stage_ms));
     return PT_OK;
 }
 int pt_debug_histograms(pt_ctx* ctx, uint64_t* out512, int reset) {

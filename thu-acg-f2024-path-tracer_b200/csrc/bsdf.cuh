@@ -41,7 +41,8 @@ PT_D d3 cosine_sample_hemisphere(Rng& rng) {  // :18-24
     double phi = rng.next() * (2.0 * kPi);
     double r2 = rng.next();
     double r2s = sqrt(r2);
-    return mk(r2s * cos(phi), r2s * sin(phi), sqrt(1.0 - r2));
+    double sp, cp; pt_sincos(phi, sp, cp);
+    return mk(r2s * cp, r2s * sp, sqrt(1.0 - r2));
 }
 PT_D double ggx_D(d3 h, double roughness) {  // :38-43
     double ct = fmax(h.z, 0.001);
@@ -64,8 +65,9 @@ PT_D d3 ggx_sample_normal(d3 v_in, double roughness, Rng& rng) {  // :57-94 (str
     double a = 1.0 / (1.0 + v.z);
     double r = sqrt(e1);
     double phi = e2 < a ? e2 / a * kPi : kPi + (e2 - a) / (1.0 - a) * kPi;
-    double p1 = r * cos(phi);
-    double p2 = r * sin(phi) * (e2 < a ? 1.0 : v.z);
+    double sp, cp; pt_sincos(phi, sp, cp);
+    double p1 = r * cp;
+    double p2 = r * sp * (e2 < a ? 1.0 : v.z);
     d3 n = p1 * t1 + p2 * t2 + sqrt(fmax(1.0 - p1 * p1 - p2 * p2, 0.0)) * v;
     d3 h = normalize(mk(a2 * n.x, a2 * n.y, fmax(n.z, 0.0)));
     return h.z < 0.0 ? -h : h;
@@ -81,7 +83,8 @@ PT_D d3 gtr1_sample_normal(double alpha, Rng& rng) {  // :127-142
     double ct = (1.0 - pow(a2, 1.0 - e1)) / (1.0 - a2);
     double st = sqrt(fmax(1.0 - ct * ct, 0.0));
     double phi = 2.0 * kPi * e2;
-    d3 h = mk(st * cos(phi), st * sin(phi), ct);
+    double sp, cp; pt_sincos(phi, sp, cp);
+    d3 h = mk(st * cp, st * sp, ct);
     return h.z < 0.0 ? -h : h;
 }
 
@@ -189,7 +192,8 @@ PT_D bool bsdf_sample_leaf(const DScene& S, const DMaterial& m, d3 ray_dir, cons
             const double z = 1.0 - 2.0 * u1;
             const double r = sqrt(fmax(0.0, 1.0 - z * z));
             const double phi = 2.0 * kPi * u2;
-            out = mk(r * cos(phi), r * sin(phi), z);
+            double sp, cp; pt_sincos(phi, sp, cp);
+            out = mk(r * cp, r * sp, z);
             return true;
         }
         default: return false;  // DiffuseLight::sample -> None (material.rs:168-170)
@@ -382,7 +386,8 @@ template <bool GENERAL> PT_D bool light_sample_object(const DScene& S, uint32_t 
         double u = rng.next(), v = rng.next();
         double theta = 2.0 * kPi * u;
         double phi = acos(2.0 * v - 1.0);
-        double x = sin(phi) * cos(theta), y = sin(phi) * sin(theta), z = cos(phi);
+        double sph, cph, sth, cth; pt_sincos(phi, sph, cph); pt_sincos(theta, sth, cth);
+        double x = sph * cth, y = sph * sth, z = cph;
         d3 p1 = mk(s.p1[0], s.p1[1], s.p1[2]), p2 = mk(s.p2[0], s.p2[1], s.p2[2]);
         d3 point = (p1 + (p2 - p1) * time) + mk(x, y, z) * fmax(s.radius, 0.0);
         dir = normalize(point - origin);

@@ -24,6 +24,7 @@ void run_k_trace_any_batch(bool wide, cudaStream_t st, const pt_ray* rays, size_
 void run_k_rays_to_pool(cudaStream_t st, const pt_ray* rays, uint32_t n, uint32_t first, PathBuf out);
 void run_k_hits_to_abi(cudaStream_t st, const pt_ray* rays, uint32_t n, const HitRec* hits, pt_hit* out, const DScene& S);
 void run_k_pool_to_abi(cudaStream_t st, PathBuf pool, uint32_t n, const HitRec* hits, pt_ray* out_rays, pt_hit* out_hits, const DScene& S);
+void run_k_check_queues(cudaStream_t st, Queues q, const HitRec* hits, uint32_t n, uint32_t* seen, uint32_t* errors, const DScene& S);
 cudaError_t debug_histograms(unsigned long long* out512, bool reset);
 
 // ---- shade_*.cu: one loop iteration of Camera::trace after intersect_all (camera.rs:180-225) per shade class

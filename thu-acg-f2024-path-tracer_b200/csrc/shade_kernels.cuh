@@ -14,6 +14,30 @@ PT_D void add_radiance(float* __restrict__ accum, uint32_t pix, d3 v, uint32_t n
     if (v.z != 0.0) atomicAdd(accum + 3ull * pix + 2, (float)v.z);
 }
 
+// The material and texture tables are small (scene 6: 14 materials, 20 textures) but sit at the end of chains of dependent
+// loads (hit -> primitive -> material -> texture -> checker child ...); the shade kernels are latency-bound, so every block
+// copies them into shared memory once and redirects the scene's pointers (generic addressing) when they fit.
+#ifndef PT_SHADE_SMEM
+#define PT_SHADE_SMEM 1
+#endif
+constexpr uint32_t kShadeTableBytes = 6144;
+PT_D void stage_tables(DScene& S) {
+#if PT_SHADE_SMEM
+    __shared__ __align__(16) unsigned char tab[kShadeTableBytes];
+    const uint32_t mb = S.n_materials * (uint32_t)sizeof(DMaterial), tb = S.n_textures * (uint32_t)sizeof(DTexture);
+    if (mb + tb <= kShadeTableBytes && mb + tb > 0) {  // block-uniform
+        const uint4* src_m = reinterpret_cast<const uint4*>(S.materials);
+        const uint4* src_t = reinterpret_cast<const uint4*>(S.textures);
+        uint4* dst = reinterpret_cast<uint4*>(tab);
+        for (uint32_t k = threadIdx.x; k < mb / 16; k += blockDim.x) dst[k] = src_m[k];
+        for (uint32_t k = threadIdx.x; k < tb / 16; k += blockDim.x) dst[mb / 16 + k] = src_t[k];
+        __syncthreads();
+        S.materials = reinterpret_cast<const DMaterial*>(tab);
+        S.textures = reinterpret_cast<const DTexture*>(tab + mb);
+    }
+#endif
+}
+
 template <int CLS> struct ClassKind { static constexpr int value = -1; };
 template <> struct ClassKind<CLS_LIGHT> { static constexpr int value = PT_MAT_LIGHT; };
 template <> struct ClassKind<CLS_DIFFUSE> { static constexpr int value = PT_MAT_DIFFUSE; };
@@ -32,9 +56,11 @@ __global__ void __launch_bounds__(kBlock, PT_SHADE_MIN_BLOCKS) k_shade(PathBuf i
     constexpr int K = ClassKind<CLS>::value;
     const uint32_t count = q.count[CLS];
     const uint32_t* __restrict__ items = q.items + (size_t)CLS * q.stride;
-    __shared__ uint32_t bin_count[8][kBlock / 32];  // survivors per (octant bin, warp), then their exclusive prefix
-    __shared__ uint32_t block_base;
-    for (uint32_t base = blockIdx.x * kBlock; base < count; base += gridDim.x * kBlock) {
+    __shared__ uint32_t bin_count[2][8][kBlock / 32];  // survivors per (octant bin, warp), then their exclusive prefix; double-buffered
+    __shared__ uint32_t block_base[2];
+    stage_tables(S);
+    uint32_t par = 0;
+    for (uint32_t base = blockIdx.x * kBlock; base < count; base += gridDim.x * kBlock, par ^= 1u) {
         const uint32_t j = base + threadIdx.x;
         bool alive = false;
         RayD next; d3 thr = mk(0, 0, 0); uint4 ids = make_uint4(0, 0, 0, 0);
@@ -98,25 +124,30 @@ __global__ void __launch_bounds__(kBlock, PT_SHADE_MIN_BLOCKS) k_shade(PathBuf i
         //      rays that walk the BVH in the same order and tend to cost the same), one atomic per block
         const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const uint32_t key = alive ? (((next.d.y < 0.0) | ((next.d.x < 0.0) << 1) | ((next.d.z < 0.0) << 2)) & rc.sort_mask) : 8u;
-        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
-        if (threadIdx.x < 8 * (kBlock / 32)) (&bin_count[0][0])[threadIdx.x] = 0;
-        __syncthreads();
-        if (alive && lane == (uint32_t)(__ffs(peers) - 1)) bin_count[key][warp] = __popc(peers);
+        uint32_t mine = 0, cnt = 0;  // lanes of my bin; lane b < 8 also holds the size of bin b
+#pragma unroll
+        for (uint32_t b = 0; b < 8; b++) {
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, key == b);
+            if (key == b) mine = m;
+            if (lane == b) cnt = __popc(m);
+        }
+        if (lane < 8) bin_count[par][lane][warp] = cnt;
         __syncthreads();
         if (threadIdx.x == 0) {
             uint32_t total = 0;
 #pragma unroll
             for (int b = 0; b < 8; b++)
 #pragma unroll
-                for (int w = 0; w < kBlock / 32; w++) { uint32_t c = bin_count[b][w]; bin_count[b][w] = total; total += c; }
-            block_base = total ? atomicAdd(out_count, total) : 0;
+                for (int w = 0; w < kBlock / 32; w++) { uint32_t c = bin_count[par][b][w]; bin_count[par][b][w] = total; total += c; }
+            block_base[par] = total ? atomicAdd(out_count, total) : 0;
         }
         __syncthreads();
         if (alive) {
-            uint32_t dst = block_base + bin_count[key][warp] + __popc(peers & ((1u << lane) - 1u));
+            uint32_t dst = block_base[par] + bin_count[par][key][warp] + __popc(mine & ((1u << lane) - 1u));
             store_path(out, dst, next, thr, ids);
         }
-        __syncthreads();  // bin_count / block_base are reused by the next grid-stride iteration
+        // no third barrier: the next iteration works on the other half of bin_count / block_base, and nobody can reach the
+        // iteration after that before every thread has passed the two barriers in between
     }
 }
 
@@ -140,6 +171,7 @@ __global__ void __launch_bounds__(kBlock, PT_NEE_MIN_BLOCKS) k_shade_nee(PathBuf
     const uint32_t* __restrict__ items = q.items + (size_t)CLS * q.stride;
     __shared__ uint32_t warp_count[kBlock / 32], warp_alive[kBlock / 32];
     __shared__ uint32_t block_base;
+    stage_tables(S);
     for (uint32_t base = blockIdx.x * kBlock; base < count; base += gridDim.x * kBlock) {
         const uint32_t j = base + threadIdx.x;
         bool alive = false, shadow = false;

@@ -1,4 +1,6 @@
 // Translation unit of the traversal-stage kernels (trace_kernels.cuh) and their launchers (launch.h).
+#include <algorithm>
+
 #include "launch.h"
 #include "trace_kernels.cuh"
 
@@ -68,6 +70,10 @@ void run_k_hits_to_abi(cudaStream_t st, const pt_ray* rays, uint32_t n, const Hi
 }
 void run_k_pool_to_abi(cudaStream_t st, PathBuf pool, uint32_t n, const HitRec* hits, pt_ray* out_rays, pt_hit* out_hits, const DScene& S) {
     k_pool_to_abi<<<grid128(n), 128, 0, st>>>(pool, n, hits, out_rays, out_hits, S);
+}
+void run_k_check_queues(cudaStream_t st, Queues q, const HitRec* hits, uint32_t n, uint32_t* seen, uint32_t* errors, const DScene& S) {
+    k_check_queues<<<dim3(std::max(1u, std::min(grid128(n), 2048u)), N_CLS), 128, 0, st>>>(q, hits, n, seen, errors, S);
+    k_check_seen<<<grid128(n), 128, 0, st>>>(seen, n, errors);
 }
 cudaError_t debug_histograms(unsigned long long* out512, bool reset) {
     cudaError_t e = cudaSuccess;

@@ -365,10 +365,14 @@ __global__ void __launch_bounds__(kBlock, 4) k_mesh_enter(PathBuf pool, uint32_t
         if (j < count) {
             const uint2 e = items[j];
             i = e.x;
-            const uint32_t k = e.y & 0xFFu, prov_cls = (e.y >> 8) & 0xFu;
+            const uint32_t k = e.y & 0xFFu;
             const bool last = (e.y >> 31) != 0;
             const DNode rb = S.refs[k];
             const HitRec h0 = hits[i];
+            // shade class of the provisional hit: in round 0 still what k_top noted in the queue entry; later an earlier round
+            // may have replaced the hit, so it is looked up again (rounds >= 1 hold about 1 % of the rays)
+            const uint32_t prov_cls = round == 0 ? ((e.y >> 8) & 0xFu)
+                                                 : (h0.ref == kNone ? (uint32_t)CLS_MISS : class_of_kind(S.materials[hit_material(S, h0.ref)].kind));
             RayD r = load_ray(pool, i);
             BoxRay br = make_boxray(r);
             const float tmax_f = __double2float_ru(h0.t);
@@ -549,6 +553,23 @@ __global__ void __launch_bounds__(kTraceBlock, kWalkMinBlocks * kBlock / kTraceB
     }
 }
 
+// Invariant of the traversal stage, checked by the parity entry points: every ray has joined exactly ONE shade-class queue,
+// the one of the material its final hit record shades with (a miss: CLS_MISS).  errors += wrong class; seen[i] counts appends.
+__global__ void k_check_queues(Queues q, const HitRec* __restrict__ hits, uint32_t n, uint32_t* __restrict__ seen, uint32_t* __restrict__ errors, DScene S) {
+    const uint32_t cls = blockIdx.y, count = q.count[cls];
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x) {
+        const uint32_t i = q.items[(size_t)cls * q.stride + j];
+        if (i >= n) { atomicAdd(errors, 1u); continue; }
+        const HitRec h = hits[i];
+        const uint32_t want = h.ref == kNone ? (uint32_t)CLS_MISS : class_of_kind(S.materials[hit_material(S, h.ref)].kind);
+        if (want != cls) atomicAdd(errors, 1u);
+        atomicAdd(seen + i, 1u);
+    }
+}
+__global__ void k_check_seen(const uint32_t* __restrict__ seen, uint32_t n, uint32_t* __restrict__ errors) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && seen[i] != 1u) atomicAdd(errors, 1u);
+}
 // pt_trace_camera_wavefront: the camera rays k_top<PRIMARY> generated into the pool and their hit records, by pixel
 __global__ void k_pool_to_abi(PathBuf pool, uint32_t n, const HitRec* __restrict__ hits, pt_ray* __restrict__ out_rays, pt_hit* __restrict__ out_hits, DScene S) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -47,7 +47,8 @@ struct RenderConst {
 PT_D void random_offsets(Rng& rng, double& x, double& y) {
     double radius = sqrt(rng.next());
     double angle = rng.next() * 2.0 * kPi;
-    x = radius * cos(angle); y = radius * sin(angle);
+    double sn, cs; pt_sincos(angle, sn, cs);
+    x = radius * cs; y = radius * sn;
 }
 struct DCameraEx { DCamera c; d3 dof_right, dof_up; };  // dof_* = right/up * lens radius (camera.rs:159-161), host-derived
 PT_D RayD generate_ray(const DCameraEx& cam, uint32_t row, uint32_t col, Rng& rng) {
@@ -93,8 +94,8 @@ PT_D d3 env_sample(const DEnvDist& E, double u1, double u2) {
     const double fr = m1 > m0 ? (u1 - m0) / (m1 - m0) : 0.5, fc = c1 > c0 ? (u2 - c0) / (c1 - c0) : 0.5;
     const double theta = (((double)r + fr) / (double)E.rows) * kPi;
     const double phi = (((double)c + fc) / (double)E.cols) * (2.0 * kPi) - kPi;
-    const double st = sin(theta);
-    return mk(st * cos(phi), cos(theta), st * sin(phi));
+    double st, ct, sp, cp; pt_sincos(theta, st, ct); pt_sincos(phi, sp, cp);
+    return mk(st * cp, ct, st * sp);
 }
 PT_D double env_pdf(const DEnvDist& E, d3 dir) {  // solid-angle density of env_sample
     const double theta = acos(dir.y), phi = atan2(dir.z, dir.x);
