@@ -139,8 +139,7 @@ def device_lib():
 def host_lib():
     global _host
     if _host is None:
-        device_lib()  # libptb200_host.so links against it
-        p = host_lib_path()
+        p = host_lib_path()  # opens libptb200.so itself, and only when a device entry point is called (host/device_api.cpp)
         if not os.path.exists(p):
             raise PtError(f"{p} is missing: build it with __graft_entry__.build()")
         lib = C.CDLL(p)

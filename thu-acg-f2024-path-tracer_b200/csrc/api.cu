@@ -685,12 +685,21 @@ int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
             if (kind == PT_OBJ_INSTANCE) { const pt_ref c = d->instances[index].child; kind = c.kind; index = c.index; }
             if (kind == PT_OBJ_VOLUME || kind == PT_PRIM_TRIANGLE) { ok = false; break; }
             if (kind == PT_OBJ_MESH) { T.mesh_bits |= 1u << k; if (d->meshes[index].n_triangles == 0) T.mesh_bits &= ~(1u << k); }
+            if (ref_kind(C.refs[k].a) == PT_PRIM_QUAD) T.quad_bits |= 1u << k;
+            if (ref_kind(C.refs[k].a) == PT_PRIM_SPHERE) T.sphere_bits |= 1u << k;
             T.cls[k] = cls_of_mat(mat_of(kind, index));
+            for (int a = 0; a < 3; a++) { T.box[k][a] = C.refs[k].lo[a]; T.box[k][3 + a] = C.refs[k].hi[a]; }
         }
         T.n = n_top;
         s->mesh_rounds = (uint32_t)__builtin_popcount(T.mesh_bits);
         s->flat = ok && s->mesh_rounds <= (uint32_t)kMeshRounds;
         s->top = T;
+    }
+    std::vector<float> quad_box(6ull * d->n_quads);
+    for (uint32_t i = 0; i < d->n_quads; i++) {
+        double lo[3], hi[3]; DNode bn{};
+        C.ref_box(pt_ref{PT_PRIM_QUAD, i}, lo, hi); C.set_box(bn, lo, hi);
+        for (int k = 0; k < 3; k++) { quad_box[6ull * i + k] = bn.lo[k]; quad_box[6ull * i + 3 + k] = bn.hi[k]; }
     }
     std::vector<uint32_t> tri_rank(d->n_triangles, 0u);
     for (const DNode& rn : C.refs) if (ref_kind(rn.a) == PT_PRIM_TRIANGLE) tri_rank[ref_index(rn.a)] = rn.b;
@@ -710,7 +719,7 @@ int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
     U.up(C.wide, &D.wide); U.up(C.nodes, &D.nodes); U.up(C.refs, &D.refs); U.up(spheres, &D.spheres); U.up(quads, &D.quads); U.up(quad_mat, &D.quad_material);
     U.up(tris, &D.tris); U.up(tri_normals, &D.tri_normals); U.up(tri_uvs, &D.tri_uvs); U.up(tri_mesh, &D.tri_mesh); U.up(cuboids, &D.cuboids);
     U.up(meshes, &D.meshes); U.up(instances, &D.instances); U.up(textures, &D.textures); U.up(images, &D.images); U.up(materials, &D.materials);
-    U.up(lights, &D.lights); U.up(tri_verts, &D.tri_verts); U.up(volumes, &D.volumes); U.up(C.wide2, &D.wide2); U.up(tri_rank, &D.tri_rank);
+    U.up(lights, &D.lights); U.up(tri_verts, &D.tri_verts); U.up(volumes, &D.volumes); U.up(C.wide2, &D.wide2); U.up(tri_rank, &D.tri_rank); U.up(quad_box, &D.quad_box);
     if ((rc = U.commit())) return rc;
     D.image_data = d_img; D.n_lights = d->n_lights; D.root_entry = world_root; D.n_materials = d->n_materials; D.n_textures = d->n_textures;
     s->n_materials = d->n_materials; s->n_images = d->n_images; s->images = images;

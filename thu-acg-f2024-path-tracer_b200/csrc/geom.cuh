@@ -103,6 +103,17 @@ PT_D float slab(const DNode& n, const BoxRay& b, float t_min, float t_max) {
     return tn <= tf ? tn : __int_as_float(0x7fc00000);  // NaN on a miss: fails every `<=` test, even against t_max = +inf
 }
 
+// the same test on a bare (lo xyz, hi xyz) box
+PT_D float slab6(const float* __restrict__ b6, const BoxRay& b, float t_min, float t_max) {
+    const bool sx = b.ix < 0.f, sy = b.iy < 0.f, sz = b.iz < 0.f;
+    float x0 = __fmaf_rn(sx ? b6[3] : b6[0], b.ix, b.nx), x1 = __fmaf_rn(sx ? b6[0] : b6[3], b.ix, b.fx);
+    float y0 = __fmaf_rn(sy ? b6[4] : b6[1], b.iy, b.ny), y1 = __fmaf_rn(sy ? b6[1] : b6[4], b.iy, b.fy);
+    float z0 = __fmaf_rn(sz ? b6[5] : b6[2], b.iz, b.nz), z1 = __fmaf_rn(sz ? b6[2] : b6[5], b.iz, b.fz);
+    float tn = fmaxf(fmaxf(x0, y0), fmaxf(z0, t_min));
+    float tf = fminf(fminf(x1, y1), fminf(z1, t_max));
+    return tn <= tf ? tn : __int_as_float(0x7fc00000);
+}
+
 // ---------------------------------------------------------------- traversal
 constexpr int kStack = 64;
 constexpr uint32_t kTagRef = 0x40000000u, kTagSentinel = 0x80000000u, kTagMask = 0xC0000000u;
@@ -127,9 +138,16 @@ PT_D void test_simple(const DScene& S, uint32_t kind, uint32_t index, const RayD
         if (quad_t(S.quads[index], r, t_min, t, a, b) && t <= c.t) consider(c, t, ref_pack(PT_PRIM_QUAD, index), inst, tie_o, tie_i);
     } else if (kind == PT_OBJ_CUBOID) {
         uint32_t fq = S.cuboids[index].first_quad;
+        // a ray that enters the box crosses two of the six faces: each face's own fp32 box (conservative like every other box
+        // here) spares the f64 plane test, division included, of the other four
+        const BoxRay fbr = make_boxray(r);
+        const float tmin_f = __double2float_rd(t_min);
 #pragma unroll 1
-        for (uint32_t k = 0; k < 6; k++)  // linear list: later quad wins ties -> inner rank = k (cuboid.rs, list.rs:57-66)
+        for (uint32_t k = 0; k < 6; k++) {  // linear list: later quad wins ties -> inner rank = k (cuboid.rs, list.rs:57-66)
+            const float tmax_f = __double2float_ru(c.t);
+            if (!(slab6(S.quad_box + 6ull * (fq + k), fbr, tmin_f, tmax_f) <= tmax_f)) continue;
             if (quad_t(S.quads[fq + k], r, t_min, t, a, b) && t <= c.t) consider(c, t, ref_pack(PT_PRIM_QUAD, fq + k), inst, tie_o, tie_i + k);
+        }
     }
 }
 

@@ -18,7 +18,7 @@ PT_D void add_radiance(float* __restrict__ accum, uint32_t pix, d3 v, uint32_t n
 // loads (hit -> primitive -> material -> texture -> checker child ...); the shade kernels are latency-bound, so every block
 // copies them into shared memory once and redirects the scene's pointers (generic addressing) when they fit.
 #ifndef PT_SHADE_SMEM
-#define PT_SHADE_SMEM 1
+#define PT_SHADE_SMEM 0   // measured: no gain (shade 15.2 ms without, 15.7 ms with, scene 6 FHD x 32 spp): the tables already hit L1
 #endif
 constexpr uint32_t kShadeTableBytes = 6144;
 PT_D void stage_tables(DScene& S) {

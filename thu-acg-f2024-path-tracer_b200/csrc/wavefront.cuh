@@ -177,7 +177,12 @@ PT_D d3 from_abi(pt_vec3 v) { return mk(v.x, v.y, v.z); }
 // not walked here but queued for the mesh rounds (k_mesh_enter + k_mesh_walk), at most kMeshRounds per ray.
 constexpr int kTopMax = 32;
 constexpr int kMeshRounds = 8;
-struct TopList { uint32_t n, mesh_bits; uint8_t cls[kTopMax]; };
+struct TopList {
+    uint32_t n, mesh_bits, quad_bits, sphere_bits;  // *_bits: references that are a mesh (or an instance of one) / a bare quad / a bare sphere
+    uint8_t cls[kTopMax];
+    float box[kTopMax][6];  // fp32 box of reference k (lo xyz, hi xyz) — a copy of refs[k]'s: as a kernel parameter it sits in the constant
+                            // bank, so the warp-uniform box loops of k_top read it through the uniform datapath with no load latency
+};
 // mesh-visit queues of one wavefront iteration: items[round * stride + j] = {path, top reference | provisional class << 8 |
 // last << 31}; walk records of the round that is being processed; counters: count[round], then the walk counter and cursor
 struct MeshQueues { uint2* items; uint32_t* count; uint32_t stride; uint4* walk; uint32_t* walk_count; };

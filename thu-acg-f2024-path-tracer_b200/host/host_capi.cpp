@@ -114,7 +114,8 @@ void pth_scene_free(pth_scene* s) { delete s; }
 // Camera::render (camera.rs:79): render through the CUDA library and write `filename` as PNG.
 int pth_scene_render(const pth_scene* s, const char* filename, uint64_t seed, int device, uint32_t nan_policy, int verbose, pt_stats* stats) {
     RenderOptions o; o.seed = seed; o.device = device; o.nan_policy = nan_policy; o.verbose = verbose != 0;
-    return render_flat(s->flat->desc, s->cam, filename, o, stats);
+    try { return render_flat(s->flat->desc, s->cam, filename, o, stats); }
+    catch (const std::exception& e) { g_err = e.what(); return PT_ERR_NO_DEVICE; }  // the CUDA library could not be loaded
 }
 int pth_write_png(const char* path, const uint8_t* rgb, uint32_t w, uint32_t h) { return write_png_rgb8(path, rgb, w, h) ? 0 : -1; }
 

@@ -5,6 +5,7 @@
 #include <stdexcept>
 
 #include "pt_host.hpp"
+#include "device_api.hpp"
 
 namespace pt {
 
@@ -215,8 +216,8 @@ struct Builder {
             const size_t n = items.size();
             std::vector<Box> ib(n); for (size_t k = 0; k < n; k++) ib[k] = boxes[items[k]];
             std::vector<double> dc(3 * n);
-            if (pt_sah_sweep(ctx, (uint32_t)n, reinterpret_cast<const double*>(ib.data()), reinterpret_cast<const double*>(&parent), dc.data()) != PT_OK)
-                throw std::runtime_error(std::string("pt_sah_sweep: ") + pt_last_error());
+            if (device_api().sah_sweep(ctx, (uint32_t)n, reinterpret_cast<const double*>(ib.data()), reinterpret_cast<const double*>(&parent), dc.data()) != PT_OK)
+                throw std::runtime_error(std::string("pt_sah_sweep: ") + device_api().last_error());
             std::vector<std::pair<double, double>> pc(n);
             for (int axis = 0; axis < 3; axis++) {
                 for (size_t k = 0; k < n; k++) pc[k] = {cent[items[k]][axis], dc[axis * n + k]};
@@ -410,7 +411,8 @@ static void report(const RenderOptions& opt, uint32_t W, uint32_t H, uint32_t sp
 }
 int render_flat(const pt_scene_desc& desc, const pt_camera& cam, const std::string& filename, const RenderOptions& opt, pt_stats* stats_out) {
     const uint32_t samples_per_pixel = cam.samples_per_pixel;
-    uint32_t H = pt_camera_image_height(&cam), W = cam.image_width;
+    const DeviceApi& dev = device_api();  // throws without the CUDA library: there is no CPU fallback
+    uint32_t H = (uint32_t)((double)cam.image_width / cam.aspect_ratio), W = cam.image_width;  // camera.rs:52
     std::vector<float> mean((size_t)W * H * 3);
     pt_render_params p{}; p.seed = opt.seed; p.sample_begin = 0; p.sample_count = samples_per_pixel; p.sample_stride = 1; p.nan_policy = opt.nan_policy;
     if (opt.nee) p.flags |= PT_RENDER_NEE;
@@ -420,29 +422,29 @@ int render_flat(const pt_scene_desc& desc, const pt_camera& cam, const std::stri
         for (int g = 0; g < opt.gpus; g++) devices[g] = opt.device + g;
         pt_stats st{};
         if (opt.verbose) printf("rendering production\n");  // camera.rs:101
-        int rc = pt_render_multi(opt.gpus, devices.data(), &desc, &cam, &p, mean.data(), &st);
-        if (rc) fprintf(stderr, "pt_render_multi: %s\n", pt_last_error());
+        int rc = dev.render_multi(opt.gpus, devices.data(), &desc, &cam, &p, mean.data(), &st);
+        if (rc) fprintf(stderr, "pt_render_multi: %s\n", dev.last_error());
         else { save_image(mean, W, H, filename); report(opt, W, H, samples_per_pixel, st); }
         if (stats_out) *stats_out = st;
         return rc;
     }
     pt_ctx* ctx = nullptr; pt_scene* scene = nullptr;
-    int rc = pt_ctx_create(opt.device, &ctx);
-    if (rc) { fprintf(stderr, "pt_ctx_create: %s\n", pt_last_error()); return rc; }
-    rc = pt_scene_create(ctx, &desc, &scene);
-    if (rc) { fprintf(stderr, "pt_scene_create: %s\n", pt_last_error()); pt_ctx_destroy(ctx); return rc; }
+    int rc = dev.ctx_create(opt.device, &ctx);
+    if (rc) { fprintf(stderr, "pt_ctx_create: %s\n", dev.last_error()); return rc; }
+    rc = dev.scene_create(ctx, &desc, &scene);
+    if (rc) { fprintf(stderr, "pt_scene_create: %s\n", dev.last_error()); dev.ctx_destroy(ctx); return rc; }
     if (opt.env_importance && cam.env_is_map) {
-        rc = pt_scene_build_env_sampler(scene, cam.env_image, 0, 0);
-        if (rc) { fprintf(stderr, "pt_scene_build_env_sampler: %s\n", pt_last_error()); pt_scene_destroy(scene); pt_ctx_destroy(ctx); return rc; }
+        rc = dev.scene_build_env_sampler(scene, cam.env_image, 0, 0);
+        if (rc) { fprintf(stderr, "pt_scene_build_env_sampler: %s\n", dev.last_error()); dev.scene_destroy(scene); dev.ctx_destroy(ctx); return rc; }
         p.flags |= PT_RENDER_ENV_IMPORTANCE;
     }
     pt_stats st{};
     if (opt.verbose) printf("rendering production\n");  // camera.rs:101
-    rc = pt_render(ctx, scene, &cam, &p, mean.data(), &st);
-    if (rc) fprintf(stderr, "pt_render: %s\n", pt_last_error());
+    rc = dev.render(ctx, scene, &cam, &p, mean.data(), &st);
+    if (rc) fprintf(stderr, "pt_render: %s\n", dev.last_error());
     else { save_image(mean, W, H, filename); report(opt, W, H, samples_per_pixel, st); }
     if (stats_out) *stats_out = st;
-    pt_scene_destroy(scene); pt_ctx_destroy(ctx);
+    dev.scene_destroy(scene); dev.ctx_destroy(ctx);
     return rc;
 }
 
