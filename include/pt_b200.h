@@ -254,6 +254,8 @@ typedef struct {
                                    * can never silently run on the other flavour */
     uint32_t queue_errors;        /* pt_trace_*_wavefront only: rays that did not join exactly one shade-class queue, or joined the
                                    * queue of another class than their hit's material (an invariant of the traversal stage; 0) */
+    uint32_t p2p_shares;          /* pt_render_multi only: shares whose radiance sums the reduce kernel read in place over peer access */
+    uint32_t _pad;
 } pt_stats;
 
 typedef struct pt_ctx pt_ctx;
@@ -294,10 +296,12 @@ int  pt_render(pt_ctx* ctx, const pt_scene* scene, const pt_camera* cam,
 /* Camera::render on several GPUs from ONE process — what a single-process host like the reference's binary calls
  * (camera.rs:79; the reference parallelises over pixels with rayon inside that call, camera.rs:102).  One host thread
  * per entry of `devices` creates its own context, uploads `desc`, and renders the samples g, g + n, g + 2n, ... of the
- * call (spp split, independent counter-based streams); the partial sums are added on the host in device
- * order and divided by sample_count.  Same image as pt_render on one device up to fp32 summation order.  The same
- * device may be listed more than once.  stats: counters summed, times = the slowest device.  bench.py and the tests'
- * multi-GPU path use one process per GPU + NCCL instead (pt_render_accumulate). */
+ * call (spp split, independent counter-based streams).  The reduce(sum) runs ON THE DEVICE: one kernel on
+ * devices[0] reads every share's fp32 sums in place — over NVLink peer access for the other GPUs (staged by one
+ * cudaMemcpyPeer where two devices cannot address each other) — adds them in share order in f64, divides by sample_count
+ * and the mean image leaves the GPU in a single D2H copy.  Same image as pt_render on one device up to fp32 summation
+ * order.  The same device may be listed more than once.  stats: counters summed, times = the slowest device.  bench.py
+ * and the tests' multi-GPU path use one process per GPU + NCCL instead (pt_render_accumulate). */
 int  pt_render_multi(int n_devices, const int* devices, const pt_scene_desc* desc, const pt_camera* cam,
                      const pt_render_params* params, float* h_mean_rgb, pt_stats* stats);
 /* sqrt-gamma, clamp(0,0.999)*256 as u8 (camera.rs:109-114,128-130). Device in, host out. */

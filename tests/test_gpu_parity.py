@@ -486,6 +486,8 @@ def test_render_multi_equals_single_device(pt, pairs):
         multi, stm = pt.render_multi(p.scene, devices, spp=7, seed=4, nan_policy=1, **kw)
         assert (stm.paths, stm.segments, stm.nonfinite) == (st1.paths, st1.segments, st1.nonfinite), kw
         assert np.allclose(multi, single, rtol=2e-5, atol=2e-6), kw
+        # the reduce runs on devices[0]: shares on other GPUs are read over peer access (NVLink) where the box allows it
+        assert stm.p2p_shares <= len(set(devices)) - 1 and (n_dev == 1 or stm.p2p_shares == len([d for d in devices if d != devices[0]]))
     two, st2 = pt.render_multi(p.scene, [0] * 5, spp=2, seed=4, nan_policy=1)      # more devices than samples: two shares
     assert np.allclose(two, p.dev.render(spp=2, seed=4, nan_policy=1)[0], rtol=2e-5, atol=2e-6) and st2.paths == 2 * 160 * 90
     with pytest.raises(pt.PtError, match="device 99"):

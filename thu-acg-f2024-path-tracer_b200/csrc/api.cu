@@ -722,6 +722,8 @@ int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
     U.up(lights, &D.lights); U.up(tri_verts, &D.tri_verts); U.up(volumes, &D.volumes); U.up(C.wide2, &D.wide2); U.up(tri_rank, &D.tri_rank); U.up(quad_box, &D.quad_box);
     if ((rc = U.commit())) return rc;
     D.image_data = d_img; D.n_lights = d->n_lights; D.root_entry = world_root; D.n_materials = d->n_materials; D.n_textures = d->n_textures;
+    D.n_nodes = (uint32_t)C.nodes.size(); D.n_refs = (uint32_t)C.refs.size(); D.n_wide = (uint32_t)C.wide.size(); D.n_wide2 = (uint32_t)C.wide2.size();
+    D.n_tris = d->n_triangles; D.n_quads = d->n_quads; D.n_spheres = d->n_spheres; D.n_instances = d->n_instances; D.n_meshes = d->n_meshes;
     s->n_materials = d->n_materials; s->n_images = d->n_images; s->images = images;
     CU(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
     *out = s.release();
@@ -1070,16 +1072,35 @@ int pt_render(pt_ctx* ctx, const pt_scene* scene, const pt_camera* cam, const pt
 
 }  // extern "C"
 
+// small RAII device buffer (parity entry points, pt_render_multi's reduce)
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) { CU(cudaMalloc(&p, bytes ? bytes : 1)); return PT_OK; }
+    int from_host(const void* h, size_t bytes, cudaStream_t st) { int rc = alloc(bytes); if (rc) return rc; if (bytes) CU(cudaMemcpyAsync(p, h, bytes, cudaMemcpyHostToDevice, st)); return PT_OK; }
+    int to_host(void* h, size_t bytes, cudaStream_t st) { if (bytes) CU(cudaMemcpyAsync(h, p, bytes, cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st)); CU(cudaGetLastError()); return PT_OK; }
+};
+}  // namespace
+
 // One device's share of pt_render_multi: own context, own copy of the scene, samples share, share + n_shares, ... of the call.
-static int render_share(int device, const pt_scene_desc* desc, const pt_camera* cam, const pt_render_params* p, uint32_t share,
-                        uint32_t n_shares, float* h_sum, size_t n, pt_stats* st) {
-    pt_ctx* ctx = nullptr; pt_scene* scene = nullptr; float* d_accum = nullptr;
-    int rc = pt_ctx_create(device, &ctx);
-    if (rc == PT_OK) rc = pt_scene_create(ctx, desc, &scene);
-    if (rc == PT_OK && (p->flags & PT_RENDER_ENV_IMPORTANCE) && cam->env_is_map) rc = pt_scene_build_env_sampler(scene, cam->env_image, 0, 0);
+// The radiance sums stay on the device (d_accum) for the peer reduce.
+struct Share {
+    int device = 0; pt_ctx* ctx = nullptr; pt_scene* scene = nullptr; float* d_accum = nullptr;
+    int rc = PT_OK; std::string err; pt_stats st{};
+    void release() {
+        if (d_accum) { cudaSetDevice(device); cudaFree(d_accum); d_accum = nullptr; }
+        if (scene) { pt_scene_destroy(scene); scene = nullptr; }
+        if (ctx) { pt_ctx_destroy(ctx); ctx = nullptr; }
+    }
+};
+static int render_share(Share& S, const pt_scene_desc* desc, const pt_camera* cam, const pt_render_params* p, uint32_t share, uint32_t n_shares, size_t n) {
+    int rc = pt_ctx_create(S.device, &S.ctx);
+    if (rc == PT_OK) rc = pt_scene_create(S.ctx, desc, &S.scene);
+    if (rc == PT_OK && (p->flags & PT_RENDER_ENV_IMPORTANCE) && cam->env_is_map) rc = pt_scene_build_env_sampler(S.scene, cam->env_image, 0, 0);
     if (rc == PT_OK) {
-        cudaError_t e = cudaMalloc(&d_accum, n * sizeof(float));
-        if (e == cudaSuccess) e = cudaMemsetAsync(d_accum, 0, n * sizeof(float), ctx->stream);
+        cudaError_t e = cudaMalloc(&S.d_accum, n * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemsetAsync(S.d_accum, 0, n * sizeof(float), S.ctx->stream);
         if (e != cudaSuccess) rc = fail(PT_ERR_CUDA, cudaGetErrorString(e));
     }
     if (rc == PT_OK) {
@@ -1088,17 +1109,39 @@ static int render_share(int device, const pt_scene_desc* desc, const pt_camera* 
         q.sample_begin = p->sample_begin + share * stride;
         q.sample_stride = stride * n_shares;
         q.sample_count = (p->sample_count - share + n_shares - 1) / n_shares;
-        rc = pt_render_accumulate(ctx, scene, cam, &q, d_accum, st);
+        rc = pt_render_accumulate(S.ctx, S.scene, cam, &q, S.d_accum, &S.st);  // returns with the stream synchronised
     }
-    if (rc == PT_OK) {
-        cudaError_t e = cudaMemcpyAsync(h_sum, d_accum, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) rc = fail(PT_ERR_CUDA, cudaGetErrorString(e));
-    }
-    if (d_accum) cudaFree(d_accum);
-    if (scene) pt_scene_destroy(scene);
-    if (ctx) pt_ctx_destroy(ctx);
     return rc;
+}
+// reduce(sum) of the shares' device buffers on the first share's GPU: peers are read in place over NVLink where the devices
+// can address each other, else staged through one cudaMemcpyPeer each; one D2H of the mean image at the end.
+static int reduce_shares(std::vector<Share>& shares, size_t n, double scale, float* h_mean, uint32_t* p2p_direct) {
+    Share& root = shares[0];
+    CU(cudaSetDevice(root.device));
+    cudaStream_t st = root.ctx->stream;
+    std::vector<const float*> src(shares.size());
+    std::vector<DevBuf> staged(shares.size());
+    *p2p_direct = 0;
+    for (size_t g = 0; g < shares.size(); g++) {
+        src[g] = shares[g].d_accum;
+        if (shares[g].device == root.device) continue;
+        int can = 0;
+        CU(cudaDeviceCanAccessPeer(&can, root.device, shares[g].device));
+        if (can) {
+            const cudaError_t e = cudaDeviceEnablePeerAccess(shares[g].device, 0);
+            if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); (*p2p_direct)++; continue; }
+            cudaGetLastError();
+        }
+        int rc = staged[g].alloc(n * sizeof(float));  // no peer addressing between this pair: one device-to-device copy
+        if (rc) return rc;
+        CU(cudaMemcpyPeerAsync(staged[g].p, root.device, shares[g].d_accum, shares[g].device, n * sizeof(float), st));
+        src[g] = (const float*)staged[g].p;
+    }
+    DevBuf d_src, d_out;
+    int rc;
+    if ((rc = d_src.from_host(src.data(), src.size() * sizeof(float*), st)) || (rc = d_out.alloc(n * sizeof(float)))) return rc;
+    run_k_reduce_peers(st, (const float* const*)d_src.p, (uint32_t)src.size(), scale, n, (float*)d_out.p);
+    return d_out.to_host(h_mean, n * sizeof(float), st);
 }
 
 extern "C" {
@@ -1109,41 +1152,38 @@ int pt_render_multi(int n_devices, const int* devices, const pt_scene_desc* desc
     if (p->sample_count == 0) return fail(PT_ERR_INVALID, "pt_render_multi: sample_count is zero");
     const size_t n = (size_t)cam->image_width * pt_camera_image_height(cam) * 3;
     const uint32_t G = std::min<uint32_t>((uint32_t)n_devices, p->sample_count);  // a share is at least one sample per pixel
-    std::vector<std::vector<float>> sums(G);
-    std::vector<int> rcs(G, PT_OK);
-    std::vector<std::string> errs(G);
-    std::vector<pt_stats> sts(G);
+    std::vector<Share> shares(G);
+    for (uint32_t g = 0; g < G; g++) shares[g].device = devices[g];
     auto work = [&](uint32_t g) {
         try {
-            sums[g].resize(n);
-            rcs[g] = render_share(devices[g], desc, cam, p, g, G, sums[g].data(), n, &sts[g]);
-            if (rcs[g] != PT_OK) errs[g] = g_err;  // the message is thread-local: carry it to the caller's thread
-        } catch (const std::exception& e) { rcs[g] = PT_ERR_CUDA; errs[g] = e.what(); }
+            shares[g].rc = render_share(shares[g], desc, cam, p, g, G, n);
+            if (shares[g].rc != PT_OK) shares[g].err = g_err;  // the message is thread-local: carry it to the caller's thread
+        } catch (const std::exception& e) { shares[g].rc = PT_ERR_CUDA; shares[g].err = e.what(); }
     };
     std::vector<std::thread> threads;
     for (uint32_t g = 1; g < G; g++) threads.emplace_back(work, g);
     work(0);
     for (auto& t : threads) t.join();
-    for (uint32_t g = 0; g < G; g++)
-        if (rcs[g] != PT_OK) return fail(rcs[g], "pt_render_multi: device " + std::to_string(devices[g]) + ": " + errs[g]);
-    // the reduce(sum) of SURVEY 8(e), on the host and in device order (deterministic given the partial sums)
-    const double inv = 1.0 / (double)p->sample_count;
-    for (size_t i = 0; i < n; i++) {
-        double acc = 0.0;
-        for (uint32_t g = 0; g < G; g++) acc += (double)sums[g][i];
-        h_mean[i] = (float)(acc * inv);
-    }
-    if (stats) {
-        pt_stats S = sts[0];
+    int rc = PT_OK; std::string msg;
+    for (uint32_t g = 0; g < G && rc == PT_OK; g++)
+        if (shares[g].rc != PT_OK) { rc = shares[g].rc; msg = "pt_render_multi: device " + std::to_string(devices[g]) + ": " + shares[g].err; }
+    uint32_t p2p_direct = 0;
+    if (rc == PT_OK && (rc = reduce_shares(shares, n, 1.0 / (double)p->sample_count, h_mean, &p2p_direct)) != PT_OK) msg = "pt_render_multi: reduce: " + g_err;
+    if (rc == PT_OK && stats) {
+        pt_stats S = shares[0].st;
         for (uint32_t g = 1; g < G; g++) {
-            const pt_stats& t = sts[g];
+            const pt_stats& t = shares[g].st;
             S.paths += t.paths; S.segments += t.segments; S.nonfinite += t.nonfinite; S.kernel_launches += t.kernel_launches;
-            S.node_pairs += t.node_pairs; S.ref_boxes += t.ref_boxes; S.prim_tests += t.prim_tests;
+            S.node_pairs += t.node_pairs; S.ref_boxes += t.ref_boxes; S.prim_tests += t.prim_tests; S.two_pass_iterations += t.two_pass_iterations;
             S.iterations = std::max(S.iterations, t.iterations); S.device_ms = std::max(S.device_ms, t.device_ms);
             S.trace_ms = std::max(S.trace_ms, t.trace_ms); S.shade_ms = std::max(S.shade_ms, t.shade_ms); S.raygen_ms = std::max(S.raygen_ms, t.raygen_ms);
         }
+        S.kernel_launches++;          // the reduce kernel
+        S.p2p_shares = p2p_direct;
         *stats = S;
     }
+    for (auto& s : shares) s.release();
+    if (rc != PT_OK) return fail(rc, msg);
     return PT_OK;
 }
 
@@ -1165,15 +1205,6 @@ int pt_tonemap_rgb8(pt_ctx* ctx, const float* d_accum, double scale, uint32_t n_
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------------ parity entry points
-namespace {
-struct DevBuf {
-    void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    int alloc(size_t bytes) { CU(cudaMalloc(&p, bytes ? bytes : 1)); return PT_OK; }
-    int from_host(const void* h, size_t bytes, cudaStream_t st) { int rc = alloc(bytes); if (rc) return rc; if (bytes) CU(cudaMemcpyAsync(p, h, bytes, cudaMemcpyHostToDevice, st)); return PT_OK; }
-    int to_host(void* h, size_t bytes, cudaStream_t st) { if (bytes) CU(cudaMemcpyAsync(h, p, bytes, cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st)); CU(cudaGetLastError()); return PT_OK; }
-};
-}  // namespace
 
 extern "C" {
 

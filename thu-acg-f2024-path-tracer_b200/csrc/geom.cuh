@@ -131,6 +131,7 @@ PT_D void consider(Closest& c, double t, uint32_t ref, uint32_t inst, uint32_t t
 PT_D void test_simple(const DScene& S, uint32_t kind, uint32_t index, const RayD& r, double t_min, Closest& c, uint32_t inst,
                       uint32_t tie_o, uint32_t tie_i) {
     double t, a, b;
+    PT_ASSERT(kind == PT_PRIM_SPHERE ? index < S.n_spheres : kind == PT_PRIM_QUAD ? index < S.n_quads : kind == PT_OBJ_CUBOID);
     if (kind == PT_PRIM_SPHERE) {
         // exclusive upper bound against the initial interval (sphere.rs:84); later ties go through the ranks
         if (sphere_t(S.spheres[index], r, t_min, t) && t <= c.t && !(c.ref == kNone && t == c.t)) consider(c, t, ref_pack(PT_PRIM_SPHERE, index), inst, tie_o, tie_i);
@@ -138,6 +139,7 @@ PT_D void test_simple(const DScene& S, uint32_t kind, uint32_t index, const RayD
         if (quad_t(S.quads[index], r, t_min, t, a, b) && t <= c.t) consider(c, t, ref_pack(PT_PRIM_QUAD, index), inst, tie_o, tie_i);
     } else if (kind == PT_OBJ_CUBOID) {
         uint32_t fq = S.cuboids[index].first_quad;
+        PT_ASSERT(fq + 6 <= S.n_quads);
         // a ray that enters the box crosses two of the six faces: each face's own fp32 box (conservative like every other box
         // here) spares the f64 plane test, division included, of the other four
         const BoxRay fbr = make_boxray(r);
@@ -247,6 +249,7 @@ PT_D bool trace_closest(const DScene& S, Reload reload, double t_min, double t_m
             }
             if (!WIDE) {  // compile-time: a scene is traversed entirely with binary pairs or entirely with wide nodes
                 // ---- binary pair (small BVHs: top-level lists of a few objects; most rays leave after one or two fetches)
+                PT_ASSERT(cur + 1 < S.n_nodes);
                 const DNode n0 = S.nodes[cur], n1 = S.nodes[cur + 1];
                 if (COUNT) c.n_pairs++;
                 const float t0 = slab(n0, br, tmin_f, tmax_f), t1 = slab(n1, br, tmin_f, tmax_f);
@@ -257,14 +260,15 @@ PT_D bool trace_closest(const DScene& S, Reload reload, double t_min, double t_m
                 const float tn = swap ? t1 : t0, tf = swap ? t0 : t1;
                 const bool hn = swap ? h1 : h0, hf = swap ? h0 : h1;
                 cur = kNone;
-                if (hf && sp < kStack) PT_PUSH(ef, tf)
+                if (hf && can_push(sp, kStack)) PT_PUSH(ef, tf)
                 if (hn) {
                     if ((en & kTagMask) == 0) cur = en;
-                    else if (sp < kStack) PT_PUSH(en, tn)
+                    else if (can_push(sp, kStack)) PT_PUSH(en, tn)
                 }
                 continue;
             }
             // ---- 4-wide node (large BVHs: meshes, big object lists): 7 x 128-bit loads, four slabs, sorted near to far
+            PT_ASSERT((cur & ~kWideBit) < S.n_wide);
             const DWide& w = S.wide[cur & ~kWideBit];
             const float4 lx = *reinterpret_cast<const float4*>(w.lo[0]), ly = *reinterpret_cast<const float4*>(w.lo[1]),
                          lz = *reinterpret_cast<const float4*>(w.lo[2]), hx = *reinterpret_cast<const float4*>(w.hi[0]),
@@ -291,12 +295,12 @@ PT_D bool trace_closest(const DScene& S, Reload reload, double t_min, double t_m
             PT_CSWAP(0, 1) PT_CSWAP(2, 3) PT_CSWAP(0, 2) PT_CSWAP(1, 3) PT_CSWAP(1, 2)  // ascending entry distance
 #undef PT_CSWAP
             cur = kNone;
-            if (t3 < kInf && sp < kStack) PT_PUSH(e3, t3)  // far children first: nearest is popped first
-            if (t2 < kInf && sp < kStack) PT_PUSH(e2, t2)
-            if (t1 < kInf && sp < kStack) PT_PUSH(e1, t1)
+            if (t3 < kInf && can_push(sp, kStack)) PT_PUSH(e3, t3)  // far children first: nearest is popped first
+            if (t2 < kInf && can_push(sp, kStack)) PT_PUSH(e2, t2)
+            if (t1 < kInf && can_push(sp, kStack)) PT_PUSH(e1, t1)
             if (t0 < kInf) {
                 if ((e0 & kTagMask) == 0) cur = e0;
-                else if (sp < kStack) PT_PUSH(e0, t0)
+                else if (can_push(sp, kStack)) PT_PUSH(e0, t0)
             }
         }
         if (pending == kNone) break;  // traversal finished
@@ -306,8 +310,10 @@ PT_D bool trace_closest(const DScene& S, Reload reload, double t_min, double t_m
             continue;
         }
         if ((pending & kTagMask) == kTagLeaf) {
+            PT_ASSERT((pending & ~kTagMask) < S.n_nodes);
             const DNode& n = S.nodes[pending & ~kTagMask];
             const uint32_t first = n.a, count = n.b;
+            PT_ASSERT(first + count <= S.n_refs);
             const float leaf_t = pending_t;  // entry distance of this leaf
             for (uint32_t k = 0; k < count; k++) {
                 const DNode rb = S.refs[first + k];  // per-reference fp32 box + (kind|index, tie rank); prefetching the next one: -5 %
@@ -317,11 +323,12 @@ PT_D bool trace_closest(const DScene& S, Reload reload, double t_min, double t_m
                 const uint32_t kind = ref_kind(rb.a), index = ref_index(rb.a);
                 if (kind == PT_PRIM_TRIANGLE) {
                     double t, u, v;
+                    PT_ASSERT(index < S.n_tris);
                     if (tri_t(S.tris[index], r, t_min, t, u, v) && t <= c.t) { consider(c, t, rb.a, cur_inst, cur_tie, rb.b); tmax_f = __double2float_ru(c.t); }
                 } else {
                     if (ANY_HIT && !(rb.b >> 31)) continue;  // shadow rays test World.objects only (world.rs:31-36)
                     if (kind <= PT_OBJ_CUBOID) { test_simple(S, kind, index, r, t_min, c, kInstNone, rb.b, 0); tmax_f = __double2float_ru(c.t); }
-                    else if (sp < kStack) {  // mesh / instance: defer (order does not matter, ties use ranks)
+                    else if (can_push(sp, kStack)) {  // mesh / instance: defer (order does not matter, ties use ranks)
                         PT_PUSH(kTagRef | (first + k), leaf_t)
                     }
                 }
@@ -363,7 +370,7 @@ PT_D bool trace_closest(const DScene& S, Reload reload, double t_min, double t_m
             }
         }
         cur_tie = rf.tie;
-        if (sp < kStack) PT_PUSH(kTagSentinel, 0.f)
+        if (can_push(sp, kStack)) PT_PUSH(kTagSentinel, 0.f)
         cur = S.meshes[mesh].root_entry;
     }
     c.is_light = c.ref != kNone && !(c.tie_outer >> 31);  // objects carry bit 31 in their outer rank (object beats light, Q31)
@@ -392,6 +399,7 @@ PT_D bool blas_round(const DScene& S, const RayD& r, const BoxRay& br, double t_
             }
             if (cur == kNone) break;
         }
+        PT_ASSERT((cur & ~kWideBit) < S.n_wide);
         const DWide& w = S.wide[cur & ~kWideBit];
         const float4 lx = *reinterpret_cast<const float4*>(w.lo[0]), ly = *reinterpret_cast<const float4*>(w.lo[1]),
                      lz = *reinterpret_cast<const float4*>(w.lo[2]), hx = *reinterpret_cast<const float4*>(w.hi[0]),
@@ -418,23 +426,26 @@ PT_D bool blas_round(const DScene& S, const RayD& r, const BoxRay& br, double t_
         PT_CSWAP(0, 1) PT_CSWAP(2, 3) PT_CSWAP(0, 2) PT_CSWAP(1, 3) PT_CSWAP(1, 2)
 #undef PT_CSWAP
         cur = kNone;
-        if (t3 < kInf && sp < kStack) { stack[sp] = make_uint2(e3, __float_as_uint(t3)); sp++; }
-        if (t2 < kInf && sp < kStack) { stack[sp] = make_uint2(e2, __float_as_uint(t2)); sp++; }
-        if (t1 < kInf && sp < kStack) { stack[sp] = make_uint2(e1, __float_as_uint(t1)); sp++; }
+        if (t3 < kInf && can_push(sp, kStack)) { stack[sp] = make_uint2(e3, __float_as_uint(t3)); sp++; }
+        if (t2 < kInf && can_push(sp, kStack)) { stack[sp] = make_uint2(e2, __float_as_uint(t2)); sp++; }
+        if (t1 < kInf && can_push(sp, kStack)) { stack[sp] = make_uint2(e1, __float_as_uint(t1)); sp++; }
         if (t0 < kInf) {
             if ((e0 & kTagMask) == 0) cur = e0;
-            else if (sp < kStack) { stack[sp] = make_uint2(e0, __float_as_uint(t0)); sp++; }
+            else if (can_push(sp, kStack)) { stack[sp] = make_uint2(e0, __float_as_uint(t0)); sp++; }
         }
     }
     if (pending == kNone) return true;
+    PT_ASSERT((pending & ~kTagMask) < S.n_nodes);
     const DNode& n = S.nodes[pending & ~kTagMask];  // phase 2: one triangle leaf
     const uint32_t first = n.a, count = n.b;
+    PT_ASSERT(first + count <= S.n_refs);
     for (uint32_t k = 0; k < count; k++) {
         const DNode rb = S.refs[first + k];
         if (COUNT) c.n_refs++;
         if (!(slab(rb, br, tmin_f, tmax_f) <= tmax_f)) continue;
         if (COUNT) c.n_prims++;
         double t, u, v;
+        PT_ASSERT(ref_kind(rb.a) == PT_PRIM_TRIANGLE && ref_index(rb.a) < S.n_tris);
         if (tri_t(S.tris[ref_index(rb.a)], r, t_min, t, u, v) && t <= c.t) { consider(c, t, rb.a, cur_inst, cur_tie, rb.b); tmax_f = __double2float_ru(c.t); }
     }
     return false;

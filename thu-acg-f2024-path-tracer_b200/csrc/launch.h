@@ -39,6 +39,7 @@ void run_k_shade_nee(int cls, unsigned grid, cudaStream_t st, const ShadeArgs& a
 
 // ---- misc.cu: ray generation, tonemap, parity entry kernels
 void run_k_generate(cudaStream_t st, PathBuf out, uint32_t slot0, uint32_t n_new, uint64_t g0, uint32_t n_pixels, const DCameraEx& cam, const RenderConst& rc);
+void run_k_reduce_peers(cudaStream_t st, const float* const* src, uint32_t n_src, double scale, size_t n_values, float* out);
 void run_k_scale(cudaStream_t st, const float* accum, float scale, uint32_t n_values, float* out);
 void run_k_tonemap(cudaStream_t st, const float* accum, double scale, uint32_t n_values, uint8_t* out);
 void run_k_bsdf_eval(cudaStream_t st, uint32_t material, size_t n, const pt_bsdf_query* q, pt_bsdf_result* out, const DScene& S);

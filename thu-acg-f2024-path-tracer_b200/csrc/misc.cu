@@ -1,4 +1,6 @@
 // Translation unit of ray generation, tonemap and the parity / test entry kernels (misc_kernels.cuh).
+#include <algorithm>
+
 #include "launch.h"
 #include "misc_kernels.cuh"
 
@@ -6,6 +8,10 @@ namespace ptd {
 static unsigned grid128(size_t n) { return (unsigned)((n + 127) / 128); }
 void run_k_generate(cudaStream_t st, PathBuf out, uint32_t slot0, uint32_t n_new, uint64_t g0, uint32_t n_pixels, const DCameraEx& cam, const RenderConst& rc) {
     k_generate<<<(n_new + kBlock - 1) / kBlock, kBlock, 0, st>>>(out, slot0, n_new, g0, n_pixels, cam, rc);
+}
+void run_k_reduce_peers(cudaStream_t st, const float* const* src, uint32_t n_src, double scale, size_t n_values, float* out) {
+    const unsigned grid = (unsigned)std::min<size_t>((n_values / 4 + 255) / 256 + 1, 148u * 8u);
+    k_reduce_peers<<<grid, 256, 0, st>>>(src, n_src, scale, n_values, out);
 }
 void run_k_scale(cudaStream_t st, const float* accum, float scale, uint32_t n_values, float* out) { k_scale<<<(n_values + 255) / 256, 256, 0, st>>>(accum, scale, n_values, out); }
 void run_k_tonemap(cudaStream_t st, const float* accum, double scale, uint32_t n_values, uint8_t* out) { k_tonemap<<<(n_values + 255) / 256, 256, 0, st>>>(accum, scale, n_values, out); }

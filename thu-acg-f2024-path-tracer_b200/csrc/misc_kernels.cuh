@@ -27,6 +27,26 @@ __global__ void k_tonemap(const float* __restrict__ accum, double scale, uint32_
     double v = clampd(g, 0.0, 0.999) * 256.0;
     out[i] = (v != v) ? 0 : (uint8_t)v;
 }
+// pt_render_multi: the reduce(sum) of SURVEY §8(e) on the device.  src[g] is the radiance-sum buffer of share g — device
+// memory of ANOTHER GPU for g > 0, read straight over NVLink (peer access) by the GPU that owns `out`; partial sums are added
+// in share order in f64 and scaled once, exactly like the host loop this replaces, so the image is bit-identical to it.
+__global__ void k_reduce_peers(const float* const* __restrict__ src, uint32_t n_src, double scale, size_t n_values, float* __restrict__ out) {
+    const size_t n4 = n_values / 4;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        for (uint32_t g = 0; g < n_src; g++) {
+            const float4 v = reinterpret_cast<const float4*>(src[g])[i];
+            a0 += (double)v.x; a1 += (double)v.y; a2 += (double)v.z; a3 += (double)v.w;
+        }
+        reinterpret_cast<float4*>(out)[i] = make_float4((float)(a0 * scale), (float)(a1 * scale), (float)(a2 * scale), (float)(a3 * scale));
+    }
+    if (blockIdx.x == 0 && threadIdx.x < n_values - 4 * n4) {  // up to three trailing values
+        const size_t i = 4 * n4 + threadIdx.x;
+        double a = 0.0;
+        for (uint32_t g = 0; g < n_src; g++) a += (double)src[g][i];
+        out[i] = (float)(a * scale);
+    }
+}
 __global__ void k_scale(const float* __restrict__ accum, float scale, uint32_t n_values, float* __restrict__ out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_values) out[i] = accum[i] * scale;

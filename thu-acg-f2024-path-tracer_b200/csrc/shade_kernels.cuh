@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(kBlock, PT_SHADE_MIN_BLOCKS) k_shade(PathBuf i
         RayD next; d3 thr = mk(0, 0, 0); uint4 ids = make_uint4(0, 0, 0, 0);
         if (j < count) {
             const uint32_t i = items[j];
+            PT_ASSERT(i < q.stride);
             RayD ray = load_ray(in, i, &ids.x, &ids.y);
             thr = load_state(in, i, ids.z, ids.w);
             const uint32_t pix = ids.x, bounces = ids.z >> 16;
@@ -144,6 +145,7 @@ __global__ void __launch_bounds__(kBlock, PT_SHADE_MIN_BLOCKS) k_shade(PathBuf i
         __syncthreads();
         if (alive) {
             uint32_t dst = block_base[par] + bin_count[par][key][warp] + __popc(mine & ((1u << lane) - 1u));
+            PT_ASSERT(dst < q.stride);
             store_path(out, dst, next, thr, ids);
         }
         // no third barrier: the next iteration works on the other half of bin_count / block_base, and nobody can reach the
@@ -178,6 +180,7 @@ __global__ void __launch_bounds__(kBlock, PT_NEE_MIN_BLOCKS) k_shade_nee(PathBuf
         RayD next, sray; d3 thr = mk(0, 0, 0), sthr = mk(0, 0, 0); uint4 ids = make_uint4(0, 0, 0, 0);
         if (j < count) {
             const uint32_t i = items[j];
+            PT_ASSERT(i < q.stride);
             RayD ray = load_ray(in, i, &ids.x, &ids.y);
             thr = load_state(in, i, ids.z, ids.w);
             const uint32_t pix = ids.x, bounces = ids.z >> 16;

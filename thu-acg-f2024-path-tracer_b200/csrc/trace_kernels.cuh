@@ -397,6 +397,7 @@ __global__ void __launch_bounds__(kBlock, PT_TOP_MIN_BLOCKS) k_top(PathBuf pool,
             uint32_t base = 0;
             if ((int)lane == leader) base = atomicAdd(mq.count + r, __popc(b));
             base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            PT_ASSERT(base + __popc(b) <= mq.stride);
             if (has) mq.items[(size_t)r * mq.stride + base + __popc(b & ((1u << lane) - 1u))] =
                          make_uint2(i, __fns(mesh_mask, 0, r + 1) | (prov_cls << 8) | (nm == r + 1 ? 0x80000000u : 0u));
         }
@@ -407,8 +408,11 @@ __global__ void __launch_bounds__(kBlock, PT_TOP_MIN_BLOCKS) k_top(PathBuf pool,
     }
 }
 
+#ifndef PT_ENTER_MIN_BLOCKS
+#define PT_ENTER_MIN_BLOCKS 4
+#endif
 template <bool COUNT>
-__global__ void __launch_bounds__(kBlock, 4) k_mesh_enter(PathBuf pool, uint32_t round, MeshQueues mq, const HitRec* __restrict__ hits, const uint2* __restrict__ ties,
+__global__ void __launch_bounds__(kBlock, PT_ENTER_MIN_BLOCKS) k_mesh_enter(PathBuf pool, uint32_t round, MeshQueues mq, const HitRec* __restrict__ hits, const uint2* __restrict__ ties,
                                                            Queues q, DScene S, TopList top, double t_min, unsigned long long* __restrict__ work) {
     const uint32_t count = mq.count[round];
     const uint2* __restrict__ items = mq.items + (size_t)round * mq.stride;
@@ -425,6 +429,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_mesh_enter(PathBuf pool, uint32_t
             i = e.x;
             const uint32_t k = e.y & 0xFFu;
             const bool last = (e.y >> 31) != 0;
+            PT_ASSERT(k < top.n && ((top.mesh_bits >> k) & 1u) && i < mq.stride);
             const DNode rb = S.refs[k];
             const HitRec h0 = hits[i];
             // shade class of the provisional hit: in round 0 still what k_top noted in the queue entry; later an earlier round
@@ -441,6 +446,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_mesh_enter(PathBuf pool, uint32_t
                     r = instance_local_ray(ins, r); br = make_boxray(r); inst = mesh; mesh = ins.child_index;
                 }
                 uint32_t ce[4]; float ct[4];
+                PT_ASSERT(mesh < S.n_meshes && S.meshes[mesh].root2 < S.n_wide2 && (inst == kInstNone || inst < S.n_instances));
                 wide2_step(S.wide2[S.meshes[mesh].root2], br, tmin_f, tmax_f, ce, ct);
                 if (COUNT) w0 += 2;
                 const float kInf = __int_as_float(0x7f800000);
@@ -469,6 +475,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_mesh_enter(PathBuf pool, uint32_t
             uint32_t wbase = 0;
             if ((int)lane == leader) wbase = atomicAdd(mq.walk_count + round, __popc(b));
             wbase = __shfl_sync(0xFFFFFFFFu, wbase, leader);
+            PT_ASSERT(wbase + __popc(b) <= mq.stride);
             if (walk) {
                 uint4* dst = mq.walk + (size_t)(wbase + __popc(b & ((1u << lane) - 1u))) * kWalkRecU4;
                 const uint4* src = reinterpret_cast<const uint4*>(&rec);
@@ -522,11 +529,13 @@ __global__ void __launch_bounds__(kTraceBlock, kWalkMinBlocks * kBlock / kTraceB
             drained = base + __popc(idle) >= count;
             const uint32_t j = base + __popc(idle & ((1u << lane) - 1u));
             if (!active && j < count) {
+                PT_ASSERT(count <= mq.stride);
                 const uint4* src = mq.walk + (size_t)j * kWalkRecU4;
                 const uint4 a0 = src[0], a1 = src[1], a2 = src[2], a3 = src[3], a4 = src[4], a5 = src[5], a6 = src[6], a7 = src[7];
                 r.o = mk(__hiloint2double((int)a0.y, (int)a0.x), __hiloint2double((int)a0.w, (int)a0.z), __hiloint2double((int)a1.y, (int)a1.x));
                 r.d = mk(__hiloint2double((int)a1.w, (int)a1.z), __hiloint2double((int)a2.y, (int)a2.x), __hiloint2double((int)a2.w, (int)a2.z));
                 c.t = __hiloint2double((int)a3.y, (int)a3.x); i = a3.z; flags = a3.w;
+                PT_ASSERT(i < mq.stride && a5.z >= 1 && a5.z <= 4);
                 c.ref = a4.x; c.inst = a4.y & 0x7FFFFFFFu; c.tie_outer = a4.z; c.tie_inner = a4.w;
                 cur_inst = a5.x; cur_tie = a5.y;
                 br = make_boxray(r);
@@ -576,6 +585,7 @@ __global__ void __launch_bounds__(kTraceBlock, kWalkMinBlocks * kBlock / kTraceB
                 // ---- triangle step (mesh.rs:50-82 in f64) for every lane that holds one
                 if (active && pend != kNone) {
                     const uint32_t tri = pend & ~kTriBit;
+                    PT_ASSERT(tri < S.n_tris);
                     pend = kNone;
                     double t, u, v;
                     if (COUNT && pend_t <= tmax_f) { w2++; n_tris++; }
@@ -590,17 +600,18 @@ __global__ void __launch_bounds__(kTraceBlock, kWalkMinBlocks * kBlock / kTraceB
             } else if (active && cur != kNone) {
                 // ---- box step: open one node, push the entered children far to near; the nearest stays in hand
                 uint32_t ce[4]; float ct[4];
+                PT_ASSERT(cur < S.n_wide2);
                 wide2_step_addr(S.wide2 + cur, br, tmin_f, tmax_f, ce, ct);
                 if (COUNT) { w0 += 2; n_nodes++; }
                 const float kInf = __int_as_float(0x7f800000);
                 cur = kNone;
-                if (ct[3] < kInf && sp < kStack2) { stack[sp] = make_uint2(ce[3], __float_as_uint(ct[3])); sp++; }
-                if (ct[2] < kInf && sp < kStack2) { stack[sp] = make_uint2(ce[2], __float_as_uint(ct[2])); sp++; }
-                if (ct[1] < kInf && sp < kStack2) { stack[sp] = make_uint2(ce[1], __float_as_uint(ct[1])); sp++; }
+                if (ct[3] < kInf && can_push(sp, kStack2)) { stack[sp] = make_uint2(ce[3], __float_as_uint(ct[3])); sp++; }
+                if (ct[2] < kInf && can_push(sp, kStack2)) { stack[sp] = make_uint2(ce[2], __float_as_uint(ct[2])); sp++; }
+                if (ct[1] < kInf && can_push(sp, kStack2)) { stack[sp] = make_uint2(ce[1], __float_as_uint(ct[1])); sp++; }
                 if (ct[0] < kInf) {
                     if (!(ce[0] & kTriBit)) cur = ce[0];
                     else if (pend == kNone) { pend = ce[0]; pend_t = ct[0]; }
-                    else if (sp < kStack2) { stack[sp] = make_uint2(ce[0], __float_as_uint(ct[0])); sp++; }
+                    else if (can_push(sp, kStack2)) { stack[sp] = make_uint2(ce[0], __float_as_uint(ct[0])); sp++; }
                 }
             }
         }

@@ -162,6 +162,7 @@ PT_D void queue_append(const Queues& q, uint32_t cls, uint32_t i) {
         uint32_t base = 0;
         if ((int)lane == leader) base = atomicAdd(q.count + cls, __popc(peers));
         base = __shfl_sync(peers, base, leader);
+        PT_ASSERT(base + __popc(peers) <= q.stride && i < q.stride);
         q.items[(size_t)cls * q.stride + base + __popc(peers & ((1u << lane) - 1u))] = i;
     }
 }
