@@ -293,7 +293,7 @@ def main():
         tacc, tst = D.render_distributed(d3, cam, args.target_spp, seed=77, nan_policy=pt.PT_NAN_DROP, pool_paths=args.pool)
         rgb8 = None
         if rank == 0:
-            rgb8 = ctx.tonemap_rgb8(tacc, 1.0 / args.target_spp)      # camera.rs:109-114 on the device, RGB8 to the host
+            rgb8 = ctx.tonemap_rgb8(tacc.data_ptr(), 1.0 / args.target_spp, H, WIDTH)  # camera.rs:109-114 on the device, RGB8 to the host
             mean = (tacc / float(args.target_spp)).cpu().numpy()
         torch.cuda.synchronize()
         wall = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)

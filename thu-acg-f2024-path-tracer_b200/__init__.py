@@ -453,6 +453,13 @@ class Context:
     def upload(self, scene):
         return DeviceScene(self, scene)
 
+    def tonemap_rgb8(self, d_accum_ptr, scale, height, width):
+        """pt_tonemap_rgb8: sqrt-gamma + 8-bit quantisation (camera.rs:109-114,128-130) of `scale * accum` on the device;
+        d_accum_ptr = device pointer of H*W*3 fp32 radiance sums.  Returns uint8 [H, W, 3] in host memory."""
+        out = np.zeros((height, width, 3), dtype=np.uint8)
+        self._check(self.lib.pt_tonemap_rgb8(self.ptr, C.c_void_p(d_accum_ptr), float(scale), height * width, _ptr(out)))
+        return out
+
     def stage_ms(self, reset=True):
         """pt_debug_stage_ms: per-kernel-family times of the traversal stage (profiling level >= 1) since the last reset."""
         out = np.zeros(16, dtype=np.float64)
