@@ -304,6 +304,8 @@ int  pt_render(pt_ctx* ctx, const pt_scene* scene, const pt_camera* cam,
  * and the tests' multi-GPU path use one process per GPU + NCCL instead (pt_render_accumulate). */
 int  pt_render_multi(int n_devices, const int* devices, const pt_scene_desc* desc, const pt_camera* cam,
                      const pt_render_params* params, float* h_mean_rgb, pt_stats* stats);
+/* pt_render_multi keeps its per-device contexts (stream, events, the path pool) between calls; this frees them. */
+void pt_render_multi_release(void);
 /* sqrt-gamma, clamp(0,0.999)*256 as u8 (camera.rs:109-114,128-130). Device in, host out. */
 int  pt_tonemap_rgb8(pt_ctx* ctx, const float* d_accum, double scale, uint32_t n_pixels,
                      uint8_t* h_rgb8);

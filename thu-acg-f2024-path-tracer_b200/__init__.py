@@ -72,7 +72,7 @@ ABI_SYMBOLS = ["pt_ctx_create", "pt_ctx_destroy", "pt_ctx_set_stream", "pt_ctx_s
                "pt_scene_create", "pt_scene_destroy", "pt_scene_device_bytes", "pt_camera_image_height", "pt_render_accumulate",
                "pt_render", "pt_tonemap_rgb8", "pt_trace_closest", "pt_trace_any", "pt_bsdf_eval_pdf", "pt_bsdf_sample",
                "pt_camera_rays", "pt_lights_sample_pdf", "pt_scene_build_env_sampler", "pt_env_sample_pdf", "pt_sah_sweep",
-               "pt_render_multi", "pt_trace_closest_wavefront", "pt_trace_camera_wavefront", "pt_debug_histograms", "pt_debug_stage_ms"]
+               "pt_render_multi", "pt_render_multi_release", "pt_trace_closest_wavefront", "pt_trace_camera_wavefront", "pt_debug_histograms", "pt_debug_stage_ms"]
 
 
 class PtError(RuntimeError):

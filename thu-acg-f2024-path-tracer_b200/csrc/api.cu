@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -1085,17 +1086,29 @@ struct DevBuf {
 
 // One device's share of pt_render_multi: own context, own copy of the scene, samples share, share + n_shares, ... of the call.
 // The radiance sums stay on the device (d_accum) for the peer reduce.
+// Contexts of pt_render_multi are kept for the life of the process (pt_render_multi_release frees them): creating one costs a
+// stream, events and above all the path pool (gigabytes of cudaMalloc), which would otherwise be paid on every call.
+static std::mutex g_multi_mutex;
+static std::vector<pt_ctx*> g_multi_idle;
+static int acquire_multi_ctx(int device, pt_ctx** out) {
+    {
+        std::lock_guard<std::mutex> lock(g_multi_mutex);
+        for (size_t k = 0; k < g_multi_idle.size(); k++)
+            if (g_multi_idle[k]->device == device) { *out = g_multi_idle[k]; g_multi_idle.erase(g_multi_idle.begin() + k); return PT_OK; }
+    }
+    return pt_ctx_create(device, out);
+}
 struct Share {
     int device = 0; pt_ctx* ctx = nullptr; pt_scene* scene = nullptr; float* d_accum = nullptr;
     int rc = PT_OK; std::string err; pt_stats st{};
     void release() {
         if (d_accum) { cudaSetDevice(device); cudaFree(d_accum); d_accum = nullptr; }
         if (scene) { pt_scene_destroy(scene); scene = nullptr; }
-        if (ctx) { pt_ctx_destroy(ctx); ctx = nullptr; }
+        if (ctx) { std::lock_guard<std::mutex> lock(g_multi_mutex); g_multi_idle.push_back(ctx); ctx = nullptr; }
     }
 };
 static int render_share(Share& S, const pt_scene_desc* desc, const pt_camera* cam, const pt_render_params* p, uint32_t share, uint32_t n_shares, size_t n) {
-    int rc = pt_ctx_create(S.device, &S.ctx);
+    int rc = acquire_multi_ctx(S.device, &S.ctx);
     if (rc == PT_OK) rc = pt_scene_create(S.ctx, desc, &S.scene);
     if (rc == PT_OK && (p->flags & PT_RENDER_ENV_IMPORTANCE) && cam->env_is_map) rc = pt_scene_build_env_sampler(S.scene, cam->env_image, 0, 0);
     if (rc == PT_OK) {
@@ -1146,6 +1159,11 @@ static int reduce_shares(std::vector<Share>& shares, size_t n, double scale, flo
 
 extern "C" {
 
+void pt_render_multi_release(void) {
+    std::lock_guard<std::mutex> lock(g_multi_mutex);
+    for (pt_ctx* c : g_multi_idle) pt_ctx_destroy(c);
+    g_multi_idle.clear();
+}
 int pt_render_multi(int n_devices, const int* devices, const pt_scene_desc* desc, const pt_camera* cam, const pt_render_params* p,
                     float* h_mean, pt_stats* stats) {
     if (n_devices < 1 || !devices || !desc || !cam || !p || !h_mean) return fail(PT_ERR_INVALID, "pt_render_multi: bad argument");
