@@ -40,6 +40,22 @@ def test_abi_struct_sizes(pt, tmp_path):
     assert got == want
 
 
+def test_rust_sys_crate_matches_header(pt, tmp_path):
+    """ffi/pt-b200-sys (the binding a maintainer of the reference adds; not compiled here — no Rust toolchain): it declares
+    exactly the entry points of include/pt_b200.h, and the struct sizes it asserts at compile time are the C compiler's."""
+    rs = open(os.path.join(ROOT, "ffi", "pt-b200-sys", "src", "lib.rs")).read()
+    declared = sorted(set(re.findall(r"pub fn (pt_[a-z0-9_]+)\(", rs)))
+    assert declared == sorted(pt.ABI_SYMBOLS)
+    sizes = dict(re.findall(r"size_of::<(pt_[a-z0-9_]+)>\(\) == (\d+)", rs))
+    assert len(sizes) >= 15
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "pt_b200.h"\nint main(){' + "".join(f'printf("{n} %zu\\n", sizeof({n}));' for n in sizes) + "return 0;}\n")
+    exe = tmp_path / "sz"
+    subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(line.split() for line in subprocess.check_output([str(exe)]).decode().splitlines())
+    assert got == sizes
+
+
 def test_no_device_fails_loudly(pt):
     """Without a GPU the product must refuse, not fall back (the CPU box has no CUDA device)."""
     lib = pt.device_lib()

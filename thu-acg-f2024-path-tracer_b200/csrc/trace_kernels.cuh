@@ -477,10 +477,10 @@ __global__ void __launch_bounds__(kBlock, PT_ENTER_MIN_BLOCKS) k_mesh_enter(Path
             wbase = __shfl_sync(0xFFFFFFFFu, wbase, leader);
             PT_ASSERT(wbase + __popc(b) <= mq.stride);
             if (walk) {
-                uint4* dst = mq.walk + (size_t)(wbase + __popc(b & ((1u << lane) - 1u))) * kWalkRecU4;
-                const uint4* src = reinterpret_cast<const uint4*>(&rec);
+                char* dst = reinterpret_cast<char*>(mq.walk + (size_t)(wbase + __popc(b & ((1u << lane) - 1u))) * kWalkRecU4);
+                const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&rec);
 #pragma unroll
-                for (int k4 = 0; k4 < kWalkRecU4; k4++) dst[k4] = src[k4];
+                for (int k4 = 0; k4 < 4; k4++) st256(dst + 32 * k4, src[4 * k4], src[4 * k4 + 1], src[4 * k4 + 2], src[4 * k4 + 3]);
             }
         }
     }
@@ -530,13 +530,17 @@ __global__ void __launch_bounds__(kTraceBlock, kWalkMinBlocks * kBlock / kTraceB
             const uint32_t j = base + __popc(idle & ((1u << lane) - 1u));
             if (!active && j < count) {
                 PT_ASSERT(count <= mq.stride);
-                const uint4* src = mq.walk + (size_t)j * kWalkRecU4;
-                const uint4 a0 = src[0], a1 = src[1], a2 = src[2], a3 = src[3], a4 = src[4], a5 = src[5], a6 = src[6], a7 = src[7];
-                r.o = mk(__hiloint2double((int)a0.y, (int)a0.x), __hiloint2double((int)a0.w, (int)a0.z), __hiloint2double((int)a1.y, (int)a1.x));
-                r.d = mk(__hiloint2double((int)a1.w, (int)a1.z), __hiloint2double((int)a2.y, (int)a2.x), __hiloint2double((int)a2.w, (int)a2.z));
-                c.t = __hiloint2double((int)a3.y, (int)a3.x); i = a3.z; flags = a3.w;
+                const char* src = reinterpret_cast<const char*>(mq.walk + (size_t)j * kWalkRecU4);
+                unsigned long long q0, q1, q2, q3, q4, q5, q6, q7, q8, q9, q10, q11, q12, q13, q14, q15;  // the 128-byte record in four 256-bit loads
+                ld256(src, q0, q1, q2, q3); ld256(src + 32, q4, q5, q6, q7); ld256(src + 64, q8, q9, q10, q11); ld256(src + 96, q12, q13, q14, q15);
+                r.o = mk(__longlong_as_double(q0), __longlong_as_double(q1), __longlong_as_double(q2));
+                r.d = mk(__longlong_as_double(q3), __longlong_as_double(q4), __longlong_as_double(q5));
+                c.t = __longlong_as_double(q6); i = (uint32_t)q7; flags = (uint32_t)(q7 >> 32);
+                const uint4 a5 = make_uint4((uint32_t)q10, (uint32_t)(q10 >> 32), (uint32_t)q11, 0u);
+                const uint4 a6 = make_uint4((uint32_t)q12, (uint32_t)(q12 >> 32), (uint32_t)q13, (uint32_t)(q13 >> 32));
+                const uint4 a7 = make_uint4((uint32_t)q14, (uint32_t)(q14 >> 32), (uint32_t)q15, (uint32_t)(q15 >> 32));
                 PT_ASSERT(i < mq.stride && a5.z >= 1 && a5.z <= 4);
-                c.ref = a4.x; c.inst = a4.y & 0x7FFFFFFFu; c.tie_outer = a4.z; c.tie_inner = a4.w;
+                c.ref = (uint32_t)q8; c.inst = (uint32_t)(q8 >> 32) & 0x7FFFFFFFu; c.tie_outer = (uint32_t)q9; c.tie_inner = (uint32_t)(q9 >> 32);
                 cur_inst = a5.x; cur_tie = a5.y;
                 br = make_boxray(r);
                 tmax_f = __double2float_ru(c.t);

@@ -110,31 +110,40 @@ PT_D double env_pdf(const DEnvDist& E, d3 dir) {  // solid-angle density of env_
     return cell * (double)E.rows * (double)E.cols / (2.0 * kPi * kPi * st);
 }
 
+// 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256): one instruction moves a whole 32-byte sector per lane, so a
+// 64-byte ray record is two loads and every access of the strided record arrays is made of full sectors.
+PT_D void ld256(const void* p, unsigned long long& a, unsigned long long& b, unsigned long long& c, unsigned long long& d) {
+    asm volatile("ld.global.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+}
+PT_D void st256(void* p, unsigned long long a, unsigned long long b, unsigned long long c, unsigned long long d) {
+    asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
+PT_D unsigned long long pack2(uint32_t lo, uint32_t hi) { return (unsigned long long)lo | ((unsigned long long)hi << 32); }
 // ids = {pixel, sample, rng_used | bounce << 16, spare} as the shade kernels carry them
 PT_D void store_path(const PathBuf& b, uint32_t i, const RayD& r, d3 thr, uint4 ids) {
-    double2* p = reinterpret_cast<double2*>(b.ray + i);
-    p[0] = make_double2(r.o.x, r.o.y); p[1] = make_double2(r.o.z, r.d.x); p[2] = make_double2(r.d.y, r.d.z);
-    reinterpret_cast<uint4*>(p)[3] = make_uint4((uint32_t)__double2loint(r.time), (uint32_t)__double2hiint(r.time), ids.x, ids.y);
-    double2* s = reinterpret_cast<double2*>(b.state + i);
-    s[0] = make_double2(thr.x, thr.y);
-    reinterpret_cast<uint4*>(s)[1] = make_uint4((uint32_t)__double2loint(thr.z), (uint32_t)__double2hiint(thr.z), ids.z, ids.w);
+    char* p = reinterpret_cast<char*>(b.ray + i);
+    st256(p, __double_as_longlong(r.o.x), __double_as_longlong(r.o.y), __double_as_longlong(r.o.z), __double_as_longlong(r.d.x));
+    st256(p + 32, __double_as_longlong(r.d.y), __double_as_longlong(r.d.z), __double_as_longlong(r.time), pack2(ids.x, ids.y));
+    st256(b.state + i, __double_as_longlong(thr.x), __double_as_longlong(thr.y), __double_as_longlong(thr.z), pack2(ids.z, ids.w));
 }
 PT_D RayD load_ray(const PathBuf& b, uint32_t i, uint32_t* pixel = nullptr, uint32_t* sample = nullptr) {
-    const double2* p = reinterpret_cast<const double2*>(b.ray + i);
-    const double2 a = p[0], c = p[1], e = p[2];
-    const uint4 g = reinterpret_cast<const uint4*>(p)[3];
+    const char* p = reinterpret_cast<const char*>(b.ray + i);
+    unsigned long long a0, a1, a2, a3, c0, c1, c2, c3;
+    ld256(p, a0, a1, a2, a3);
+    ld256(p + 32, c0, c1, c2, c3);
     RayD r;
-    r.o = mk(a.x, a.y, c.x); r.d = mk(c.y, e.x, e.y); r.time = __hiloint2double((int)g.y, (int)g.x);
-    if (pixel) *pixel = g.z;
-    if (sample) *sample = g.w;
+    r.o = mk(__longlong_as_double(a0), __longlong_as_double(a1), __longlong_as_double(a2));
+    r.d = mk(__longlong_as_double(a3), __longlong_as_double(c0), __longlong_as_double(c1));
+    r.time = __longlong_as_double(c2);
+    if (pixel) *pixel = (uint32_t)c3;
+    if (sample) *sample = (uint32_t)(c3 >> 32);
     return r;
 }
 PT_D d3 load_state(const PathBuf& b, uint32_t i, uint32_t& rng_bounce, uint32_t& spare) {
-    const double2* s = reinterpret_cast<const double2*>(b.state + i);
-    const double2 a = s[0];
-    const uint4 g = reinterpret_cast<const uint4*>(s)[1];
-    rng_bounce = g.z; spare = g.w;
-    return mk(a.x, a.y, __hiloint2double((int)g.y, (int)g.x));
+    unsigned long long a0, a1, a2, a3;
+    ld256(b.state + i, a0, a1, a2, a3);
+    rng_bounce = (uint32_t)a3; spare = (uint32_t)(a3 >> 32);
+    return mk(__longlong_as_double(a0), __longlong_as_double(a1), __longlong_as_double(a2));
 }
 
 // Shade classes: one queue and one specialised shade kernel per class, so warps shade one material kind.

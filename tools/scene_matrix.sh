@@ -21,8 +21,9 @@ import json, sys
 try:
     l = json.loads([x for x in open(sys.argv[1]) if x.startswith("{")][-1])
     cb = l.get("cpu_baseline") or {}
+    r = l["roofline"]; oc = r["survey_model"]["oracle_counters_per_segment"]
     print(f'{l["config"]["workload"]:44s} N={l["n_gpus"]} {l["value"]:9.1f} Mrays/s {l["samples_per_s"]:.3e} samples/s e2e {l["e2e"]["value"]:9.1f} '
-          f'roofline {l["roofline"]["kernel"]} {l["roofline"]["frac"]:.2f} (device counters {l["roofline"]["k_trace_device_counters"]["frac"]:.2f}) '
+          f'seg/path {l["segments_per_path"]:.2f} stages {r["stage_ms_per_step"]} oracle counters/seg boxes {oc["boxes"]:.1f} sph {oc["spheres"]:.2f} quad {oc["quads"]:.2f} tri {oc["triangles"]:.2f} '
           f'cpu {cb.get("value", float("nan")):.2f} Mrays/s x{cb.get("cores", 0)} cores')
 except Exception as e:
     print(sys.argv[1], "FAILED", e)
