@@ -50,17 +50,17 @@ template <> struct ClassKind<CLS_PRINCIPLED> { static constexpr int value = PT_M
 // VAR bit 0: environment importance sampling joins the mixture; bit 1: World.lights holds more than quads and spheres
 // (cuboid / mesh / instance lights).  The reference's shipped scenes need neither, and their kernels carry none of that code.
 template <int CLS, int VAR = 0>
-__global__ void __launch_bounds__(kBlock, PT_SHADE_MIN_BLOCKS) k_shade(PathBuf in, Queues q, const HitRec* __restrict__ hits, PathBuf out,
+__global__ void __launch_bounds__(kShadeBlock, PT_SHADE_MIN_BLOCKS * 128 / kShadeBlock) k_shade(PathBuf in, Queues q, const HitRec* __restrict__ hits, PathBuf out,
                                                     uint32_t* __restrict__ out_count, float* __restrict__ accum,
                                                     unsigned long long* __restrict__ nonfinite, DScene S, DCameraEx cam, RenderConst rc) {
     constexpr int K = ClassKind<CLS>::value;
     const uint32_t count = q.count[CLS];
     const uint32_t* __restrict__ items = q.items + (size_t)CLS * q.stride;
-    __shared__ uint32_t bin_count[2][8][kBlock / 32];  // survivors per (octant bin, warp), then their exclusive prefix; double-buffered
+    __shared__ uint32_t bin_count[2][8][kShadeBlock / 32];  // survivors per (octant bin, warp), then their exclusive prefix; double-buffered
     __shared__ uint32_t block_base[2];
     stage_tables(S);
     uint32_t par = 0;
-    for (uint32_t base = blockIdx.x * kBlock; base < count; base += gridDim.x * kBlock, par ^= 1u) {
+    for (uint32_t base = blockIdx.x * kShadeBlock; base < count; base += gridDim.x * kShadeBlock, par ^= 1u) {
         const uint32_t j = base + threadIdx.x;
         bool alive = false;
         RayD next; d3 thr = mk(0, 0, 0); uint4 ids = make_uint4(0, 0, 0, 0);
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(kBlock, PT_SHADE_MIN_BLOCKS) k_shade(PathBuf i
 #pragma unroll
             for (int b = 0; b < 8; b++)
 #pragma unroll
-                for (int w = 0; w < kBlock / 32; w++) { uint32_t c = bin_count[par][b][w]; bin_count[par][b][w] = total; total += c; }
+                for (int w = 0; w < kShadeBlock / 32; w++) { uint32_t c = bin_count[par][b][w]; bin_count[par][b][w] = total; total += c; }
             block_base[par] = total ? atomicAdd(out_count, total) : 0;
         }
         __syncthreads();

@@ -21,6 +21,10 @@ constexpr int kBlock = 128;
 // one warp per block measured 2-3 % faster than 128 threads on the mesh scenes (scene 6 FHD trace 38.1 -> 37.0 ms).
 // MIN_BLOCKS in its launch bounds is stated for 128-thread blocks and scaled.
 constexpr int kTraceBlock = PT_TRACE_BLOCK;
+#ifndef PT_SHADE_BLOCK
+#define PT_SHADE_BLOCK 128   // threads per block of the k_shade<class> kernels (the block is the unit of the survivor compaction)
+#endif
+constexpr int kShadeBlock = PT_SHADE_BLOCK;
 #ifndef PT_SHADE_MIN_BLOCKS
 #define PT_SHADE_MIN_BLOCKS 4  // resident blocks per SM the shade kernels must allow (register cap 128)
 #endif
