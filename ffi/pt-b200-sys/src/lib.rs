@@ -64,7 +64,7 @@ pub const PT_RENDER_ENV_IMPORTANCE: u32 = 0x1; pub const PT_RENDER_NEE: u32 = 0x
 #[repr(C)] #[derive(Clone, Copy, Default, Debug)] pub struct pt_stats { pub paths: u64, pub segments: u64, pub nonfinite: u64, pub kernel_launches: u64,
     pub iterations: u32, pub width: u32, pub height: u32, pub device_ms: f32, pub trace_ms: f32, pub shade_ms: f32, pub raygen_ms: f32,
     pub node_pairs: u64, pub ref_boxes: u64, pub prim_tests: u64,
-    pub two_pass_iterations: u32, pub queue_errors: u32, pub p2p_shares: u32, pub _pad: u32 }
+    pub two_pass_iterations: u32, pub queue_errors: u32, pub p2p_shares: u32, pub tail_paths: u32 }
 #[repr(C)] #[derive(Clone, Copy, Default)] pub struct pt_ray { pub origin: pt_vec3, pub direction: pt_vec3, pub time: f64 }
 #[repr(C)] #[derive(Clone, Copy, Default)] pub struct pt_hit { pub t: f64, pub u: f64, pub v: f64, pub point: pt_vec3, pub geometric_normal: pt_vec3,
     pub shading_normal: pt_vec3, pub hit: u32, pub prim_kind: u32, pub prim_index: u32, pub instance: u32, pub material: u32,

@@ -255,7 +255,7 @@ typedef struct {
     uint32_t queue_errors;        /* pt_trace_*_wavefront only: rays that did not join exactly one shade-class queue, or joined the
                                    * queue of another class than their hit's material (an invariant of the traversal stage; 0) */
     uint32_t p2p_shares;          /* pt_render_multi only: shares whose radiance sums the reduce kernel read in place over peer access */
-    uint32_t _pad;
+    uint32_t tail_paths;          /* paths the tail megakernel ran to their end in one launch (0: the render never took that path) */
 } pt_stats;
 
 typedef struct pt_ctx pt_ctx;
@@ -383,7 +383,7 @@ int  pt_env_sample_pdf(pt_ctx* ctx, const pt_scene* scene, size_t n, const doubl
 int  pt_debug_histograms(pt_ctx* ctx, uint64_t* out512, int reset);
 /* Diagnostics (profiling level >= 1): CUDA-event time per kernel family of the traversal stage since the last reset, ms:
  * [0] k_top on surviving paths, [1] k_top on new paths (camera rays generated in the kernel), [2] k_mesh_enter,
- * [3] k_mesh_walk, [4] BVH trace kernels (k_trace, k_trace_blas*), [5] k_generate.  out16 may be NULL. */
+ * [3] k_mesh_walk, [4] BVH trace kernels (k_trace, k_trace_blas*), [5] k_generate, [6] k_tail (the tail megakernel).  out16 may be NULL. */
 int  pt_debug_stage_ms(pt_ctx* ctx, double* out16, int reset);
 
 #ifdef __cplusplus

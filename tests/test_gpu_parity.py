@@ -425,14 +425,24 @@ def test_volumes_match_oracle(pt, orc, ctx):
 
 
 # ---------------------------------------------------------------- renders
+_ORACLE_RENDERS = {}
+
+
 @pytest.mark.parametrize("scene_id,width,spp", [(3, 96, 8), (1, 128, 8), (7, 96, 8), (6, 128, 6), (5, 128, 8), (4, 128, 8), (6, 256, 4), (70, 192, 4)])
 @pytest.mark.parametrize("policy", [0, 1])
-def test_render_matches_oracle_sample_for_sample(pt, pairs, scene_id, width, spp, policy):
+@pytest.mark.parametrize("flags", [0, 0x4000])
+def test_render_matches_oracle_sample_for_sample(pt, pairs, scene_id, width, spp, policy, flags):
     """Same Philox streams => the device follows the same paths as the oracle.  A path diverges only where a
-    transcendental (CUDA vs glibc, <= 2 ulp) flips a branch or a texel, so all but a few pixels agree to fp32 accumulation."""
+    transcendental (CUDA vs glibc, <= 2 ulp) flips a branch or a texel, so all but a few pixels agree to fp32 accumulation.
+    flags 0: the render ends in the tail megakernel (at these sizes it takes over after the first iterations);
+    0x4000: wavefront iterations (per-class shade kernels) to the last path."""
     p = pairs(scene_id, width)
-    img, st = p.dev.render(spp=spp, seed=21, nan_policy=policy)
-    ref, ost = p.ora.render(p.scene.camera, spp, seed=21, nan_policy=policy)
+    img, st = p.dev.render(spp=spp, seed=21, nan_policy=policy, flags=flags)
+    key = (scene_id, width, spp, policy)
+    if key not in _ORACLE_RENDERS:
+        _ORACLE_RENDERS[key] = p.ora.render(p.scene.camera, spp, seed=21, nan_policy=policy)
+    ref, ost = _ORACLE_RENDERS[key]
+    assert st.tail_paths == 0 if flags else (st.tail_paths > 0 or scene_id in (4, 5, 2))   # short-lived paths may all end before the threshold is checked
     assert st.paths == ost.paths == img.shape[0] * img.shape[1] * spp
     # the two mesh scenes at >= 65 536 paths in flight go through the two-pass traversal, like every benchmarked iteration
     assert (st.two_pass_iterations > 0) == (scene_id in (6, 70) and st.paths >= TWO_PASS_MIN)
@@ -460,10 +470,13 @@ def test_virtual_rank_split_equals_single_rank(pt, pairs):
 
 @pytest.mark.parametrize("scene_id,width,spp", [(3, 96, 8), (6, 160, 8)])
 def test_scheduling_knobs_do_not_change_the_image(pt, pairs, scene_id, width, spp):
-    """The batched tail (8 iterations per host round trip), the forked shade streams and the octant grouping of survivors
-    only reorder work: same paths, same segments, same iteration count, same image (up to fp32 atomic-add order)."""
+    """The tail megakernel (one launch runs the last <= 64 Ki paths to their end; flag 0x4000 = the wavefront iterations
+    instead), the forked shade streams and the octant grouping of survivors only reorder work: same paths, same segments,
+    same iteration count, same image (up to fp32 atomic-add order)."""
     p = pairs(scene_id, width)
     base, st0 = p.dev.render(spp=spp, seed=9, nan_policy=1)
+    assert 0 < st0.tail_paths <= 65536                                       # the default path did end in the megakernel
+    assert p.dev.render(spp=spp, seed=9, nan_policy=1, flags=0x4000)[1].tail_paths == 0
     for flags in (0x4000, 0x2000, 0x8000, 0x100000, 0x400000, 0x400000 | 0x200000, 0x4000 | 0x2000 | 0x8000 | (5 << 16) | 0x100000):
         img, st = p.dev.render(spp=spp, seed=9, nan_policy=1, flags=flags)
         assert (st.paths, st.segments, st.iterations, st.nonfinite) == (st0.paths, st0.segments, st0.iterations, st0.nonfinite), hex(flags)

@@ -50,7 +50,7 @@ class Stats(C.Structure):  # pt_stats
                 ("iterations", C.c_uint32), ("width", C.c_uint32), ("height", C.c_uint32), ("device_ms", C.c_float),
                 ("trace_ms", C.c_float), ("shade_ms", C.c_float), ("raygen_ms", C.c_float),
                 ("node_pairs", C.c_uint64), ("ref_boxes", C.c_uint64), ("prim_tests", C.c_uint64),
-                ("two_pass_iterations", C.c_uint32), ("queue_errors", C.c_uint32), ("p2p_shares", C.c_uint32), ("_pad", C.c_uint32)]
+                ("two_pass_iterations", C.c_uint32), ("queue_errors", C.c_uint32), ("p2p_shares", C.c_uint32), ("tail_paths", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -465,7 +465,7 @@ class Context:
         out = np.zeros(16, dtype=np.float64)
         self.lib.pt_debug_stage_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         self._check(self.lib.pt_debug_stage_ms(self.ptr, _ptr(out), int(reset)))
-        names = ("top_old", "top_new", "mesh_enter", "mesh_walk", "bvh", "generate", "-", "-", "miss", "light", "diffuse", "metal", "glass", "principled", "other")
+        names = ("top_old", "top_new", "mesh_enter", "mesh_walk", "bvh", "generate", "tail", "-", "miss", "light", "diffuse", "metal", "glass", "principled", "other")
         return {k: v for k, v in zip(names, out.tolist()) if k != "-"}
 
     def histograms(self, reset=True):

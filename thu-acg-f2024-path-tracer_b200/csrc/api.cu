@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -26,6 +27,18 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 // back to back, each reading its ray count from the survivors counter of the one before, and the host reads all the
 // counters in one round trip.  Grids are sized by the live count at the start of the batch (an upper bound).
 constexpr int kTailBatch = 8;
+// Tail megakernel (tail_kernels.cuh): once nothing is left to generate and at most tail_max_paths() paths are alive, ONE launch of
+// k_tail runs every one of them to its end instead of ~45 more wavefront iterations.  The threshold depends on what a small
+// wavefront iteration costs on the scene (measured, profiles/r2_ab/r2_o_tail_threshold.log): scenes whose small iterations run
+// the fused BVH kernel (a large World, or meshes) gain up to 64 Ki paths (scene 6 FHD x 32 spp: 36.4 -> 32.1 ms; scene 1:
+// 15.0 -> 13.4 ms); flat scenes without meshes iterate in ~65 us (k_top + three shade kernels) and the megakernel — 196
+// registers, 4 of 32 lanes, every instruction an I-cache miss — only wins below a few thousand paths (scene 3: 20 Ki paths
+// +1.3 ms, 700 paths -0.4 ms).  PT_B200_TAIL_MAX overrides the threshold (developer knob; 0 switches the megakernel off).
+static uint32_t tail_max_paths(bool cheap_iterations) {  // cheap_iterations: flat scene without meshes
+    static const long v = [] { const char* e = getenv("PT_B200_TAIL_MAX"); return e ? (long)strtoul(e, nullptr, 10) : -1l; }();
+    if (v >= 0) return (uint32_t)v;
+    return cheap_iterations ? (1u << 12) : (1u << 16);
+}
 constexpr int kSlot = 64;  // uint32 counters per wavefront iteration (see pt_ctx::d_count)
 constexpr uint32_t kTailBatchMaxLive = 1u << 22;
 
@@ -989,7 +1002,23 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
     };
     // flag 0x4000: opt out of the batched tail (A/B measurements)
     const bool tail_batching = !nee && !ctx->profiling && !(p->flags & 0x4000u);
+    // the megakernel shades with the reference mixture (k_shade<class, 0>) and the fused BVH traversal without media
+    const bool tail_mega = !nee && !(p->flags & 0x4000u) && ctx->profiling < 2 && !scene->has_volumes && !scene->general_lights && !rcst.env_importance;
     while (dcam.c.max_depth > 0 && (live > 0 || generated < total)) {
+        if (tail_mega && generated == total && live > 0 && live <= tail_max_paths(scene->flat && scene->mesh_rounds == 0)) {
+            // ---- tail megakernel: every remaining path runs to its end in one launch
+            CU(cudaMemsetAsync(ctx->d_count, 0, 2 * sizeof(uint32_t), st));
+            ctx->mark(-1);
+            const TailArgs ta{path_buf(ctx, cur), live, d_accum, ctx->d_nonfinite, scene->d, dcam, rcst, tstage.t_min, ctx->d_count};
+            if (scene->wide) run_k_tail_wide(st, ta); else run_k_tail_bin(st, ta);
+            ctx->mark(6);
+            CU(cudaMemcpyAsync(ctx->h_count, ctx->d_count, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            if (ctx->profiling) ctx->collect_marks();
+            S.segments += ctx->h_count[0]; S.iterations += ctx->h_count[1]; S.kernel_launches++; S.tail_paths = live;
+            live = 0;
+            continue;
+        }
         if (tail_batching && generated == total && live <= kTailBatchMaxLive) {
             // ---- batched tail: kTailBatch iterations per host round trip (see kTailBatch)
             const uint32_t n0 = live;

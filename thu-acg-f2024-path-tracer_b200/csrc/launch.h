@@ -1,5 +1,5 @@
 // Host-callable launchers of the sm_100a kernels.  The kernels live in four translation units that are compiled in
-// parallel (trace.cu, shade_ref.cu, shade_var.cu, shade_nee.cu, misc.cu); api.cu holds no device code.
+// parallel (trace.cu, shade_ref.cu, shade_var.cu, shade_nee.cu, tail_wide.cu, tail_bin.cu, misc.cu); api.cu holds no device code.
 #pragma once
 #include "wavefront.cuh"
 
@@ -36,6 +36,14 @@ struct ShadeArgs {
 void run_k_shade_ref(int cls, unsigned grid, cudaStream_t st, const ShadeArgs& a);            // shade_ref.cu (var 0)
 void run_k_shade_var(int cls, int var, unsigned grid, cudaStream_t st, const ShadeArgs& a);   // shade_var.cu (var 2, 3)
 void run_k_shade_nee(int cls, unsigned grid, cudaStream_t st, const ShadeArgs& a);            // shade_nee.cu (PT_RENDER_NEE)
+
+// ---- tail_wide.cu / tail_bin.cu: the tail megakernel (tail_kernels.cuh): every path of a small wavefront runs to its end in one launch
+// counters: [0] += segments traced, [1] = max segments of one path (= the wavefront iterations the launch replaces)
+struct TailArgs {
+    PathBuf in; uint32_t n; float* accum; unsigned long long* nonfinite; DScene S; DCameraEx cam; RenderConst rc; double t_min; uint32_t* counters;
+};
+void run_k_tail_wide(cudaStream_t st, const TailArgs& a);
+void run_k_tail_bin(cudaStream_t st, const TailArgs& a);
 
 // ---- misc.cu: ray generation, tonemap, parity entry kernels
 void run_k_generate(cudaStream_t st, PathBuf out, uint32_t slot0, uint32_t n_new, uint64_t g0, uint32_t n_pixels, const DCameraEx& cam, const RenderConst& rc);

@@ -38,6 +38,22 @@ PT_D void stage_tables(DScene& S) {
 #endif
 }
 
+// PT_SHADE_PREFETCH: the path records of a thread's NEXT loop iteration are prefetched into L1 while the current path is shaded
+// (the gathers queue -> path -> ray / state / hit are a chain of dependent loads: 26 % of the diffuse kernel's stall samples).
+#ifndef PT_SHADE_PREFETCH
+#define PT_SHADE_PREFETCH 1   // measured: scene 6 FHD +1.4 %, scene 7m +0.7 %, scene 3 +1.7 % (profiles/r2_ab/r2_n_ab1.log)
+#endif
+// PT_SHADE_WARP_COMPACT: survivors are compacted per WARP (grouped by octant inside the warp, one atomicAdd per warp) instead of per
+// block: no shared memory and no __syncthreads in the loop (barrier stalls: 5-11 % of the shade kernels' samples).
+#ifndef PT_SHADE_WARP_COMPACT
+#define PT_SHADE_WARP_COMPACT 0   // measured: scene 6 +0.5 %, scenes 7m / 3 -2.2 % (the block-wide octant grouping is worth more than the barriers cost)
+#endif
+PT_D void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+PT_D void prefetch_path(const PathBuf& b, const HitRec* __restrict__ hits, uint32_t i, bool with_hit) {
+    prefetch_l1(b.ray + i); prefetch_l1(b.state + i);
+    if (with_hit) prefetch_l1(hits + i);
+}
+
 template <int CLS> struct ClassKind { static constexpr int value = -1; };
 template <> struct ClassKind<CLS_LIGHT> { static constexpr int value = PT_MAT_LIGHT; };
 template <> struct ClassKind<CLS_DIFFUSE> { static constexpr int value = PT_MAT_DIFFUSE; };
@@ -45,86 +61,147 @@ template <> struct ClassKind<CLS_METAL> { static constexpr int value = PT_MAT_ME
 template <> struct ClassKind<CLS_GLASS> { static constexpr int value = PT_MAT_GLASS; };
 template <> struct ClassKind<CLS_PRINCIPLED> { static constexpr int value = PT_MAT_PRINCIPLED; };
 
-// One loop iteration of Camera::trace after intersect_all (camera.rs:180-225) for the paths of ONE shade class.
-// Grid-stride over the class queue; survivors are written compacted into `out` (ballot + block prefix + one atomic).
+// One loop iteration of Camera::trace after intersect_all (camera.rs:180-225) for ONE path whose closest hit shades with class CLS:
+// miss / environment, emission, Russian roulette, the light / BSDF mixture sample, eval / pdf, the next ray.  Returns true when
+// the path continues: `next`, `thr` and `ids` then describe it.  Shared by the per-class wavefront kernels (k_shade) and by the
+// tail megakernel (tail_kernels.cuh).  `after_hit()` runs once the path's own records have been consumed (prefetch hook).
 // VAR bit 0: environment importance sampling joins the mixture; bit 1: World.lights holds more than quads and spheres
 // (cuboid / mesh / instance lights).  The reference's shipped scenes need neither, and their kernels carry none of that code.
+struct NoHook { PT_D void operator()() const {} };
+template <int CLS, int VAR, class Hook = NoHook>
+PT_D bool shade_one(const DScene& S, const DCameraEx& cam, const RenderConst& rc, float* __restrict__ accum, unsigned long long* __restrict__ nonfinite,
+                    const RayD& ray, const HitRec& hr, d3& thr, uint4& ids, RayD& next, Hook after_hit = Hook()) {
+    constexpr int K = ClassKind<CLS>::value;
+    const uint32_t pix = ids.x, bounces = ids.z >> 16;
+    bool dead = false, alive = false;
+    if (CLS == CLS_MISS) {  // camera.rs:180-183
+        after_hit();
+        add_radiance(accum, pix, thr * sample_environment(S, cam.c, ray.d), rc.nan_policy, nonfinite, dead);
+        return false;
+    }
+    Rng rng; rng.init(rc.seed, pix, ids.y, ids.z & 0xFFFFu);
+    HitInfoD h;
+    reconstruct_hit<false>(S, ray, hr.ref, hr.inst_light & 0x7FFFFFFFu, hr.t, h);
+    after_hit();
+    const DMaterial& m = S.materials[h.material];
+    // camera.rs:186-187: `radiance += throughput * emitted` runs for every hit; for non-emitters it only
+    // matters when the throughput is already inf/NaN (inf * 0 = NaN poisons the pixel, Q32).
+    if (CLS == CLS_LIGHT || !finite3(thr)) {
+        d3 em = CLS == CLS_LIGHT ? texture_value(S, m.base_color_tex, h.u, h.v, h.point) : mk(0, 0, 0);
+        add_radiance(accum, pix, thr * em, rc.nan_policy, nonfinite, dead);
+    }
+    bool go = !dead;
+    if (go && bounces > 5) {  // Russian roulette, camera.rs:190-196
+        double p = clampd(luminance(thr), 0.01, 1.0);
+        if (rng.next() > p) go = false;
+        else thr = thr / p;
+    }
+    if (go) {
+        // camera.rs:199-200: p_light = 0.5 iff lights exist.  With PT_RENDER_ENV_IMPORTANCE (ours) the environment map
+        // joins the mixture as a third sampler: p_bsdf = 0.5, the other half is split between lights and environment.
+        constexpr bool env_is = (VAR & 1) != 0, GEN = (VAR & 2) != 0;
+        const double p_env = env_is ? (S.n_lights == 0 ? 0.5 : 0.25) : 0.0;
+        const double p_light = S.n_lights == 0 ? 0.0 : 0.5 - p_env, p_bsdf = env_is ? 0.5 : 1.0 - p_light;
+        const double rsel = rng.next();
+        d3 dir;
+        bool ok;
+        if (rsel < p_light) ok = lights_sample<GEN>(S, h.point, ray.time, rng, dir);
+        else if (env_is && rsel < p_light + p_env) { const double u1 = rng.next(), u2 = rng.next(); dir = env_sample(rc.env, u1, u2); ok = true; }
+        else ok = bsdf_sample<K>(S, h.material, ray.d, h, rng, dir);
+        if (ok) {  // camera.rs:212-225
+            d3 f; double bsdf_pdf;
+            bsdf_eval_pdf<K>(S, h.material, -ray.d, dir, h, f, bsdf_pdf);
+            double light_pdf = lights_pdf<GEN>(S, h.point, dir, ray.time);
+            double pdf = p_bsdf * bsdf_pdf + p_light * light_pdf;
+            if (env_is) pdf = pdf + p_env * env_pdf(rc.env, dir);
+            d3 attenuation = f / pdf;
+            double e = 1e-3 * signum(dot(dir, h.gn));
+            next = make_ray(h.point + e * h.gn, dir, ray.time);
+            thr = thr * attenuation;
+            alive = bounces + 1 < cam.c.max_depth;  // `for bounces in 0..max_depth`, camera.rs:177
+            if (rc.nan_policy == PT_NAN_DROP && !finite3(thr)) { atomicAdd(nonfinite, 1ull); alive = false; }
+            ids.z = (rng.used & 0xFFFFu) | ((bounces + 1) << 16);
+        }
+    }
+    return alive;
+}
+
+// The paths of ONE shade class: grid-stride over the class queue, shade_one per path; survivors are written compacted into `out`
+// (ballot + block prefix + one atomic).
+struct PrefetchHook {
+    const PathBuf& b; const HitRec* __restrict__ hits; uint32_t i; bool go, with_hit;
+    PT_D void operator()() const { if (go) prefetch_path(b, hits, i, with_hit); }
+};
 template <int CLS, int VAR = 0>
 __global__ void __launch_bounds__(kShadeBlock, PT_SHADE_MIN_BLOCKS * 128 / kShadeBlock) k_shade(PathBuf in, Queues q, const HitRec* __restrict__ hits, PathBuf out,
                                                     uint32_t* __restrict__ out_count, float* __restrict__ accum,
                                                     unsigned long long* __restrict__ nonfinite, DScene S, DCameraEx cam, RenderConst rc) {
-    constexpr int K = ClassKind<CLS>::value;
     const uint32_t count = q.count[CLS];
     const uint32_t* __restrict__ items = q.items + (size_t)CLS * q.stride;
     __shared__ uint32_t bin_count[2][8][kShadeBlock / 32];  // survivors per (octant bin, warp), then their exclusive prefix; double-buffered
     __shared__ uint32_t block_base[2];
     stage_tables(S);
     uint32_t par = 0;
+#if PT_SHADE_PREFETCH
+    uint32_t i_next = blockIdx.x * kShadeBlock + threadIdx.x < count ? items[blockIdx.x * kShadeBlock + threadIdx.x] : 0u;
+#endif
     for (uint32_t base = blockIdx.x * kShadeBlock; base < count; base += gridDim.x * kShadeBlock, par ^= 1u) {
         const uint32_t j = base + threadIdx.x;
         bool alive = false;
         RayD next; d3 thr = mk(0, 0, 0); uint4 ids = make_uint4(0, 0, 0, 0);
+#if PT_SHADE_PREFETCH
+        // the queue entry of this thread's NEXT iteration is read one iteration ahead; its path records are prefetched into L1
+        // by shade_one's hook, once this path's own loads have landed
+        const uint32_t i = i_next;
+        const uint32_t jn = j + gridDim.x * kShadeBlock;
+        const bool has_next = jn < count;
+        if (has_next) i_next = items[jn];
+#endif
         if (j < count) {
+#if !PT_SHADE_PREFETCH
             const uint32_t i = items[j];
+#endif
             PT_ASSERT(i < q.stride);
-            RayD ray = load_ray(in, i, &ids.x, &ids.y);
+            const RayD ray = load_ray(in, i, &ids.x, &ids.y);
             thr = load_state(in, i, ids.z, ids.w);
-            const uint32_t pix = ids.x, bounces = ids.z >> 16;
-            bool dead = false;
-            if (CLS == CLS_MISS) {  // camera.rs:180-183
-                add_radiance(accum, pix, thr * sample_environment(S, cam.c, ray.d), rc.nan_policy, nonfinite, dead);
-            } else {
-                const HitRec hr = hits[i];
-                Rng rng; rng.init(rc.seed, pix, ids.y, ids.z & 0xFFFFu);
-                HitInfoD h;
-                reconstruct_hit<false>(S, ray, hr.ref, hr.inst_light & 0x7FFFFFFFu, hr.t, h);
-                const DMaterial& m = S.materials[h.material];
-                // camera.rs:186-187: `radiance += throughput * emitted` runs for every hit; for non-emitters it only
-                // matters when the throughput is already inf/NaN (inf * 0 = NaN poisons the pixel, Q32).
-                if (CLS == CLS_LIGHT || !finite3(thr)) {
-                    d3 em = CLS == CLS_LIGHT ? texture_value(S, m.base_color_tex, h.u, h.v, h.point) : mk(0, 0, 0);
-                    add_radiance(accum, pix, thr * em, rc.nan_policy, nonfinite, dead);
-                }
-                bool go = !dead;
-                if (go && bounces > 5) {  // Russian roulette, camera.rs:190-196
-                    double p = clampd(luminance(thr), 0.01, 1.0);
-                    if (rng.next() > p) go = false;
-                    else thr = thr / p;
-                }
-                if (go) {
-                    // camera.rs:199-200: p_light = 0.5 iff lights exist.  With PT_RENDER_ENV_IMPORTANCE (ours) the environment map
-                    // joins the mixture as a third sampler: p_bsdf = 0.5, the other half is split between lights and environment.
-                    constexpr bool env_is = (VAR & 1) != 0, GEN = (VAR & 2) != 0;
-                    const double p_env = env_is ? (S.n_lights == 0 ? 0.5 : 0.25) : 0.0;
-                    const double p_light = S.n_lights == 0 ? 0.0 : 0.5 - p_env, p_bsdf = env_is ? 0.5 : 1.0 - p_light;
-                    const double rsel = rng.next();
-                    d3 dir;
-                    bool ok;
-                    if (rsel < p_light) ok = lights_sample<GEN>(S, h.point, ray.time, rng, dir);
-                    else if (env_is && rsel < p_light + p_env) { const double u1 = rng.next(), u2 = rng.next(); dir = env_sample(rc.env, u1, u2); ok = true; }
-                    else ok = bsdf_sample<K>(S, h.material, ray.d, h, rng, dir);
-                    if (ok) {  // camera.rs:212-225
-                        d3 f; double bsdf_pdf;
-                        bsdf_eval_pdf<K>(S, h.material, -ray.d, dir, h, f, bsdf_pdf);
-                        double light_pdf = lights_pdf<GEN>(S, h.point, dir, ray.time);
-                        double pdf = p_bsdf * bsdf_pdf + p_light * light_pdf;
-                        if (env_is) pdf = pdf + p_env * env_pdf(rc.env, dir);
-                        d3 attenuation = f / pdf;
-                        double e = 1e-3 * signum(dot(dir, h.gn));
-                        next = make_ray(h.point + e * h.gn, dir, ray.time);
-                        thr = thr * attenuation;
-                        alive = bounces + 1 < cam.c.max_depth;  // `for bounces in 0..max_depth`, camera.rs:177
-                        if (rc.nan_policy == PT_NAN_DROP && !finite3(thr)) { atomicAdd(nonfinite, 1ull); alive = false; }
-                        ids.z = (rng.used & 0xFFFFu) | ((bounces + 1) << 16);
-                    }
-                }
-            }
+            HitRec hr; hr.t = 0.0; hr.ref = kNone; hr.inst_light = 0;
+            if (CLS != CLS_MISS) hr = hits[i];
+#if PT_SHADE_PREFETCH
+            alive = shade_one<CLS, VAR>(S, cam, rc, accum, nonfinite, ray, hr, thr, ids, next, PrefetchHook{in, hits, i_next, has_next, CLS != CLS_MISS});
+#else
+            alive = shade_one<CLS, VAR>(S, cam, rc, accum, nonfinite, ray, hr, thr, ids, next);
+#endif
         }
         if (CLS == CLS_MISS) continue;  // a miss ends the path: nothing to compact
         // ---- compaction: survivors grouped by direction octant within the block (warps of the next trace launch then hold
         //      rays that walk the BVH in the same order and tend to cost the same), one atomic per block
         const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const uint32_t key = alive ? (((next.d.y < 0.0) | ((next.d.x < 0.0) << 1) | ((next.d.z < 0.0) << 2)) & rc.sort_mask) : 8u;
+#if PT_SHADE_WARP_COMPACT
+        {
+            uint32_t mine_w = 0, before = 0;  // lanes of my bin; survivors of this warp in lower bins
+#pragma unroll
+            for (uint32_t b = 0; b < 8; b++) {
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, key == b);
+                if (key == b) mine_w = m;
+                if (b < key) before += __popc(m);
+            }
+            const uint32_t live = __ballot_sync(0xFFFFFFFFu, alive);
+            uint32_t wbase = 0;
+            if (live) {
+                const int leader = __ffs(live) - 1;
+                if ((int)lane == leader) wbase = atomicAdd(out_count, __popc(live));
+                wbase = __shfl_sync(0xFFFFFFFFu, wbase, leader);
+            }
+            if (alive) {
+                const uint32_t dst = wbase + before + __popc(mine_w & ((1u << lane) - 1u));
+                PT_ASSERT(dst < q.stride);
+                store_path(out, dst, next, thr, ids);
+            }
+            (void)warp;
+            continue;
+        }
+#endif
         uint32_t mine = 0, cnt = 0;  // lanes of my bin; lane b < 8 also holds the size of bin b
 #pragma unroll
         for (uint32_t b = 0; b < 8; b++) {

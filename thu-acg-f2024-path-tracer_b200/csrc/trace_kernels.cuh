@@ -499,6 +499,9 @@ __global__ void __launch_bounds__(kBlock, PT_ENTER_MIN_BLOCKS) k_mesh_enter(Path
 #ifndef PT_WALK_TRI_MIN
 #define PT_WALK_TRI_MIN 10     // lanes holding a triangle that trigger a triangle step while other lanes still have nodes to open
 #endif
+#ifndef PT_WALK_TOS
+#define PT_WALK_TOS 1          // the top stack entry lives in registers: a pop uses it at once and only PREFETCHES the entry below
+#endif                         // (the dependent local-memory load of a pop was 13 % of the kernel's stall samples, profiles/r2_kernels_ncu.md)
 constexpr int kWalkMinBlocks = PT_WALK_MIN_BLOCKS;
 template <bool COUNT>
 __global__ void __launch_bounds__(kTraceBlock, kWalkMinBlocks * kBlock / kTraceBlock) k_mesh_walk(uint32_t round, MeshQueues mq, HitRec* __restrict__ hits, uint2* __restrict__ ties,
@@ -508,6 +511,7 @@ __global__ void __launch_bounds__(kTraceBlock, kWalkMinBlocks * kBlock / kTraceB
     const uint32_t lane = threadIdx.x & 31;
     const float tmin_f = __double2float_rd(t_min);
     uint2 stack[kStack2];
+    uint2 tos = make_uint2(0u, 0u);  // PT_WALK_TOS: copy of stack[sp - 1] while sp > 0
     int sp = 0;
     RayD r = make_ray(mk(0, 0, 0), mk(0, 0, 1), 0.0);
     BoxRay br = make_boxray(r);
@@ -551,6 +555,7 @@ __global__ void __launch_bounds__(kTraceBlock, kWalkMinBlocks * kBlock / kTraceB
                 if (ni > 2) { stack[sp] = make_uint2(a7.x, a7.y); sp++; }
                 if (ni > 1) { stack[sp] = make_uint2(a6.z, a6.w); sp++; }
                 stack[sp] = make_uint2(a6.x, a6.y); sp++;
+                tos = make_uint2(a6.x, a6.y);
                 cur = kNone; pend = kNone; improved = false; active = true;
                 if (COUNT) { n_nodes = 1; n_tris = 0; }
             }
@@ -564,6 +569,19 @@ __global__ void __launch_bounds__(kTraceBlock, kWalkMinBlocks * kBlock / kTraceB
         for (int s = 0; s < PT_WALK_BURST; s++) {
             // ---- every active lane takes the nearest entries off its stack until it holds a node, or a second triangle turns up
             if (active && cur == kNone) {
+#if PT_WALK_TOS
+                while (sp > 0) {
+                    const uint2 top = tos;
+                    const bool beyond = !(__uint_as_float(top.y) <= tmax_f);  // beyond the closest hit
+                    if (!beyond && (top.x & kTriBit) && pend != kNone) break;   // a second triangle: stays on the stack
+                    sp--;
+                    if (sp > 0) tos = stack[sp - 1];                            // prefetch: needed by the NEXT pop only
+                    if (beyond) continue;
+                    if (top.x & kTriBit) { pend = top.x; pend_t = __uint_as_float(top.y); continue; }
+                    cur = top.x;
+                    break;
+                }
+#else
                 while (sp > 0) {
                     const uint2 top = stack[sp - 1];
                     if (!(__uint_as_float(top.y) <= tmax_f)) { sp--; continue; }  // beyond the closest hit
@@ -571,6 +589,7 @@ __global__ void __launch_bounds__(kTraceBlock, kWalkMinBlocks * kBlock / kTraceB
                     cur = top.x; sp--;
                     break;
                 }
+#endif
                 if (cur == kNone && pend == kNone) {  // stack empty: this visit is finished
                     active = false;
                     const bool last = (flags >> 31) != 0;
@@ -609,14 +628,16 @@ __global__ void __launch_bounds__(kTraceBlock, kWalkMinBlocks * kBlock / kTraceB
                 if (COUNT) { w0 += 2; n_nodes++; }
                 const float kInf = __int_as_float(0x7f800000);
                 cur = kNone;
-                if (ct[3] < kInf && can_push(sp, kStack2)) { stack[sp] = make_uint2(ce[3], __float_as_uint(ct[3])); sp++; }
-                if (ct[2] < kInf && can_push(sp, kStack2)) { stack[sp] = make_uint2(ce[2], __float_as_uint(ct[2])); sp++; }
-                if (ct[1] < kInf && can_push(sp, kStack2)) { stack[sp] = make_uint2(ce[1], __float_as_uint(ct[1])); sp++; }
+#define PT_WALK_PUSH(K) { const uint2 e_ = make_uint2(ce[K], __float_as_uint(ct[K])); stack[sp] = e_; tos = e_; sp++; }
+                if (ct[3] < kInf && can_push(sp, kStack2)) PT_WALK_PUSH(3)
+                if (ct[2] < kInf && can_push(sp, kStack2)) PT_WALK_PUSH(2)
+                if (ct[1] < kInf && can_push(sp, kStack2)) PT_WALK_PUSH(1)
                 if (ct[0] < kInf) {
                     if (!(ce[0] & kTriBit)) cur = ce[0];
                     else if (pend == kNone) { pend = ce[0]; pend_t = ct[0]; }
-                    else if (can_push(sp, kStack2)) { stack[sp] = make_uint2(ce[0], __float_as_uint(ct[0])); sp++; }
+                    else if (can_push(sp, kStack2)) PT_WALK_PUSH(0)
                 }
+#undef PT_WALK_PUSH
             }
         }
     }
