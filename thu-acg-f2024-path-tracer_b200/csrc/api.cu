@@ -740,6 +740,8 @@ int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
     D.n_tris = d->n_triangles; D.n_quads = d->n_quads; D.n_spheres = d->n_spheres; D.n_instances = d->n_instances; D.n_meshes = d->n_meshes;
     s->n_materials = d->n_materials; s->n_images = d->n_images; s->images = images;
     CU(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+    // the tail megakernel this scene's renders end in: load its code now (tail_wide.cu), not inside the first render
+    if (!s->has_volumes && !s->general_lights) { if (s->wide) preload_k_tail_wide(); else preload_k_tail_bin(); }
     *out = s.release();
     return PT_OK;
 }

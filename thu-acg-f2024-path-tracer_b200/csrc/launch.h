@@ -44,6 +44,8 @@ struct TailArgs {
 };
 void run_k_tail_wide(cudaStream_t st, const TailArgs& a);
 void run_k_tail_bin(cudaStream_t st, const TailArgs& a);
+void preload_k_tail_wide();
+void preload_k_tail_bin();
 
 // ---- misc.cu: ray generation, tonemap, parity entry kernels
 void run_k_generate(cudaStream_t st, PathBuf out, uint32_t slot0, uint32_t n_new, uint64_t g0, uint32_t n_pixels, const DCameraEx& cam, const RenderConst& rc);

@@ -48,7 +48,6 @@ PT_D void stage_tables(DScene& S) {
 #ifndef PT_SHADE_WARP_COMPACT
 #define PT_SHADE_WARP_COMPACT 0   // measured: scene 6 +0.5 %, scenes 7m / 3 -2.2 % (the block-wide octant grouping is worth more than the barriers cost)
 #endif
-PT_D void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 PT_D void prefetch_path(const PathBuf& b, const HitRec* __restrict__ hits, uint32_t i, bool with_hit) {
     prefetch_l1(b.ray + i); prefetch_l1(b.state + i);
     if (with_hit) prefetch_l1(hits + i);

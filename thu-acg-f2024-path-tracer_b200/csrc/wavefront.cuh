@@ -122,6 +122,7 @@ PT_D void ld256(const void* p, unsigned long long& a, unsigned long long& b, uns
 PT_D void st256(void* p, unsigned long long a, unsigned long long b, unsigned long long c, unsigned long long d) {
     asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
 }
+PT_D void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 PT_D unsigned long long pack2(uint32_t lo, uint32_t hi) { return (unsigned long long)lo | ((unsigned long long)hi << 32); }
 // ids = {pixel, sample, rng_used | bounce << 16, spare} as the shade kernels carry them
 PT_D void store_path(const PathBuf& b, uint32_t i, const RayD& r, d3 thr, uint4 ids) {
