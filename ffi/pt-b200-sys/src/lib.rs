@@ -117,6 +117,7 @@ extern "C" {
     // diagnostics
     pub fn pt_debug_histograms(ctx: *mut pt_ctx, out512: *mut u64, reset: c_int) -> c_int;
     pub fn pt_debug_stage_ms(ctx: *mut pt_ctx, out16: *mut f64, reset: c_int) -> c_int;
+    pub fn pt_debug_div_check(ctx: *mut pt_ctx, n: u64, seed: u64, mismatches: *mut u64) -> c_int;
 }
 
 /// The message of the last failure on the calling thread.

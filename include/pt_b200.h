@@ -378,6 +378,9 @@ int  pt_sah_sweep(pt_ctx* ctx, uint32_t n, const double* boxes6, const double* p
 /* The environment sampler of pt_scene_build_env_sampler: direction from 2 uniforms per query and its solid-angle pdf. */
 int  pt_env_sample_pdf(pt_ctx* ctx, const pt_scene* scene, size_t n, const double* uniforms2, pt_vec3* dir, double* pdf);
 
+/* Self-check of the device's shared-reciprocal vector division (csrc/device_scene.cuh: div3_shared, what `DVec3 / f64` compiles to in
+ * the shade kernels) against the plain IEEE `/` operator on n pseudo-random operand triples, bit for bit; *mismatches = differing quotients. */
+int  pt_debug_div_check(pt_ctx* ctx, uint64_t n, uint64_t seed, uint64_t* mismatches);
 /* Diagnostics (profiling level 2 only): eight 64-bin histograms of per-ray / per-mesh-visit traversal work gathered by the
  * counting kernel variants since the last reset (layout: csrc/kernels.cuh, g_hist).  out512 may be NULL. */
 int  pt_debug_histograms(pt_ctx* ctx, uint64_t* out512, int reset);

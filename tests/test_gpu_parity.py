@@ -224,6 +224,14 @@ def test_ragged_meshes_and_motion_blur(pt, orc, ctx):
 
 
 # ---------------------------------------------------------------- BSDF
+def test_shared_reciprocal_division_is_the_ieee_division(ctx):
+    """`DVec3 / f64` of the shade kernels shares one reciprocal between its three divisions (device_scene.cuh: div3_shared).  On
+    6e8 quotients — every exponent incl. denormals, inf, NaN, zero, and a stream restricted to the ranges shading divides in —
+    the bits must be those of the `/` operator."""
+    assert ctx.div_check(200_000_000, seed=1) == 0
+    assert ctx.div_check(1_000_003, seed=0xDEADBEEFCAFE) == 0
+
+
 def test_bsdf_eval_pdf_sample_match_oracle(pt, orc, ctx):
     scene, n_mat = _material_world(pt)
     dev, ora = ctx.upload(scene), orc.OracleScene(scene.desc, pt)

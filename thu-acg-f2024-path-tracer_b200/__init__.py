@@ -72,7 +72,7 @@ ABI_SYMBOLS = ["pt_ctx_create", "pt_ctx_destroy", "pt_ctx_set_stream", "pt_ctx_s
                "pt_scene_create", "pt_scene_destroy", "pt_scene_device_bytes", "pt_camera_image_height", "pt_render_accumulate",
                "pt_render", "pt_tonemap_rgb8", "pt_trace_closest", "pt_trace_any", "pt_bsdf_eval_pdf", "pt_bsdf_sample",
                "pt_camera_rays", "pt_lights_sample_pdf", "pt_scene_build_env_sampler", "pt_env_sample_pdf", "pt_sah_sweep",
-               "pt_render_multi", "pt_render_multi_release", "pt_trace_closest_wavefront", "pt_trace_camera_wavefront", "pt_debug_histograms", "pt_debug_stage_ms"]
+               "pt_render_multi", "pt_render_multi_release", "pt_trace_closest_wavefront", "pt_trace_camera_wavefront", "pt_debug_histograms", "pt_debug_stage_ms", "pt_debug_div_check"]
 
 
 class PtError(RuntimeError):
@@ -467,6 +467,13 @@ class Context:
         self._check(self.lib.pt_debug_stage_ms(self.ptr, _ptr(out), int(reset)))
         names = ("top_old", "top_new", "mesh_enter", "mesh_walk", "bvh", "generate", "tail", "-", "miss", "light", "diffuse", "metal", "glass", "principled", "other")
         return {k: v for k, v in zip(names, out.tolist()) if k != "-"}
+
+    def div_check(self, n, seed=1):
+        """pt_debug_div_check: quotients of the shared-reciprocal DVec3 / f64 that differ from the `/` operator's bits (must be 0)."""
+        out = C.c_uint64(0)
+        self.lib.pt_debug_div_check.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
+        self._check(self.lib.pt_debug_div_check(self.ptr, int(n), int(seed), C.byref(out)))
+        return int(out.value)
 
     def histograms(self, reset=True):
         """pt_debug_histograms: [8, 64] counters of the profiling-level-2 kernel variants since the last reset."""

@@ -1354,6 +1354,16 @@ int pt_debug_stage_ms(pt_ctx* ctx, double* out16, int reset) {
     if (reset) memset(ctx->stage_ms, 0, sizeof(ctx->stage_ms));
     return PT_OK;
 }
+int pt_debug_div_check(pt_ctx* ctx, uint64_t n, uint64_t seed, uint64_t* mismatches) {
+    if (!ctx || !mismatches) return fail(PT_ERR_INVALID, "pt_debug_div_check: null argument");
+    if (n > (1ull << 31) * 256ull) return fail(PT_ERR_INVALID, "pt_debug_div_check: n too large");
+    CU(cudaSetDevice(ctx->device));
+    DevBuf d; int rc;
+    if ((rc = d.alloc(sizeof(unsigned long long)))) return rc;
+    CU(cudaMemsetAsync(d.p, 0, sizeof(unsigned long long), ctx->stream));
+    if (n) run_k_div_check(ctx->stream, n, seed, (unsigned long long*)d.p);
+    return d.to_host(mismatches, sizeof(unsigned long long), ctx->stream);
+}
 int pt_debug_histograms(pt_ctx* ctx, uint64_t* out512, int reset) {
     if (!ctx) return fail(PT_ERR_INVALID, "pt_debug_histograms: null ctx");
     CU(cudaSetDevice(ctx->device));

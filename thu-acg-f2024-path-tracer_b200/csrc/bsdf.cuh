@@ -137,47 +137,73 @@ PT_D PrincipledLobes principled_lobes(const DMaterial& m) {  // principled.rs:79
 }
 PT_D double principled_alpha_g(const DMaterial& m) { double g = m.p[PT_P_CLEARCOAT_GLOSS]; return (1.0 - g) * 0.1 + g * 0.001; }
 
+// What BOTH BxDFMaterial::sample and ::{eval, pdf} derive from the hit alone — the rotation of the material's frame normal onto +z
+// (sampling.rs:8-16: shading normal; the principled BSDF uses the geometric normal, Q18), the view direction in that frame and the
+// roughness texture value.  The reference recomputes them in each of its three calls; the per-class shade kernels compute them once
+// (bsdf_prepare) and hand them to both functions: same expressions on the same inputs, hence the same bits.  cx == nullptr (the
+// parity entry points, mix materials): every function derives them itself as before.
+#ifndef PT_BSDF_CTX
+#define PT_BSDF_CTX 1
+#endif
+struct BsdfCtx { q4 q; d3 v; double rough; };
+PT_D d3 to_local_q(const q4& q, d3 w) { return quat_mul(q, w); }
+PT_D d3 to_world_q(q4 q, d3 w) { q.x = -q.x; q.y = -q.y; q.z = -q.z; return quat_mul(q, w); }
+template <int K>
+PT_D BsdfCtx bsdf_prepare(const DScene& S, const DMaterial& m, d3 view_dir, const HitInfoD& h) {
+    BsdfCtx c;
+    c.q = rotation_to_z(K == PT_MAT_PRINCIPLED ? h.gn : h.sn);
+    c.v = K == PT_MAT_DIFFUSE ? mk(0, 0, 0) : to_local_q(c.q, view_dir);
+    c.rough = (K == PT_MAT_METAL || K == PT_MAT_GLASS) ? texture_value(S, m.roughness_tex, h.u, h.v, h.point).x : 0.0;
+    return c;
+}
+
 // BxDFMaterial::sample (leaf materials). ray_dir = incoming ray direction; returns false for None.
 // K >= 0: the material kind is known at compile time (per-class shade kernels) and the switch folds away.
 template <int K = -1>
-PT_D bool bsdf_sample_leaf(const DScene& S, const DMaterial& m, d3 ray_dir, const HitInfoD& h, Rng& rng, d3& out) {
+PT_D bool bsdf_sample_leaf(const DScene& S, const DMaterial& m, d3 ray_dir, const HitInfoD& h, Rng& rng, d3& out, const BsdfCtx* cx = nullptr) {
     switch (K >= 0 ? (uint32_t)K : m.kind) {
-        case PT_MAT_DIFFUSE: out = to_world(h.sn, cosine_sample_hemisphere(rng)); return true;  // diffuse.rs:51-54
+        case PT_MAT_DIFFUSE: {  // diffuse.rs:51-54
+            const d3 w = cosine_sample_hemisphere(rng);
+            out = cx ? to_world_q(cx->q, w) : to_world(h.sn, w);
+            return true;
+        }
         case PT_MAT_METAL: {  // metal.rs:39-54
-            d3 v = to_local(h.sn, -ray_dir);
-            double rough = texture_value(S, m.roughness_tex, h.u, h.v, h.point).x;
+            d3 v = cx ? cx->v : to_local(h.sn, -ray_dir);
+            double rough = cx ? cx->rough : texture_value(S, m.roughness_tex, h.u, h.v, h.point).x;
             d3 hh = ggx_sample_normal(v, rough, rng);
-            out = to_world(h.sn, reflect(-v, hh));
+            out = cx ? to_world_q(cx->q, reflect(-v, hh)) : to_world(h.sn, reflect(-v, hh));
             return !(dot(out, h.sn) <= 0.0);
         }
         case PT_MAT_GLASS: {  // glass.rs:66-90
-            d3 v = to_local(h.sn, -ray_dir);
-            double rough = texture_value(S, m.roughness_tex, h.u, h.v, h.point).x;
+            d3 v = cx ? cx->v : to_local(h.sn, -ray_dir);
+            double rough = cx ? cx->rough : texture_value(S, m.roughness_tex, h.u, h.v, h.point).x;
             double ior = m.p[PT_P_IOR];
             double eta_i = h.front_face ? 1.0 : ior, eta_o = h.front_face ? ior : 1.0;
-            out = to_world(h.sn, glass_sample_local(v, rough, eta_i, eta_o, rng));
+            const d3 w = glass_sample_local(v, rough, eta_i, eta_o, rng);
+            out = cx ? to_world_q(cx->q, w) : to_world(h.sn, w);
             return true;
         }
         case PT_MAT_PRINCIPLED: {  // principled.rs:262-277 (geometric normal, Q18)
             PrincipledLobes L = principled_lobes(m);
             double r = rng.next();
             d3 n = h.gn;
-            if (r < L.dp) { out = to_world(n, cosine_sample_hemisphere(rng)); return true; }
-            d3 v = to_local(n, -ray_dir);
+            if (r < L.dp) { const d3 w = cosine_sample_hemisphere(rng); out = cx ? to_world_q(cx->q, w) : to_world(n, w); return true; }
+            d3 v = cx ? cx->v : to_local(n, -ray_dir);
             double rough = m.p[PT_P_ROUGHNESS];
             if (r < L.dp + L.sp) {
                 d3 hh = ggx_sample_normal(v, rough, rng);
-                out = to_world(n, reflect(-v, hh));
+                out = cx ? to_world_q(cx->q, reflect(-v, hh)) : to_world(n, reflect(-v, hh));
                 return !(dot(out, n) <= 0.0);
             }
             if (r < L.dp + L.sp + L.gp) {
                 double ior = m.p[PT_P_IOR];
                 double eta_i = h.front_face ? 1.0 : ior, eta_o = h.front_face ? ior : 1.0;
-                out = to_world(n, glass_sample_local(v, rough, eta_i, eta_o, rng));
+                const d3 w = glass_sample_local(v, rough, eta_i, eta_o, rng);
+                out = cx ? to_world_q(cx->q, w) : to_world(n, w);
                 return true;
             }
             d3 hh = gtr1_sample_normal(0.25, rng);  // fixed alpha 0.25 (Q16)
-            out = to_world(n, reflect(-v, hh));
+            out = cx ? to_world_q(cx->q, reflect(-v, hh)) : to_world(n, reflect(-v, hh));
             return !(dot(out, n) <= 0.0);
         }
         case PT_MAT_SHEEN: out = to_world(h.gn, cosine_sample_hemisphere(rng)); return true;  // sheen.rs:26-29
@@ -213,19 +239,19 @@ PT_D d3 clearcoat_eval(d3 v, d3 l, d3 h, double alpha_g) {  // extra |l.z| (Q17)
 
 // BxDFMaterial::{pdf, eval} for leaf materials, computed together (they share frames and half vectors).
 template <int K = -1>
-PT_D void bsdf_eval_pdf_leaf(const DScene& S, const DMaterial& m, d3 view_dir, d3 light_dir, const HitInfoD& hi, d3& f_out, double& pdf_out) {
+PT_D void bsdf_eval_pdf_leaf(const DScene& S, const DMaterial& m, d3 view_dir, d3 light_dir, const HitInfoD& hi, d3& f_out, double& pdf_out, const BsdfCtx* cx = nullptr) {
     switch (K >= 0 ? (uint32_t)K : m.kind) {
         case PT_MAT_DIFFUSE: {  // diffuse.rs:56-65
             d3 color = texture_value(S, m.base_color_tex, hi.u, hi.v, hi.point);
-            d3 l = to_local(hi.sn, light_dir);
+            d3 l = cx ? to_local_q(cx->q, light_dir) : to_local(hi.sn, light_dir);
             pdf_out = fabs(l.z) / kPi;
             f_out = fabs(l.z) * (color / kPi);
             return;
         }
         case PT_MAT_METAL: {  // metal.rs:56-80
-            d3 v = to_local(hi.sn, view_dir), l = to_local(hi.sn, light_dir);
+            d3 v = cx ? cx->v : to_local(hi.sn, view_dir), l = cx ? to_local_q(cx->q, light_dir) : to_local(hi.sn, light_dir);
             d3 h = normalize(v + l);
-            double rough = texture_value(S, m.roughness_tex, hi.u, hi.v, hi.point).x;
+            double rough = cx ? cx->rough : texture_value(S, m.roughness_tex, hi.u, hi.v, hi.point).x;
             d3 color = texture_value(S, m.base_color_tex, hi.u, hi.v, hi.point);
             double d = ggx_D(h, rough);
             double pdf_h = ggx_G1(v, rough) * fabs(dot(v, h)) * d / fabs(v.z);
@@ -236,12 +262,12 @@ PT_D void bsdf_eval_pdf_leaf(const DScene& S, const DMaterial& m, d3 view_dir, d
             return;
         }
         case PT_MAT_GLASS: {  // glass.rs:92-163 (colourless, Q19)
-            d3 v = to_local(hi.sn, view_dir), l = to_local(hi.sn, light_dir);
+            d3 v = cx ? cx->v : to_local(hi.sn, view_dir), l = cx ? to_local_q(cx->q, light_dir) : to_local(hi.sn, light_dir);
             bool refl = l.z * v.z > 0.0;
             double ior = m.p[PT_P_IOR];
             double eta_i = hi.front_face ? 1.0 : ior, eta_o = hi.front_face ? ior : 1.0;
             d3 h = generalized_half(v, l, eta_i, eta_o, refl);
-            double rough = texture_value(S, m.roughness_tex, hi.u, hi.v, hi.point).x;
+            double rough = cx ? cx->rough : texture_value(S, m.roughness_tex, hi.u, hi.v, hi.point).x;
             pdf_out = glass_pdf(v, l, h, rough, eta_i, eta_o, refl);
             f_out = splat(glass_factor(v, l, h, rough, eta_i, eta_o, refl)) * fabs(l.z);
             return;
@@ -249,15 +275,26 @@ PT_D void bsdf_eval_pdf_leaf(const DScene& S, const DMaterial& m, d3 view_dir, d
         case PT_MAT_PRINCIPLED: {  // principled.rs:279-366
             d3 color = texture_value(S, m.base_color_tex, hi.u, hi.v, hi.point);
             PrincipledLobes L = principled_lobes(m);
-            d3 v = to_local(hi.gn, view_dir), l = to_local(hi.gn, light_dir);
+            d3 v = cx ? cx->v : to_local(hi.gn, view_dir), l = cx ? to_local_q(cx->q, light_dir) : to_local(hi.gn, light_dir);
             bool refl = l.z * v.z > 0.0;
             double ior = m.p[PT_P_IOR], rough = m.p[PT_P_ROUGHNESS];
             double eta_i = hi.front_face ? 1.0 : ior, eta_o = hi.front_face ? ior : 1.0;
             d3 h = generalized_half(v, l, eta_i, eta_o, refl);
             double pdf = 0.0; d3 brdf = mk(0, 0, 0);
+            // The specular and the glass lobe evaluate the same GGX terms (principled.rs:215-260 and glass.rs:92-163 call ggx_d, ggx_g1,
+            // fresnel_dielectric with the same arguments), the diffuse and the specular lobe the same tint: each is computed once here —
+            // same expression, same inputs, same bits as the reference's repeated calls.
+            const bool spec_on = L.sp > 0.0 && refl, glass_on = L.gp > 0.0;
+            double ggx_d_h = 0.0, g1_v = 0.0, g1_l = 0.0, f_diel = 0.0, pdf_h = 0.0;
+            if (spec_on || glass_on) {
+                ggx_d_h = ggx_D(h, rough); g1_v = ggx_G1(v, rough); g1_l = ggx_G1(l, rough);
+                f_diel = fresnel_dielectric(v, h, eta_i, eta_o);
+                pdf_h = g1_v * fabs(dot(v, h)) * ggx_d_h / fabs(v.z);
+            }
+            const d3 tint_c = refl && (L.dp > 0.0 || L.sp > 0.0) ? tint(color) : mk(1, 1, 1);
             if (L.dp > 0.0 && refl) {
                 pdf += L.dp * (fabs(l.z) / kPi);
-                d3 c_sheen = lerp3(mk(1, 1, 1), tint(color), m.p[PT_P_SHEEN_TINT]);
+                d3 c_sheen = lerp3(mk(1, 1, 1), tint_c, m.p[PT_P_SHEEN_TINT]);
                 d3 sheen_term = m.p[PT_P_SHEEN] * c_sheen * schlick_weight(fabs(dot(l, h)));
                 // eval_diffuse, principled.rs:196-213
                 double lh = dot(l, h);
@@ -271,21 +308,31 @@ PT_D void bsdf_eval_pdf_leaf(const DScene& S, const DMaterial& m, d3 view_dir, d
                 d3 diffuse_term = color / kPi * lerp1(f_d + f_retro, ss, m.p[PT_P_SUBSURFACE]);
                 brdf = brdf + L.dw * (diffuse_term + sheen_term);
             }
-            if (L.sp > 0.0 && refl) {
-                double d = ggx_D(h, rough);
-                double pdf_h = ggx_G1(v, rough) * fabs(dot(v, h)) * d / fabs(v.z);
+            if (spec_on) {
                 pdf += L.sp * (pdf_h * (1.0 / (4.0 * fabs(dot(l, h)))));
-                d3 ks = lerp3(mk(1, 1, 1), tint(color), m.p[PT_P_SPECULAR_TINT]);
+                d3 ks = lerp3(mk(1, 1, 1), tint_c, m.p[PT_P_SPECULAR_TINT]);
                 d3 c0 = lerp3(m.p[PT_P_SPECULAR] * r0f(eta_i / eta_o) * ks, color, m.p[PT_P_METALLIC]);
                 d3 mf = fresnel_schlick(c0, dot(l, h));
-                d3 df = splat(fresnel_dielectric(v, h, eta_i, eta_o));
+                d3 df = splat(f_diel);
                 d3 fr = lerp3(df, mf, m.p[PT_P_METALLIC]);
-                double g = ggx_G(v, l, rough);
-                brdf = brdf + L.sw * (fr * g * d / (4.0 * fabs(l.z) * fabs(v.z)));
+                double g = g1_v * g1_l;
+                brdf = brdf + L.sw * (fr * g * ggx_d_h / (4.0 * fabs(l.z) * fabs(v.z)));
             }
-            if (L.gp > 0.0) {
-                pdf += L.gp * glass_pdf(v, l, h, rough, eta_i, eta_o, refl);
-                brdf = brdf + L.gw * splat(glass_factor(v, l, h, rough, eta_i, eta_o, refl));
+            if (glass_on) {  // glass_pdf / glass_factor with the shared terms
+                double jac, factor;
+                const double g = g1_v * g1_l;
+                if (refl) {
+                    jac = f_diel * 1.0 / (4.0 * fabs(dot(l, h)));
+                    factor = f_diel * g * ggx_d_h / (4.0 * fabs(l.z) * fabs(v.z));
+                } else {
+                    double vh = dot(v, h), lh = dot(l, h);
+                    jac = (1.0 - f_diel) * (eta_o * eta_o * fabs(lh)) / powi2(eta_i * vh + eta_o * lh);
+                    double term1 = fabs((lh * vh) / (l.z * v.z));
+                    double term2 = (eta_o * eta_o) / powi2(eta_i * vh + eta_o * lh);
+                    factor = term1 * term2 * (1.0 - f_diel) * g * ggx_d_h;
+                }
+                pdf += L.gp * (pdf_h * jac);
+                brdf = brdf + L.gw * splat(factor);
             }
             if (L.cp > 0.0 && refl) {
                 double ag = principled_alpha_g(m);
@@ -323,9 +370,9 @@ PT_D void bsdf_eval_pdf_leaf(const DScene& S, const DMaterial& m, d3 view_dir, d
 // MixBxDf (mix.rs:24-45) is a binary tree over leaf materials; walked with a small explicit stack.
 constexpr int kMixDepth = 8;
 template <int K = -1>
-PT_D bool bsdf_sample(const DScene& S, uint32_t mat, d3 ray_dir, const HitInfoD& h, Rng& rng, d3& out) {
+PT_D bool bsdf_sample(const DScene& S, uint32_t mat, d3 ray_dir, const HitInfoD& h, Rng& rng, d3& out, const BsdfCtx* cx = nullptr) {
     if constexpr (K >= 0) {
-        return bsdf_sample_leaf<K>(S, S.materials[mat], ray_dir, h, rng, out);
+        return bsdf_sample_leaf<K>(S, S.materials[mat], ray_dir, h, rng, out, cx);
     } else {
         for (int d = 0; d < kMixDepth; d++) {
             const DMaterial& m = S.materials[mat];
@@ -337,9 +384,9 @@ PT_D bool bsdf_sample(const DScene& S, uint32_t mat, d3 ray_dir, const HitInfoD&
     }
 }
 template <int K = -1>
-PT_D void bsdf_eval_pdf(const DScene& S, uint32_t mat, d3 view_dir, d3 light_dir, const HitInfoD& h, d3& f_out, double& pdf_out) {
+PT_D void bsdf_eval_pdf(const DScene& S, uint32_t mat, d3 view_dir, d3 light_dir, const HitInfoD& h, d3& f_out, double& pdf_out, const BsdfCtx* cx = nullptr) {
     const DMaterial& m0 = S.materials[mat];
-    if (K >= 0) { bsdf_eval_pdf_leaf<K>(S, m0, view_dir, light_dir, h, f_out, pdf_out); return; }
+    if (K >= 0) { bsdf_eval_pdf_leaf<K>(S, m0, view_dir, light_dir, h, f_out, pdf_out, cx); return; }
     if (m0.kind != PT_MAT_MIX) { bsdf_eval_pdf_leaf(S, m0, view_dir, light_dir, h, f_out, pdf_out); return; }
     // post-order evaluation of w1 = (1-t)*f1, w2 = t*f2, w1 + w2 (mix.rs:34-44)
     struct Frame { uint32_t mat; int state; d3 f1; double p1; };

@@ -57,6 +57,7 @@ void run_k_bsdf_sample(cudaStream_t st, uint32_t material, size_t n, const pt_bs
 void run_k_camera_rays(cudaStream_t st, const DCameraEx& cam, uint64_t seed, size_t n, const uint32_t* row, const uint32_t* col, const uint32_t* sample, pt_ray* out);
 void run_k_lights(cudaStream_t st, size_t n, const pt_vec3* origin, const double* time, const double* uniforms4, pt_vec3* dir, uint32_t* valid, double* pdf, const DScene& S);
 void run_k_sah_sweep(cudaStream_t st, uint32_t n, const SahBox* boxes, const SahBox& parent, double* cost);
+void run_k_div_check(cudaStream_t st, uint64_t n, uint64_t seed, unsigned long long* mismatches);
 void run_k_env(cudaStream_t st, size_t n, const double* uniforms2, pt_vec3* dir, double* pdf, const DEnvDist& E);
 
 }  // namespace ptd

@@ -29,4 +29,5 @@ void run_k_sah_sweep(cudaStream_t st, uint32_t n, const SahBox* boxes, const Sah
     k_sah_sweep<<<(3u * n + kSahTile - 1) / kSahTile, kSahTile, 0, st>>>(n, boxes, parent, cost);
 }
 void run_k_env(cudaStream_t st, size_t n, const double* uniforms2, pt_vec3* dir, double* pdf, const DEnvDist& E) { k_env<<<grid128(n), 128, 0, st>>>(n, uniforms2, dir, pdf, E); }
+void run_k_div_check(cudaStream_t st, uint64_t n, uint64_t seed, unsigned long long* mismatches) { k_div_check<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, seed, mismatches); }
 }  // namespace ptd

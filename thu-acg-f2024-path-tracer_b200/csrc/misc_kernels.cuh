@@ -149,4 +149,47 @@ __global__ void k_env(size_t n, const double* __restrict__ uniforms2, pt_vec3* _
     pdf[i] = env_pdf(E, d);
 }
 
+// pt_debug_div_check: div3_shared (device_scene.cuh) against the `/` operator on n pseudo-random (numerator, divisor) pairs, bit for
+// bit.  Bit patterns come from Philox, so every exponent — denormals, infinities, NaNs, zeros — turns up; a second stream restricts
+// both operands to the ranges the shade kernels divide in (|x| in [1e-12, 1e12]).  mismatches += pairs whose bits differ.
+__global__ void k_div_check(uint64_t n, uint64_t seed, unsigned long long* __restrict__ mismatches) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t x0 = (uint32_t)i, x1 = (uint32_t)(i >> 32), x2 = 0x2545F491u, x3 = 0u, a = (uint32_t)seed, c = (uint32_t)(seed >> 32);
+    uint32_t w[8];
+#pragma unroll
+    for (int blk = 0; blk < 2; blk++) {
+        uint32_t y0 = x0, y1 = x1, y2 = x2, y3 = (uint32_t)blk, ka = a, kc = c;
+#pragma unroll
+        for (int r = 0; r < 10; r++) {
+            uint32_t hi0 = __umulhi(0xD2511F53u, y0), lo0 = 0xD2511F53u * y0;
+            uint32_t hi1 = __umulhi(0xCD9E8D57u, y2), lo1 = 0xCD9E8D57u * y2;
+            uint32_t n0 = hi1 ^ y1 ^ ka, n2 = hi0 ^ y3 ^ kc;
+            y0 = n0; y1 = lo1; y2 = n2; y3 = lo0;
+            ka += 0x9E3779B9u; kc += 0xBB67AE85u;
+        }
+        w[4 * blk] = y0; w[4 * blk + 1] = y1; w[4 * blk + 2] = y2; w[4 * blk + 3] = y3;
+    }
+    (void)x3;
+    double v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint32_t hi = w[2 * k], lo = w[2 * k + 1];
+        if (i & 1) hi = (hi & 0x800FFFFFu) | ((0x3FFu - 40u + (hi >> 20) % 80u) << 20);  // odd pairs: exponent within 2^-40 .. 2^39
+        v[k] = __hiloint2double((int)hi, (int)lo);
+    }
+    const double s = v[3];
+    const d3 q = div3_shared(mk(v[0], v[1], v[2]), s);
+    const double e[3] = {v[0] / s, v[1] / s, v[2] / s};
+    const double g[3] = {q.x, q.y, q.z};
+    uint32_t bad = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const long long bq = __double_as_longlong(g[k]), be = __double_as_longlong(e[k]);
+        const bool both_nan = g[k] != g[k] && e[k] != e[k];  // NaN payloads may differ between the two routes; NaN-ness may not
+        if (bq != be && !both_nan) bad++;
+    }
+    if (bad) atomicAdd(mismatches, (unsigned long long)bad);
+}
+
 }  // namespace ptd

@@ -104,12 +104,17 @@ PT_D bool shade_one(const DScene& S, const DCameraEx& cam, const RenderConst& rc
         const double rsel = rng.next();
         d3 dir;
         bool ok;
+        // frame, view direction and roughness of this hit: derived once for sample AND eval / pdf (bsdf.cuh: BsdfCtx)
+        constexpr bool kCtx = PT_BSDF_CTX && (K == PT_MAT_DIFFUSE || K == PT_MAT_METAL || K == PT_MAT_GLASS || K == PT_MAT_PRINCIPLED);
+        BsdfCtx cxv;
+        if (kCtx) cxv = bsdf_prepare<K>(S, m, -ray.d, h);
+        const BsdfCtx* cx = kCtx ? &cxv : nullptr;
         if (rsel < p_light) ok = lights_sample<GEN>(S, h.point, ray.time, rng, dir);
         else if (env_is && rsel < p_light + p_env) { const double u1 = rng.next(), u2 = rng.next(); dir = env_sample(rc.env, u1, u2); ok = true; }
-        else ok = bsdf_sample<K>(S, h.material, ray.d, h, rng, dir);
+        else ok = bsdf_sample<K>(S, h.material, ray.d, h, rng, dir, cx);
         if (ok) {  // camera.rs:212-225
             d3 f; double bsdf_pdf;
-            bsdf_eval_pdf<K>(S, h.material, -ray.d, dir, h, f, bsdf_pdf);
+            bsdf_eval_pdf<K>(S, h.material, -ray.d, dir, h, f, bsdf_pdf, cx);
             double light_pdf = lights_pdf<GEN>(S, h.point, dir, ray.time);
             double pdf = p_bsdf * bsdf_pdf + p_light * light_pdf;
             if (env_is) pdf = pdf + p_env * env_pdf(rc.env, dir);
