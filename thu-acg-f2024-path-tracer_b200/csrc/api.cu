@@ -599,6 +599,9 @@ int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
         const pt_quad& p = d->quads[i];
         DQuad o{}; const pt_vec3* src[5] = {&p.q, &p.u, &p.v, &p.w, &p.normal}; double* dst[5] = {o.q, o.u, o.v, o.w, o.n};
         for (int k = 0; k < 5; k++) { dst[k][0] = src[k]->x; dst[k][1] = src[k]->y; dst[k][2] = src[k]->z; }
+        const d3 un = normalize(mk(o.n[0], o.n[1], o.n[2]));
+        o.un[0] = un.x; o.un[1] = un.y; o.un[2] = un.z;
+        o.area = length(cross(mk(o.u[0], o.u[1], o.u[2]), mk(o.v[0], o.v[1], o.v[2])));
         o.d = p.d; quads[i] = o; quad_mat[i] = p.material;
     }
     std::vector<DTri> tris(d->n_triangles);

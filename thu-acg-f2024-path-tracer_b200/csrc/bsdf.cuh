@@ -461,8 +461,9 @@ template <bool GENERAL> PT_D double light_pdf_prim(const DScene& S, uint32_t kin
         double t, a, b;
         if (!quad_t(q, ray, 0.0, t, a, b)) return 0.0;
         HitInfoD h;
-        finish_hit(S, ray, ray_at(ray, t), mk(q.n[0], q.n[1], q.n[2]), t, S.quad_material[index], a, b, h);
-        double area = length(cross(mk(q.u[0], q.u[1], q.u[2]), mk(q.v[0], q.v[1], q.v[2])));
+        const d3 un = mk(q.un[0], q.un[1], q.un[2]);
+        finish_hit(S, ray, ray_at(ray, t), mk(q.n[0], q.n[1], q.n[2]), t, S.quad_material[index], a, b, h, &un);
+        double area = q.area;  // |u x v|, derived on upload
         double cos_theta = fabs(dot(ray.d, h.sn));  // shading normal (Q9)
         return (t * t) / (cos_theta * area);
     }

@@ -480,9 +480,11 @@ PT_D d3 image_value(const DScene& S, uint32_t image, double u, double v) {  // t
     const double s = 1.0 / 255.0;
     return mk(s * (double)px[0], s * (double)px[1], s * (double)px[2]);
 }
-PT_D void finish_hit(const DScene& S, const RayD& r, d3 point, d3 normal, double t, uint32_t material, double u, double v, HitInfoD& h) {
+// `unit`: normalize(normal) when the caller holds it precomputed (quads: DQuad::un)
+PT_D void finish_hit(const DScene& S, const RayD& r, d3 point, d3 normal, double t, uint32_t material, double u, double v, HitInfoD& h, const d3* unit = nullptr) {
     bool ff = dot(r.d, normal) < 0.0;
-    d3 gn = ff ? normalize(normal) : -normalize(normal);
+    const d3 nn = unit ? *unit : normalize(normal);
+    d3 gn = ff ? nn : -nn;
     d3 sn = gn;
     const DMaterial& m = S.materials[material];
     if (m.kind == PT_MAT_DIFFUSE && m.normal_map != kNone) {  // only DiffuseBRDF overrides normal_map() (diffuse.rs:81-83)
@@ -522,7 +524,8 @@ PT_D void reconstruct_hit(const DScene& S, const RayD& world_ray, uint32_t ref, 
         d3 w = mk(qd.w[0], qd.w[1], qd.w[2]);
         double alpha = dot(w, cross(p, mk(qd.v[0], qd.v[1], qd.v[2])));
         double beta = dot(w, cross(mk(qd.u[0], qd.u[1], qd.u[2]), p));
-        finish_hit(S, r, ray_at(r, t), mk(qd.n[0], qd.n[1], qd.n[2]), t, S.quad_material[index], alpha, beta, h);
+        const d3 un = mk(qd.un[0], qd.un[1], qd.un[2]);
+        finish_hit(S, r, ray_at(r, t), mk(qd.n[0], qd.n[1], qd.n[2]), t, S.quad_material[index], alpha, beta, h, &un);
     } else if (kind == PT_OBJ_VOLUME) {  // scatter point inside a medium: arbitrary normal (1,0,0), u = v = 0 (pt_volume)
         finish_hit(S, r, ray_at(r, t), mk(1.0, 0.0, 0.0), t, S.volumes[index].material, 0.0, 0.0, h);
     } else {  // triangle, mesh.rs:84-111
