@@ -502,6 +502,9 @@ __global__ void __launch_bounds__(kBlock, PT_ENTER_MIN_BLOCKS) k_mesh_enter(Path
 #ifndef PT_WALK_TOS
 #define PT_WALK_TOS 1          // the top stack entry lives in registers: a pop uses it at once and only PREFETCHES the entry below
 #endif                         // (the dependent local-memory load of a pop was 13 % of the kernel's stall samples, profiles/r2_kernels_ncu.md)
+#ifndef PT_WALK_PREFETCH
+#define PT_WALK_PREFETCH 0     // bit 0: the node a lane will open next, bit 1: the triangle it will test next, prefetched into L1 as soon as known; measured: no gain (profiles/r2_ab/r2_q_walk_prefetch.log)
+#endif
 constexpr int kWalkMinBlocks = PT_WALK_MIN_BLOCKS;
 template <bool COUNT>
 __global__ void __launch_bounds__(kTraceBlock, kWalkMinBlocks * kBlock / kTraceBlock) k_mesh_walk(uint32_t round, MeshQueues mq, HitRec* __restrict__ hits, uint2* __restrict__ ties,
@@ -577,8 +580,13 @@ __global__ void __launch_bounds__(kTraceBlock, kWalkMinBlocks * kBlock / kTraceB
                     sp--;
                     if (sp > 0) tos = stack[sp - 1];                            // prefetch: needed by the NEXT pop only
                     if (beyond) continue;
-                    if (top.x & kTriBit) { pend = top.x; pend_t = __uint_as_float(top.y); continue; }
+                    if (top.x & kTriBit) {
+                        pend = top.x; pend_t = __uint_as_float(top.y);
+                        if (PT_WALK_PREFETCH & 2) prefetch_l1(S.tris + (pend & ~kTriBit));
+                        continue;
+                    }
                     cur = top.x;
+                    if (PT_WALK_PREFETCH & 1) prefetch_l1(S.wide2 + cur);
                     break;
                 }
 #else
@@ -633,8 +641,8 @@ __global__ void __launch_bounds__(kTraceBlock, kWalkMinBlocks * kBlock / kTraceB
                 if (ct[2] < kInf && can_push(sp, kStack2)) PT_WALK_PUSH(2)
                 if (ct[1] < kInf && can_push(sp, kStack2)) PT_WALK_PUSH(1)
                 if (ct[0] < kInf) {
-                    if (!(ce[0] & kTriBit)) cur = ce[0];
-                    else if (pend == kNone) { pend = ce[0]; pend_t = ct[0]; }
+                    if (!(ce[0] & kTriBit)) { cur = ce[0]; if (PT_WALK_PREFETCH & 1) prefetch_l1(S.wide2 + cur); }
+                    else if (pend == kNone) { pend = ce[0]; pend_t = ct[0]; if (PT_WALK_PREFETCH & 2) prefetch_l1(S.tris + (pend & ~kTriBit)); }
                     else if (can_push(sp, kStack2)) PT_WALK_PUSH(0)
                 }
 #undef PT_WALK_PUSH
