@@ -178,6 +178,8 @@ __global__ void k_div_check(uint64_t n, uint64_t seed, unsigned long long* __res
         if (i & 1) hi = (hi & 0x800FFFFFu) | ((0x3FFu - 40u + (hi >> 20) % 80u) << 20);  // odd pairs: exponent within 2^-40 .. 2^39
         v[k] = __hiloint2double((int)hi, (int)lo);
     }
+    if ((i & 15) == 3) { v[0] = 0.0; v[1] = -0.0; }                                   // zero numerators: the shade kernels' commonest special case
+    if ((i & 255) == 7) v[3] = (i & 256) ? 0.0 : __longlong_as_double(0x7ff0000000000000ll);  // ... over a zero / infinite divisor
     const double s = v[3];
     const d3 q = div3_shared(mk(v[0], v[1], v[2]), s);
     const double e[3] = {v[0] / s, v[1] / s, v[2] / s};
