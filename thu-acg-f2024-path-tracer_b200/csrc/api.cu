@@ -991,7 +991,14 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
         if (fork) CU(cudaEventRecord(ctx->ev_fork, st));
         const ShadeArgs sa{in, q, ctx->hits, outb, out_count, d_accum, ctx->d_nonfinite, scene->d, dcam, rcst};
         ctx->mark(-1);
-        for (int cls = 0; cls < N_CLS; cls++) {
+#ifndef PT_SHADE_ORDER_LPT
+#define PT_SHADE_ORDER_LPT 0   // measured: scene 3 +1.1 %, scene 6 -0.8 %, scene 7m +-0 (profiles/r2_ab/r2_r_shade_launch_order.log): class order kept
+#endif
+        // forked launches: the costliest classes first (longest-processing-time order), so that the stage does not end on a long kernel
+        // that started last
+        static const int order_lpt[N_CLS] = {CLS_PRINCIPLED, CLS_DIFFUSE, CLS_GLASS, CLS_OTHER, CLS_METAL, CLS_MISS, CLS_LIGHT};
+        for (int k = 0; k < N_CLS; k++) {
+            const int cls = PT_SHADE_ORDER_LPT && fork ? order_lpt[k] : k;
             if (!(scene->class_mask & (1u << cls))) continue;
             cudaStream_t ss = fork ? ctx->shade_stream[cls] : st;
             if (fork) CU(cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
