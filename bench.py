@@ -371,7 +371,7 @@ def main():
                          "issue": {k: v["useful_lane_issue"] for k, v in kernels.items() if "useful_lane_issue" in v},
                          "issue_note": f"issue-slot utilisation x active lanes / 32 per kernel family ({NCU_SOURCE})",
                          "kernels": kernels,
-                         "stage_ms_per_step": {"traversal": trace_ms / args.steps, "shade": shade_ms / args.steps},
+                         "stage_ms_per_step": {"traversal": trace_ms / args.steps, "shade": shade_ms / args.steps, "tail_megakernel": fam_ms.get("tail", 0.0) / args.steps},
                          "survey_model": {"bytes_per_segment": b_trace, "achieved": survey_gbs, "frac": survey_gbs / hbm,
                                           "note": "SURVEY §8(d): the reference's per-segment box / primitive counts (oracle counters) x struct sizes / traversal-stage time; "
                                                   "over-states the device, which fetches far fewer nodes and serves them from L1/L2",

@@ -14,5 +14,5 @@ python tools/ncu_summary.py /tmp/prof_$TAG.ncu-rep "$TAG: first two wavefront it
 for K in k_top k_mesh_walk k_mesh_enter; do
   ncu -i /tmp/prof_$TAG.ncu-rep --page source --csv -k regex:$K 2>/dev/null | gzip > $O/${TAG}_src_$K.csv.gz
 done
-ncu -i /tmp/prof_$TAG.ncu-rep --page source --csv -k regex:"k_shade<2|k_shade<5" 2>/dev/null | gzip > $O/${TAG}_src_k_shade.csv.gz
+ncu -i /tmp/prof_$TAG.ncu-rep --page source --csv -k regex:"k_shade<.int.2|k_shade<.int.5" 2>/dev/null | gzip > $O/${TAG}_src_k_shade.csv.gz
 ls -la $O/${TAG}_* /tmp/prof_$TAG.ncu-rep
