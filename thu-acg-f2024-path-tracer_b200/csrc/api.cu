@@ -987,7 +987,10 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
     // one specialised kernel per shade class present in the scene; each walks its queue grid-stride (n: upper bound of the
     // paths in all queues together).  fork: the class kernels run on side streams and join `st` again.
     auto launch_shades = [&](const PathBuf& in, const PathBuf& outb, uint32_t n, const Queues& q, uint32_t* out_count, bool fork) -> int {
-        const unsigned sg = std::min<unsigned>((n + kBlock - 1) / kBlock, 148u * 16u);
+#ifndef PT_SHADE_GRID_WAVES
+#define PT_SHADE_GRID_WAVES 16   // grid of a shade kernel = at most this many 128-thread blocks per SM; its threads walk the class queue grid-stride
+#endif
+        const unsigned sg = std::min<unsigned>((n + kBlock - 1) / kBlock, 148u * PT_SHADE_GRID_WAVES);
         if (fork) CU(cudaEventRecord(ctx->ev_fork, st));
         const ShadeArgs sa{in, q, ctx->hits, outb, out_count, d_accum, ctx->d_nonfinite, scene->d, dcam, rcst};
         ctx->mark(-1);
