@@ -465,7 +465,7 @@ class Context:
         out = np.zeros(16, dtype=np.float64)
         self.lib.pt_debug_stage_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         self._check(self.lib.pt_debug_stage_ms(self.ptr, _ptr(out), int(reset)))
-        names = ("top_old", "top_new", "mesh_enter", "mesh_walk", "bvh", "generate", "tail", "-", "miss", "light", "diffuse", "metal", "glass", "principled", "other")
+        names = ("top_old", "top_new", "mesh_enter", "mesh_walk", "bvh", "generate", "tail", "mesh_multi", "miss", "light", "diffuse", "metal", "glass", "principled", "other")
         return {k: v for k, v in zip(names, out.tolist()) if k != "-"}
 
     def div_check(self, n, seed=1):

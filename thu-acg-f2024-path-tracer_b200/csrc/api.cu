@@ -915,13 +915,25 @@ static void launch_trace(const TraceStage& T, const PathBuf& in, uint32_t n_old,
         if (n_new) { run_k_top(true, wk != nullptr, st, in, n_old, n_new, ctx->hits, q, scene->d, scene->top, mq, ctx->ties, T.t_min, *gen, nullptr, wk); S.kernel_launches++; ctx->mark(1); }
         const unsigned eg = std::min<unsigned>((n + kBlock - 1) / kBlock, 148u * 16u);
         const unsigned wg = std::min<unsigned>((n + kTraceBlock - 1) / kTraceBlock, mesh_walk_resident_warps());
-        for (uint32_t r = 0; r < scene->mesh_rounds; r++) {
+        // rays that entered several mesh boxes (queue 1): k_mesh_multi, on a side stream next to the entry pass + walk of queue 0
+        // (on the main stream when per-stage events are wanted or the iteration is small)
+        const bool multi = kMeshMulti && scene->mesh_rounds >= 2;
+        const bool side = multi && !ctx->profiling && n >= (1u << 18);
+        if (multi) {
+            cudaStream_t ms = side ? ctx->shade_stream[0] : st;
+            if (side) { cudaEventRecord(ctx->ev_fork, st); cudaStreamWaitEvent(ms, ctx->ev_fork, 0); }
+            run_k_mesh_multi(wk != nullptr, std::min<unsigned>((n + kTraceBlock - 1) / kTraceBlock, 148u * 28u), ms, in, mq, ctx->hits, ctx->ties, q, scene->d, T.t_min, wk);
+            if (side) cudaEventRecord(ctx->ev_join[0], ms); else ctx->mark(7);
+            S.kernel_launches++;
+        }
+        for (uint32_t r = 0; r < (multi ? 1u : scene->mesh_rounds); r++) {
             run_k_mesh_enter(wk != nullptr, eg, st, in, r, mq, ctx->hits, ctx->ties, q, scene->d, scene->top, T.t_min, wk);
             ctx->mark(2);
             run_k_mesh_walk(wk != nullptr, wg, st, r, mq, ctx->hits, ctx->ties, q, scene->d, T.t_min, wk);
             ctx->mark(3);
             S.kernel_launches += 2;
         }
+        if (side) cudaStreamWaitEvent(st, ctx->ev_join[0], 0);
         if (scene->mesh_rounds) S.two_pass_iterations++;
         return;
     }

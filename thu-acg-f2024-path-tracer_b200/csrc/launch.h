@@ -18,6 +18,9 @@ void run_k_mesh_enter(bool count, unsigned grid, cudaStream_t st, PathBuf pool, 
                       const DScene& S, const TopList& top, double t_min, unsigned long long* work);
 void run_k_mesh_walk(bool count, unsigned grid, cudaStream_t st, uint32_t round, MeshQueues mq, HitRec* hits, uint2* ties, Queues q, const DScene& S, double t_min,
                      unsigned long long* work);
+void run_k_mesh_multi(bool count, unsigned grid, cudaStream_t st, PathBuf pool, MeshQueues mq, HitRec* hits, const uint2* ties, Queues q, const DScene& S, double t_min,
+                      unsigned long long* work);
+constexpr bool kMeshMulti = PT_MESH_MULTI != 0;
 unsigned mesh_walk_resident_warps();  // persistent grid of k_mesh_walk: one warp per resident slot
 void run_k_trace_batch(bool wide, cudaStream_t st, const pt_ray* rays, size_t n, double t_min, pt_hit* out, const DScene& S);
 void run_k_trace_any_batch(bool wide, cudaStream_t st, const pt_ray* rays, size_t n, double t_min, const double* t_max, uint8_t* out, const DScene& S);

@@ -52,6 +52,11 @@ void run_k_mesh_walk(bool count, unsigned grid, cudaStream_t st, uint32_t round,
     if (count) k_mesh_walk<true><<<grid, kTraceBlock, 0, st>>>(round, mq, hits, ties, q, S, t_min, work);
     else k_mesh_walk<false><<<grid, kTraceBlock, 0, st>>>(round, mq, hits, ties, q, S, t_min, work);
 }
+void run_k_mesh_multi(bool count, unsigned grid, cudaStream_t st, PathBuf pool, MeshQueues mq, HitRec* hits, const uint2* ties, Queues q, const DScene& S, double t_min,
+                      unsigned long long* work) {
+    if (count) k_mesh_multi<true><<<grid, kTraceBlock, 0, st>>>(pool, mq, hits, ties, q, S, t_min, work);
+    else k_mesh_multi<false><<<grid, kTraceBlock, 0, st>>>(pool, mq, hits, ties, q, S, t_min, work);
+}
 unsigned mesh_walk_resident_warps() { return 148u * 4u * (unsigned)kWalkMinBlocks; }
 static unsigned grid128(size_t n) { return (unsigned)((n + 127) / 128); }
 void run_k_trace_batch(bool wide, cudaStream_t st, const pt_ray* rays, size_t n, double t_min, pt_hit* out, const DScene& S) {

@@ -386,10 +386,27 @@ __global__ void __launch_bounds__(kBlock, PT_TOP_MIN_BLOCKS) k_top(PathBuf pool,
     }
     __syncwarp();
     queue_append(q, cls, i);
-    if (top.mesh_bits) {  // queue the r-th entered mesh of every ray for round r (warp-aggregated appends)
+    if (top.mesh_bits) {  // queue the mesh visits (warp-aggregated appends)
         const uint32_t lane = threadIdx.x & 31, nm = __popc(mesh_mask);
+#if PT_MESH_MULTI
+        // a ray that enters ONE mesh box goes to the entry pass + walk (queue 0); the 1-4 % that enter several go, with their whole mask,
+        // to queue 1: k_mesh_multi walks all their meshes in one thread, concurrently with the walk of queue 0
 #pragma unroll 1
-        for (uint32_t r = 0; r < (uint32_t)kMeshRounds; r++) {
+        for (uint32_t r = 0; r < 2u; r++) {
+            const bool has = r == 0 ? nm == 1u : nm > 1u;
+            const uint32_t b = __ballot_sync(0xFFFFFFFFu, has);
+            if (!b) continue;
+            const int leader = __ffs(b) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(mq.count + r, __popc(b));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            PT_ASSERT(base + __popc(b) <= mq.stride);
+            if (has) mq.items[(size_t)r * mq.stride + base + __popc(b & ((1u << lane) - 1u))] =
+                         r == 0 ? make_uint2(i, ((uint32_t)__ffs((int)mesh_mask) - 1u) | (prov_cls << 8) | 0x80000000u) : make_uint2(i, mesh_mask);
+        }
+#else
+#pragma unroll 1
+        for (uint32_t r = 0; r < (uint32_t)kMeshRounds; r++) {  // the r-th entered mesh of every ray for round r
             const bool has = nm > r;
             const uint32_t b = __ballot_sync(0xFFFFFFFFu, has);
             if (!b) break;
@@ -401,10 +418,63 @@ __global__ void __launch_bounds__(kBlock, PT_TOP_MIN_BLOCKS) k_top(PathBuf pool,
             if (has) mq.items[(size_t)r * mq.stride + base + __popc(b & ((1u << lane) - 1u))] =
                          make_uint2(i, __fns(mesh_mask, 0, r + 1) | (prov_cls << 8) | (nm == r + 1 ? 0x80000000u : 0u));
         }
+#endif
     }
     if (COUNT) {
         w1 = __reduce_add_sync(0xFFFFFFFFu, w1); w2 = __reduce_add_sync(0xFFFFFFFFu, w2);
         if ((threadIdx.x & 31) == 0) { atomicAdd(work + 1, (unsigned long long)w1); atomicAdd(work + 2, (unsigned long long)w2); }
+    }
+}
+
+// Rays whose top-level pass entered SEVERAL mesh boxes (queue 1 of k_top: {path, mask of the entered mesh references}): one thread walks
+// all of them against the provisional hit — world box against the current closest hit, ray into the mesh's space, trace_blas over the
+// mesh's own BVH — and the ray joins its shade-class queue.  As rounds 1.. of k_mesh_enter + k_mesh_walk these few rays were four more
+// launches per wavefront iteration whose duration was the latency of their longest walk (a third of the mesh time of a 2.5 M-ray
+// iteration for 1-4 % of the visits); here they run on a side stream while queue 0 is walked.
+template <bool COUNT>
+__global__ void __launch_bounds__(kTraceBlock, 7 * kBlock / kTraceBlock) k_mesh_multi(PathBuf pool, MeshQueues mq, HitRec* __restrict__ hits, const uint2* __restrict__ ties,
+                                                                                        Queues q, DScene S, double t_min, unsigned long long* __restrict__ work) {
+    const uint32_t count = mq.count[1];
+    const uint2* __restrict__ items = mq.items + (size_t)mq.stride;
+    const float tmin_f = __double2float_rd(t_min);
+    uint32_t w0 = 0, w1 = 0, w2 = 0;
+    for (uint32_t j = blockIdx.x * kTraceBlock + threadIdx.x; j - (threadIdx.x & 31) < count; j += gridDim.x * kTraceBlock) {
+        uint32_t cls = N_CLS, i = 0;
+        if (j < count) {
+            const uint2 e = items[j];
+            i = e.x;
+            const HitRec h0 = hits[i];
+            const uint2 tie = ties[i];
+            Closest c; c.t = h0.t; c.ref = h0.ref; c.inst = h0.inst_light & 0x7FFFFFFFu; c.tie_outer = tie.x; c.tie_inner = tie.y;
+            c.is_light = (h0.inst_light >> 31) != 0;
+            c.n_pairs = 0; c.n_wide = 0; c.n_refs = 0; c.n_prims = 0;
+            const RayD rw = load_ray(pool, i);
+            const BoxRay brw = make_boxray(rw);
+#pragma unroll 1
+            for (uint32_t todo = e.y; todo; todo &= todo - 1u) {
+                const uint32_t k = (uint32_t)__ffs((int)todo) - 1u;
+                const DNode rb = S.refs[k];  // a = kind | index of the mesh or instance, b = its outer tie rank
+                const float tmax_f = __double2float_ru(c.t);
+                if (!(slab(rb, brw, tmin_f, tmax_f) <= tmax_f)) { if (COUNT) hist_add(7, 0); continue; }  // fallen behind the closest hit
+                const uint32_t kind = ref_kind(rb.a), index = ref_index(rb.a);
+                RayD r = rw;
+                uint32_t mesh = index, inst = kInstNone;
+                if (kind == PT_OBJ_INSTANCE) { const DInstance& ins = S.instances[index]; r = instance_local_ray(ins, rw); mesh = ins.child_index; inst = index; }
+                PT_ASSERT(mesh < S.n_meshes);
+                trace_blas<COUNT>(S, S.meshes[mesh].root_entry, r, t_min, c, inst, rb.b);
+                if (COUNT) hist_add(7, 1);
+            }
+            if (COUNT) { w0 += c.n_pairs + 2 * c.n_wide; w1 += c.n_refs; w2 += c.n_prims; }
+            HitRec h; h.t = c.t; h.ref = c.ref; h.inst_light = (c.inst & 0x7FFFFFFFu) | (c.is_light ? 0x80000000u : 0u);
+            hits[i] = h;
+            cls = c.ref == kNone ? (uint32_t)CLS_MISS : class_of_kind(S.materials[hit_material(S, c.ref)].kind);
+        }
+        __syncwarp();
+        queue_append(q, cls, i);
+    }
+    if (COUNT) {
+        w0 = __reduce_add_sync(0xFFFFFFFFu, w0); w1 = __reduce_add_sync(0xFFFFFFFFu, w1); w2 = __reduce_add_sync(0xFFFFFFFFu, w2);
+        if ((threadIdx.x & 31) == 0 && (w0 | w1 | w2)) { atomicAdd(work, (unsigned long long)w0); atomicAdd(work + 1, (unsigned long long)w1); atomicAdd(work + 2, (unsigned long long)w2); }
     }
 }
 

@@ -190,6 +190,9 @@ PT_D d3 from_abi(pt_vec3 v) { return mk(v.x, v.y, v.z); }
 // warp-uniform and only the box-hit predicate diverges.  refs[0 .. n) are the top-level references (lights, then objects);
 // cls[k] = shade class of what a hit on reference k shades with; mesh_bit k set = a mesh or an instance of one, which is
 // not walked here but queued for the mesh rounds (k_mesh_enter + k_mesh_walk), at most kMeshRounds per ray.
+#ifndef PT_MESH_MULTI
+#define PT_MESH_MULTI 1   // rays that enter several mesh boxes: one thread walks all their meshes (k_mesh_multi) instead of rounds 1.. of the entry pass + walk
+#endif
 constexpr int kTopMax = 32;
 constexpr int kMeshRounds = 8;
 struct TopList {
