@@ -6,7 +6,7 @@ import csv
 import json
 import sys
 
-FAMILY = [("k_top<1", "top_new"), ("k_top<(bool)1", "top_new"), ("k_top<0", "top_old"), ("k_top<(bool)0", "top_old"), ("k_mesh_enter", "mesh_enter"),
+FAMILY = [("k_top<1", "top_new"), ("k_top<(bool)1", "top_new"), ("k_top<0", "top_old"), ("k_top<(bool)0", "top_old"), ("k_mesh_multi", "mesh_multi"), ("k_mesh_enter", "mesh_enter"),
           ("k_mesh_walk", "mesh_walk"), ("k_shade<0", "miss"), ("k_shade<(int)0", "miss"), ("k_shade<1", "light"), ("k_shade<(int)1", "light"),
           ("k_shade<2", "diffuse"), ("k_shade<(int)2", "diffuse"), ("k_shade<3", "metal"), ("k_shade<(int)3", "metal"), ("k_shade<4", "glass"),
           ("k_shade<(int)4", "glass"), ("k_shade<5", "principled"), ("k_shade<(int)5", "principled")]
