@@ -27,10 +27,11 @@ def main():
         dev.close()
 
     s6 = pt.Scene.build(6, width=384, spp=1, seed=1)          # 384 x 216 = 82 944 paths per sample: above the floor
-    render("scene 6: k_top + k_mesh_enter + k_mesh_walk, forked shade, batched tail", s6)
+    render("scene 6: k_top + k_mesh_enter + k_mesh_walk + k_mesh_multi, forked shade, tail megakernel", s6)
+    render("scene 6, 800 px (360 000 paths): k_mesh_multi on its side stream", pt.Scene.build(6, width=800, spp=1, seed=1))
     render("scene 6: BVH kernels, k_trace<DEFER> + k_trace_blas_refill", s6, flags=0x400000)
     render("scene 6: BVH kernels, grid-stride mesh rounds", s6, flags=0x400000 | 0x200000)
-    render("scene 6: fused BVH kernel, unforked shade, unbatched tail", s6, flags=0x100000 | 0x2000 | 0x4000)
+    render("scene 6: fused BVH kernel, unforked shade, wavefront iterations to the last path (no tail megakernel)", s6, flags=0x100000 | 0x2000 | 0x4000)
     render("scene 70: k_top + mesh rounds", pt.Scene.build(70, width=288, spp=1, seed=1))
     render("scene 3: k_top, quad light", pt.Scene.build(3, width=288, spp=1, seed=1))
     render("scene 3: NEE shadow paths", pt.Scene.build(3, width=96, spp=2, seed=1), flags=pt.PT_RENDER_NEE)
