@@ -1,6 +1,7 @@
 // C ABI implementation (include/pt_b200.h): context, scene upload, the wavefront render loop and the
 // parity entry points.  There is NO CPU fallback: without a CUDA device every call fails loudly.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -215,8 +216,18 @@ struct Uploader {
         return PT_OK;
     }
 };
-float round_down(double v) { float f = (float)v; if ((double)f > v) f = std::nextafterf(f, -INFINITY); return f; }
-float round_up(double v) { float f = (float)v; if ((double)f < v) f = std::nextafterf(f, INFINITY); return f; }
+// the neighbouring fp32 value towards -inf / +inf, as std::nextafterf gives it, by bit arithmetic (the library call was half of the
+// box conversion's time: three calls per box, 50 000 boxes on scene 6)
+float next_down(float f) {
+    if (!(f == f) || f == -INFINITY) return f;
+    uint32_t u; memcpy(&u, &f, 4);
+    if (f == 0.0f) u = 0x80000001u;           // +-0 -> the smallest negative denormal
+    else if (f > 0.0f) u -= 1u; else u += 1u;
+    memcpy(&f, &u, 4); return f;
+}
+float next_up(float f) { return -next_down(-f); }
+float round_down(double v) { float f = (float)v; if ((double)f > v) f = next_down(f); return f; }
+float round_up(double v) { float f = (float)v; if ((double)f < v) f = next_up(f); return f; }
 
 constexpr uint32_t kWideMinItems = 64;  // BVHs over at least this many items are collapsed to 4-wide nodes
 
@@ -359,48 +370,62 @@ struct Converter {
     uint32_t wide2_depth = 0;
     struct Item { bool tri; uint32_t id; };  // tri: index into refs (a triangle reference); else a binary node slot
     const DNode& item_box(const Item& it) const { return it.tri ? refs[it.id] : nodes[it.id]; }
-    uint32_t make_wide2(std::vector<Item> items, uint32_t depth) {
+    // No heap traffic per node: an item list never grows beyond four while leaves and nodes are opened (the loop only opens what
+    // fits), and the one case with more than four items — the triangles of an oversized leaf — is a contiguous run of refs.
+    // (pt_scene_create runs inside the timed region of an end-to-end step: scene 6's 30 000 nodes took 4.3 ms with std::vector items.)
+    static void empty_wide2(DWide2& w) {
+        for (int i = 0; i < 4; i++) { for (int k = 0; k < 3; k++) { w.lo[k][i] = INFINITY; w.hi[k][i] = -INFINITY; } w.child[i] = kNone; w.pad[i] = 0; }
+    }
+    // a node over the triangle references refs[first .. first + count): up to four as direct children, more as four runs
+    uint32_t make_wide2_tris(uint32_t first, uint32_t count, uint32_t depth) {
         wide2_depth = std::max(wide2_depth, depth);
+        const uint32_t wi = (uint32_t)wide2.size();
+        wide2.emplace_back();
+        DWide2 w{}; empty_wide2(w);
+        const uint32_t n_slots = std::min(count, 4u);
+        for (uint32_t g = 0; g < n_slots; g++) {
+            const uint32_t b0 = count <= 4 ? g : (uint32_t)((uint64_t)count * g / 4), b1 = count <= 4 ? g + 1 : (uint32_t)((uint64_t)count * (g + 1) / 4);
+            float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+            for (uint32_t k = b0; k < b1; k++) { const DNode& b = refs[first + k]; for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], b.lo[a]); hi[a] = std::max(hi[a], b.hi[a]); } }
+            for (int a = 0; a < 3; a++) { w.lo[a][g] = lo[a]; w.hi[a][g] = hi[a]; }
+            w.child[g] = b1 - b0 == 1 ? (kTriBit | ref_index(refs[first + b0].a)) : make_wide2_tris(first + b0, b1 - b0, depth + 1);
+        }
+        wide2[wi] = w;
+        return wi;
+    }
+    uint32_t make_wide2(const Item* in, size_t n_in, uint32_t depth) {
+        wide2_depth = std::max(wide2_depth, depth);
+        Item items[4]; size_t n = 0;
+        for (; n < n_in && n < 4; n++) items[n] = in[n];
         // open the largest openable item until four are held: an internal node into its two children, a leaf into its
         // triangles (when they fit)
-        while (items.size() < 4) {
+        while (n < 4) {
             int best = -1; float best_area = -1.f;
-            for (size_t i = 0; i < items.size(); i++) {
+            for (size_t i = 0; i < n; i++) {
                 if (items[i].tri) continue;
-                const DNode& n = nodes[items[i].id];
-                const size_t grow = n.b == kNone ? 2 : n.b;
-                if (items.size() - 1 + grow > 4 || (n.b != kNone && n.b == 0)) continue;
-                if (half_area(n) > best_area) { best = (int)i; best_area = half_area(n); }
+                const DNode& nd = nodes[items[i].id];
+                const size_t grow = nd.b == kNone ? 2 : nd.b;
+                if (n - 1 + grow > 4 || (nd.b != kNone && nd.b == 0)) continue;
+                if (half_area(nd) > best_area) { best = (int)i; best_area = half_area(nd); }
             }
             if (best < 0) break;
-            const DNode n = nodes[items[best].id];
-            std::vector<Item> repl;
-            if (n.b == kNone) repl = {Item{false, n.a}, Item{false, n.a + 1}};
-            else for (uint32_t k = 0; k < n.b; k++) repl.push_back(Item{true, n.a + k});
-            items.erase(items.begin() + best);
-            items.insert(items.begin() + best, repl.begin(), repl.end());
+            const DNode nd = nodes[items[best].id];
+            const size_t grow = nd.b == kNone ? 2 : nd.b;
+            for (size_t i = n; i-- > (size_t)best + 1;) items[i + grow - 1] = items[i];  // make room in place, order kept
+            for (size_t k = 0; k < grow; k++) items[best + k] = nd.b == kNone ? Item{false, nd.a + (uint32_t)k} : Item{true, nd.a + (uint32_t)k};
+            n += grow - 1;
         }
         const uint32_t wi = (uint32_t)wide2.size();
         wide2.emplace_back();
-        DWide2 w{};
-        for (int i = 0; i < 4; i++) { for (int k = 0; k < 3; k++) { w.lo[k][i] = INFINITY; w.hi[k][i] = -INFINITY; } w.child[i] = kNone; w.pad[i] = 0; }
-        // more than four items can only be the triangles of one oversized leaf (a failed SAH split, bvh.rs:37-42, or an
-        // un-built mesh): group them into four runs, each run becomes a child node
-        std::vector<std::vector<Item>> slots;
-        if (items.size() <= 4) for (auto& it : items) slots.push_back({it});
-        else for (size_t g = 0; g < 4; g++) slots.emplace_back(items.begin() + items.size() * g / 4, items.begin() + items.size() * (g + 1) / 4);
-        for (size_t i = 0; i < slots.size(); i++) {
-            const auto& sl = slots[i];
-            float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-            for (const Item& it : sl) { const DNode& b = item_box(it); for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], b.lo[k]); hi[k] = std::max(hi[k], b.hi[k]); } }
-            for (int k = 0; k < 3; k++) { w.lo[k][i] = lo[k]; w.hi[k][i] = hi[k]; }
-            if (sl.size() == 1 && sl[0].tri) w.child[i] = kTriBit | ref_index(refs[sl[0].id].a);
-            else if (sl.size() == 1) {
-                const DNode& n = nodes[sl[0].id];
-                if (n.b == kNone) w.child[i] = make_wide2({Item{false, n.a}, Item{false, n.a + 1}}, depth + 1);
-                else if (n.b == 0) { w.child[i] = kNone; for (int k = 0; k < 3; k++) { w.lo[k][i] = INFINITY; w.hi[k][i] = -INFINITY; } }
-                else { std::vector<Item> tr; for (uint32_t k = 0; k < n.b; k++) tr.push_back(Item{true, n.a + k}); w.child[i] = make_wide2(tr, depth + 1); }
-            } else w.child[i] = make_wide2(sl, depth + 1);
+        DWide2 w{}; empty_wide2(w);
+        for (size_t i = 0; i < n; i++) {
+            const DNode& b = item_box(items[i]);
+            for (int k = 0; k < 3; k++) { w.lo[k][i] = b.lo[k]; w.hi[k][i] = b.hi[k]; }
+            if (items[i].tri) { w.child[i] = kTriBit | ref_index(refs[items[i].id].a); continue; }
+            const DNode nd = nodes[items[i].id];
+            if (nd.b == kNone) { const Item ch[2] = {Item{false, nd.a}, Item{false, nd.a + 1}}; w.child[i] = make_wide2(ch, 2, depth + 1); }
+            else if (nd.b == 0) { w.child[i] = kNone; for (int k = 0; k < 3; k++) { w.lo[k][i] = INFINITY; w.hi[k][i] = -INFINITY; } }
+            else w.child[i] = make_wide2_tris(nd.a, nd.b, depth + 1);  // a leaf that did not fit: its triangles become a node of their own
         }
         wide2[wi] = w;
         return wi;
@@ -414,19 +439,19 @@ struct Converter {
         return ex * ey + ex * ez + ey * ez;
     }
     // children: binary node slots.  Internal children are opened, largest box first, until four are held.
-    uint32_t make_wide(std::vector<uint32_t> children, uint32_t depth) {
+    uint32_t make_wide(const uint32_t* in, size_t n_in, uint32_t depth) {
         wide_depth = std::max(wide_depth, depth);
-        std::vector<uint32_t> kept;
-        for (uint32_t c : children) if (!(nodes[c].b != kNone && nodes[c].b == 0)) kept.push_back(c);  // drop empty dummy leaves
-        children.swap(kept);
-        while (children.size() < 4) {
+        uint32_t children[4]; size_t n = 0;
+        for (size_t i = 0; i < n_in && n < 4; i++) if (!(nodes[in[i]].b != kNone && nodes[in[i]].b == 0)) children[n++] = in[i];  // drop empty dummy leaves
+        while (n < 4) {
             int best = -1; float best_area = -1.f;
-            for (size_t i = 0; i < children.size(); i++)
+            for (size_t i = 0; i < n; i++)
                 if (nodes[children[i]].b == kNone && half_area(nodes[children[i]]) > best_area) { best = (int)i; best_area = half_area(nodes[children[i]]); }
             if (best < 0) break;
             const uint32_t pair = nodes[children[best]].a;
-            children[best] = pair;
-            children.insert(children.begin() + best + 1, pair + 1);
+            for (size_t i = n; i-- > (size_t)best + 1;) children[i + 1] = children[i];
+            children[best] = pair; children[best + 1] = pair + 1;
+            n++;
         }
         const uint32_t wi = (uint32_t)wide.size();
         wide.emplace_back();
@@ -435,10 +460,11 @@ struct Converter {
             for (int k = 0; k < 3; k++) { w.lo[k][i] = INFINITY; w.hi[k][i] = -INFINITY; }
             w.child[i] = kNone; w.pad[i] = 0;
         }
-        for (size_t i = 0; i < children.size(); i++) {
-            const DNode n = nodes[children[i]];
-            for (int k = 0; k < 3; k++) { w.lo[k][i] = n.lo[k]; w.hi[k][i] = n.hi[k]; }
-            w.child[i] = n.b == kNone ? (0x20000000u | make_wide({n.a, n.a + 1}, depth + 1)) : (0xC0000000u | children[i]);
+        for (size_t i = 0; i < n; i++) {
+            const DNode nd = nodes[children[i]];
+            for (int k = 0; k < 3; k++) { w.lo[k][i] = nd.lo[k]; w.hi[k][i] = nd.hi[k]; }
+            const uint32_t ch[2] = {nd.a, nd.a + 1};
+            w.child[i] = nd.b == kNone ? (0x20000000u | make_wide(ch, 2, depth + 1)) : (0xC0000000u | children[i]);
         }
         wide[wi] = w;
         return wi;
@@ -537,8 +563,14 @@ int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
     s->ctx = ctx;
     Uploader U{s.get()};
     Converter C; C.d = d;
+    const bool timing = getenv("PT_B200_TIMING") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto t0 = now();
+    auto lap = [&](const char* what) { if (timing) { auto t1 = now(); fprintf(stderr, "[pt_scene_create] %-28s %.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count()); t0 = t1; } };
 
     // ---- BVH: pair 0 = (objects root, lights root); every mesh gets its own (root, dummy) pair
+    C.nodes.reserve(2ull * d->n_nodes + 2ull * d->n_meshes + 8); C.refs.reserve((size_t)d->n_leaf_refs + d->n_objects + d->n_lights + d->n_triangles);
+    C.wide.reserve(d->n_nodes / 2 + 8); C.wide2.reserve((size_t)d->n_nodes + d->n_triangles / 2 + 8);
     C.nodes.resize(2);
     auto top_list = [&](uint32_t slot, uint32_t root, const pt_ref* items, uint32_t n, uint32_t top_bit) -> bool {
         if (n == 0) { C.dummy(slot); return true; }
@@ -575,18 +607,20 @@ int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
         } else if (!C.fill(pair, m.bvh_root, 0u, 1)) return fail(PT_ERR_INVALID, C.err);
         // large BVHs are collapsed to 4-wide nodes; small ones keep the binary pairs (cheaper when most rays leave at once)
         uint32_t root_entry = pair, depth_slots = C.max_depth;
-        if (use_wide) { C.wide_depth = 0; root_entry = 0x20000000u | C.make_wide({pair}, 1); depth_slots = 3 * C.wide_depth; }
+        if (use_wide) { C.wide_depth = 0; root_entry = 0x20000000u | C.make_wide(&pair, 1, 1); depth_slots = 3 * C.wide_depth; }
         blas_depth = std::max(blas_depth, depth_slots);
-        const uint32_t root2 = m.n_triangles ? C.make_wide2({Converter::Item{false, pair}}, 1) : 0u;
+        const Converter::Item root_item{false, pair};
+        const uint32_t root2 = m.n_triangles ? C.make_wide2(&root_item, 1, 1) : 0u;
         meshes[mi] = DMesh{root_entry, m.first_triangle, m.n_triangles, m.material, m.has_normals, m.has_uvs, m.bvh_root == PT_NONE, root2};
     }
     uint32_t world_root = 0, tlas_slots = tlas_depth;
-    if (use_wide) { C.wide_depth = 0; world_root = 0x20000000u | C.make_wide({0u, 1u}, 1); tlas_slots = 3 * C.wide_depth; }
+    if (use_wide) { C.wide_depth = 0; const uint32_t tops[2] = {0u, 1u}; world_root = 0x20000000u | C.make_wide(tops, 2, 1); tlas_slots = 3 * C.wide_depth; }
     // stack bound: one pending sibling per binary level / three per wide level + the mesh / instance / volume references one
     // top-level leaf can defer (counted while converting: a failed SAH split leaves a leaf of any size, bvh.rs:37-42) + sentinel
     s->max_stack = tlas_slots + blas_depth + 2 + std::max(C.max_deferred_in_leaf, 8u);
     if (s->max_stack > (uint32_t)kStack) return fail(PT_ERR_UNSUPPORTED, "BVH too deep for the device traversal stack (" + std::to_string(s->max_stack) + " > " + std::to_string(kStack) + ")");
 
+    lap("BVH conversion");
     // ---- primitives
     std::vector<DSphere> spheres(d->n_spheres);
     for (uint32_t i = 0; i < d->n_spheres; i++) {
@@ -632,6 +666,7 @@ int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
         volumes[i] = DVolume{d->volumes[i].boundary.kind, d->volumes[i].boundary.index, d->volumes[i].material, 0, -1.0 / d->volumes[i].density, 0.0};
     s->has_volumes = d->n_volumes > 0;
     s->defer_meshes = s->wide && d->n_meshes > 0 && !s->has_volumes;
+    lap("primitives");
     // ---- textures, images, materials
     std::vector<DTexture> textures(d->n_textures);
     for (uint32_t i = 0; i < d->n_textures; i++) {
@@ -737,12 +772,15 @@ int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
     U.up(tris, &D.tris); U.up(tri_normals, &D.tri_normals); U.up(tri_uvs, &D.tri_uvs); U.up(tri_mesh, &D.tri_mesh); U.up(cuboids, &D.cuboids);
     U.up(meshes, &D.meshes); U.up(instances, &D.instances); U.up(textures, &D.textures); U.up(images, &D.images); U.up(materials, &D.materials);
     U.up(lights, &D.lights); U.up(tri_verts, &D.tri_verts); U.up(volumes, &D.volumes); U.up(C.wide2, &D.wide2); U.up(tri_rank, &D.tri_rank); U.up(quad_box, &D.quad_box);
+    lap("textures, top list, misc");
     if ((rc = U.commit())) return rc;
+    lap("staging copy + H2D enqueue");
     D.image_data = d_img; D.n_lights = d->n_lights; D.root_entry = world_root; D.n_materials = d->n_materials; D.n_textures = d->n_textures;
     D.n_nodes = (uint32_t)C.nodes.size(); D.n_refs = (uint32_t)C.refs.size(); D.n_wide = (uint32_t)C.wide.size(); D.n_wide2 = (uint32_t)C.wide2.size();
     D.n_tris = d->n_triangles; D.n_quads = d->n_quads; D.n_spheres = d->n_spheres; D.n_instances = d->n_instances; D.n_meshes = d->n_meshes;
     s->n_materials = d->n_materials; s->n_images = d->n_images; s->images = images;
     CU(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+    lap("stream synchronize");
     // the tail megakernel this scene's renders end in: load its code now (tail_wide.cu), not inside the first render
     if (!s->has_volumes && !s->general_lights) { if (s->wide) preload_k_tail_wide(); else preload_k_tail_bin(); }
     *out = s.release();
