@@ -229,6 +229,21 @@ float next_up(float f) { return -next_down(-f); }
 float round_down(double v) { float f = (float)v; if ((double)f > v) f = next_down(f); return f; }
 float round_up(double v) { float f = (float)v; if ((double)f < v) f = next_up(f); return f; }
 
+// Reciprocals for path_pixel (wavefront.cuh).  With 2^K = d k + r (0 < r < d) and M = k + 1: x M / 2^K = q + (q (d - r) + s (k + 1)) / 2^K for
+// x = d q + s, so mulhi(x, M) = q = x / d as long as q (d - 1) + (d - 1)(k + 1) < 2^K, i.e. q_max (d - 1) < k + 1 + r - d.  0 = "divide".
+template <class U, class W> static U exact_reciprocal(U d, uint64_t x_end) {  // for every x < x_end; U = uint32_t / uint64_t, W = the double-width type
+    if (d < 2 || (d & (d - 1)) == 0 || x_end == 0) return 0;                 // powers of two: the division is a shift anyway
+    const U k = (U)(~(U)0 / d), r = (U)(0 - d * k);                           // floor(2^K / d) (d does not divide 2^K), 2^K - d k
+    const uint64_t q_max = (x_end - 1) / d;
+    if ((W)k + 1 + r <= (W)d || (W)q_max * (d - 1) >= (W)k + 1 + r - d) return 0;
+    return (U)(k + 1);
+}
+static void set_index_reciprocals(RenderConst& rc, uint32_t n_pixels, uint64_t total_paths, uint32_t width) {
+    rc.inv_pixels = exact_reciprocal<uint64_t, unsigned __int128>(n_pixels, total_paths);
+    rc.inv_tiles_x = exact_reciprocal<uint32_t, uint64_t>(width >> 3, (uint64_t)(n_pixels >> 5) + 1);
+    rc.inv_width = exact_reciprocal<uint32_t, uint64_t>(width, n_pixels);
+}
+
 constexpr uint32_t kWideMinItems = 64;  // BVHs over at least this many items are collapsed to 4-wide nodes
 
 struct Converter {
@@ -1024,6 +1039,7 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
     }
     // experiment knob: flag 0x8000 overrides the octant mask of the survivor grouping with flag bits 16-18
     rcst.sort_mask = (p->flags & 0x8000u) ? ((p->flags >> 16) & 7u) : 7u;
+    set_index_reciprocals(rcst, n_pixels, total, dcam.c.width);
     cudaStream_t st = ctx->stream;
     CU(cudaMemsetAsync(ctx->d_nonfinite, 0, 4 * sizeof(unsigned long long), st));
     pt_stats S{}; S.width = dcam.c.width; S.height = dcam.c.height;
@@ -1397,7 +1413,8 @@ int pt_trace_camera_wavefront(pt_ctx* ctx, const pt_scene* scene, const pt_camer
     pt_stats S{}; S.width = dcam.c.width; S.height = dcam.c.height;
     DevBuf d_rays, d_hits;
     if ((rc = d_rays.alloc((size_t)n * sizeof(pt_ray))) || (rc = d_hits.alloc((size_t)n * sizeof(pt_hit)))) return rc;
-    const RenderConst rcst{seed, sample, 1u, PT_NAN_REFERENCE, 0, DEnvDist{nullptr, nullptr, 0, 0}};
+    RenderConst rcst{seed, sample, 1u, PT_NAN_REFERENCE, 0, DEnvDist{nullptr, nullptr, 0, 0}};
+    set_index_reciprocals(rcst, n, n, dcam.c.width);
     const GenArgs gen{0, n, dcam, rcst};
     const TraceStage T{ctx, scene, flags, seed, 1e-3, nullptr, &S};  // Interval::new(eps, INFINITY), camera.rs:171,179
     const PathBuf in = path_buf(ctx, 0);

@@ -10,11 +10,11 @@ __global__ void __launch_bounds__(kBlock) k_generate(PathBuf out, uint32_t slot0
                                                       DCameraEx cam, RenderConst rc) {
     uint32_t i = blockIdx.x * kBlock + threadIdx.x;
     if (i >= n_new) return;
-    uint32_t s_local, pix;
-    path_pixel(g0 + i, n_pixels, cam.c, pix, s_local);
+    uint32_t s_local, pix, row, col;
+    path_pixel(g0 + i, n_pixels, cam.c, rc, pix, s_local, row, col);
     uint32_t sample = rc.sample_begin + s_local * rc.sample_stride;
     Rng rng; rng.init(rc.seed, pix, sample, 0);
-    RayD r = generate_ray(cam, pix / cam.c.width, pix % cam.c.width, rng);
+    RayD r = generate_ray(cam, row, col, rng);
     store_path(out, slot0 + i, r, mk(1, 1, 1), make_uint4(pix, sample, rng.used, 0));
 }
 

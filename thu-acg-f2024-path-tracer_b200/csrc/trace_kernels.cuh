@@ -325,11 +325,11 @@ __global__ void __launch_bounds__(kBlock, PT_TOP_MIN_BLOCKS) k_top(PathBuf pool,
     if (j < n) {
         RayD r;
         if (PRIMARY) {
-            uint32_t s_local, pix;
-            path_pixel(gen.g0 + j, gen.n_pixels, gen.cam.c, pix, s_local);
+            uint32_t s_local, pix, row, col;
+            path_pixel(gen.g0 + j, gen.n_pixels, gen.cam.c, gen.rc, pix, s_local, row, col);
             const uint32_t sample = gen.rc.sample_begin + s_local * gen.rc.sample_stride;
             Rng rng; rng.init(gen.rc.seed, pix, sample, 0);
-            r = generate_ray(gen.cam, pix / gen.cam.c.width, pix % gen.cam.c.width, rng);
+            r = generate_ray(gen.cam, row, col, rng);
             store_path(pool, i, r, mk(1, 1, 1), make_uint4(pix, sample, rng.used, 0));
         } else r = load_ray(pool, i);
         const BoxRay br = make_boxray(r);

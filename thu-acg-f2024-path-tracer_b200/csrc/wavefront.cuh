@@ -45,6 +45,9 @@ struct RenderConst {
     uint64_t seed; uint32_t sample_begin, sample_stride, nan_policy, env_importance;
     DEnvDist env;
     uint32_t sort_mask = 0;  // survivors of a shade block are grouped by (direction octant & sort_mask): bit 0 = y, 1 = x, 2 = z
+    // path index -> (sample, pixel tile, row, column) without integer divisions: floor(2^64 / pixels) + 1, floor(2^32 / tiles per row) + 1,
+    // floor(2^32 / width) + 1 where the host has checked that the multiply-high is exact for every index of the render, else 0 (divide)
+    uint64_t inv_pixels = 0; uint32_t inv_tiles_x = 0, inv_width = 0;
 };
 
 // ---------------------------------------------------------------- camera.rs:133-168
@@ -67,11 +70,16 @@ PT_D RayD generate_ray(const DCameraEx& cam, uint32_t row, uint32_t col, Rng& rn
 }
 // g = index of a path within one render call -> (pixel, local sample): sample-major, and within a sample a warp covers an
 // 8x4 pixel tile (tighter ray bundles than a 32x1 strip) when the image size allows
-PT_D void path_pixel(uint64_t g, uint32_t n_pixels, const DCamera& cam, uint32_t& pix, uint32_t& s_local) {
-    s_local = (uint32_t)(g / n_pixels); pix = (uint32_t)(g % n_pixels);
+PT_D void path_pixel(uint64_t g, uint32_t n_pixels, const DCamera& cam, const RenderConst& rc, uint32_t& pix, uint32_t& s_local, uint32_t& row, uint32_t& col) {
+    if (rc.inv_pixels) { s_local = (uint32_t)__umul64hi(g, rc.inv_pixels); pix = (uint32_t)(g - (uint64_t)s_local * n_pixels); }
+    else { s_local = (uint32_t)(g / n_pixels); pix = (uint32_t)(g % n_pixels); }
     if ((cam.width & 7u) == 0 && (cam.height & 3u) == 0) {
         const uint32_t tile = pix >> 5, within = pix & 31u, tiles_x = cam.width >> 3;
-        pix = ((tile / tiles_x) * 4u + (within >> 3)) * cam.width + (tile % tiles_x) * 8u + (within & 7u);
+        const uint32_t ty = rc.inv_tiles_x ? __umulhi(tile, rc.inv_tiles_x) : tile / tiles_x, tx = tile - ty * tiles_x;
+        row = ty * 4u + (within >> 3); col = tx * 8u + (within & 7u);
+        pix = row * cam.width + col;
+    } else {
+        row = rc.inv_width ? __umulhi(pix, rc.inv_width) : pix / cam.width; col = pix - row * cam.width;
     }
 }
 PT_D d3 sample_environment(const DScene& S, const DCamera& cam, d3 dir) {  // camera.rs:140-151
