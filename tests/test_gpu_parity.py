@@ -113,7 +113,7 @@ def test_render_traversal_stage_matches_oracle(pt, orc, ctx, pairs, scene_id, wi
     assert_hits_equal(pt, small, want[:TWO_PASS_MIN - 1], f"scene {scene_id} below the two-pass floor")
 
 
-@pytest.mark.parametrize("scene_id,width", [(6, 400), (70, 300), (3, 128), (5, 160), (1, 160)])
+@pytest.mark.parametrize("scene_id,width", [(6, 400), (70, 300), (3, 128), (5, 160), (1, 160), (3, 150), (4, 1001)])  # 150 / 1001: no 8x4 pixel tiles, row = pixel / width
 def test_start_of_path_stage_matches_oracle(pt, orc, ctx, pairs, scene_id, width):
     """pt_trace_camera_wavefront = the first iteration of a render: on flat scenes k_top<PRIMARY> generates the camera ray in
     registers and traces it in the same launch (there is no k_generate).  Rays equal the oracle's generate_ray for the same
