@@ -952,14 +952,17 @@ struct TraceStage {
 };
 // `in` holds n_old live paths in slots [0, n_old); n_new more are STARTED in slots [n_old, n_old + n_new) — camera rays
 // (camera.rs:153-168) generated by the top-level kernel itself on flat scenes, by k_generate otherwise.
+// flat top level (k_top) + mesh kernels: every scene with a small World; with meshes not for small iterations (two more launches);
+// flags 0x100000 / 0x400000 opt out (A/B measurements, and the tests that pin this path to the BVH kernels)
+static bool takes_flat_path(const pt_scene* scene, uint32_t flags, uint32_t n) {
+    return scene->flat && !(flags & 0x500000u) && (scene->mesh_rounds == 0 || n >= (1u << 16));
+}
 static void launch_trace(const TraceStage& T, const PathBuf& in, uint32_t n_old, uint32_t n_new, const GenArgs* gen, const Queues& q, const uint32_t* n_dev) {
     pt_ctx* ctx = T.ctx; const pt_scene* scene = T.scene; pt_stats& S = *T.S;
     unsigned long long* const wk = T.wk;
     cudaStream_t st = ctx->stream;
     const uint32_t n = n_old + n_new;
-    // flat top level (k_top) + mesh rounds: every scene with a small World; with meshes not for small iterations (two more
-    // launches per round); flags 0x100000 / 0x400000 opt out (A/B measurements, and the tests that pin this path to the BVH kernels)
-    if (scene->flat && !(T.flags & 0x500000u) && (scene->mesh_rounds == 0 || n >= (1u << 16))) {
+    if (takes_flat_path(scene, T.flags, n)) {
         uint32_t* slot = q.count - 4;
         const MeshQueues mq{ctx->mq_items, slot + 12, ctx->pool, ctx->walk, slot + 20};
         static const GenArgs no_gen{};
@@ -1088,6 +1091,7 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
     while (dcam.c.max_depth > 0 && (live > 0 || generated < total)) {
         if (tail_mega && generated == total && live > 0 && live <= tail_max_paths(scene->flat && scene->mesh_rounds == 0)) {
             // ---- tail megakernel: every remaining path runs to its end in one launch
+            rcst.fresh_from = 0xFFFFFFFFu;
             CU(cudaMemsetAsync(ctx->d_count, 0, 2 * sizeof(uint32_t), st));
             ctx->mark(-1);
             const TailArgs ta{path_buf(ctx, cur), live, d_accum, ctx->d_nonfinite, scene->d, dcam, rcst, tstage.t_min, ctx->d_count};
@@ -1102,6 +1106,7 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
         }
         if (tail_batching && generated == total && live <= kTailBatchMaxLive) {
             // ---- batched tail: kTailBatch iterations per host round trip (see kTailBatch)
+            rcst.fresh_from = 0xFFFFFFFFu;  // nothing is started any more: every state record is real
             const uint32_t n0 = live;
             CU(cudaMemsetAsync(ctx->d_count, 0, kTailBatch * kSlot * sizeof(uint32_t), st));
             for (int k = 0; k < kTailBatch; k++) {
@@ -1127,6 +1132,9 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
         CU(cudaMemsetAsync(ctx->d_count, 0, kSlot * sizeof(uint32_t), st));
         const Queues q{ctx->q_items, ctx->d_count + 4, ctx->pool};
         if (ctx->profiling) CU(cudaEventRecord(ctx->evs[1], st));
+        // flat scenes: k_top<PRIMARY> starts the n_new paths in slots [live, n) and leaves their state record implicit (wavefront.cuh:
+        // RenderConst::fresh_from); the NEE shade kernels and the k_generate route keep real state records
+        rcst.fresh_from = (!nee && n_new > 0 && takes_flat_path(scene, p->flags, n)) ? live : 0xFFFFFFFFu;
         const GenArgs gen{generated, n_pixels, dcam, rcst};  // the n_new camera rays of this iteration are generated inside the traversal stage
         launch_trace(tstage, in, live, n_new, &gen, q, nullptr);
         if (ctx->profiling) CU(cudaEventRecord(ctx->evs[2], st));

@@ -48,8 +48,9 @@ PT_D void stage_tables(DScene& S) {
 #ifndef PT_SHADE_WARP_COMPACT
 #define PT_SHADE_WARP_COMPACT 0   // measured: scene 6 +0.5 %, scenes 7m / 3 -2.2 % (the block-wide octant grouping is worth more than the barriers cost)
 #endif
-PT_D void prefetch_path(const PathBuf& b, const HitRec* __restrict__ hits, uint32_t i, bool with_hit) {
-    prefetch_l1(b.ray + i); prefetch_l1(b.state + i);
+PT_D void prefetch_path(const PathBuf& b, const HitRec* __restrict__ hits, uint32_t i, bool with_hit, uint32_t fresh_from) {
+    prefetch_l1(b.ray + i);
+    if (i < fresh_from) prefetch_l1(b.state + i);
     if (with_hit) prefetch_l1(hits + i);
 }
 
@@ -133,8 +134,8 @@ PT_D bool shade_one(const DScene& S, const DCameraEx& cam, const RenderConst& rc
 // The paths of ONE shade class: grid-stride over the class queue, shade_one per path; survivors are written compacted into `out`
 // (ballot + block prefix + one atomic).
 struct PrefetchHook {
-    const PathBuf& b; const HitRec* __restrict__ hits; uint32_t i; bool go, with_hit;
-    PT_D void operator()() const { if (go) prefetch_path(b, hits, i, with_hit); }
+    const PathBuf& b; const HitRec* __restrict__ hits; uint32_t i; bool go, with_hit; uint32_t fresh_from;
+    PT_D void operator()() const { if (go) prefetch_path(b, hits, i, with_hit, fresh_from); }
 };
 template <int CLS, int VAR = 0>
 __global__ void __launch_bounds__(kShadeBlock, PT_SHADE_MIN_BLOCKS * 128 / kShadeBlock) k_shade(PathBuf in, Queues q, const HitRec* __restrict__ hits, PathBuf out,
@@ -167,11 +168,12 @@ __global__ void __launch_bounds__(kShadeBlock, PT_SHADE_MIN_BLOCKS * 128 / kShad
 #endif
             PT_ASSERT(i < q.stride);
             const RayD ray = load_ray(in, i, &ids.x, &ids.y);
-            thr = load_state(in, i, ids.z, ids.w);
+            if (i >= rc.fresh_from) { thr = mk(1, 1, 1); ids.z = kFreshDraws; ids.w = 0; }  // started this iteration: implicit state
+            else thr = load_state(in, i, ids.z, ids.w);
             HitRec hr; hr.t = 0.0; hr.ref = kNone; hr.inst_light = 0;
             if (CLS != CLS_MISS) hr = hits[i];
 #if PT_SHADE_PREFETCH
-            alive = shade_one<CLS, VAR>(S, cam, rc, accum, nonfinite, ray, hr, thr, ids, next, PrefetchHook{in, hits, i_next, has_next, CLS != CLS_MISS});
+            alive = shade_one<CLS, VAR>(S, cam, rc, accum, nonfinite, ray, hr, thr, ids, next, PrefetchHook{in, hits, i_next, has_next, CLS != CLS_MISS, rc.fresh_from});
 #else
             alive = shade_one<CLS, VAR>(S, cam, rc, accum, nonfinite, ray, hr, thr, ids, next);
 #endif

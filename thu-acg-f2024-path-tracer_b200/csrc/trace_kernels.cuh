@@ -330,7 +330,9 @@ __global__ void __launch_bounds__(kBlock, PT_TOP_MIN_BLOCKS) k_top(PathBuf pool,
             const uint32_t sample = gen.rc.sample_begin + s_local * gen.rc.sample_stride;
             Rng rng; rng.init(gen.rc.seed, pix, sample, 0);
             r = generate_ray(gen.cam, row, col, rng);
-            store_path(pool, i, r, mk(1, 1, 1), make_uint4(pix, sample, rng.used, 0));
+            PT_ASSERT(rng.used == kFreshDraws);
+            if (gen.rc.fresh_from != 0xFFFFFFFFu) store_ray(pool, i, r, pix, sample);  // the state of a fresh path is implicit (RenderConst::fresh_from)
+            else store_path(pool, i, r, mk(1, 1, 1), make_uint4(pix, sample, rng.used, 0));
         } else r = load_ray(pool, i);
         const BoxRay br = make_boxray(r);
         const float tmin_f = __double2float_rd(t_min);

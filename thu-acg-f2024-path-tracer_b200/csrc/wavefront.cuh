@@ -48,7 +48,12 @@ struct RenderConst {
     // path index -> (sample, pixel tile, row, column) without integer divisions: floor(2^64 / pixels) + 1, floor(2^32 / tiles per row) + 1,
     // floor(2^32 / width) + 1 where the host has checked that the multiply-high is exact for every index of the render, else 0 (divide)
     uint64_t inv_pixels = 0; uint32_t inv_tiles_x = 0, inv_width = 0;
+    // Path slots >= fresh_from hold paths that were STARTED in this wavefront iteration (k_top<PRIMARY>): their state record is implicit —
+    // throughput (1, 1, 1), bounce 0, kFreshDraws uniforms consumed by generate_ray — and is neither written by k_top nor read by the
+    // shade kernels (32 B less to store and 32 B less to gather for half of all segments).  0xFFFFFFFF: every state record is real.
+    uint32_t fresh_from = 0xFFFFFFFFu;
 };
+constexpr uint32_t kFreshDraws = 5;  // generate_ray: two draws per random_offsets call (pixel jitter, lens), one for the time (camera.rs:153-168)
 
 // ---------------------------------------------------------------- camera.rs:133-168
 PT_D void random_offsets(Rng& rng, double& x, double& y) {
@@ -138,6 +143,11 @@ PT_D void store_path(const PathBuf& b, uint32_t i, const RayD& r, d3 thr, uint4 
     st256(p, __double_as_longlong(r.o.x), __double_as_longlong(r.o.y), __double_as_longlong(r.o.z), __double_as_longlong(r.d.x));
     st256(p + 32, __double_as_longlong(r.d.y), __double_as_longlong(r.d.z), __double_as_longlong(r.time), pack2(ids.x, ids.y));
     st256(b.state + i, __double_as_longlong(thr.x), __double_as_longlong(thr.y), __double_as_longlong(thr.z), pack2(ids.z, ids.w));
+}
+PT_D void store_ray(const PathBuf& b, uint32_t i, const RayD& r, uint32_t pixel, uint32_t sample) {  // the ray record alone (fresh paths)
+    char* p = reinterpret_cast<char*>(b.ray + i);
+    st256(p, __double_as_longlong(r.o.x), __double_as_longlong(r.o.y), __double_as_longlong(r.o.z), __double_as_longlong(r.d.x));
+    st256(p + 32, __double_as_longlong(r.d.y), __double_as_longlong(r.d.z), __double_as_longlong(r.time), pack2(pixel, sample));
 }
 PT_D RayD load_ray(const PathBuf& b, uint32_t i, uint32_t* pixel = nullptr, uint32_t* sample = nullptr) {
     const char* p = reinterpret_cast<const char*>(b.ray + i);
