@@ -48,6 +48,11 @@ PT_D void stage_tables(DScene& S) {
 #ifndef PT_SHADE_WARP_COMPACT
 #define PT_SHADE_WARP_COMPACT 0   // measured: scene 6 +0.5 %, scenes 7m / 3 -2.2 % (the block-wide octant grouping is worth more than the barriers cost)
 #endif
+// PT_SHADE_WARP_SCAN: the block prefix of the survivor compaction is computed by warp 0 with shuffles (one lane per counter) instead of
+// serially by thread 0, which every other thread of the block waits for at the second barrier.
+#ifndef PT_SHADE_WARP_SCAN
+#define PT_SHADE_WARP_SCAN 1
+#endif
 PT_D void prefetch_path(const PathBuf& b, const HitRec* __restrict__ hits, uint32_t i, bool with_hit, uint32_t fresh_from) {
     prefetch_l1(b.ray + i);
     if (i < fresh_from) prefetch_l1(b.state + i);
@@ -217,6 +222,19 @@ __global__ void __launch_bounds__(kShadeBlock, PT_SHADE_MIN_BLOCKS * 128 / kShad
         }
         if (lane < 8) bin_count[par][lane][warp] = cnt;
         __syncthreads();
+#if PT_SHADE_WARP_SCAN
+        if (warp == 0) {  // exclusive prefix over the 8 x (warps per block) counters, bin-major, by one warp: lane l <-> (bin l / nw, warp l % nw)
+            constexpr uint32_t nw = kShadeBlock / 32;
+            static_assert(8 * nw <= 32, "one lane per (bin, warp) counter");
+            const uint32_t c = lane < 8 * nw ? bin_count[par][lane / nw][lane % nw] : 0u;
+            uint32_t incl = c;
+#pragma unroll
+            for (uint32_t d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
+            const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            if (lane < 8 * nw) bin_count[par][lane / nw][lane % nw] = incl - c;
+            if (lane == 0) block_base[par] = total ? atomicAdd(out_count, total) : 0;
+        }
+#else
         if (threadIdx.x == 0) {
             uint32_t total = 0;
 #pragma unroll
@@ -225,6 +243,7 @@ __global__ void __launch_bounds__(kShadeBlock, PT_SHADE_MIN_BLOCKS * 128 / kShad
                 for (int w = 0; w < kShadeBlock / 32; w++) { uint32_t c = bin_count[par][b][w]; bin_count[par][b][w] = total; total += c; }
             block_base[par] = total ? atomicAdd(out_count, total) : 0;
         }
+#endif
         __syncthreads();
         if (alive) {
             uint32_t dst = block_base[par] + bin_count[par][key][warp] + __popc(mine & ((1u << lane) - 1u));
