@@ -974,7 +974,10 @@ static void launch_trace(const TraceStage& T, const PathBuf& in, uint32_t n_old,
         // rays that entered several mesh boxes (queue 1): k_mesh_multi, on a side stream next to the entry pass + walk of queue 0
         // (on the main stream when per-stage events are wanted or the iteration is small)
         const bool multi = kMeshMulti && scene->mesh_rounds >= 2;
-        const bool side = multi && !ctx->profiling && n >= (1u << 18);
+#ifndef PT_MULTI_SIDE_MIN
+#define PT_MULTI_SIDE_MIN (1u << 16)   // measured flat from 64 Ki to 1 Mi rays (profiles/r2_ab/r2_x_multi_side_threshold.log)
+#endif
+        const bool side = multi && !ctx->profiling && n >= PT_MULTI_SIDE_MIN;
         if (multi) {
             cudaStream_t ms = side ? ctx->shade_stream[0] : st;
             if (side) { cudaEventRecord(ctx->ev_fork, st); cudaStreamWaitEvent(ms, ctx->ev_fork, 0); }
