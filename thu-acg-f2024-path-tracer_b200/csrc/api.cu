@@ -1080,6 +1080,7 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
             if (nee) run_k_shade_nee(cls, sg, ss, sa);
             else if (rcst.env_importance) run_k_shade_var(cls, 3, sg, ss, sa);
             else if (scene->general_lights) run_k_shade_var(cls, 2, sg, ss, sa);
+            else if (scene->d.n_lights == 0) run_k_shade_nolights(cls, sg, ss, sa);
             else run_k_shade_ref(cls, sg, ss, sa);
             if (fork) { CU(cudaEventRecord(ctx->ev_join[cls], ss)); CU(cudaStreamWaitEvent(st, ctx->ev_join[cls], 0)); }
             else ctx->mark(8 + cls);

@@ -1,5 +1,5 @@
 // Host-callable launchers of the sm_100a kernels.  The kernels live in four translation units that are compiled in
-// parallel (trace.cu, shade_ref.cu, shade_var.cu, shade_nee.cu, tail_wide.cu, tail_bin.cu, misc.cu); api.cu holds no device code.
+// parallel (trace.cu, shade_ref.cu, shade_nol.cu, shade_var.cu, shade_nee.cu, tail_wide.cu, tail_bin.cu, misc.cu); api.cu holds no device code.
 #pragma once
 #include "wavefront.cuh"
 
@@ -37,6 +37,7 @@ struct ShadeArgs {
     DScene S; DCameraEx cam; RenderConst rc;
 };
 void run_k_shade_ref(int cls, unsigned grid, cudaStream_t st, const ShadeArgs& a);            // shade_ref.cu (var 0)
+void run_k_shade_nolights(int cls, unsigned grid, cudaStream_t st, const ShadeArgs& a);       // shade_nol.cu (var 4: World.lights is empty)
 void run_k_shade_var(int cls, int var, unsigned grid, cudaStream_t st, const ShadeArgs& a);   // shade_var.cu (var 2, 3)
 void run_k_shade_nee(int cls, unsigned grid, cudaStream_t st, const ShadeArgs& a);            // shade_nee.cu (PT_RENDER_NEE)
 
