@@ -15,7 +15,10 @@
 
 namespace ptd {
 
-constexpr int kTailBlock = 64;
+#ifndef PT_TAIL_BLOCK
+#define PT_TAIL_BLOCK 64
+#endif
+constexpr int kTailBlock = PT_TAIL_BLOCK;
 template <bool WIDE>
 __global__ void __launch_bounds__(kTailBlock) k_tail(PathBuf in, uint32_t n, float* __restrict__ accum, unsigned long long* __restrict__ nonfinite,
                                                       DScene S, DCameraEx cam, RenderConst rc, double t_min, uint32_t* __restrict__ counters) {
