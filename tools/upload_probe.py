@@ -1,5 +1,7 @@
+#!/usr/bin/env python3
+"""Developer probe (GPU box): time of pt_scene_create (scene conversion + H2D) per scene; with PT_B200_TIMING=1 the library prints its phases."""
 import os, sys, time
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import __graft_entry__ as ge
 pt = ge.load_package()
 ctx = pt.Context(0)
