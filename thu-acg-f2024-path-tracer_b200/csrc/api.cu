@@ -797,7 +797,7 @@ int pt_scene_create(pt_ctx* ctx, const pt_scene_desc* d, pt_scene** out) {
     CU(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
     lap("stream synchronize");
     // the tail megakernel this scene's renders end in: load its code now (tail_wide.cu), not inside the first render
-    if (!s->has_volumes && !s->general_lights) { if (s->wide) preload_k_tail_wide(); else preload_k_tail_bin(); }
+    if (!s->has_volumes && !s->general_lights) { if (s->flat) preload_k_tail_flat(); else if (s->wide) preload_k_tail_wide(); else preload_k_tail_bin(); }
     *out = s.release();
     return PT_OK;
 }
@@ -1099,7 +1099,8 @@ int pt_render_accumulate(pt_ctx* ctx, const pt_scene* scene, const pt_camera* ca
             CU(cudaMemsetAsync(ctx->d_count, 0, 2 * sizeof(uint32_t), st));
             ctx->mark(-1);
             const TailArgs ta{path_buf(ctx, cur), live, d_accum, ctx->d_nonfinite, scene->d, dcam, rcst, tstage.t_min, ctx->d_count};
-            if (scene->wide) run_k_tail_wide(st, ta); else run_k_tail_bin(st, ta);
+            if (scene->flat && !(p->flags & 0x500000u)) run_k_tail_flat(st, ta, scene->top);  // flags 0x100000 / 0x400000 pin the BVH kernels
+            else if (scene->wide) run_k_tail_wide(st, ta); else run_k_tail_bin(st, ta);
             ctx->mark(6);
             CU(cudaMemcpyAsync(ctx->h_count, ctx->d_count, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));

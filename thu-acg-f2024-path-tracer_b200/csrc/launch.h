@@ -1,5 +1,5 @@
 // Host-callable launchers of the sm_100a kernels.  The kernels live in four translation units that are compiled in
-// parallel (trace.cu, shade_ref.cu, shade_nol.cu, shade_var.cu, shade_nee.cu, tail_wide.cu, tail_bin.cu, misc.cu); api.cu holds no device code.
+// parallel (trace.cu, shade_ref.cu, shade_nol.cu, shade_var.cu, shade_nee.cu, tail_wide.cu, tail_bin.cu, tail_flat.cu, misc.cu); api.cu holds no device code.
 #pragma once
 #include "wavefront.cuh"
 
@@ -48,8 +48,10 @@ struct TailArgs {
 };
 void run_k_tail_wide(cudaStream_t st, const TailArgs& a);
 void run_k_tail_bin(cudaStream_t st, const TailArgs& a);
+void run_k_tail_flat(cudaStream_t st, const TailArgs& a, const TopList& top);  // tail_flat.cu: flat scenes
 void preload_k_tail_wide();
 void preload_k_tail_bin();
+void preload_k_tail_flat();
 
 // ---- misc.cu: ray generation, tonemap, parity entry kernels
 void run_k_generate(cudaStream_t st, PathBuf out, uint32_t slot0, uint32_t n_new, uint64_t g0, uint32_t n_pixels, const DCameraEx& cam, const RenderConst& rc);
